@@ -1,0 +1,151 @@
+/* pfb200.h — C ABI of libpfb200.so, the B200-native ELBO-and-resample engine.
+ *
+ * The reference (mlcolab/Pathfinder.jl v0.10.7) has no FFI layer: its hot path is entered
+ * through ordinary Julia functions.  Each entry point below names the reference call it
+ * replaces (paths relative to the reference repo).  INTEGRATION.md shows the Julia `ccall`
+ * shim and the Python ctypes binding (pathfinder_b200/_lib.py) that a maintainer would add.
+ *
+ * Conventions
+ *   - all reals are IEEE double, all matrices column-major (Julia layout), indices 1-based
+ *     where the reference's are (best_iter, inds, ids);
+ *   - the caller owns every host buffer; the engine never keeps a host pointer after return;
+ *   - return 0 = OK, < 0 = argument/shape error (ArgumentError / DimensionMismatch),
+ *     > 0 = CUDA runtime error code; pfb_last_error() gives the text;
+ *   - numerical failure is data, not an error: a non-positive-definite iteration gets
+ *     ELBO = NaN (the reference throws PosDefException from cholesky, src/woodbury.jl:205),
+ *     non-finite log densities propagate as in src/elbo.jl:16-17, success[] mirrors
+ *     src/singlepath.jl:309-314.
+ */
+#ifndef PFB200_H
+#define PFB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFB_OK 0
+#define PFB_ERR_ARG (-1)
+#define PFB_ERR_SHAPE (-2)
+#define PFB_ERR_UNSUPPORTED (-3)
+#define PFB_ERR_STATE (-4)
+
+/* registered device-side target log densities */
+#define PFB_MODEL_ISONORMAL 0 /* logp(x) = -|x|^2/2          test/singlepath.jl:15          */
+#define PFB_MODEL_FUNNEL 1    /* Neal's funnel               docs/src/examples/quickstart.md:229-234 */
+#define PFB_MODEL_DIAGNORMAL 2 /* independent normals; blob = { mean[n], sd[n] }  test/elbo.jl:8-12 */
+
+typedef struct pfb_engine* pfb_handle;
+
+/* Keyword defaults of the reference (src/Pathfinder.jl:24-27, src/inverse_hessian.jl:25). */
+typedef struct {
+    int32_t device;          /* CUDA device ordinal                                          */
+    int32_t history_length;  /* J, DEFAULT_HISTORY_LENGTH = 6                                 */
+    int32_t ndraws_elbo;     /* K, DEFAULT_NDRAWS_ELBO = 5                                    */
+    int32_t materialize_all; /* 1: keep the draws of every iteration on the device (mode M,
+                                the ELBOEstimate.draws payload of src/elbo.jl:19); 0: lean    */
+    double eps;              /* curvature tolerance, 1e-12                                    */
+} pfb_config;
+
+/* Outputs of pfb_elbo_batch / pfb_batch_download.  Any pointer may be NULL (skipped).
+ * U = sum_p L_p units; unit order = path-major, iteration-minor (elbo_estimates[l] of path p). */
+typedef struct {
+    double* elbo;        /* [U]        ELBOEstimate.value                      src/elbo.jl:17 */
+    double* elbo_se;     /* [U]        ELBOEstimate.std_err                    src/elbo.jl:18 */
+    double* logp;        /* [K x U]    log_densities_target per iteration      src/elbo.jl:15 */
+    double* logq;        /* [K x U]    log_densities_fit                        src/mvnormal.jl:36 */
+    int64_t* best_iter;  /* [P]        fit_iteration, 1-based, 0 = none         src/elbo.jl:8  */
+    int32_t* success;    /* [P]                                       src/singlepath.jl:309-314 */
+    int64_t* n_rejected; /* [P]        num_bfgs_updates_rejected      src/inverse_hessian.jl:57 */
+    double* draws;       /* [n x K x P] draws of the best iteration  src/singlepath.jl:231-232 */
+    double* draws_logp;  /* [K x P]                                                            */
+    double* draws_logq;  /* [K x P]                                                            */
+    /* best-iteration fit_distribution in the reference's WoodburyPDMat form (f4):            */
+    double* fit_mu;      /* [n x P]    MvNormal.mu                              src/mvnormal.jl:17 */
+    double* fit_alpha;   /* [n x P]    diag(A)                                                 */
+    double* fit_vh;      /* [n x KP x P] Householder reflectors of F.Q (unit diagonal explicit) */
+    double* fit_T;       /* [KP x KP x P] compact-WY T of F.Q, row-major                       */
+    double* fit_Vc;      /* [KP x KP x P] F.V (upper Cholesky factor), row-major               */
+    double* fit_logdet;  /* [P]        logdet(Sigma)                     src/woodbury.jl:77-80 */
+    int32_t* fit_jeff;   /* [P]        history_length_effective                                */
+    double* all_draws;   /* [n x K x U] every iteration's draws (only if materialize_all)       */
+} pfb_elbo_out;
+
+/* Outputs of the PSIS + resample stage. Any pointer may be NULL. */
+typedef struct {
+    double* log_weights; /* [N] normalised smoothed log weights     PSISResult.log_weights     */
+    double* weights;     /* [N] exp(log_weights)                    PSISResult.weights         */
+    double* pareto_k;    /* [1] PSISResult.pareto_shape                                        */
+    int64_t* tail_len;   /* [1] PSISResult.tail_length                                         */
+    int64_t* inds;       /* [ndraws] sample_inds, 1-based           src/resample.jl:60-67      */
+    int64_t* ids;        /* [ndraws] draw_component_ids             src/resample.jl:70         */
+    double* draws;       /* [n x ndraws]                            src/resample.jl:68         */
+} pfb_resample_out;
+
+/* lifetime ---------------------------------------------------------------------------------- */
+int pfb_create(pfb_handle* out, const pfb_config* cfg);
+int pfb_destroy(pfb_handle h);
+const char* pfb_last_error(pfb_handle h);
+int pfb_kp(pfb_handle h); /* padded reflector count KP (12, 20 or 24) for history_length     */
+
+/* Target density: replaces the Julia closure logp(x) (src/singlepath.jl:186, src/multipath.jl:159)
+ * by a registered device-side family + parameter blob (doubles). */
+int pfb_register_model(pfb_handle h, int family, int n, const double* blob, size_t ndoubles);
+
+/* One call for the whole ELBO stage of P paths.  Replaces, batched over (path x iteration):
+ *   fit_mvnormals(optim_trace.points, optim_trace.gradients; history_length)   src/singlepath.jl:301-303
+ *   maximize_elbo(rng, logp, fit_distributions[2:end], ndraws_elbo, ntasks)    src/singlepath.jl:306-308
+ *   success / draw selection                                             src/singlepath.jl:309-314, 224-233
+ * offsets[P+1]: first column of each path in positions/gradients (path p has L_p + 1 points);
+ * positions, gradients: n x offsets[P] column-major (gradients of the LOG density, src/optimize.jl:96);
+ * seeds[U]: the UInt64 seeds drawn as in src/elbo.jl:2, unit order;
+ * normals_or_null: parity mode, u[n x K x U] supplied by the host RNG (src/mvnormal.jl:30). */
+int pfb_elbo_batch(pfb_handle h, int n, int P, const int64_t* offsets, const double* positions,
+                   const double* gradients, const uint64_t* seeds, const double* normals_or_null,
+                   pfb_elbo_out* out);
+
+/* The same, split so that callers can keep inputs resident / overlap / time the stages. */
+int pfb_batch_upload(pfb_handle h, int n, int P, const int64_t* offsets, const double* positions,
+                     const double* gradients, const uint64_t* seeds, const double* normals_or_null);
+int pfb_batch_run(pfb_handle h);  /* K1..K5, asynchronous on the engine stream */
+int pfb_batch_sync(pfb_handle h);
+int pfb_batch_download(pfb_handle h, pfb_elbo_out* out);
+
+/* Replaces _compute_psis_result + _resample (src/multipath.jl:220-225, src/resample.jl:58-95)
+ * on the pool produced by the last batch (N = P * K draws; log ratios reuse the ELBO stage's
+ * logp - logq, which src/resample.jl:81-95 recomputes).  importance = 0: uniform resampling
+ * (psis_result === nothing, src/resample.jl:61). */
+int pfb_psis_resample(pfb_handle h, uint64_t seed, int ndraws, int importance, pfb_resample_out* out);
+
+/* PSIS + resampling on caller-supplied log ratios (host): log_ratios[N]; pool_or_null[n x N].
+ * Used by resample() re-entry (src/resample.jl:20-46) and by the parity tests. */
+int pfb_psis_resample_host(pfb_handle h, int n, int64_t N, int K_run, const double* log_ratios,
+                           const double* pool_or_null, uint64_t seed, int ndraws, int importance,
+                           pfb_resample_out* out);
+
+/* Device views for multi-GPU plumbing (NCCL all-gather of the pool by the host layer). */
+typedef struct {
+    void* pool_draws; /* double [n x K x P]  */
+    void* pool_logp;  /* double [K x P]      */
+    void* pool_logq;  /* double [K x P]      */
+    void* elbo;       /* double [U]          */
+    void* stream;     /* cudaStream_t        */
+    int64_t n, K, P, U;
+} pfb_device_view;
+int pfb_batch_device_view(pfb_handle h, pfb_device_view* view);
+
+/* PSIS + resampling on DEVICE buffers (an all-gathered pool): d_logp/d_logq [N], d_pool [n x N];
+ * outputs in `out` are HOST pointers. */
+int pfb_psis_resample_device(pfb_handle h, int n, int64_t N, int K_run, const void* d_logp,
+                             const void* d_logq, const void* d_pool, uint64_t seed, int ndraws,
+                             int importance, pfb_resample_out* out);
+
+/* Timings of the last batch in milliseconds (CUDA events on the engine stream):
+ * ms[0..5] = K1, K2, K3, K4, K5, total; returns the number of kernels launched. */
+int pfb_get_timings(pfb_handle h, double* ms6);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFB200_H */

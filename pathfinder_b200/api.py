@@ -1,0 +1,254 @@
+"""Host-side mirror of the reference's public API for the accelerated path.
+
+Same names, keyword meaning and failure behaviour as Pathfinder.jl (paths relative to the
+reference repo):
+
+  pathfinder        src/singlepath.jl:101-257     PathfinderResult       src/singlepath.jl:53-70
+  multipathfinder   src/multipath.jl:94-245       MultiPathfinderResult  src/multipath.jl:31-44
+  resample          src/resample.jl:20-46
+
+The sequential L-BFGS stays on the host (optimize.py); everything the reference does after it
+(`fit_mvnormals`, `maximize_elbo`, draw selection, `_compute_psis_result`, `_resample`) is one
+batched call into libpfb200.so.  The per-path calls of `_chunk_tmap` (src/multipath.jl:190-208)
+are hoisted: all trajectories first, one engine call, then result assembly; paths that fail
+(src/singlepath.jl:309-314) are re-initialised and sent as a further batch, up to `ntries`
+(src/singlepath.jl:259-283).
+"""
+from __future__ import annotations
+
+import warnings
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .engine import Engine
+from .optimize import OptimizationTrace, optimize_with_trace
+
+DEFAULT_HISTORY_LENGTH = 6  # src/Pathfinder.jl:24
+DEFAULT_NDRAWS_ELBO = 5     # src/Pathfinder.jl:27
+
+
+@dataclass
+class ELBOEstimate:
+    """src/elbo.jl:22-29 (draws / per-draw densities are kept for the best iteration only;
+    the engine regenerates any other iteration's on demand from its seed)."""
+
+    value: float
+    std_err: float
+
+
+@dataclass
+class FitDistribution:
+    """MvNormal(mu, Sigma) with Sigma = WoodburyPDMat in factored form (src/woodbury.jl:259)."""
+
+    mu: np.ndarray
+    alpha: np.ndarray     # diag(A)
+    vh: np.ndarray        # n x KP Householder reflectors of F.Q
+    T: np.ndarray         # KP x KP compact-WY factor of F.Q
+    Vc: np.ndarray        # KP x KP upper Cholesky factor F.V
+    logdet: float
+    history_length_effective: int
+
+
+@dataclass
+class PathfinderResult:
+    input: object
+    rng: object
+    fit_distribution: FitDistribution | None
+    draws: np.ndarray                  # [n, ndraws]
+    fit_iteration: int                 # 1-based; 0 = failed before any iteration
+    num_tries: int
+    optim_trace: OptimizationTrace
+    elbo_estimates: list
+    num_bfgs_updates_rejected: int
+    success: bool = True
+    draws_logp: np.ndarray | None = None
+    draws_logq: np.ndarray | None = None
+
+
+@dataclass
+class PSISResult:
+    log_weights: np.ndarray
+    weights: np.ndarray
+    pareto_shape: float
+    tail_length: int
+
+
+@dataclass
+class MultiPathfinderResult:
+    input: object
+    rng: object
+    draws: np.ndarray                  # [n, ndraws]
+    draw_component_ids: np.ndarray     # [ndraws] 1-based
+    pathfinder_results: list
+    psis_result: PSISResult | None
+    sample_inds: np.ndarray = field(default=None, repr=False)
+    engine: Engine = field(default=None, repr=False)
+
+
+def _uniform_init(rng, n, scale):
+    """UniformSampler (src/singlepath.jl:332-344): iid U[-scale, scale]."""
+    return (rng.random(n) * 2.0 - 1.0) * scale
+
+
+def _draw_seeds(rng, m):
+    return rng.integers(0, 2**64, size=m, dtype=np.uint64)
+
+
+def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntries, init_scale):
+    """Optimise every path on the host, run the ELBO stage as one batch, retry failures."""
+    P = len(inits)
+    final = [None] * P
+    todo = list(range(P))
+    tries = [0] * P
+    cur_init = list(inits)
+    last = None
+    while todo:
+        traces, seeds = [], []
+        for p in todo:
+            tries[p] += 1
+            tr = optimize_with_trace(model, cur_init[p], history_length, maxiters)
+            if len(tr) == 0:  # non-finite at the initial point: an empty trace, L = 0
+                x0 = np.asarray(cur_init[p], dtype=np.float64)[:, None]
+                tr = OptimizationTrace(x0, np.array([np.nan]), np.zeros_like(x0))
+            traces.append(tr)
+            seeds.append(_draw_seeds(path_rngs[p], len(tr) - 1))  # src/elbo.jl:2
+        offsets, X, G = Engine.pack([(t.points, t.gradients) for t in traces])
+        res = engine.elbo_batch(offsets, X, G, np.concatenate(seeds) if seeds else np.zeros(0, np.uint64),
+                                draws=True, fit=True)
+        last = (todo[:], res, traces)
+        retry = []
+        for j, p in enumerate(todo):
+            ok = bool(res.success[j])
+            if ok or tries[p] >= ntries:
+                final[p] = (j, res, traces[j], tries[p])
+            else:
+                cur_init[p] = _uniform_init(path_rngs[p], model.n, init_scale)  # src/singlepath.jl:278
+                retry.append(p)
+        if retry and len(retry) < len(todo):
+            # keep the successful paths' device-resident results: assemble them now
+            pass
+        todo = retry
+    return final, last
+
+
+def _assemble_path(model, rng, entry, ndraws, K):
+    j, res, trace, ntry = entry
+    sl = res.unit_slice(j)
+    ests = [ELBOEstimate(float(v), float(s)) for v, s in zip(res.elbo[sl], res.elbo_se[sl])]
+    ok = bool(res.success[j])
+    if not ok:
+        warnings.warn(f"Pathfinder failed after {ntry} tries. Increase `ntries`, inspect the model for "
+                      "numerical instability, or provide a more suitable `init_sampler`.")
+    rej = int(res.n_rejected[j])
+    if rej > 0:
+        perc = round(rej * 100.0 / len(trace), 1)
+        warnings.warn(f"{rej} ({perc}%) updates to the inverse Hessian estimate were rejected to keep it "
+                      "positive definite.")
+    fit = None
+    if res.fit is not None and res.best_iter[j] > 0:
+        f = res.fit
+        fit = FitDistribution(f["mu"][:, j].copy(), f["alpha"][:, j].copy(), f["vh"][:, :, j].copy(),
+                              f["T"][j].copy(), f["Vc"][j].copy(), float(f["logdet"][j]), int(f["jeff"][j]))
+    draws = res.draws[:, :ndraws, j].copy()
+    return PathfinderResult(model, rng, fit, draws, int(res.best_iter[j]), ntry, trace, ests, rej, ok,
+                            res.draws_logp[:ndraws, j].copy(), res.draws_logq[:ndraws, j].copy())
+
+
+def pathfinder(model, *, init=None, init_scale=2.0, ndraws_elbo=DEFAULT_NDRAWS_ELBO, ndraws=None, rng=None,
+               history_length=DEFAULT_HISTORY_LENGTH, ntries=1000, maxiters=1000, device=0, engine=None):
+    """Single-path Pathfinder (src/singlepath.jl:101-139)."""
+    rng = np.random.default_rng() if rng is None else rng
+    ndraws = ndraws_elbo if ndraws is None else ndraws
+    if ndraws > ndraws_elbo:
+        raise NotImplementedError("ndraws > ndraws_elbo (top-up draws, src/singlepath.jl:228-230) is not "
+                                  "accelerated yet; raise ndraws_elbo")
+    x0 = _uniform_init(rng, model.n, init_scale) if init is None else np.asarray(init, dtype=np.float64)
+    if x0.shape != (model.n,):
+        raise ValueError("init has the wrong dimension")
+    own = engine is None
+    if own:
+        engine = Engine(model.n, model.family, model.blob, history_length, ndraws_elbo, device)
+    try:
+        final, _ = _run_paths(engine, model, [x0], [rng], history_length=history_length, maxiters=maxiters,
+                              ntries=ntries, init_scale=init_scale)
+        return _assemble_path(model, rng, final[0], ndraws, ndraws_elbo)
+    finally:
+        if own:
+            engine.close()
+
+
+def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT_NDRAWS_ELBO,
+                    ndraws_per_run=None, importance=True, rng=None, history_length=DEFAULT_HISTORY_LENGTH,
+                    init_scale=2.0, ntries=1000, maxiters=1000, device=0, engine=None):
+    """Multi-path Pathfinder (src/multipath.jl:94-245)."""
+    rng = np.random.default_rng() if rng is None else rng
+    if init is None:
+        if nruns is None or nruns <= 0:
+            raise ValueError("A positive `nruns` must be set or `init` must be provided.")  # :146-148
+        inits = [None] * nruns
+    else:
+        inits = [np.asarray(x, dtype=np.float64) for x in init]
+    nruns = len(inits)
+    if ndraws_per_run is None:
+        ndraws_per_run = max(ndraws_elbo, -(-ndraws // max(nruns, 1)))  # src/multipath.jl:138
+    if ndraws_per_run > ndraws_elbo:
+        raise NotImplementedError("ndraws_per_run > ndraws_elbo (top-up draws) is not accelerated yet")
+    if ndraws > ndraws_per_run * nruns:
+        warnings.warn("More draws requested than total number of draws across replicas. Draws will not be unique.")
+    run_seeds = _draw_seeds(rng, nruns)  # src/multipath.jl:162
+    path_rngs = [np.random.Generator(np.random.Philox(key=int(s))) for s in run_seeds]
+    inits = [(_uniform_init(path_rngs[p], model.n, init_scale) if x is None else x) for p, x in enumerate(inits)]
+    own = engine is None
+    if own:
+        engine = Engine(model.n, model.family, model.blob, history_length, ndraws_elbo, device)
+    final, last = _run_paths(engine, model, inits, path_rngs, history_length=history_length, maxiters=maxiters,
+                             ntries=ntries, init_scale=init_scale)
+    results = [_assemble_path(model, path_rngs[p], final[p], ndraws_per_run, ndraws_elbo) for p in range(nruns)]
+    # PSIS pool: draw-fastest, component-slowest (test/resample.jl:81-88)
+    K_run = ndraws_per_run
+    single_batch = last is not None and len(last[0]) == nruns and K_run == ndraws_elbo
+    seed = int(_draw_seeds(rng, 1)[0])
+    if single_batch:
+        r = engine.psis_resample(seed, ndraws, importance)  # pool still resident on the device
+    else:
+        pool = np.concatenate([pr.draws for pr in results], axis=1)
+        logr = np.concatenate([pr.draws_logp - pr.draws_logq for pr in results])
+        r = engine.psis_resample_host(logr if importance else None, K_run, seed, ndraws, importance, pool=pool)
+    psis = PSISResult(r["log_weights"], r["weights"], r["pareto_k"], r["tail_len"]) if importance else None
+    return MultiPathfinderResult(model, rng, r["draws"], r["ids"], results, psis, r["inds"],
+                                 engine if not own else _close_and_none(engine))
+
+
+def _close_and_none(engine):
+    engine.close()
+    return None
+
+
+def resample(result: MultiPathfinderResult, ndraws, *, rng=None, replace=True, importance=True,
+             ndraws_per_run=None, device=0):
+    """Re-resample a fitted result (src/resample.jl:20-46) from its stored draws."""
+    if not replace:
+        raise NotImplementedError("replace=false is not accelerated yet")
+    if ndraws_per_run is not None:
+        raise NotImplementedError("fresh draws per run (src/resample.jl:102-109) are not accelerated yet")
+    rng = result.rng if rng is None else rng
+    prs = result.pathfinder_results
+    model = result.input
+    pool = np.concatenate([pr.draws for pr in prs], axis=1)
+    K_run = prs[0].draws.shape[1]
+    seed = int(_draw_seeds(rng, 1)[0])
+    eng = Engine(model.n, model.family, model.blob, DEFAULT_HISTORY_LENGTH, K_run, device)
+    try:
+        if importance:
+            # the log ratios of the stored draws are the ELBO stage's logp - logq (what
+            # _compute_log_importance_ratios, src/resample.jl:81-95, recomputes)
+            logr = np.concatenate([pr.draws_logp - pr.draws_logq for pr in prs])
+            r = eng.psis_resample_host(logr, K_run, seed, ndraws, True, pool=pool)
+            psis = PSISResult(r["log_weights"], r["weights"], r["pareto_k"], r["tail_len"])
+        else:
+            r = eng.psis_resample_host(None, K_run, seed, ndraws, False, pool=pool)
+            psis = None
+    finally:
+        eng.close()
+    return MultiPathfinderResult(model, rng, r["draws"], r["ids"], prs, psis, r["inds"], None)

@@ -1,0 +1,372 @@
+// K2 woodbury_build — one CTA per unit (path p, iteration l >= 1).
+//
+// Replaces, for H0 = Diagonal(alpha):
+//   lbfgs_inverse_hessian   (reference: src/inverse_hessian.jl:98-133)   B = [alpha.*Y | S], D
+//   pdfactorize             (reference: src/woodbury.jl:201-207)          U = sqrt(alpha),
+//                           Q,R = qr(U' \ B) (Householder, LAPACK dlarfg/dlarft conventions so
+//                           that the full n x n Q equals the reference's), V = chol(I + R D R')
+//   logabsdet               (reference: src/woodbury.jl:77-80)
+//   mu = Sigma * g + theta  (reference: src/mvnormal.jl:17 -> src/woodbury.jl:346-349, :64-68)
+//
+// Output: the unit's factor record rows { Vh[i][0..KP), sqrt(alpha_i), mu_i } and header
+// { T, Vc, logdet, pd flag, k_eff } (layout: pfb_common.cuh).  The QR runs in place in the
+// record rows (global memory, L1/L2 resident: n * (KP+2) * 8 bytes per unit); every thread owns
+// whole rows, so the only cross-thread traffic is the block reductions.
+#include "pfb_common.cuh"
+
+#define PFB_K2_THREADS 256
+
+template <int KP>
+__global__ void __launch_bounds__(PFB_K2_THREADS)
+pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* __restrict__ G,
+                      const int32_t* __restrict__ unit_col, const double* __restrict__ alpha_all,
+                      const int32_t* __restrict__ hist, const int32_t* __restrict__ hist_cnt,
+                      double* __restrict__ FR, double* __restrict__ HDR) {
+    constexpr int RS = KP + 2;
+    constexpr int JM = KP / 2;
+    __shared__ double scratch[KP * 32];
+    __shared__ double sStY[JM][JM], sYaY[JM][JM], sNRinv[JM][JM], sM[JM][JM];
+    __shared__ double sD[KP][KP], sRq[KP][KP], sE[KP][KP], sC[KP][KP], sVc[KP][KP], sT[KP][KP];
+    __shared__ double sVtV[KP][KP];
+    __shared__ double sTau[KP], sHead[KP], sW[KP], sW2[KP];
+    __shared__ double sBcast[2];
+    __shared__ int sFlag;
+
+    const int u = blockIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int jeff = hist_cnt[u];
+    const int kc = 2 * jeff;
+    const int kq = min(n, kc);
+    double* fr = FR + (int64_t)u * n * RS;
+    double* hdr = HDR + (int64_t)u * pfb_hs_of(KP);
+    const double* alpha = alpha_all + (int64_t)u * n;
+    const int64_t col = unit_col[u];
+    const double* theta = X + col * n;
+    const double* g = G + col * n;
+    const int32_t* hu = hist + (int64_t)u * J;
+
+    // ---- Phase A: A~ = U' \ B = [ (alpha .* Y) ./ sqrt(alpha) | S ./ sqrt(alpha) ] -------------
+    for (int i = tid; i < n; i += nt) {
+        double a = alpha[i];
+        double sa = sqrt(a);
+        double* row = fr + (int64_t)i * RS;
+        for (int j = 0; j < jeff; ++j) {
+            int64_t c = hu[j];
+            double s = X[(c + 1) * n + i] - X[c * n + i];
+            double y = G[c * n + i] - G[(c + 1) * n + i];
+            row[j] = (a * y) / sa;
+            row[jeff + j] = s / sa;
+        }
+        for (int j = kc; j < KP; ++j) row[j] = 0.0;
+        row[KP] = sa;
+        row[KP + 1] = sa * g[i];  // scratch for phase H: t = U g
+    }
+    if (tid == 0) sFlag = 1;
+    // zero-init small matrices
+    for (int e = tid; e < KP * KP; e += nt) {
+        (&sD[0][0])[e] = 0.0;
+        (&sT[0][0])[e] = 0.0;
+        (&sRq[0][0])[e] = 0.0;
+        (&sVtV[0][0])[e] = 0.0;
+        (&sVc[0][0])[e] = ((e / KP) == (e % KP)) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+
+    if (jeff > 0) {
+        // ---- Gram blocks of A~: S'Y = A2' A1, Y' diag(alpha) Y = A1' A1 ------------------------
+        for (int a = 0; a < jeff; ++a) {
+            double acc[KP];
+#pragma unroll
+            for (int b = 0; b < KP; ++b) acc[b] = 0.0;
+            for (int i = tid; i < n; i += nt) {
+                const double* row = fr + (int64_t)i * RS;
+                double sa_ = row[jeff + a], ya_ = row[a];
+#pragma unroll
+                for (int b = 0; b < JM; ++b) {
+                    if (b < jeff) {
+                        double yb = row[b];
+                        acc[b] = fma(sa_, yb, acc[b]);
+                        acc[JM + b] = fma(ya_, yb, acc[JM + b]);
+                    }
+                }
+            }
+            pfb_block_sum<KP>(acc, scratch);
+            if (tid == 0) {
+#pragma unroll
+                for (int b = 0; b < JM; ++b) {
+                    if (b < jeff) {
+                        sStY[a][b] = acc[b];
+                        sYaY[a][b] = acc[JM + b];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- D  (src/inverse_hessian.jl:119-130) ----------------------------------------------
+        // R = triu(S'Y); nRinv = -R^-1 (back substitution, one column per thread)
+        if (tid < jeff) {
+            const int b = tid;
+            for (int a = jeff - 1; a >= 0; --a) {
+                double rhs = (a == b) ? -1.0 : 0.0;
+                for (int c = a + 1; c < jeff; ++c) rhs -= sStY[a][c] * sNRinv[c][b];
+                sNRinv[a][b] = (a <= b) ? rhs / sStY[a][a] : 0.0;
+            }
+        }
+        __syncthreads();
+        // M = Diagonal(R) + Y' H0 Y, symmetrised from its upper triangle (copytri! 'U')
+        for (int e = tid; e < jeff * jeff; e += nt) {
+            int a = e / jeff, b = e % jeff;
+            int lo = min(a, b), hi = max(a, b);
+            sM[a][b] = sYaY[lo][hi] + ((a == b) ? sStY[a][a] : 0.0);
+        }
+        __syncthreads();
+        // tmp = M * nRinv (rmul!), D22 = nRinv' * tmp (lmul!)
+        for (int e = tid; e < jeff * jeff; e += nt) {
+            int a = e / jeff, b = e % jeff;
+            double s = 0.0;
+            for (int c = 0; c <= b; ++c) s = fma(sM[a][c], sNRinv[c][b], s);
+            sE[a][b] = s;
+        }
+        __syncthreads();
+        for (int e = tid; e < jeff * jeff; e += nt) {
+            int a = e / jeff, b = e % jeff;
+            double s = 0.0;
+            for (int c = 0; c <= a; ++c) s = fma(sNRinv[c][a], sE[c][b], s);
+            sD[jeff + a][jeff + b] = s;
+            sD[a][jeff + b] = sNRinv[a][b];
+            sD[jeff + a][b] = sNRinv[b][a];
+        }
+        __syncthreads();
+
+        // ---- Phase C: Householder QR in place (dgeqr2 / dlarfg / dlarf conventions) ------------
+        for (int j = 0; j < kq; ++j) {
+            double ss[1] = {0.0};
+            for (int i = tid; i < n; i += nt) {
+                if (i > j) {
+                    double x = fr[(int64_t)i * RS + j];
+                    ss[0] = fma(x, x, ss[0]);
+                }
+                if (i == j) sBcast[0] = fr[(int64_t)i * RS + j];
+            }
+            pfb_block_sum<1>(ss, scratch);
+            const double ajj = sBcast[0];
+            double tau = 0.0, beta = ajj, scale = 0.0;
+            if (ss[0] != 0.0) {
+                beta = -copysign(sqrt(fma(ajj, ajj, ss[0])), ajj);
+                tau = (beta - ajj) / beta;
+                scale = 1.0 / (ajj - beta);
+            }
+            double acc[KP];
+#pragma unroll
+            for (int c = 0; c < KP; ++c) acc[c] = 0.0;
+            if (tau != 0.0) {
+                for (int i = tid; i < n; i += nt) {
+                    double* row = fr + (int64_t)i * RS;
+                    if (i > j) {
+                        double v = row[j] * scale;
+                        row[j] = v;
+#pragma unroll
+                        for (int c = 0; c < KP; ++c)
+                            if (c < kc && c != j) acc[c] = fma(v, row[c], acc[c]);
+                    } else if (i == j) {
+#pragma unroll
+                        for (int c = 0; c < KP; ++c)
+                            if (c < kc && c != j) acc[c] += row[c];
+                    }
+                }
+                pfb_block_sum<KP>(acc, scratch);
+                for (int i = tid; i < n; i += nt) {
+                    double* row = fr + (int64_t)i * RS;
+                    if (i > j) {
+                        double v = row[j];
+#pragma unroll
+                        for (int c = 0; c < KP; ++c)
+                            if (c > j && c < kc) row[c] = fma(v, -tau * acc[c], row[c]);
+                    } else if (i == j) {
+#pragma unroll
+                        for (int c = 0; c < KP; ++c)
+                            if (c > j && c < kc) row[c] = row[c] - tau * acc[c];
+                        row[j] = beta;
+                    }
+                }
+            }
+            if (tid == 0) {
+                sTau[j] = tau;
+#pragma unroll
+                for (int c = 0; c < KP; ++c)
+                    if (c < j) sVtV[c][j] = acc[c];  // V(:,c)' v_j for c < j  (0 when tau == 0)
+            }
+            __syncthreads();
+        }
+
+        // ---- Phase D: T (dlarft, forward columnwise), lane a owns row a -------------------------
+        if (tid < 32) {
+            for (int j = 0; j < kq; ++j) {
+                const double tau = sTau[j];
+                double tv = 0.0;
+                if (tid < j) {
+                    for (int b = tid; b < j; ++b) tv = fma(sT[tid][b], sVtV[b][j], tv);
+                    tv = -tau * tv;
+                }
+                __syncwarp();
+                if (tid < j) sT[tid][j] = tv;
+                if (tid == j) sT[j][j] = tau;
+                __syncwarp();
+            }
+        }
+        // ---- Phase E: Rq to smem, fix up Vh (unit diagonal, zeros above / in padded columns) ----
+        for (int i = tid; i < n; i += nt) {
+            double* row = fr + (int64_t)i * RS;
+            if (i < kq) {
+                for (int c = i; c < kc; ++c) sRq[i][c] = row[c];
+                row[i] = 1.0;
+                for (int c = i + 1; c < KP; ++c) row[c] = 0.0;
+            } else {
+                for (int c = kq; c < kc; ++c) row[c] = 0.0;
+            }
+        }
+        __syncthreads();
+        // E = D * Rq'  (kc x kq),  C = I + Rq * E  (kq x kq, upper triangle used)
+        for (int e = tid; e < kc * kq; e += nt) {
+            int c = e / kq, b = e % kq;
+            double s = 0.0;
+            for (int d = b; d < kc; ++d) s = fma(sD[c][d], sRq[b][d], s);
+            sE[c][b] = s;
+        }
+        __syncthreads();
+        for (int e = tid; e < kq * kq; e += nt) {
+            int a = e / kq, b = e % kq;
+            double s = 0.0;
+            for (int c = a; c < kc; ++c) s = fma(sRq[a][c], sE[c][b], s);
+            sC[a][b] = s + ((a == b) ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        // Cholesky C = Vc' Vc (upper), dpotrf semantics: fail on pivot <= 0 or NaN
+        if (tid < 32) {
+            for (int j = 0; j < kq; ++j) {
+                double d = sC[j][j];
+                for (int m = 0; m < j; ++m) d = fma(-sVc[m][j], sVc[m][j], d);
+                const bool ok = (d > 0.0);
+                const double vjj = sqrt(d);
+                if (tid == 0) {
+                    sVc[j][j] = ok ? vjj : NAN;
+                    if (!ok) sFlag = 0;
+                }
+                for (int b = j + 1 + tid; b < kq; b += 32) {
+                    double s = sC[j][b];
+                    for (int m = 0; m < j; ++m) s = fma(-sVc[m][j], sVc[m][b], s);
+                    sVc[j][b] = ok ? s / vjj : NAN;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- Phase G: logdet = 2 (logdet U + logdet V) ---------------------------------------------
+    double ld[1] = {0.0};
+    for (int i = tid; i < n; i += nt) ld[0] += log(fr[(int64_t)i * RS + KP]);
+    pfb_block_sum<1>(ld, scratch);
+    double ldv = 0.0;
+    for (int j = 0; j < kq; ++j) ldv += log(sVc[j][j]);
+    const double logdet = 2.0 * (ld[0] + ldv);
+
+    // ---- Phase H: mu = theta + L (R g),  t = U g already in the mu slot ------------------------
+    if (kq > 0) {
+        for (int pass = 0; pass < 2; ++pass) {
+            // w = Vh' t
+            double acc[KP];
+#pragma unroll
+            for (int c = 0; c < KP; ++c) acc[c] = 0.0;
+            for (int i = tid; i < n; i += nt) {
+                const double* row = fr + (int64_t)i * RS;
+                double t = row[KP + 1];
+#pragma unroll
+                for (int c = 0; c < KP; ++c) acc[c] = fma(row[c], t, acc[c]);
+            }
+            pfb_block_sum<KP>(acc, scratch);
+            if (tid == 0) {
+#pragma unroll
+                for (int c = 0; c < KP; ++c) sW2[c] = acc[c];
+            }
+            __syncthreads();
+            // pass 0: Q' t = t - Vh (T' w);   pass 1: Q t = t - Vh (T w)
+            if (tid < kq) {
+                double s = 0.0;
+                if (pass == 0) {
+                    for (int c = 0; c <= tid; ++c) s = fma(sT[c][tid], sW2[c], s);
+                } else {
+                    for (int c = tid; c < kq; ++c) s = fma(sT[tid][c], sW2[c], s);
+                }
+                sW[tid] = s;
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += nt) {
+                double* row = fr + (int64_t)i * RS;
+                double t = row[KP + 1];
+#pragma unroll
+                for (int c = 0; c < KP; ++c)
+                    if (c < kq) t = fma(-row[c], sW[c], t);
+                row[KP + 1] = t;
+                if (pass == 0 && i < kq) sHead[i] = t;
+            }
+            __syncthreads();
+            if (pass == 0) {
+                // head <- Vc' (Vc head)      (lmul!(R.V, .) then lmul!(R.V', .))
+                if (tid < kq) {
+                    double s = 0.0;
+                    for (int c = tid; c < kq; ++c) s = fma(sVc[tid][c], sHead[c], s);
+                    sW2[tid] = s;
+                }
+                __syncthreads();
+                if (tid < kq) {
+                    double s = 0.0;
+                    for (int c = 0; c <= tid; ++c) s = fma(sVc[c][tid], sW2[c], s);
+                    fr[(int64_t)tid * RS + KP + 1] = s;
+                }
+                __syncthreads();
+            }
+        }
+    }
+    for (int i = tid; i < n; i += nt) {
+        double* row = fr + (int64_t)i * RS;
+        // kq == 0: Sigma = diag(alpha): t = sqrt(alpha) g, mu = theta + sqrt(alpha) t
+        row[KP + 1] = fma(row[KP], row[KP + 1], theta[i]);
+    }
+    // ---- header ---------------------------------------------------------------------------------
+    for (int e = tid; e < KP * KP; e += nt) {
+        hdr[e] = (&sT[0][0])[e];
+        hdr[KP * KP + e] = (&sVc[0][0])[e];
+    }
+    if (tid == 0) {
+        hdr[PFB_HDR_LOGDET(KP)] = logdet;
+        hdr[PFB_HDR_FLAG(KP)] = (double)sFlag;
+        hdr[PFB_HDR_KEFF(KP)] = (double)kq;
+    }
+}
+
+template <int KP>
+static cudaError_t launch_k2(cudaStream_t st, int n, int U, int J, const double* X, const double* G,
+                             const int32_t* unit_col, const double* alpha, const int32_t* hist,
+                             const int32_t* hist_cnt, double* FR, double* HDR) {
+    int threads = n >= PFB_K2_THREADS ? PFB_K2_THREADS : ((n + 31) / 32) * 32;
+    if (threads < 64) threads = 64;  // >= KP threads are needed by the small-matrix phases
+    pfb_k2_woodbury_build<KP><<<U, threads, 0, st>>>(n, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t pfb_launch_k2(cudaStream_t st, int KP, int n, int U, int J, const double* X,
+                                     const double* G, const int32_t* unit_col, const double* alpha,
+                                     const int32_t* hist, const int32_t* hist_cnt, double* FR,
+                                     double* HDR) {
+    if (U <= 0) return cudaSuccess;
+    switch (KP) {
+#define PFB_K2_CASE(k) \
+    case k: return launch_k2<k>(st, n, U, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR);
+        PFB_K2_CASE(12)
+        PFB_K2_CASE(20)
+        PFB_K2_CASE(24)
+#undef PFB_K2_CASE
+    }
+    return cudaErrorInvalidValue;
+}

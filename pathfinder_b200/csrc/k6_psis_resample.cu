@@ -1,0 +1,349 @@
+// K6 psis_pool + K7 resample_gather.
+//
+// K6 replaces PSIS.psis(log_ratios) as called from _compute_psis_result (reference:
+// src/resample.jl:74-79).  PSIS.jl is not in the reference tree; this is the published
+// algorithm (Vehtari et al., PSIS; Zhang & Stephens 2009 GPD fit with the weakly informative
+// shape prior) exactly as restated in oracle/psis.py — the two are written operation for
+// operation alike (same pf_math.h transcendentals, same canonical summation orders, this file
+// is compiled with -fmad=false), so weights are bit-identical to the oracle's.
+//
+// K7 replaces _resample (src/resample.jl:58-72): inverse-CDF sampling on the fixed-point (2^52)
+// cumulative weight table with 64 Philox bits per draw, column gather, component ids
+// cld(ind, K_run).  Indices are 1-based like the reference's.
+//
+// K6 is latency-bound (N = pool size ~ 64 k): a single CTA of 1024 threads keeps every
+// reduction in one deterministic order.  Top-(M+1) selection = 12-pass MSB radix select on the
+// composite key (ordered double bits, index), then a shared-memory bitonic sort of the M+1
+// candidates; M + 1 <= 8192 (N <= ~7.4 M).
+#include "pfb_common.cuh"
+#include "pf_rng.h"
+
+#define PFB_K6_THREADS 1024
+#define PFB_K6_MAXCAND 8192
+
+__device__ __forceinline__ uint64_t pfb_ordered_key(double x) {
+    uint64_t u = (uint64_t)__double_as_longlong(x);
+    if (x != x) return 0xFFFFFFFFFFFFFFFFull;  // NaN sorts last (Julia isless)
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+// canonical 32-lane sum: lane-strided sequential partials (done by the caller), xor-butterfly
+__device__ __forceinline__ double pfb_butterfly32(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+struct pfb_psis_scalars {
+    double pareto_k;
+    double lse;
+    double sigma;
+    double logu;
+    uint64_t Z;
+    int64_t tail_len;
+    int64_t smoothed;  // 1 if the tail was replaced
+};
+
+__global__ void __launch_bounds__(PFB_K6_THREADS)
+pfb_k6_psis(int N, int M, int m_grid, const double* __restrict__ logp, const double* __restrict__ logq,
+            const double* __restrict__ logr_in, double* __restrict__ logw, double* __restrict__ weights,
+            uint64_t* __restrict__ cum, pfb_psis_scalars* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* cKey = reinterpret_cast<uint64_t*>(smem_raw);       // MAXCAND
+    double* sX = reinterpret_cast<double*>(cKey + PFB_K6_MAXCAND);  // MAXCAND   tail sample x
+    uint32_t* cIdx = reinterpret_cast<uint32_t*>(sX + PFB_K6_MAXCAND);  // MAXCAND
+    __shared__ uint32_t hist[256];
+    __shared__ double sB[128], sKj[128], sLL[128], sWj[128];
+    __shared__ double scratch[32];
+    __shared__ uint64_t sScanU[PFB_K6_THREADS / 32];
+    __shared__ uint64_t sKthKey;
+    __shared__ uint32_t sKthIdx, sWant, sCnt;
+    __shared__ int sAllFinite;
+    __shared__ double sScal[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = PFB_K6_THREADS;
+
+    // ---- 0. log ratios ---------------------------------------------------------------------------
+    for (int i = tid; i < N; i += NT) logw[i] = logr_in ? logr_in[i] : (logp[i] - logq[i]);
+    __syncthreads();
+
+    double pareto_k = NAN, sigma = NAN, logu = NAN;
+    int smoothed = 0;
+    if (M >= 5) {
+        // ---- 1. radix select of the (M+1)-th largest composite (key, idx) -------------------------
+        if (tid == 0) { sKthKey = 0; sKthIdx = 0; sWant = (uint32_t)(M + 1); }
+        __syncthreads();
+        for (int d = 0; d < 12; ++d) {
+            for (int b = tid; b < 256; b += NT) hist[b] = 0;
+            __syncthreads();
+            const uint64_t pk = sKthKey;
+            const uint32_t pi = sKthIdx;
+            for (int i = tid; i < N; i += NT) {
+                const uint64_t key = pfb_ordered_key(logw[i]);
+                bool match;
+                uint32_t digit;
+                if (d < 8) {
+                    const int sh = 64 - 8 * d;  // bits above the current digit
+                    match = (d == 0) || ((key >> sh) == (pk >> sh));
+                    digit = (uint32_t)(key >> (sh - 8)) & 255u;
+                } else {
+                    const int sh = 32 - 8 * (d - 8);
+                    match = (key == pk) && ((d == 8) || (((uint32_t)i >> sh) == (pi >> sh)));
+                    digit = ((uint32_t)i >> (sh - 8)) & 255u;
+                }
+                if (match) atomicAdd(&hist[digit], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t want = sWant, acc = 0;
+                int b = 255;
+                for (; b > 0; --b) {
+                    if (acc + hist[b] >= want) break;
+                    acc += hist[b];
+                }
+                sWant = want - acc;
+                if (d < 8) sKthKey |= (uint64_t)b << (56 - 8 * d);
+                else sKthIdx |= (uint32_t)b << (24 - 8 * (d - 8));
+            }
+            __syncthreads();
+        }
+        // ---- 2. compact the M+1 selected elements, bitonic sort ascending by (key, idx) ------------
+        int P2 = 1;
+        while (P2 < M + 1) P2 <<= 1;
+        for (int t = tid; t < P2; t += NT) { cKey[t] = 0xFFFFFFFFFFFFFFFFull; cIdx[t] = 0xFFFFFFFFu; }
+        if (tid == 0) sCnt = 0;
+        __syncthreads();
+        {
+            const uint64_t kk = sKthKey;
+            const uint32_t ki = sKthIdx;
+            for (int i = tid; i < N; i += NT) {
+                const uint64_t key = pfb_ordered_key(logw[i]);
+                if (key > kk || (key == kk && (uint32_t)i >= ki)) {
+                    uint32_t pos = atomicAdd(&sCnt, 1u);
+                    cKey[pos] = key;
+                    cIdx[pos] = (uint32_t)i;
+                }
+            }
+        }
+        __syncthreads();
+        for (int size = 2; size <= P2; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = tid; t < P2 / 2; t += NT) {
+                    const int lo = 2 * t - (t & (stride - 1));  // index with bit `stride` clear
+                    const int hi = lo + stride;
+                    const bool up = ((lo & size) == 0);
+                    const uint64_t ka = cKey[lo], kb = cKey[hi];
+                    const uint32_t ia = cIdx[lo], ib = cIdx[hi];
+                    const bool a_gt_b = (ka > kb) || (ka == kb && ia > ib);
+                    if (a_gt_b == up) {
+                        cKey[lo] = kb; cKey[hi] = ka;
+                        cIdx[lo] = ib; cIdx[hi] = ia;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // cIdx[0] = cutoff element, cIdx[1..M] = tail ascending
+        if (tid == 0) sAllFinite = 1;
+        __syncthreads();
+        for (int t = tid; t < M; t += NT) {
+            const double v = logw[cIdx[1 + t]];
+            if (!(fabs(v) <= 1.7976931348623157e308)) sAllFinite = 0;  // NaN or Inf
+        }
+        __syncthreads();
+        logu = logw[cIdx[0]];
+        if (sAllFinite) {
+            const double lw_max = logw[cIdx[M]];
+            const double mu_s = pf_exp(logu - lw_max);
+            for (int t = tid; t < M; t += NT) sX[t] = pf_exp(logw[cIdx[1 + t]] - lw_max) - mu_s;
+            __syncthreads();
+            // ---- 3. Zhang & Stephens empirical-Bayes fit ------------------------------------------
+            const double dM = (double)M;
+            const double xmax = sX[M - 1];
+            const double xq = sX[(int)floor(dM / 4.0 + 0.5) - 1];
+            if (tid < m_grid) {
+                const double jj = (double)(tid + 1);
+                sB[tid] = 1.0 / xmax + (1.0 - sqrt((double)m_grid / (jj - 0.5))) / (3.0 * xq);
+            }
+            __syncthreads();
+            for (int j = warp; j < m_grid; j += NT / 32) {
+                const double b = sB[j];
+                double acc = 0.0;
+                for (int i = lane; i < M; i += 32) acc = acc + pf_log1p(-(b * sX[i]));
+                acc = pfb_butterfly32(acc);
+                if (lane == 0) {
+                    const double kj = acc / dM;
+                    sKj[j] = kj;
+                    sLL[j] = dM * (pf_log(-(b / kj)) - kj - 1.0);
+                }
+            }
+            __syncthreads();
+            for (int j = warp; j < m_grid; j += NT / 32) {
+                const double lj = sLL[j];
+                double acc = 0.0;
+                for (int i = lane; i < m_grid; i += 32) acc = acc + pf_exp(sLL[i] - lj);
+                acc = pfb_butterfly32(acc);
+                if (lane == 0) sWj[j] = 1.0 / acc;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double acc = 0.0;
+                for (int i = lane; i < m_grid; i += 32) acc = acc + sWj[i];
+                const double wsum = pfb_butterfly32(acc);
+                acc = 0.0;
+                for (int i = lane; i < m_grid; i += 32) acc = acc + sB[i] * (sWj[i] / wsum);
+                const double b_post = pfb_butterfly32(acc);
+                acc = 0.0;
+                for (int i = lane; i < M; i += 32) acc = acc + pf_log1p(-(b_post * sX[i]));
+                const double k_post = pfb_butterfly32(acc) / dM;
+                if (lane == 0) {
+                    sScal[0] = k_post;
+                    sScal[1] = -k_post / b_post;                  // sigma
+                    sScal[2] = (k_post * dM + 5.0) / (dM + 10.0);  // prior-adjusted shape
+                }
+            }
+            __syncthreads();
+            sigma = sScal[1];
+            pareto_k = sScal[2];
+            // ---- 4. replace the tail by GPD quantiles ---------------------------------------------
+            if (fabs(pareto_k) <= 1.7976931348623157e308) {
+                smoothed = 1;
+                for (int t = tid; t < M; t += NT) {
+                    const double p = ((double)t + 0.5) / dM;
+                    const double l1p = pf_log1p(-p);
+                    double z;
+                    if (fabs(pareto_k) < 2.220446049250313e-16) z = -l1p;
+                    else z = pf_expm1(-(pareto_k * l1p)) / pareto_k;
+                    const double qv = sigma * z;
+                    const double val = pf_log(qv + mu_s);
+                    const double mn = (val != val) ? val : (val < 0.0 ? val : 0.0);
+                    logw[cIdx[1 + t]] = mn + lw_max;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- 5. normalise: logw -= logsumexp(logw); weights = exp(logw) --------------------------------
+    double mx = -INFINITY;
+    for (int i = tid; i < N; i += NT) mx = fmax(mx, logw[i]);  // fmax ignores NaN
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if (lane == 0) scratch[warp] = mx;
+    __syncthreads();
+    mx = scratch[lane];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    __syncthreads();
+    double acc = 0.0;
+    for (int i = tid; i < N; i += NT) acc = acc + pf_exp(logw[i] - mx);
+    acc = pfb_butterfly32(acc);
+    if (lane == 0) scratch[warp] = acc;
+    __syncthreads();
+    const double ssum = pfb_butterfly32(scratch[lane]);
+    const double lse = mx + pf_log(ssum);
+    // ---- 6. fixed-point weights and their inclusive prefix sums ------------------------------------
+    const int per = (N + NT - 1) / NT;
+    const int i0 = min(N, tid * per), i1 = min(N, i0 + per);
+    uint64_t local = 0;
+    for (int i = i0; i < i1; ++i) {
+        const double lw = logw[i] - lse;
+        const double wv = pf_exp(lw);
+        logw[i] = lw;
+        weights[i] = wv;
+        const uint64_t qv = (wv > 0.0) ? (uint64_t)(wv * 4503599627370496.0) : 0ull;
+        local += qv;
+        cum[i] = qv;  // converted to the running sum below
+    }
+    uint64_t incl = local;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint64_t t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) sScanU[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t v = sScanU[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint64_t t = __shfl_up_sync(0xffffffffu, v, off);
+            if (lane >= off) v += t;
+        }
+        sScanU[lane] = v;
+    }
+    __syncthreads();
+    uint64_t run = (incl - local) + (warp > 0 ? sScanU[warp - 1] : 0ull);
+    for (int i = i0; i < i1; ++i) {
+        run += cum[i];
+        cum[i] = run;
+    }
+    if (tid == 0) {
+        out->pareto_k = pareto_k;
+        out->lse = lse;
+        out->sigma = sigma;
+        out->logu = logu;
+        out->Z = sScanU[31];
+        out->tail_len = M;
+        out->smoothed = smoothed;
+    }
+}
+
+// K7: one CTA per output draw.  cum == nullptr => uniform sampling (importance = false).
+__global__ void __launch_bounds__(128)
+pfb_k7_resample_gather(int n, int N, int K_run, uint64_t seed, const uint64_t* __restrict__ cum,
+                       const pfb_psis_scalars* __restrict__ sc, const double* __restrict__ pool,
+                       int64_t* __restrict__ inds, int64_t* __restrict__ ids,
+                       double* __restrict__ draws_out) {
+    __shared__ int64_t sIdx;
+    const int t = blockIdx.x;
+    if (threadIdx.x == 0) {
+        const uint64_t bits = pf_resample_bits((uint64_t)t, (uint32_t)seed, (uint32_t)(seed >> 32));
+        int64_t idx;
+        const uint64_t Z = (cum != nullptr) ? sc->Z : 0ull;
+        if (Z == 0ull) {
+            idx = (int64_t)pf_mulhi64(bits, (uint64_t)N);
+        } else {
+            const uint64_t target = pf_mulhi64(bits, Z);
+            int lo = 0, hi = N - 1;  // first i with cum[i] > target
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (cum[mid] > target) hi = mid; else lo = mid + 1;
+            }
+            idx = lo;
+        }
+        sIdx = idx;
+        inds[t] = idx + 1;
+        ids[t] = idx / K_run + 1;  // cld(idx + 1, K_run)
+    }
+    __syncthreads();
+    if (pool != nullptr && draws_out != nullptr) {
+        const double* src = pool + sIdx * (int64_t)n;
+        double* dst = draws_out + (int64_t)t * n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+extern "C" size_t pfb_psis_scalars_size() { return sizeof(pfb_psis_scalars); }
+
+extern "C" cudaError_t pfb_launch_k6(cudaStream_t st, int N, int M, int m_grid, const double* logp,
+                                     const double* logq, const double* logr, double* logw, double* weights,
+                                     uint64_t* cum, void* scalars) {
+    if (N <= 0) return cudaErrorInvalidValue;
+    if (M + 1 > PFB_K6_MAXCAND || m_grid > 128) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)PFB_K6_MAXCAND * (8 + 8 + 4);
+    cudaError_t e = cudaFuncSetAttribute(pfb_k6_psis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pfb_k6_psis<<<1, PFB_K6_THREADS, smem, st>>>(N, M, m_grid, logp, logq, logr, logw, weights, cum,
+                                                 (pfb_psis_scalars*)scalars);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t pfb_launch_k7(cudaStream_t st, int n, int N, int K_run, uint64_t seed, int ndraws,
+                                     const uint64_t* cum, const void* scalars, const double* pool,
+                                     int64_t* inds, int64_t* ids, double* draws_out) {
+    if (ndraws <= 0) return cudaSuccess;
+    pfb_k7_resample_gather<<<ndraws, 128, 0, st>>>(n, N, K_run, seed, cum, (const pfb_psis_scalars*)scalars,
+                                                   pool, inds, ids, draws_out);
+    return cudaGetLastError();
+}

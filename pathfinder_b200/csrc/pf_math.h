@@ -17,8 +17,10 @@
 
 #if defined(__CUDACC__)
 #define PF_HD __host__ __device__ __forceinline__
+#define PF_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define PF_HD static inline
+#define PF_HD_NOINLINE static __attribute__((noinline))
 #endif
 
 PF_HD uint64_t pf_d2u(double x) {

@@ -111,12 +111,22 @@ PF_HD double pf_zig_slow(uint64_t bits, uint32_t row_pair, uint32_t draw, uint32
 }
 
 // The two standard normals of elements (2*row_pair, draw) and (2*row_pair + 1, draw).
-PF_HD void pf_normal_pair(uint32_t row_pair, uint32_t draw, uint32_t k0, uint32_t k1,
+PF_HD_NOINLINE void pf_normal_pair(uint32_t row_pair, uint32_t draw, uint32_t k0, uint32_t k1,
                           const pf_zig_kw_t* kw, const double* ftab, double* z0, double* z1) {
     uint64_t a, b;
     pf_philox4x32_10(row_pair, draw, 0u, 0u, k0, k1, &a, &b);
     if (!pf_zig_fast(a, kw, z0)) *z0 = pf_zig_slow(a, row_pair, draw, 1u, k0, k1, kw, ftab);
     if (!pf_zig_fast(b, kw, z1)) *z1 = pf_zig_slow(b, row_pair, draw, 2u, k0, k1, kw, ftab);
+}
+
+// Slow-path continuation of element (row, draw) from scratch: recomputes the element's first
+// word (so that any thread can finish any element; used by the warp-balanced deferred slow
+// path of K3).  Must only be called for elements whose first word failed pf_zig_fast.
+PF_HD_NOINLINE double pf_normal_finish_slow(uint32_t row, uint32_t draw, uint32_t k0, uint32_t k1,
+                                            const pf_zig_kw_t* kw, const double* ftab) {
+    uint64_t a, b;
+    pf_philox4x32_10(row >> 1, draw, 0u, 0u, k0, k1, &a, &b);
+    return pf_zig_slow((row & 1u) ? b : a, row >> 1, draw, 1u + (row & 1u), k0, k1, kw, ftab);
 }
 
 // 64 random bits for resample draw t (two per Philox call), stream 3.

@@ -1,0 +1,527 @@
+// pfb_api.cu — the C ABI of libpfb200.so (declared in include/pfb200.h): engine handle,
+// device workspace (grow-only, engine-owned), and the orchestration of K1..K7 on one stream.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pfb200.h"
+#include "pfb_common.cuh"
+
+extern "C" {
+cudaError_t pfb_launch_k1(cudaStream_t, int, int, int, double, const double*, const double*, const int64_t*,
+                          double*, int32_t*, int32_t*, int64_t*);
+cudaError_t pfb_launch_k2(cudaStream_t, int, int, int, int, const double*, const double*, const int32_t*,
+                          const double*, const int32_t*, const int32_t*, double*, double*);
+#define PFB_DECL_K3(name)                                                                                  \
+    cudaError_t name(cudaStream_t, int, int, int, int, const int32_t*, const double*, const double*,        \
+                     const uint64_t*, const double*, const double*, const double*, double, double*, double*, \
+                     double*);
+PFB_DECL_K3(pfb_launch_k3_kp12)
+PFB_DECL_K3(pfb_launch_k3_kp20)
+PFB_DECL_K3(pfb_launch_k3_kp24)
+cudaError_t pfb_launch_k4(cudaStream_t, int, int, const int64_t*, const double*, const double*, double*,
+                          double*, int64_t*, int32_t*, int32_t*);
+size_t pfb_psis_scalars_size();
+cudaError_t pfb_launch_k6(cudaStream_t, int, int, int, const double*, const double*, const double*, double*,
+                          double*, uint64_t*, void*);
+cudaError_t pfb_launch_k7(cudaStream_t, int, int, int, uint64_t, int, const uint64_t*, const void*,
+                          const double*, int64_t*, int64_t*, double*);
+}
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct psis_scalars_host {
+    double pareto_k, lse, sigma, logu;
+    uint64_t Z;
+    int64_t tail_len, smoothed;
+};
+
+}  // namespace
+
+struct pfb_engine {
+    pfb_config cfg;
+    int KP = 12;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[7] = {};
+    std::string err;
+    // model
+    int model = -1, model_n = 0;
+    DevBuf dModel;
+    double model_c0 = 0.0;
+    // batch state
+    int n = 0, P = 0, K = 0;
+    int64_t T = 0, U = 0;
+    bool have_batch = false, ran = false, have_normals = false;
+    int launches = 0;
+    std::vector<int64_t> h_off;
+    DevBuf dX, dG, dOff, dSeeds, dUnitCol, dNormals;
+    DevBuf dAlpha, dHist, dHistCnt, dRej, dFR, dHDR, dLogp, dLogq, dElbo, dSe, dBestIter, dBestUnit, dSucc;
+    DevBuf dPool, dPoolLogp, dPoolLogq, dAllDraws;
+    DevBuf dFitMu, dFitAlpha, dFitVh, dFitT, dFitVc, dFitLogdet, dFitJeff;
+    // psis
+    DevBuf dLogw, dW, dCum, dScal, dInds, dIds, dOutDraws, dTmpLogr, dTmpPool;
+};
+
+#define PFB_FAIL(h, code, msg)     \
+    do {                           \
+        (h)->err = (msg);          \
+        return (code);             \
+    } while (0)
+
+#define PFB_CUDA(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                        \
+            return (int)e_ > 0 ? (int)e_ : 1;                                                     \
+        }                                                                                         \
+    } while (0)
+
+static thread_local std::string g_create_err;
+
+extern "C" int pfb_create(pfb_handle* out, const pfb_config* cfg) {
+    if (!out || !cfg) return PFB_ERR_ARG;
+    *out = nullptr;
+    if (cfg->history_length < 1 || cfg->ndraws_elbo < 1) {
+        g_create_err = "history_length and ndraws_elbo must be positive";
+        return PFB_ERR_ARG;
+    }
+    int kp = pfb_kp_of(cfg->history_length);
+    if (kp == 0) {
+        g_create_err = "history_length > 12 is not supported";
+        return PFB_ERR_UNSUPPORTED;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return e != cudaSuccess ? (int)e : 100;  // cudaErrorNoDevice
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) {
+        g_create_err = "bad device ordinal";
+        return PFB_ERR_ARG;
+    }
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e);
+        return (int)e;
+    }
+    pfb_engine* h = new pfb_engine();
+    h->cfg = *cfg;
+    if (h->cfg.eps == 0.0) h->cfg.eps = 1e-12;
+    h->KP = kp;
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e);
+        delete h;
+        return (int)e;
+    }
+    for (auto& ev : h->ev) cudaEventCreate(&ev);
+    *out = h;
+    return PFB_OK;
+}
+
+extern "C" int pfb_destroy(pfb_handle h) {
+    if (!h) return PFB_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->dModel, &h->dX, &h->dG, &h->dOff, &h->dSeeds, &h->dUnitCol, &h->dNormals, &h->dAlpha,
+                      &h->dHist, &h->dHistCnt, &h->dRej, &h->dFR, &h->dHDR, &h->dLogp, &h->dLogq, &h->dElbo,
+                      &h->dSe, &h->dBestIter, &h->dBestUnit, &h->dSucc, &h->dPool, &h->dPoolLogp,
+                      &h->dPoolLogq, &h->dAllDraws, &h->dFitMu, &h->dFitAlpha, &h->dFitVh, &h->dFitT,
+                      &h->dFitVc, &h->dFitLogdet, &h->dFitJeff, &h->dLogw, &h->dW, &h->dCum, &h->dScal,
+                      &h->dInds, &h->dIds, &h->dOutDraws, &h->dTmpLogr, &h->dTmpPool};
+    for (auto* b : bufs) b->release();
+    for (auto& ev : h->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return PFB_OK;
+}
+
+extern "C" const char* pfb_last_error(pfb_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+extern "C" int pfb_kp(pfb_handle h) { return h ? h->KP : 0; }
+
+extern "C" int pfb_register_model(pfb_handle h, int family, int n, const double* blob, size_t ndoubles) {
+    if (!h) return PFB_ERR_ARG;
+    if (n < 1) PFB_FAIL(h, PFB_ERR_ARG, "model dimension must be positive");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    switch (family) {
+        case PFB_MODEL_ISONORMAL:
+        case PFB_MODEL_FUNNEL:
+            break;
+        case PFB_MODEL_DIAGNORMAL: {
+            if (!blob || ndoubles != (size_t)2 * n) PFB_FAIL(h, PFB_ERR_SHAPE, "DIAGNORMAL blob = {mean[n], sd[n]}");
+            std::vector<double> tmp(2 * (size_t)n);
+            double c0 = -0.5 * n * PFB_LOG2PI;
+            for (int i = 0; i < n; ++i) {
+                if (!(blob[n + i] > 0.0)) PFB_FAIL(h, PFB_ERR_ARG, "DIAGNORMAL sd must be positive");
+                tmp[i] = blob[i];
+                tmp[n + i] = 1.0 / blob[n + i];
+                c0 -= log(blob[n + i]);
+            }
+            PFB_CUDA(h, h->dModel.ensure(tmp.size() * 8));
+            PFB_CUDA(h, cudaMemcpyAsync(h->dModel.p, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, h->stream));
+            PFB_CUDA(h, cudaStreamSynchronize(h->stream));
+            h->model_c0 = c0;
+            break;
+        }
+        default:
+            PFB_FAIL(h, PFB_ERR_UNSUPPORTED, "unknown model family");
+    }
+    h->model = family;
+    h->model_n = n;
+    return PFB_OK;
+}
+
+extern "C" int pfb_batch_upload(pfb_handle h, int n, int P, const int64_t* offsets, const double* positions,
+                                const double* gradients, const uint64_t* seeds, const double* normals) {
+    if (!h) return PFB_ERR_ARG;
+    if (n < 1 || P < 0 || !offsets) PFB_FAIL(h, PFB_ERR_ARG, "bad n / P / offsets");
+    if (h->model < 0) PFB_FAIL(h, PFB_ERR_STATE, "no model registered");
+    if (h->model_n != n) PFB_FAIL(h, PFB_ERR_SHAPE, "dimension differs from the registered model's");
+    if (offsets[0] != 0) PFB_FAIL(h, PFB_ERR_ARG, "offsets[0] must be 0");
+    for (int p = 0; p < P; ++p)
+        if (offsets[p + 1] < offsets[p] + 1) PFB_FAIL(h, PFB_ERR_SHAPE, "every path needs at least one point");
+    const int64_t T = offsets[P], U = T - P;
+    if (T > 2147483647LL) PFB_FAIL(h, PFB_ERR_UNSUPPORTED, "too many trajectory points");
+    if (T > 0 && (!positions || !gradients)) PFB_FAIL(h, PFB_ERR_ARG, "positions / gradients are NULL");
+    if (U > 0 && !seeds) PFB_FAIL(h, PFB_ERR_ARG, "seeds is NULL");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int K = h->cfg.ndraws_elbo, J = h->cfg.history_length, KP = h->KP;
+    h->n = n; h->P = P; h->K = K; h->T = T; h->U = U;
+    h->h_off.assign(offsets, offsets + P + 1);
+    h->have_batch = false; h->ran = false;
+    std::vector<int32_t> unit_col((size_t)U);
+    for (int p = 0; p < P; ++p) {
+        const int64_t L = offsets[p + 1] - offsets[p] - 1;
+        for (int64_t l = 1; l <= L; ++l) unit_col[(size_t)(offsets[p] - p + l - 1)] = (int32_t)(offsets[p] + l);
+    }
+    const size_t nT = (size_t)n * (size_t)T, nU = (size_t)n * (size_t)U;
+    PFB_CUDA(h, h->dX.ensure(nT * 8 + 8));
+    PFB_CUDA(h, h->dG.ensure(nT * 8 + 8));
+    PFB_CUDA(h, h->dOff.ensure((size_t)(P + 1) * 8));
+    PFB_CUDA(h, h->dSeeds.ensure((size_t)U * 8 + 8));
+    PFB_CUDA(h, h->dUnitCol.ensure((size_t)U * 4 + 8));
+    PFB_CUDA(h, h->dAlpha.ensure(nU * 8 + 8));
+    PFB_CUDA(h, h->dHist.ensure((size_t)U * J * 4 + 8));
+    PFB_CUDA(h, h->dHistCnt.ensure((size_t)U * 4 + 8));
+    PFB_CUDA(h, h->dRej.ensure((size_t)P * 8 + 8));
+    PFB_CUDA(h, h->dFR.ensure(nU * (size_t)pfb_rs_of(KP) * 8 + 16));
+    PFB_CUDA(h, h->dHDR.ensure((size_t)U * pfb_hs_of(KP) * 8 + 8));
+    PFB_CUDA(h, h->dLogp.ensure((size_t)U * K * 8 + 8));
+    PFB_CUDA(h, h->dLogq.ensure((size_t)U * K * 8 + 8));
+    PFB_CUDA(h, h->dElbo.ensure((size_t)U * 8 + 8));
+    PFB_CUDA(h, h->dSe.ensure((size_t)U * 8 + 8));
+    PFB_CUDA(h, h->dBestIter.ensure((size_t)P * 8 + 8));
+    PFB_CUDA(h, h->dBestUnit.ensure((size_t)P * 4 + 8));
+    PFB_CUDA(h, h->dSucc.ensure((size_t)P * 4 + 8));
+    PFB_CUDA(h, h->dPool.ensure((size_t)n * K * (size_t)P * 8 + 8));
+    PFB_CUDA(h, h->dPoolLogp.ensure((size_t)K * P * 8 + 8));
+    PFB_CUDA(h, h->dPoolLogq.ensure((size_t)K * P * 8 + 8));
+    if (h->cfg.materialize_all) PFB_CUDA(h, h->dAllDraws.ensure(nU * (size_t)K * 8 + 8));
+    cudaStream_t st = h->stream;
+    if (T > 0) {
+        PFB_CUDA(h, cudaMemcpyAsync(h->dX.p, positions, nT * 8, cudaMemcpyHostToDevice, st));
+        PFB_CUDA(h, cudaMemcpyAsync(h->dG.p, gradients, nT * 8, cudaMemcpyHostToDevice, st));
+    }
+    PFB_CUDA(h, cudaMemcpyAsync(h->dOff.p, offsets, (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (U > 0) {
+        PFB_CUDA(h, cudaMemcpyAsync(h->dSeeds.p, seeds, (size_t)U * 8, cudaMemcpyHostToDevice, st));
+        PFB_CUDA(h, cudaMemcpyAsync(h->dUnitCol.p, unit_col.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
+    }
+    h->have_normals = (normals != nullptr);
+    if (normals && U > 0) {
+        PFB_CUDA(h, h->dNormals.ensure(nU * (size_t)K * 8));
+        PFB_CUDA(h, cudaMemcpyAsync(h->dNormals.p, normals, nU * (size_t)K * 8, cudaMemcpyHostToDevice, st));
+    }
+    PFB_CUDA(h, cudaStreamSynchronize(st));  // unit_col is a stack-owned staging vector
+    h->have_batch = true;
+    return PFB_OK;
+}
+
+static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list, double* logp, double* logq,
+                             double* draws) {
+    const double* mp0 = h->dModel.as<double>();
+    const double* mp1 = mp0 ? mp0 + h->model_n : nullptr;
+    const double* un = h->have_normals ? h->dNormals.as<double>() : nullptr;
+    auto fn = h->KP == 12 ? pfb_launch_k3_kp12 : (h->KP == 20 ? pfb_launch_k3_kp20 : pfb_launch_k3_kp24);
+    return fn(h->stream, h->model, h->n, h->K, nslots, unit_list, h->dFR.as<double>(), h->dHDR.as<double>(),
+              h->dSeeds.as<uint64_t>(), un, mp0, mp1, h->model_c0, logp, logq, draws);
+}
+
+extern "C" int pfb_batch_run(pfb_handle h) {
+    if (!h) return PFB_ERR_ARG;
+    if (!h->have_batch) PFB_FAIL(h, PFB_ERR_STATE, "pfb_batch_upload has not been called");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const int n = h->n, P = h->P, K = h->K, J = h->cfg.history_length, KP = h->KP;
+    const int U = (int)h->U;
+    h->launches = 0;
+    PFB_CUDA(h, cudaEventRecord(h->ev[0], st));
+    PFB_CUDA(h, pfb_launch_k1(st, n, P, J, h->cfg.eps, h->dX.as<double>(), h->dG.as<double>(),
+                              h->dOff.as<int64_t>(), h->dAlpha.as<double>(), h->dHist.as<int32_t>(),
+                              h->dHistCnt.as<int32_t>(), h->dRej.as<int64_t>()));
+    h->launches += (P > 0);
+    PFB_CUDA(h, cudaEventRecord(h->ev[1], st));
+    PFB_CUDA(h, pfb_launch_k2(st, KP, n, U, J, h->dX.as<double>(), h->dG.as<double>(), h->dUnitCol.as<int32_t>(),
+                              h->dAlpha.as<double>(), h->dHist.as<int32_t>(), h->dHistCnt.as<int32_t>(),
+                              h->dFR.as<double>(), h->dHDR.as<double>()));
+    h->launches += (U > 0);
+    PFB_CUDA(h, cudaEventRecord(h->ev[2], st));
+    PFB_CUDA(h, launch_k3(h, U, nullptr, h->dLogp.as<double>(), h->dLogq.as<double>(),
+                          h->cfg.materialize_all ? h->dAllDraws.as<double>() : nullptr));
+    h->launches += (U > 0);
+    PFB_CUDA(h, cudaEventRecord(h->ev[3], st));
+    PFB_CUDA(h, pfb_launch_k4(st, P, K, h->dOff.as<int64_t>(), h->dLogp.as<double>(), h->dLogq.as<double>(),
+                              h->dElbo.as<double>(), h->dSe.as<double>(), h->dBestIter.as<int64_t>(),
+                              h->dBestUnit.as<int32_t>(), h->dSucc.as<int32_t>()));
+    h->launches += (P > 0);
+    PFB_CUDA(h, cudaEventRecord(h->ev[4], st));
+    // K5: materialise the best iteration of every path into the pool (regenerated, identical
+    // to the ELBO draws because the RNG is counter based)
+    PFB_CUDA(h, launch_k3(h, P, h->dBestUnit.as<int32_t>(), h->dPoolLogp.as<double>(), h->dPoolLogq.as<double>(),
+                          h->dPool.as<double>()));
+    h->launches += (P > 0);
+    PFB_CUDA(h, cudaEventRecord(h->ev[5], st));
+    h->ran = true;
+    return PFB_OK;
+}
+
+extern "C" int pfb_batch_sync(pfb_handle h) {
+    if (!h) return PFB_ERR_ARG;
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    PFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFB_OK;
+}
+
+// gather of the best-iteration factor in the reference's WoodburyPDMat form
+__global__ void pfb_gather_fit(int n, int KP, const int32_t* __restrict__ best_unit,
+                               const double* __restrict__ FR, const double* __restrict__ HDR,
+                               const double* __restrict__ alpha, const int32_t* __restrict__ hist_cnt,
+                               double* mu, double* al, double* vh, double* Tm, double* Vc, double* logdet,
+                               int32_t* jeff) {
+    const int p = blockIdx.x;
+    const int u = best_unit[p];
+    const int RS = KP + 2, HS = 2 * KP * KP + 4;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (u >= 0) {
+            const double* row = FR + ((int64_t)u * n + i) * RS;
+            mu[(int64_t)p * n + i] = row[KP + 1];
+            al[(int64_t)p * n + i] = alpha[(int64_t)u * n + i];
+            for (int j = 0; j < KP; ++j) vh[((int64_t)p * KP + j) * n + i] = row[j];
+        } else {
+            mu[(int64_t)p * n + i] = NAN;
+            al[(int64_t)p * n + i] = NAN;
+            for (int j = 0; j < KP; ++j) vh[((int64_t)p * KP + j) * n + i] = NAN;
+        }
+    }
+    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
+        Tm[(int64_t)p * KP * KP + e] = u >= 0 ? HDR[(int64_t)u * HS + e] : NAN;
+        Vc[(int64_t)p * KP * KP + e] = u >= 0 ? HDR[(int64_t)u * HS + KP * KP + e] : NAN;
+    }
+    if (threadIdx.x == 0) {
+        logdet[p] = u >= 0 ? HDR[(int64_t)u * HS + 2 * KP * KP] : NAN;
+        jeff[p] = u >= 0 ? hist_cnt[u] : 0;
+    }
+}
+
+extern "C" int pfb_batch_download(pfb_handle h, pfb_elbo_out* o) {
+    if (!h || !o) return PFB_ERR_ARG;
+    if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "pfb_batch_run has not been called");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const size_t n = h->n, P = h->P, K = h->K, U = (size_t)h->U, KP = h->KP;
+#define PFB_D2H(dst, src, bytes)                                                                   \
+    do {                                                                                           \
+        if ((dst) && (bytes) > 0)                                                                  \
+            PFB_CUDA(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, st));        \
+    } while (0)
+    PFB_D2H(o->elbo, h->dElbo.p, U * 8);
+    PFB_D2H(o->elbo_se, h->dSe.p, U * 8);
+    PFB_D2H(o->logp, h->dLogp.p, U * K * 8);
+    PFB_D2H(o->logq, h->dLogq.p, U * K * 8);
+    PFB_D2H(o->best_iter, h->dBestIter.p, P * 8);
+    PFB_D2H(o->success, h->dSucc.p, P * 4);
+    PFB_D2H(o->n_rejected, h->dRej.p, P * 8);
+    PFB_D2H(o->draws, h->dPool.p, n * K * P * 8);
+    PFB_D2H(o->draws_logp, h->dPoolLogp.p, K * P * 8);
+    PFB_D2H(o->draws_logq, h->dPoolLogq.p, K * P * 8);
+    if (o->all_draws) {
+        if (!h->cfg.materialize_all) PFB_FAIL(h, PFB_ERR_STATE, "all_draws needs materialize_all = 1");
+        PFB_D2H(o->all_draws, h->dAllDraws.p, n * K * U * 8);
+    }
+    const bool want_fit = o->fit_mu || o->fit_alpha || o->fit_vh || o->fit_T || o->fit_Vc || o->fit_logdet ||
+                          o->fit_jeff;
+    if (want_fit && P > 0) {
+        PFB_CUDA(h, h->dFitMu.ensure(n * P * 8));
+        PFB_CUDA(h, h->dFitAlpha.ensure(n * P * 8));
+        PFB_CUDA(h, h->dFitVh.ensure(n * KP * P * 8));
+        PFB_CUDA(h, h->dFitT.ensure(KP * KP * P * 8));
+        PFB_CUDA(h, h->dFitVc.ensure(KP * KP * P * 8));
+        PFB_CUDA(h, h->dFitLogdet.ensure(P * 8));
+        PFB_CUDA(h, h->dFitJeff.ensure(P * 4));
+        pfb_gather_fit<<<(unsigned)P, 256, 0, st>>>((int)n, (int)KP, h->dBestUnit.as<int32_t>(),
+                                                    h->dFR.as<double>(), h->dHDR.as<double>(),
+                                                    h->dAlpha.as<double>(), h->dHistCnt.as<int32_t>(),
+                                                    h->dFitMu.as<double>(), h->dFitAlpha.as<double>(),
+                                                    h->dFitVh.as<double>(), h->dFitT.as<double>(),
+                                                    h->dFitVc.as<double>(), h->dFitLogdet.as<double>(),
+                                                    h->dFitJeff.as<int32_t>());
+        PFB_CUDA(h, cudaGetLastError());
+        PFB_D2H(o->fit_mu, h->dFitMu.p, n * P * 8);
+        PFB_D2H(o->fit_alpha, h->dFitAlpha.p, n * P * 8);
+        PFB_D2H(o->fit_vh, h->dFitVh.p, n * KP * P * 8);
+        PFB_D2H(o->fit_T, h->dFitT.p, KP * KP * P * 8);
+        PFB_D2H(o->fit_Vc, h->dFitVc.p, KP * KP * P * 8);
+        PFB_D2H(o->fit_logdet, h->dFitLogdet.p, P * 8);
+        PFB_D2H(o->fit_jeff, h->dFitJeff.p, P * 4);
+    }
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    return PFB_OK;
+}
+
+extern "C" int pfb_elbo_batch(pfb_handle h, int n, int P, const int64_t* offsets, const double* positions,
+                              const double* gradients, const uint64_t* seeds, const double* normals,
+                              pfb_elbo_out* out) {
+    int rc = pfb_batch_upload(h, n, P, offsets, positions, gradients, seeds, normals);
+    if (rc) return rc;
+    rc = pfb_batch_run(h);
+    if (rc) return rc;
+    return pfb_batch_download(h, out);
+}
+
+extern "C" int pfb_batch_device_view(pfb_handle h, pfb_device_view* v) {
+    if (!h || !v) return PFB_ERR_ARG;
+    if (!h->have_batch) PFB_FAIL(h, PFB_ERR_STATE, "no batch");
+    v->pool_draws = h->dPool.p;
+    v->pool_logp = h->dPoolLogp.p;
+    v->pool_logq = h->dPoolLogq.p;
+    v->elbo = h->dElbo.p;
+    v->stream = (void*)h->stream;
+    v->n = h->n; v->K = h->K; v->P = h->P; v->U = h->U;
+    return PFB_OK;
+}
+
+static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const double* d_logp,
+                              const double* d_logq, const double* d_logr, const double* d_pool, uint64_t seed,
+                              int ndraws, int importance, pfb_resample_out* o) {
+    if (N < 1 || N > 2147483647LL) PFB_FAIL(h, PFB_ERR_SHAPE, "pool size out of range");
+    if (K_run < 1 || ndraws < 0) PFB_FAIL(h, PFB_ERR_ARG, "bad K_run / ndraws");
+    cudaStream_t st = h->stream;
+    PFB_CUDA(h, h->dScal.ensure(pfb_psis_scalars_size()));
+    PFB_CUDA(h, h->dInds.ensure((size_t)ndraws * 8 + 8));
+    PFB_CUDA(h, h->dIds.ensure((size_t)ndraws * 8 + 8));
+    const bool want_draws = (o->draws != nullptr) && (d_pool != nullptr);
+    if (want_draws) PFB_CUDA(h, h->dOutDraws.ensure((size_t)n * ndraws * 8 + 8));
+    if (importance) {
+        // tail_length(r_eff = 1, S) = min(cld(S, 5), ceil(3 sqrt(S)));  grid m = 30 + floor(sqrt(M))
+        const int M = (int)std::min<int64_t>((N + 4) / 5, (int64_t)ceil(3.0 * sqrt((double)N)));
+        const int m_grid = 30 + (int)floor(sqrt((double)M));
+        if (M + 1 > 8192) PFB_FAIL(h, PFB_ERR_UNSUPPORTED, "pool too large for the single-CTA PSIS kernel");
+        PFB_CUDA(h, h->dLogw.ensure((size_t)N * 8));
+        PFB_CUDA(h, h->dW.ensure((size_t)N * 8));
+        PFB_CUDA(h, h->dCum.ensure((size_t)N * 8));
+        PFB_CUDA(h, pfb_launch_k6(st, (int)N, M, m_grid, d_logp, d_logq, d_logr, h->dLogw.as<double>(),
+                                  h->dW.as<double>(), h->dCum.as<uint64_t>(), h->dScal.p));
+    }
+    PFB_CUDA(h, pfb_launch_k7(st, n, (int)N, K_run, seed, ndraws, importance ? h->dCum.as<uint64_t>() : nullptr,
+                              h->dScal.p, want_draws ? d_pool : nullptr, h->dInds.as<int64_t>(),
+                              h->dIds.as<int64_t>(), want_draws ? h->dOutDraws.as<double>() : nullptr));
+    psis_scalars_host sc;
+    memset(&sc, 0, sizeof(sc));
+    if (importance) {
+        PFB_D2H(o->log_weights, h->dLogw.p, (size_t)N * 8);
+        PFB_D2H(o->weights, h->dW.p, (size_t)N * 8);
+        PFB_CUDA(h, cudaMemcpyAsync(&sc, h->dScal.p, sizeof(sc), cudaMemcpyDeviceToHost, st));
+    }
+    PFB_D2H(o->inds, h->dInds.p, (size_t)ndraws * 8);
+    PFB_D2H(o->ids, h->dIds.p, (size_t)ndraws * 8);
+    if (want_draws) PFB_D2H(o->draws, h->dOutDraws.p, (size_t)n * ndraws * 8);
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    if (o->pareto_k) *o->pareto_k = importance ? sc.pareto_k : NAN;
+    if (o->tail_len) *o->tail_len = importance ? sc.tail_len : 0;
+    return PFB_OK;
+}
+
+extern "C" int pfb_psis_resample(pfb_handle h, uint64_t seed, int ndraws, int importance, pfb_resample_out* o) {
+    if (!h || !o) return PFB_ERR_ARG;
+    if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "pfb_batch_run has not been called");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    return psis_resample_impl(h, h->n, (int64_t)h->P * h->K, h->K, h->dPoolLogp.as<double>(),
+                              h->dPoolLogq.as<double>(), nullptr, h->dPool.as<double>(), seed, ndraws,
+                              importance, o);
+}
+
+extern "C" int pfb_psis_resample_device(pfb_handle h, int n, int64_t N, int K_run, const void* d_logp,
+                                        const void* d_logq, const void* d_pool, uint64_t seed, int ndraws,
+                                        int importance, pfb_resample_out* o) {
+    if (!h || !o) return PFB_ERR_ARG;
+    if (importance && (!d_logp || !d_logq)) PFB_FAIL(h, PFB_ERR_ARG, "d_logp / d_logq are NULL");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    return psis_resample_impl(h, n, N, K_run, (const double*)d_logp, (const double*)d_logq, nullptr,
+                              (const double*)d_pool, seed, ndraws, importance, o);
+}
+
+extern "C" int pfb_psis_resample_host(pfb_handle h, int n, int64_t N, int K_run, const double* log_ratios,
+                                      const double* pool, uint64_t seed, int ndraws, int importance,
+                                      pfb_resample_out* o) {
+    if (!h || !o) return PFB_ERR_ARG;
+    if (N < 1) PFB_FAIL(h, PFB_ERR_SHAPE, "empty pool");
+    if (importance && !log_ratios) PFB_FAIL(h, PFB_ERR_ARG, "log_ratios is NULL");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const double* d_logr = nullptr;
+    const double* d_pool = nullptr;
+    if (importance) {
+        PFB_CUDA(h, h->dTmpLogr.ensure((size_t)N * 8));
+        PFB_CUDA(h, cudaMemcpyAsync(h->dTmpLogr.p, log_ratios, (size_t)N * 8, cudaMemcpyHostToDevice, st));
+        d_logr = h->dTmpLogr.as<double>();
+    }
+    if (pool && o->draws) {
+        PFB_CUDA(h, h->dTmpPool.ensure((size_t)n * N * 8));
+        PFB_CUDA(h, cudaMemcpyAsync(h->dTmpPool.p, pool, (size_t)n * N * 8, cudaMemcpyHostToDevice, st));
+        d_pool = h->dTmpPool.as<double>();
+    }
+    return psis_resample_impl(h, n, N, K_run, nullptr, nullptr, d_logr, d_pool, seed, ndraws, importance, o);
+}
+
+extern "C" int pfb_get_timings(pfb_handle h, double* ms6) {
+    if (!h || !ms6) return PFB_ERR_ARG;
+    if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "no batch has run");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    PFB_CUDA(h, cudaEventSynchronize(h->ev[5]));
+    float t;
+    for (int i = 0; i < 5; ++i) {
+        PFB_CUDA(h, cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]));
+        ms6[i] = t;
+    }
+    PFB_CUDA(h, cudaEventElapsedTime(&t, h->ev[0], h->ev[5]));
+    ms6[5] = t;
+    return h->launches;
+}

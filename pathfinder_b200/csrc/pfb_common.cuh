@@ -1,0 +1,125 @@
+// pfb_common.cuh — shared device helpers and the HBM layout of the engine (sm_100a only).
+//
+// Layout of one batch in HBM (all FP64 unless noted; "unit" = one (path p, iteration l>=1)):
+//   X, G        [n x T]   column-major trajectory points / log-density gradients, T = sum(L_p+1)
+//   point_off   [P+1]     first column of each path (int64)
+//   seeds       [U]       per-unit UInt64 seed, U = sum(L_p); unit u of path p, iteration l is
+//                         u = point_off[p] - p + (l-1), its point column is point_off[p] + l
+//   alpha       [n x U]   diagonal of H0 per unit                          (K1 -> K2)
+//   hist        [U x J]   point columns of the accepted (s,y) pairs, oldest first (int32)
+//   hist_cnt    [U]       J_eff (int32)
+//   FR          [U][n][RS]  "factor record" rows: RS = KP + 2 doubles per row =
+//                         { Vh[i][0..KP), sqrt(alpha_i), mu_i }           (K2 -> K3)
+//   HDR         [U][HS]   unit header: T[KP*KP] row-major, Vc[KP*KP] row-major (upper),
+//                         logdet, flag (1 = PD ok), k_eff
+//   logp, logq  [U x K]   per-draw log densities                            (K3 -> K4)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define PFB_MAX_KP 24  // history_length <= 12
+
+// padded reflector count: 12 (J <= 6), 20 (J <= 10), 24 (J <= 12); 0 = unsupported
+__host__ __device__ inline int pfb_kp_of(int J) { return J <= 6 ? 12 : (J <= 10 ? 20 : (J <= 12 ? 24 : 0)); }
+__host__ __device__ inline int pfb_rs_of(int KP) { return KP + 2; }
+__host__ __device__ inline int pfb_hs_of(int KP) { return 2 * KP * KP + 4; }
+#define PFB_HDR_LOGDET(KP) (2 * (KP) * (KP))
+#define PFB_HDR_FLAG(KP) (2 * (KP) * (KP) + 1)
+#define PFB_HDR_KEFF(KP) (2 * (KP) * (KP) + 2)
+
+#define PFB_LOG2PI 1.8378770664093453
+
+// model family ids (registered device-side target log densities): the
+// PFB_MODEL_* macros of include/pfb200.h
+#include "../../include/pfb200.h"
+
+// ---- deterministic reductions ---------------------------------------------------------------
+__device__ __forceinline__ double pfb_warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Block-wide sum of NV values per thread; result broadcast to every thread.  `scratch` needs
+// NV * 32 doubles.  Fixed order: warp butterfly, then butterfly over the warp sums.
+template <int NV>
+__device__ __forceinline__ void pfb_block_sum(double (&v)[NV], double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int a = 0; a < NV; ++a) v[a] = pfb_warp_sum(v[a]);
+    __syncthreads();  // scratch may still be read from a previous call
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < NV; ++a) scratch[a * 32 + warp] = v[a];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < NV; ++a) {
+        double t = (lane < nwarp) ? scratch[a * 32 + lane] : 0.0;
+        v[a] = pfb_warp_sum(t);
+    }
+}
+
+// Runtime-count variant: values live in shared memory vals[t * stride + a]? No — each thread
+// passes a pointer to its private array of `nv` values (nv <= NVMAX, loops fully unrolled).
+template <int NVMAX>
+__device__ __forceinline__ void pfb_block_sum_n(double (&v)[NVMAX], int nv, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int a = 0; a < NVMAX; ++a)
+        if (a < nv) v[a] = pfb_warp_sum(v[a]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < NVMAX; ++a)
+            if (a < nv) scratch[a * 32 + warp] = v[a];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < NVMAX; ++a) {
+        if (a < nv) {
+            double t = (lane < nwarp) ? scratch[a * 32 + lane] : 0.0;
+            v[a] = pfb_warp_sum(t);
+        }
+    }
+}
+
+// ---- mbarrier + 1-D bulk TMA (cp.async.bulk, SASS: UBLKCP) ------------------------------------
+__device__ __forceinline__ uint32_t pfb_smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void pfb_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pfb_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void pfb_fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void pfb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pfb_smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void pfb_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(pfb_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned),
+// completion signalled on `bar` through complete_tx.
+__device__ __forceinline__ void pfb_tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                                uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            pfb_smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(pfb_smem_u32(bar))
+        : "memory");
+}

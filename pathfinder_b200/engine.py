@@ -1,0 +1,217 @@
+"""Engine: NumPy-facing wrapper of one libpfb200 handle (one GPU).
+
+Host buffers in, host buffers out — exactly what a Julia shim does through ``ccall`` — plus
+the split upload / run / download calls used by ``bench.py`` to time the kernels with inputs
+resident in HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import pfb_config, pfb_device_view, pfb_elbo_out, pfb_resample_out
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class ElboBatchResult:
+    """Per-batch outputs (unit order: path-major, iteration-minor)."""
+
+    offsets: np.ndarray          # [P+1] point offsets
+    elbo: np.ndarray             # [U]
+    elbo_se: np.ndarray          # [U]
+    best_iter: np.ndarray        # [P] 1-based fit_iteration, 0 = none
+    success: np.ndarray          # [P] bool
+    n_rejected: np.ndarray       # [P]
+    draws: np.ndarray | None = None        # [n, K, P] (F-order) best-iteration draws
+    draws_logp: np.ndarray | None = None   # [K, P]
+    draws_logq: np.ndarray | None = None   # [K, P]
+    logp: np.ndarray | None = None         # [K, U]
+    logq: np.ndarray | None = None         # [K, U]
+    fit: dict | None = None                # best-iteration factors (reference WoodburyPDMat form)
+    all_draws: np.ndarray | None = None    # [n, K, U] when materialize_all
+
+    def unit_slice(self, p):
+        o = self.offsets
+        return slice(int(o[p] - p), int(o[p + 1] - p - 1))
+
+
+class Engine:
+    def __init__(self, n, model_family, model_blob=None, history_length=6, ndraws_elbo=5,
+                 device=0, materialize_all=False, eps=1e-12):
+        self.lib = _lib.load()
+        self.n = int(n)
+        self.K = int(ndraws_elbo)
+        self.J = int(history_length)
+        cfg = pfb_config(int(device), self.J, self.K, int(bool(materialize_all)), float(eps))
+        h = C.c_void_p()
+        rc = self.lib.pfb_create(C.byref(h), C.byref(cfg))
+        if rc != 0:
+            raise _lib.PfbError(rc, (self.lib.pfb_last_error(None) or b"").decode())
+        self.h = h
+        self.KP = self.lib.pfb_kp(self.h)
+        self.materialize_all = bool(materialize_all)
+        blob = None if model_blob is None else np.ascontiguousarray(model_blob, dtype=np.float64)
+        _lib.check(self.h, self.lib.pfb_register_model(
+            self.h, int(model_family), self.n, _ptr(blob), 0 if blob is None else blob.size))
+        self._P = 0
+        self._U = 0
+        self._offsets = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pfb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- ELBO stage ------------------------------------------------------------------------
+    @staticmethod
+    def pack(trajectories):
+        """trajectories: list of (points [n, L+1], gradients [n, L+1]) -> offsets, X, G (F-order)."""
+        P = len(trajectories)
+        offsets = np.zeros(P + 1, dtype=np.int64)
+        for p, (x, _) in enumerate(trajectories):
+            offsets[p + 1] = offsets[p] + x.shape[1]
+        n = trajectories[0][0].shape[0] if P else 0
+        X = np.empty((n, int(offsets[-1])), dtype=np.float64, order="F")
+        G = np.empty_like(X)
+        for p, (x, g) in enumerate(trajectories):
+            X[:, offsets[p]:offsets[p + 1]] = x
+            G[:, offsets[p]:offsets[p + 1]] = g
+        return offsets, X, G
+
+    def upload(self, offsets, X, G, seeds, normals=None):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        P = offsets.size - 1
+        U = int(offsets[-1]) - P
+        X = np.asfortranarray(X, dtype=np.float64)
+        G = np.asfortranarray(G, dtype=np.float64)
+        if X.shape != (self.n, int(offsets[-1])) or G.shape != X.shape:
+            raise ValueError("positions / gradients must be n x offsets[-1]")
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        if seeds.size != U:
+            raise ValueError("need one seed per (path, iteration)")
+        if normals is not None:
+            normals = np.asfortranarray(normals, dtype=np.float64)
+            if normals.shape != (self.n, self.K, U):
+                raise ValueError("normals must be n x K x U")
+        _lib.check(self.h, self.lib.pfb_batch_upload(self.h, self.n, P, _ptr(offsets), _ptr(X), _ptr(G),
+                                                     _ptr(seeds), _ptr(normals)))
+        self._P, self._U, self._offsets = P, U, offsets.copy()
+
+    def run(self):
+        _lib.check(self.h, self.lib.pfb_batch_run(self.h))
+
+    def sync(self):
+        _lib.check(self.h, self.lib.pfb_batch_sync(self.h))
+
+    def download(self, draws=True, per_draw=False, fit=False, all_draws=False) -> ElboBatchResult:
+        n, K, P, U, KP = self.n, self.K, self._P, self._U, self.KP
+        out = pfb_elbo_out()
+        elbo = np.empty(U); se = np.empty(U)
+        best = np.empty(P, dtype=np.int64); succ = np.empty(P, dtype=np.int32)
+        rej = np.empty(P, dtype=np.int64)
+        out.elbo, out.elbo_se = _ptr(elbo), _ptr(se)
+        out.best_iter, out.success, out.n_rejected = _ptr(best), _ptr(succ), _ptr(rej)
+        res = ElboBatchResult(self._offsets, elbo, se, best, None, rej)
+        if draws:
+            res.draws = np.empty((n, K, P), order="F")
+            res.draws_logp = np.empty((K, P), order="F")
+            res.draws_logq = np.empty((K, P), order="F")
+            out.draws, out.draws_logp, out.draws_logq = _ptr(res.draws), _ptr(res.draws_logp), _ptr(res.draws_logq)
+        if per_draw:
+            res.logp = np.empty((K, U), order="F")
+            res.logq = np.empty((K, U), order="F")
+            out.logp, out.logq = _ptr(res.logp), _ptr(res.logq)
+        if fit:
+            f = dict(mu=np.empty((n, P), order="F"), alpha=np.empty((n, P), order="F"),
+                     vh=np.empty((n, KP, P), order="F"), T=np.empty((P, KP, KP)),
+                     Vc=np.empty((P, KP, KP)), logdet=np.empty(P), jeff=np.empty(P, dtype=np.int32))
+            out.fit_mu, out.fit_alpha, out.fit_vh = _ptr(f["mu"]), _ptr(f["alpha"]), _ptr(f["vh"])
+            out.fit_T, out.fit_Vc = _ptr(f["T"]), _ptr(f["Vc"])
+            out.fit_logdet, out.fit_jeff = _ptr(f["logdet"]), _ptr(f["jeff"])
+            res.fit = f
+        if all_draws:
+            res.all_draws = np.empty((n, K, U), order="F")
+            out.all_draws = _ptr(res.all_draws)
+        _lib.check(self.h, self.lib.pfb_batch_download(self.h, C.byref(out)))
+        res.success = succ.astype(bool)
+        return res
+
+    def elbo_batch(self, offsets, X, G, seeds, normals=None, **kw) -> ElboBatchResult:
+        self.upload(offsets, X, G, seeds, normals)
+        self.run()
+        return self.download(**kw)
+
+    def timings(self):
+        ms = np.zeros(6)
+        nl = self.lib.pfb_get_timings(self.h, _ptr(ms))
+        return dict(k1=ms[0], k2=ms[1], k3=ms[2], k4=ms[3], k5=ms[4], total=ms[5], launches=nl)
+
+    def device_view(self) -> pfb_device_view:
+        v = pfb_device_view()
+        _lib.check(self.h, self.lib.pfb_batch_device_view(self.h, C.byref(v)))
+        return v
+
+    # ---- PSIS + resample stage -------------------------------------------------------------
+    def _resample_out(self, N, ndraws, importance, want_draws):
+        out = pfb_resample_out()
+        r = dict(inds=np.empty(ndraws, dtype=np.int64), ids=np.empty(ndraws, dtype=np.int64),
+                 pareto_k=np.full(1, np.nan), tail_len=np.zeros(1, dtype=np.int64))
+        out.inds, out.ids = _ptr(r["inds"]), _ptr(r["ids"])
+        out.pareto_k, out.tail_len = _ptr(r["pareto_k"]), _ptr(r["tail_len"])
+        if importance:
+            r["log_weights"] = np.empty(N)
+            r["weights"] = np.empty(N)
+            out.log_weights, out.weights = _ptr(r["log_weights"]), _ptr(r["weights"])
+        if want_draws:
+            r["draws"] = np.empty((self.n, ndraws), order="F")
+            out.draws = _ptr(r["draws"])
+        return out, r
+
+    @staticmethod
+    def _finish(r):
+        r["pareto_k"] = float(r["pareto_k"][0])
+        r["tail_len"] = int(r["tail_len"][0])
+        return r
+
+    def psis_resample(self, seed, ndraws, importance=True):
+        """On the pool of the last batch (device resident)."""
+        N = self._P * self.K
+        out, r = self._resample_out(N, ndraws, importance, True)
+        _lib.check(self.h, self.lib.pfb_psis_resample(self.h, C.c_uint64(int(seed)), int(ndraws),
+                                                      int(bool(importance)), C.byref(out)))
+        return self._finish(r)
+
+    def psis_resample_host(self, log_ratios, K_run, seed, ndraws, importance=True, pool=None):
+        lr = None if log_ratios is None else np.ascontiguousarray(log_ratios, dtype=np.float64)
+        if pool is not None:
+            pool = np.asfortranarray(pool, dtype=np.float64)
+            N = pool.shape[1]
+        else:
+            N = lr.size
+        out, r = self._resample_out(N, ndraws, importance, pool is not None)
+        _lib.check(self.h, self.lib.pfb_psis_resample_host(
+            self.h, self.n, N, int(K_run), _ptr(lr), _ptr(pool), C.c_uint64(int(seed)), int(ndraws),
+            int(bool(importance)), C.byref(out)))
+        return self._finish(r)
+
+    def psis_resample_device(self, N, K_run, d_logp, d_logq, d_pool, seed, ndraws, importance=True):
+        """d_* are raw device pointers (ints), e.g. torch tensors' data_ptr()."""
+        out, r = self._resample_out(N, ndraws, importance, d_pool is not None)
+        _lib.check(self.h, self.lib.pfb_psis_resample_device(
+            self.h, self.n, int(N), int(K_run), C.c_void_p(d_logp), C.c_void_p(d_logq),
+            C.c_void_p(d_pool) if d_pool else None, C.c_uint64(int(seed)), int(ndraws),
+            int(bool(importance)), C.byref(out)))
+        return self._finish(r)
