@@ -1,0 +1,422 @@
+#!/usr/bin/env python3
+"""bench.py — ELBO Monte-Carlo samples/s of the hot path (BASELINE.json metric).
+
+One "step" = one pass of the whole hot path over one batch: K1 history scan -> K2 Woodbury
+build -> K3 fused sampling/logq/logp -> K4 ELBO reduce + argmax -> K5 best-iteration draws ->
+(NCCL all-gather of the per-path log ratios when N > 1) -> K6 PSIS -> K7 resample + gather.
+
+Workload (config.workload): BASELINE config 3 — multipathfinder on a 1024-dim Neal's funnel,
+64 paths per GPU, K = 1000 draws per iteration, history 6; trajectories come from the host
+L-BFGS (master seed 20261017, per-path seed = master + global path index, init U[-10, 10]).
+Paths shard across ranks with no data-path collective until the PSIS pool (weak scaling).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU restatement on all host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MASTER_SEED = 20261017
+METRIC = "elbo_mc_samples_per_sec"
+UNIT = "samples/s"
+
+CONFIGS = {
+    # name: (n, paths per GPU, K, J, init_scale, ndraws)
+    "cfg3_funnel1024_p64_k1000_j6": (1024, 64, 1000, 6, 10.0, 1000),
+    "cfg2_funnel100_p8_k1000_j6": (100, 8, 1000, 6, 10.0, 1000),
+}
+
+
+def build_workload(name, rank, world):
+    import pathfinder_b200 as pf
+
+    n, P, K, J, scale, ndraws = CONFIGS[name]
+    model = pf.Funnel(n)
+    trajs, seeds = [], []
+    for p in range(P):
+        gp = rank * P + p
+        rng = np.random.default_rng(MASTER_SEED + gp)
+        x0 = (rng.random(n) * 2.0 - 1.0) * scale
+        tr = pf.optimize_with_trace(model, x0, J, 1000)
+        trajs.append((tr.points, tr.gradients))
+        seeds.append(rng.integers(0, 2**64, size=len(tr) - 1, dtype=np.uint64))
+    return model, trajs, seeds, (n, P, K, J, ndraws)
+
+
+def algorithmic_flops(trajs, n, K, J):
+    """SURVEY §8(d) mode-F count per sample: 2n (|u|^2) + k^2 (Vc') + 4nk (Vh'u, Vh w) +
+    2k^2 (T) + 2n (scale, shift) + 3n (funnel), k = 2 min(l, J)."""
+    total = 0.0
+    for X, _ in trajs:
+        for l in range(1, X.shape[1]):
+            k = 2 * min(l, J)
+            total += K * (2 * n + k * k + 4 * n * k + 2 * k * k + 2 * n + 3 * n)
+    return total
+
+
+def algorithmic_bytes_mode_m(trajs, n, K, J):
+    """SURVEY §8(d) mode-M bytes: 8n + 24 per sample + [16n + 16n(2J+2)] per unit."""
+    U = sum(X.shape[1] - 1 for X, _ in trajs)
+    return U * (K * (8 * n + 24) + 16 * n + 16 * n * (2 * J + 2))
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_elbo_stage(model_n, trajs, seeds, K, J, budget_s, max_paths=None):
+    """The CPU restatement (oracle) of the ELBO stage on a bounded sample; returns
+    (samples done, seconds)."""
+    from oracle import pf_oracle as O
+
+    done, t0 = 0, time.perf_counter()
+    for p, (X, G) in enumerate(trajs):
+        if max_paths is not None and p >= max_paths:
+            break
+        mus, Hs, _ = O.fit_mvnormals(X, G, history_length=J)
+        L = X.shape[1] - 1
+        for l in range(1, L + 1):
+            u = O.contract_normals(int(seeds[p][l - 1]), model_n, K)
+            O.elbo_and_samples(u, O.logp_funnel, mus[:, l], Hs[l])
+            done += K
+            if time.perf_counter() - t0 > budget_s:
+                return done, time.perf_counter() - t0
+    return done, time.perf_counter() - t0
+
+
+def _ref_worker(args):
+    from threadpoolctl import threadpool_limits
+
+    n, X, G, sd, K, J, budget = args
+    with threadpool_limits(limits=1):  # one BLAS thread per worker process, one process per core
+        return oracle_elbo_stage(n, [(X, G)], [sd], K, J, budget)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; Julia cannot run here) on
+    all host cores, paths across processes like ntasks = nthreads (src/multipath.jl:190)."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    name = args.config
+    model, trajs, seeds, (n, P, K, J, ndraws) = build_workload(name, 0, 1)
+    cores = os.cpu_count() or 1
+    per_step_budget = 6.0
+    ctx = mp.get_context("fork")
+    vals = []
+    with ctx.Pool(cores) as pool:
+        for step in range(args.warmup + args.steps):
+            jobs = [(n, trajs[c % P][0], trajs[c % P][1], seeds[c % P], K, J, per_step_budget) for c in range(cores)]
+            t0 = time.perf_counter()
+            out = pool.map(_ref_worker, jobs)
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                vals.append(sum(o[0] for o in out) / dt)
+    v = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * per_step_budget, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "n": n, "paths": P, "K": K, "history": J},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"ELBO stage (fit_mvnormals + maximize_elbo) of the oracle port, one path per "
+                                   f"core for {per_step_budget:.0f} s per step; Julia is not installed so the "
+                                   f"reference itself cannot run"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg3_funnel1024_p64_k1000_j6", choices=list(CONFIGS))
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-mode-m", action="store_true", help="skip the secondary mode-M (materialise) timing")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import pathfinder_b200 as pf
+    from pathfinder_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists for the product path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    name = args.config
+    model, trajs, seeds, (n, P, K, J, ndraws) = build_workload(name, rank, world)
+    U = sum(X.shape[1] - 1 for X, _ in trajs)
+    offsets, X, G = pf.Engine.pack(trajs)
+    seeds_cat = np.concatenate(seeds)
+
+    lib = _lib.load()
+    import ctypes as C
+    peak = C.c_double(0.0)
+    lib.pfb_measure_fp64_fma_tflops(local_rank, 5, C.byref(peak))
+    fp64_peak = peak.value
+
+    eng = pf.Engine(n, model.family, model.blob, J, K, local_rank)
+    eng.upload(offsets, X, G, seeds_cat)  # inputs resident in HBM before the timed region
+    view = eng.device_view()
+    ext = torch.cuda.ExternalStream(view.stream, device=local_rank)
+
+    def wrap(ptr, numel):
+        class _A:
+            __cuda_array_interface__ = {"shape": (numel,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_A(), device=f"cuda:{local_rank}")
+
+    pool_logp = wrap(view.pool_logp, K * P)
+    pool_logq = wrap(view.pool_logq, K * P)
+    pool_draws = wrap(view.pool_draws, n * K * P).view(K * P, n)
+    if world > 1:
+        g_logp = torch.empty(world * K * P, dtype=torch.float64, device=f"cuda:{local_rank}")
+        g_logq = torch.empty_like(g_logp)
+        out_draws = torch.zeros(ndraws, n, dtype=torch.float64, device=f"cuda:{local_rank}")
+
+    resample_seed = MASTER_SEED
+
+    def step():
+        eng.run()
+        if world == 1:
+            return eng.psis_resample(resample_seed, ndraws, True)
+        # C1 (lean variant): all-gather the per-draw log densities (16 B per pool draw); PSIS and
+        # the index draw run replicated and deterministic on every rank; each rank contributes
+        # the selected columns it owns, summed into the n x ndraws result.
+        with torch.cuda.stream(ext):
+            dist.all_gather_into_tensor(g_logp, pool_logp)
+            dist.all_gather_into_tensor(g_logq, pool_logq)
+        ext.synchronize()
+        r = eng.psis_resample_device(world * K * P, K, g_logp.data_ptr(), g_logq.data_ptr(), None,
+                                     resample_seed, ndraws, True)
+        inds = torch.from_numpy(r["inds"] - 1).to(f"cuda:{local_rank}")
+        with torch.cuda.stream(ext):
+            mine = (inds >= rank * K * P) & (inds < (rank + 1) * K * P)
+            out_draws.zero_()
+            out_draws[mine] = pool_draws[(inds[mine] - rank * K * P)]
+            dist.all_reduce(out_draws)
+        ext.synchronize()
+        r["draws"] = out_draws
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k3_ms, stage_ms = [], []
+    with torch.cuda.stream(ext):
+        ev0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        tm = eng.timings()
+        k3_ms.append(tm["k3"]); stage_ms.append(tm)
+    with torch.cuda.stream(ext):
+        ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    tt = torch.tensor([dev_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    uu = torch.tensor([float(U)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(uu, op=dist.ReduceOp.SUM)
+    max_ms = float(tt.item())
+    total_units = float(uu.item())
+    value = total_units * K * args.steps / (max_ms * 1e-3)
+
+    # ---- e2e: the public call with HOST buffers (pinned), copies inside the timed region ---------
+    _keep = []
+
+    def pinned(a):
+        t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8).pin_memory()
+        _keep.append(t)
+        v = t.numpy()[: a.nbytes].view(a.dtype).reshape(a.shape)
+        v[...] = a
+        return v
+    XT, GT = pinned(np.ascontiguousarray(X.T)), pinned(np.ascontiguousarray(G.T))  # F-order == C-order of .T
+    Xp, Gp = XT.T, GT.T
+    sp, op_ = pinned(seeds_cat), pinned(offsets)
+
+    def e2e_step():
+        res = eng.elbo_batch(op_, Xp, Gp, sp, draws=False, fit=True)
+        if world == 1:
+            r = eng.psis_resample(resample_seed, ndraws, True)
+        else:
+            r = step_after_run()
+        return res, r
+
+    def step_after_run():
+        with torch.cuda.stream(ext):
+            dist.all_gather_into_tensor(g_logp, pool_logp)
+            dist.all_gather_into_tensor(g_logq, pool_logq)
+        ext.synchronize()
+        return eng.psis_resample_device(world * K * P, K, g_logp.data_ptr(), g_logq.data_ptr(), None,
+                                        resample_seed, ndraws, True)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res, r = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_units * K * args.steps / float(te.item())
+    KP = eng.KP
+    h2d = 2 * X.nbytes + seeds_cat.nbytes + offsets.nbytes
+    Npool = world * K * P
+    d2h = 16 * U + 20 * P + (n * P * 2 + n * KP * P + 2 * KP * KP * P + P) * 8 + 4 * P \
+        + 16 * Npool + 16 * ndraws + (8 * n * ndraws if world == 1 else 0)
+
+    # ---- roofline of the dominant kernel (K3, lean mode: FP64-pipe bound) -------------------------
+    k3_avg_ms = float(np.mean(k3_ms))
+    flops = algorithmic_flops(trajs, n, K, J)
+    ach_tf = flops / (k3_avg_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": ach_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                "kernel": "pfb_k3_elbo_sample (lean mode F)", "kernel_ms": k3_avg_ms,
+                "peak_source": "measured live: DFMA-chain microbenchmark pfb_measure_fp64_fma_tflops "
+                               "(MEASURED_PEAKS.json has no FP64 figure)",
+                "k3_share_of_step": k3_avg_ms * args.steps / max_ms}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "n": n, "paths_per_gpu": P, "K": K, "history": J, "ndraws": ndraws,
+                   "units_per_gpu_rank0": U, "mode": "F (lean: per-draw logp/logq only; best-iteration draws "
+                   "re-materialised by K5)", "l2": "per-step working set (factor records %.0f MB) exceeds the "
+                   "126 MB L2" % (U * n * (KP + 2) * 8 / 1e6), "parallelism": f"paths sharded over {world} GPU(s)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int((stage_ms[-1]["launches"] + 2) * args.steps),
+        "clocks": clocks,
+        "roofline": roofline,
+        "stage_ms": {k: float(np.mean([s[k] for s in stage_ms])) for k in ("k1", "k2", "k3", "k4", "k5", "total")},
+        "wall_s_timed_region": wall,
+    }
+
+    if rank == 0 and world == 1 and not args.no_mode_m:
+        # secondary accounting: reference-faithful mode M (every iteration's draws written to HBM)
+        engm = pf.Engine(n, model.family, model.blob, J, K, local_rank, materialize_all=True)
+        engm.upload(offsets, X, G, seeds_cat)
+        for _ in range(2):
+            engm.run(); engm.sync()
+        ms = []
+        for _ in range(max(3, args.steps // 2)):
+            engm.run(); engm.sync()
+            ms.append(engm.timings()["k3"])
+        by = algorithmic_bytes_mode_m(trajs, n, K, J)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        gbs = by / (float(np.mean(ms)) * 1e-3) / 1e9
+        line["roofline_mode_m"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": gbs / hbm_peak, "traffic": None, "kernel_ms": float(np.mean(ms)),
+                                   "value_samples_per_s": U * K / (float(np.mean(ms)) * 1e-3),
+                                   "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}
+        engm.close()
+
+    if rank == 0:
+        # ---- cpu_baseline: the oracle port on one host core, bounded sample -----------------------
+        from threadpoolctl import threadpool_limits
+
+        with threadpool_limits(limits=1):
+            done, secs = oracle_elbo_stage(n, trajs, seeds, K, J, args.cpu_budget)
+        line["cpu_baseline"] = {"value": done / secs, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"oracle ELBO stage on the first {done // K} (path, iteration) units of "
+                                          f"this workload, {secs:.1f} s, single thread"}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

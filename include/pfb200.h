@@ -145,6 +145,9 @@ int pfb_psis_resample_device(pfb_handle h, int n, int64_t N, int K_run, const vo
  * ms[0..5] = K1, K2, K3, K4, K5, total; returns the number of kernels launched. */
 int pfb_get_timings(pfb_handle h, double* ms6);
 
+/* Measurement utility: FP64 FMA peak of `device` in TFLOP/s (DFMA chains, best of reps). */
+int pfb_measure_fp64_fma_tflops(int device, int reps, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,7 @@ SYMBOLS = {
     "pfb_psis_resample_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, _dp, _dp, _dp,
                                            C.c_uint64, C.c_int, C.c_int, C.POINTER(pfb_resample_out)]),
     "pfb_get_timings": (C.c_int, [C.c_void_p, _dp]),
+    "pfb_measure_fp64_fma_tflops": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 
 _lib = None
