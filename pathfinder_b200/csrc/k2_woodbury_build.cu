@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(PFB_K2_THREADS)
 pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* __restrict__ G,
                       const int32_t* __restrict__ unit_col, const double* __restrict__ alpha_all,
                       const int32_t* __restrict__ hist, const int32_t* __restrict__ hist_cnt,
-                      double* __restrict__ FR, double* __restrict__ HDR) {
+                      double* __restrict__ FR, double* __restrict__ HDR, double* __restrict__ FR2) {
     constexpr int RS = KP + 2;
     constexpr int JM = KP / 2;
     __shared__ double scratch[KP * 32];
@@ -332,6 +332,23 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
         double* row = fr + (int64_t)i * RS;
         // kq == 0: Sigma = diag(alpha): t = sqrt(alpha) g, mu = theta + sqrt(alpha) t
         row[KP + 1] = fma(row[KP], row[KP + 1], theta[i]);
+        if (FR2 != nullptr) {
+            // second copy in the tensor-core layout of K3 (pfb_common.cuh): RS2 doubles per row,
+            // 4-double groups XOR-swizzled by pfb_swz(row)
+            constexpr int RS2 = (KP == 12) ? 16 : 32;
+            double* r2 = FR2 + ((int64_t)u * pfb_npad8(n) + i) * RS2;
+            const int sw = pfb_swz(i);
+#pragma unroll
+            for (int c = 0; c < RS2; ++c) {
+                double v = (c < KP) ? row[c] : (c == KP ? row[KP] : (c == KP + 1 ? row[KP + 1] : 0.0));
+                r2[c ^ sw] = v;
+            }
+        }
+    }
+    if (FR2 != nullptr) {
+        constexpr int RS2 = (KP == 12) ? 16 : 32;
+        const int npad = pfb_npad8(n);
+        for (int e = n * RS2 + tid; e < npad * RS2; e += nt) FR2[(int64_t)u * npad * RS2 + e] = 0.0;
     }
     // ---- header ---------------------------------------------------------------------------------
     for (int e = tid; e < KP * KP; e += nt) {
@@ -348,21 +365,21 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
 template <int KP>
 static cudaError_t launch_k2(cudaStream_t st, int n, int U, int J, const double* X, const double* G,
                              const int32_t* unit_col, const double* alpha, const int32_t* hist,
-                             const int32_t* hist_cnt, double* FR, double* HDR) {
+                             const int32_t* hist_cnt, double* FR, double* HDR, double* FR2) {
     int threads = n >= PFB_K2_THREADS ? PFB_K2_THREADS : ((n + 31) / 32) * 32;
     if (threads < 64) threads = 64;  // >= KP threads are needed by the small-matrix phases
-    pfb_k2_woodbury_build<KP><<<U, threads, 0, st>>>(n, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR);
+    pfb_k2_woodbury_build<KP><<<U, threads, 0, st>>>(n, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR, FR2);
     return cudaGetLastError();
 }
 
 extern "C" cudaError_t pfb_launch_k2(cudaStream_t st, int KP, int n, int U, int J, const double* X,
                                      const double* G, const int32_t* unit_col, const double* alpha,
                                      const int32_t* hist, const int32_t* hist_cnt, double* FR,
-                                     double* HDR) {
+                                     double* HDR, double* FR2) {
     if (U <= 0) return cudaSuccess;
     switch (KP) {
 #define PFB_K2_CASE(k) \
-    case k: return launch_k2<k>(st, n, U, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR);
+    case k: return launch_k2<k>(st, n, U, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR, FR2);
         PFB_K2_CASE(12)
         PFB_K2_CASE(20)
         PFB_K2_CASE(24)

@@ -1,0 +1,651 @@
+// K3 elbo_sample_fused on the FP64 tensor cores (and K5 materialize_best: the same kernel with a
+// draws pointer).
+//
+// Replaces rand_and_logpdf + the per-draw part of elbo_and_samples:
+//   u ~ N(0, I_n)            (reference: src/mvnormal.jl:30; here the engine's Philox/ziggurat
+//                             contract of pf_rng.h, or host-supplied normals in parity mode)
+//   |u|^2                    (src/mvnormal.jl:31)
+//   x = L u + mu, L = U' Q diag(Vc', I)       (src/mvnormal.jl:32-33 -> src/woodbury.jl:136-143)
+//       Q applied in compact-WY form  Q = I - Vh T Vh'  (what LAPACK dgemqrt does)
+//   logq = -(n log 2pi + logdet + |u|^2) / 2  (src/mvnormal.jl:36)
+//   logp = log pi(x) for the registered model  (src/elbo.jl:15)
+//
+// Mapping.  A warp owns 8 * DS draws; lane (g = lane / 4, t = lane % 4) owns, for draw g of each
+// draw set, the rows {8 b + 2 t, 8 b + 2 t + 1} of every 8-row block b — exactly one Philox call
+// (row pair 4 b + t) per block and draw.  With that ownership both halves of the Q-apply are
+// DMMA m8n8k4 products whose A / C fragments are the lane's own normals:
+//   pass 0   w[draw][j]  += sum_rows  u~[draw][row] * Vh[row][j]      A = u~ (8 draws x 4 rows),
+//                                                                     B = Vh  (4 rows x 8 j)
+//   pass 1   z[draw][row] = u~[draw][row] - sum_j c[draw][j] Vh[row][j]   C = u~, A = -c = -T w,
+//                                                                     B = Vh' (4 j x 8 rows)
+// then x = sqrt(alpha) .* z + mu and the model's per-element accumulation.  The normals are
+// regenerated in pass 1 from the counter-based RNG instead of being stored.
+//
+// The unit's factor record (rows of RS2 doubles {Vh[0..KP), sqrt(alpha), mu, pad}, 4-double groups
+// XOR-swizzled per row so both fragment access patterns are bank-conflict free; written by K2) is
+// brought into shared memory by 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx) in chunks of
+// PFB_K3_RC rows: all chunks stay resident when they fit (n <= ~1150 at history 6), otherwise they
+// stream through a ring, twice per sweep.  A CTA loops over the sweeps (256 draws) of its unit so
+// the record is loaded once per unit.  The ziggurat layer table is replicated 8x in shared memory
+// (one copy per 16-byte bank) so the random layer lookups are conflict free.  Elements that leave
+// the ziggurat fast path (1.5 %) are deferred and finished warp-cooperatively per chunk.
+// Lean mode writes 16 B per draw (logp, logq); with a draws pointer x is written as well.
+#include "pfb_common.cuh"
+#include "pf_rng.h"
+
+#ifndef PFB_K3_KP
+#define PFB_K3_KP 12
+#define PFB_K3_ENTRY pfb_launch_k3_kp12
+#endif
+
+#define PFB_K3_MAXWARPS 16
+#define PFB_K3_DS 2      // draw sets (8 draws each) per warp
+#define PFB_K3_RC 128    // record rows per TMA chunk (16 blocks of 8 rows)
+#define PFB_K3_DCAP 64   // deferred-list capacity per warp and round
+
+struct pfb_model_params {
+    const double* p0;  // DIAGNORMAL: mean[n]
+    const double* p1;  // DIAGNORMAL: 1/sd[n]
+    double c0;         // DIAGNORMAL: -sum(log sd) - n/2 log(2 pi)
+};
+
+template <int MODEL>
+struct pfb_model_acc {
+    double a, b;
+    __device__ __forceinline__ void init() { a = 0.0; b = 0.0; }
+    // general element (any row index i < n)
+    __device__ __forceinline__ void add(int i, double x, const pfb_model_params& mp) {
+        if (MODEL == PFB_MODEL_ISONORMAL) {
+            a = fma(x, x, a);
+        } else if (MODEL == PFB_MODEL_FUNNEL) {
+            if (i == 0) b = x; else a = fma(x, x, a);
+        } else if (MODEL == PFB_MODEL_DIAGNORMAL) {
+            double z = (x - __ldg(mp.p0 + i)) * __ldg(mp.p1 + i);
+            a = fma(z, z, a);
+        }
+    }
+    // element with i > 0 guaranteed (body blocks)
+    __device__ __forceinline__ void add_nz(int i, double x, const pfb_model_params& mp) {
+        if (MODEL == PFB_MODEL_DIAGNORMAL) add(i, x, mp); else a = fma(x, x, a);
+    }
+    // combine the partial accumulators of the 4 lanes that share a draw
+    __device__ __forceinline__ void group_reduce() {
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        b += __shfl_xor_sync(0xffffffffu, b, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        b += __shfl_xor_sync(0xffffffffu, b, 2);
+    }
+    __device__ __forceinline__ double finish(int n, const pfb_model_params& mp) const {
+        if (MODEL == PFB_MODEL_ISONORMAL) return a / -2.0;
+        if (MODEL == PFB_MODEL_FUNNEL) {
+            // ((tau/3)^2 + (n-1) tau + exp(-tau) * sum beta^2) / -2
+            double t3 = b / 3.0;
+            return (fma(t3, t3, (double)(n - 1) * b) + exp(-b) * a) / -2.0;
+        }
+        if (MODEL == PFB_MODEL_DIAGNORMAL) return fma(a, -0.5, mp.c0);
+        return NAN;
+    }
+};
+
+// replicated ziggurat table entry (16 B): w, high word of the fast-accept threshold
+struct __align__(16) pfb_zig_e {
+    double w;
+    uint32_t kqh;
+    uint32_t pad;
+};
+
+struct pfb_k3_warp_list {
+    double z[PFB_K3_DCAP];
+    uint16_t row[PFB_K3_DCAP];  // row offset inside the chunk
+    uint8_t src[PFB_K3_DCAP];   // owner lane
+    uint8_t ds[PFB_K3_DCAP];    // draw set
+};
+
+__device__ __forceinline__ void pfb_dmma(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
+}
+
+// Fast ziggurat step on the replicated table: returns true when accepted; z is valid only then.
+__device__ __forceinline__ bool pfb_zig_fast_rep(uint64_t bits, const pfb_zig_e* __restrict__ zig_lane,
+                                                 double& z) {
+    const uint32_t hi = (uint32_t)(bits >> 32), lo = (uint32_t)bits;
+    const pfb_zig_e e = zig_lane[(hi >> 24) * 8];
+    const uint32_t mh = (hi & 0xFFFFFu) | 0x43300000u;
+    const double m = __hiloint2double((int)mh, (int)lo);
+    const double x = fma(m, e.w, pf_zig_negw52(e.w));
+    z = __hiloint2double(__double2hiint(x) ^ (int)((hi << 8) & 0x80000000u), __double2loint(x));
+    return mh < e.kqh;
+}
+
+template <int KP, int MODEL>
+__global__ void __launch_bounds__(PFB_K3_MAXWARPS * 32, 1)
+pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__ unit_list,
+                   const double* __restrict__ FR2, const double* __restrict__ HDR,
+                   const uint64_t* __restrict__ seeds, const double* __restrict__ u_host,
+                   pfb_model_params mp, double* __restrict__ logp_out, double* __restrict__ logq_out,
+                   double* __restrict__ draws_out) {
+    constexpr int RS2 = (KP == 12) ? 16 : 32;
+    constexpr int RC = PFB_K3_RC;
+    constexpr int DS = PFB_K3_DS;
+    constexpr int NT0 = (KP + 7) / 8;  // j tiles of pass 0
+    constexpr int NS1 = KP / 4;        // j steps of pass 1
+    constexpr int HB = (KP + 7) / 8;   // head blocks (rows < KP get the Vc' multiply)
+    constexpr int NHP = (KP / 2 + 3) / 4;  // head row pairs generated per lane
+    static_assert(RC / 8 * 2 * DS <= 64, "pending mask is 64 bits per chunk");
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sStage = reinterpret_cast<double*>(smem_raw);                      // NS * RC * RS2
+    pfb_zig_e* sZig = reinterpret_cast<pfb_zig_e*>(sStage + (size_t)NS * RC * RS2);  // 256 * 8
+    double* sT = reinterpret_cast<double*>(sZig + PF_ZIG_LAYERS * 8);          // KP*KP
+    double* sVc = sT + KP * KP;                                                // KP*KP
+    double* sC = sVc + KP * KP;                                                // NW * DS * 8 * KP
+    pfb_k3_warp_list* sList = reinterpret_cast<pfb_k3_warp_list*>(sC + (size_t)NW * DS * 8 * KP);
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sList + NW);                  // NS
+
+    const int slot = blockIdx.x / splits;
+    const int split = blockIdx.x - slot * splits;
+    const int unit = unit_list ? unit_list[slot] : slot;
+    const int DPS = NW * DS * 8;                 // draws per sweep
+    const int S = (K + DPS - 1) / DPS;           // sweeps of this unit
+    if (unit < 0) {  // path without a usable iteration (K5 only)
+        for (int sw = split; sw < S; sw += splits)
+            for (int k = sw * DPS + tid; k < min(K, (sw + 1) * DPS); k += blockDim.x) {
+                logp_out[(int64_t)slot * K + k] = NAN;
+                logq_out[(int64_t)slot * K + k] = NAN;
+            }
+        return;
+    }
+    const int npad = pfb_npad8(n);
+    const double* fr = FR2 + (int64_t)unit * npad * RS2;
+    const double* hdr = HDR + (int64_t)unit * pfb_hs_of(KP);
+    const uint64_t seed = seeds[unit];
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const bool HOST_U = (u_host != nullptr);
+    const bool MATERIALIZE = (draws_out != nullptr);
+
+    const int C = (npad + RC - 1) / RC;  // chunks per pass
+    const bool resident = (C <= NS);
+    const int nsweeps_cta = (S - split + splits - 1) / splits;
+    const int Q = resident ? C : 2 * C * nsweeps_cta;  // TMA loads issued by this CTA
+
+    for (int e = tid; e < KP * KP; e += blockDim.x) {
+        sT[e] = hdr[e];
+        sVc[e] = hdr[KP * KP + e];
+    }
+    for (int e = tid; e < PF_ZIG_LAYERS * 8; e += blockDim.x) {
+        const pf_zig_kw_t kw = PF_ZIG_KW_DEV[e >> 3];
+        pfb_zig_e ze;
+        ze.w = kw.w;
+        ze.kqh = pf_zig_kqh(kw.kq);
+        ze.pad = 0u;
+        sZig[e] = ze;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) pfb_mbar_init(&sBar[s], 1);
+        pfb_fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](int q) {
+        const int c = q % C, s = q % NS;
+        const int r0 = c * RC;
+        const int rows = min(RC, npad - r0);
+        const uint32_t bytes = (uint32_t)(rows * RS2 * 8);
+        pfb_mbar_expect_tx(&sBar[s], bytes);
+        pfb_tma_load_1d(sStage + (size_t)s * RC * RS2, fr + (int64_t)r0 * RS2, bytes, &sBar[s]);
+    };
+    if (tid == 0) {
+        for (int q = 0; q < NS && q < Q; ++q) issue(q);
+    }
+    const double logdet = hdr[PFB_HDR_LOGDET(KP)];
+    const bool pd_ok = hdr[PFB_HDR_FLAG(KP)] != 0.0;
+    const int H = min(KP, n);          // head rows
+    const int nblk = npad >> 3;        // 8-row blocks
+    const bool tail_special = (n & 7) != 0;
+
+    // lane-constant fragment offsets (doubles) inside an 8-row block
+    int off0[2][NT0];  // pass 0: Vh[row 2t+e][j = 8h+g]
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int h = 0; h < NT0; ++h) off0[e][h] = (2 * t + e) * RS2 + ((8 * h + g) ^ pfb_swz(2 * t + e));
+    int off1[NS1];     // pass 1: Vh[row g][j = 4s+t]
+#pragma unroll
+    for (int s = 0; s < NS1; ++s) off1[s] = g * RS2 + ((4 * s + t) ^ pfb_swz(g));
+    int offam[2];      // {sqrt(alpha), mu} of row 2t+e
+#pragma unroll
+    for (int e = 0; e < 2; ++e) offam[e] = (2 * t + e) * RS2 + (KP ^ pfb_swz(2 * t + e));
+
+    const pfb_zig_e* zig_lane = sZig + (lane & 7);
+    pfb_k3_warp_list& wl = sList[warp];
+    double* cw = sC + (size_t)warp * DS * 8 * KP;  // this warp's [DS][8][KP]
+
+    int q = 0;  // TMA load sequence number of the next chunk to consume (ring mode)
+    bool first_pass = true;
+#pragma unroll 1
+    for (int sw = split; sw < S; sw += splits) {
+        uint32_t kd[DS];      // draw index (clamped)
+        bool active[DS];
+        const double* uh[DS];
+        double* xout[DS];
+#pragma unroll
+        for (int d = 0; d < DS; ++d) {
+            const int kraw = sw * DPS + (warp * DS + d) * 8 + g;
+            active[d] = kraw < K;
+            kd[d] = (uint32_t)(active[d] ? kraw : K - 1);
+            uh[d] = HOST_U ? u_host + ((int64_t)unit * K + kd[d]) * n : nullptr;
+            xout[d] = MATERIALIZE ? draws_out + ((int64_t)slot * K + kd[d]) * n : nullptr;
+        }
+        double unormsq[DS];
+        pfb_model_acc<MODEL> macc[DS];
+        double zhd[DS][HB][2];  // u~ of this lane's head rows
+#pragma unroll
+        for (int d = 0; d < DS; ++d) {
+            unormsq[d] = 0.0;
+            macc[d].init();
+        }
+        // ---- head: u~[0..H) = Vc' u[0..H)  (src/woodbury.jl:139) ------------------------------------
+#pragma unroll
+        for (int d = 0; d < DS; ++d) {
+            double own[NHP][2];
+#pragma unroll
+            for (int r = 0; r < NHP; ++r) {
+                const int jj = 4 * r + t;  // row pair generated by this lane
+                double z0 = 0.0, z1 = 0.0;
+                if (2 * jj < H) {
+                    if (HOST_U) {
+                        z0 = uh[d][2 * jj];
+                        if (2 * jj + 1 < H) z1 = uh[d][2 * jj + 1];
+                    } else {
+                        pf_normal_pair((uint32_t)jj, kd[d], k0, k1, PF_ZIG_KW_DEV, PF_ZIG_F_DEV, &z0, &z1);
+                        if (2 * jj + 1 >= H) z1 = 0.0;
+                    }
+                }
+                own[r][0] = z0;
+                own[r][1] = z1;
+                unormsq[d] = fma(z0, z0, unormsq[d]);
+                unormsq[d] = fma(z1, z1, unormsq[d]);
+            }
+            double zh[KP];
+#pragma unroll
+            for (int jj = 0; jj < KP / 2; ++jj) {
+                const int srcl = (lane & ~3) | (jj & 3);
+                zh[2 * jj] = __shfl_sync(0xffffffffu, own[jj >> 2][0], srcl);
+                zh[2 * jj + 1] = __shfl_sync(0xffffffffu, own[jj >> 2][1], srcl);
+            }
+#pragma unroll
+            for (int bb = 0; bb < HB; ++bb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 8 * bb + 2 * t + e;
+                    double acc = 0.0;
+                    if (j < KP) {
+#pragma unroll
+                        for (int m = 0; m < KP; ++m)
+                            if (m <= j) acc = fma(sVc[m * KP + j], zh[m], acc);
+                    }
+                    zhd[d][bb][e] = acc;
+                }
+        }
+
+        double wacc[DS][NT0][2];  // pass 0 accumulators: w[draw g][j = 8h + 2t + {0,1}]
+        double ncf[DS][NS1];      // pass 1 A fragments: -c[draw g][j = 4s + t]
+#pragma unroll
+        for (int d = 0; d < DS; ++d)
+#pragma unroll
+            for (int h = 0; h < NT0; ++h) wacc[d][h][0] = wacc[d][h][1] = 0.0;
+
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+                int s;
+                if (resident) {
+                    s = c;
+                    if (first_pass) pfb_mbar_wait(&sBar[s], 0u);  // loaded once, stays resident
+                } else {
+                    s = q % NS;
+                    pfb_mbar_wait(&sBar[s], (uint32_t)((q / NS) & 1));
+                }
+                const double* st = sStage + (size_t)s * RC * RS2;
+                const int r0 = c * RC;
+                const int nb = (min(npad, r0 + RC) - r0) >> 3;
+                unsigned long long pend = 0ull;  // bit ((o*2 + e)*DS + d): element deferred
+#pragma unroll 1
+                for (int o = 0; o < nb; ++o) {
+                    const int b = (r0 >> 3) + o;
+                    const double* blk = st + o * 8 * RS2;
+                    const int R = r0 + o * 8 + 2 * t;  // this lane's first row of the block
+                    const bool special = HOST_U || (b < HB) || (tail_special && b == nblk - 1);
+                    double z[DS][2];
+                    bool ok[DS][2];
+                    if (!special) {
+#pragma unroll
+                        for (int d = 0; d < DS; ++d) {
+                            uint64_t wa, wb;
+                            pf_bits((uint32_t)(4 * b + t), 0u, kd[d], k0, k1, 0u, &wa, &wb);
+                            ok[d][0] = pfb_zig_fast_rep(wa, zig_lane, z[d][0]) || !active[d];
+                            ok[d][1] = pfb_zig_fast_rep(wb, zig_lane, z[d][1]) || !active[d];
+                        }
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < DS; ++d) {
+                            ok[d][0] = ok[d][1] = true;
+                            z[d][0] = z[d][1] = 0.0;
+                            if (R < H) {
+                                // head rows come in pairs (H is a multiple of 4 unless n < KP, and
+                                // then rows >= n are zero)
+#pragma unroll
+                                for (int bb = 0; bb < HB; ++bb)
+                                    if (bb == b) {
+                                        z[d][0] = zhd[d][bb][0];
+                                        z[d][1] = (R + 1 < H) ? zhd[d][bb][1] : 0.0;
+                                    }
+                            } else if (R < n) {
+                                if (HOST_U) {
+                                    z[d][0] = uh[d][R];
+                                    if (R + 1 < n) z[d][1] = uh[d][R + 1];
+                                } else {
+                                    uint64_t wa, wb;
+                                    pf_bits((uint32_t)(4 * b + t), 0u, kd[d], k0, k1, 0u, &wa, &wb);
+                                    ok[d][0] = pfb_zig_fast_rep(wa, zig_lane, z[d][0]) || !active[d];
+                                    ok[d][1] = pfb_zig_fast_rep(wb, zig_lane, z[d][1]) || !active[d];
+                                    if (R + 1 >= n) {
+                                        ok[d][1] = true;
+                                        z[d][1] = 0.0;
+                                    }
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int d = 0; d < DS; ++d)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            if (!ok[d][e]) {
+                                z[d][e] = 0.0;
+                                pend |= 1ull << ((o * 2 + e) * DS + d);
+                            }
+                    if (pass == 0) {
+                        if (!(special && R < H)) {  // head rows' |u|^2 was added with the raw normals
+#pragma unroll
+                            for (int d = 0; d < DS; ++d) {
+                                unormsq[d] = fma(z[d][0], z[d][0], unormsq[d]);
+                                unormsq[d] = fma(z[d][1], z[d][1], unormsq[d]);
+                            }
+                        }
+                        double vf[2][NT0];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+#pragma unroll
+                            for (int h = 0; h < NT0; ++h) vf[e][h] = blk[off0[e][h]];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+#pragma unroll
+                            for (int d = 0; d < DS; ++d)
+#pragma unroll
+                                for (int h = 0; h < NT0; ++h)
+                                    pfb_dmma(wacc[d][h][0], wacc[d][h][1], z[d][e], vf[e][h]);
+                    } else {
+                        double bf[NS1];
+#pragma unroll
+                        for (int s1 = 0; s1 < NS1; ++s1) bf[s1] = blk[off1[s1]];
+                        double2 am[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) am[e] = *reinterpret_cast<const double2*>(blk + offam[e]);
+#pragma unroll
+                        for (int d = 0; d < DS; ++d) {
+                            double d0 = z[d][0], d1 = z[d][1];
+#pragma unroll
+                            for (int s1 = 0; s1 < NS1; ++s1) pfb_dmma(d0, d1, ncf[d][s1], bf[s1]);
+                            const double x0 = fma(am[0].x, d0, am[0].y);
+                            const double x1 = fma(am[1].x, d1, am[1].y);
+                            if (!special) {
+                                if (ok[d][0]) macc[d].add_nz(R, x0, mp);
+                                if (ok[d][1]) macc[d].add_nz(R + 1, x1, mp);
+                                if (MATERIALIZE && active[d]) {
+                                    if ((n & 1) == 0) {
+                                        // both rows exist; a pending one is rewritten by the fix-up
+                                        *reinterpret_cast<double2*>(xout[d] + R) = make_double2(x0, x1);
+                                    } else {
+                                        xout[d][R] = x0;
+                                        xout[d][R + 1] = x1;
+                                    }
+                                }
+                            } else {
+                                if (R < n) {
+                                    if (ok[d][0]) macc[d].add(R, x0, mp);
+                                    if (MATERIALIZE && active[d]) xout[d][R] = x0;
+                                }
+                                if (R + 1 < n) {
+                                    if (ok[d][1]) macc[d].add(R + 1, x1, mp);
+                                    if (MATERIALIZE && active[d]) xout[d][R + 1] = x1;
+                                }
+                            }
+                        }
+                    }
+                }
+                // ---- deferred ziggurat slow path (warp-cooperative, deterministic order) -----------
+                if (!HOST_U) {
+                    const int cnt = __popcll(pend);
+                    int incl = cnt;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        int v = __shfl_up_sync(0xffffffffu, incl, off);
+                        if (lane >= off) incl += v;
+                    }
+                    const int excl = incl - cnt;
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll 1
+                    for (int base = 0; base < total; base += PFB_K3_DCAP) {
+                        {
+                            unsigned long long a0 = pend;
+                            int flat = excl - base;
+                            while (a0) {
+                                const int bit = __ffsll((long long)a0) - 1;
+                                a0 &= a0 - 1;
+                                if (flat >= 0 && flat < PFB_K3_DCAP) {
+                                    const int oe = bit / DS;  // o*2 + e
+                                    wl.row[flat] = (uint16_t)((oe >> 1) * 8 + 2 * t + (oe & 1));
+                                    wl.src[flat] = (uint8_t)lane;
+                                    wl.ds[flat] = (uint8_t)(bit % DS);
+                                }
+                                ++flat;
+                            }
+                        }
+                        __syncwarp();
+                        const int nitems = min(PFB_K3_DCAP, total - base);
+                        for (int it = lane; it < nitems; it += 32) {
+                            const uint32_t row = (uint32_t)(r0 + wl.row[it]);
+                            const int kraw = sw * DPS + (warp * DS + wl.ds[it]) * 8 + (wl.src[it] >> 2);
+                            wl.z[it] = pf_normal_finish_slow(row, (uint32_t)kraw, k0, k1, PF_ZIG_KW_DEV,
+                                                             PF_ZIG_F_DEV);
+                        }
+                        __syncwarp();
+                        if (pass == 0) {
+                            // every lane folds the items of its draw group into its own w slots
+                            for (int it = 0; it < nitems; ++it) {
+                                const int srcl = wl.src[it];
+                                if ((srcl >> 2) != g) continue;
+                                const double zz = wl.z[it];
+                                const int row = wl.row[it];
+                                const int dsi = wl.ds[it];
+                                const double* rr = st + row * RS2;
+                                const int swz = pfb_swz(row);
+#pragma unroll
+                                for (int d = 0; d < DS; ++d)
+                                    if (d == dsi) {
+                                        if (srcl == lane) unormsq[d] = fma(zz, zz, unormsq[d]);
+#pragma unroll
+                                        for (int h = 0; h < NT0; ++h) {
+                                            wacc[d][h][0] = fma(rr[(8 * h + 2 * t) ^ swz], zz, wacc[d][h][0]);
+                                            wacc[d][h][1] = fma(rr[(8 * h + 2 * t + 1) ^ swz], zz, wacc[d][h][1]);
+                                        }
+                                    }
+                            }
+                        } else {
+                            unsigned long long a0 = pend;
+                            int flat = excl - base;
+                            while (a0) {
+                                const int bit = __ffsll((long long)a0) - 1;
+                                a0 &= a0 - 1;
+                                if (flat >= 0 && flat < PFB_K3_DCAP) {
+                                    const int oe = bit / DS, dsi = bit % DS;
+                                    const int row = (oe >> 1) * 8 + 2 * t + (oe & 1);
+                                    const double* rr = st + row * RS2;
+                                    const int swz = pfb_swz(row);
+                                    const double* cv = cw + (dsi * 8 + g) * KP;
+                                    double zz = wl.z[flat];
+#pragma unroll
+                                    for (int j = 0; j < KP; ++j) zz = fma(-rr[j ^ swz], cv[j], zz);
+                                    const double2 am = *reinterpret_cast<const double2*>(rr + (KP ^ swz));
+                                    const double x = fma(am.x, zz, am.y);
+#pragma unroll
+                                    for (int d = 0; d < DS; ++d)
+                                        if (d == dsi) {
+                                            macc[d].add(r0 + row, x, mp);
+                                            if (MATERIALIZE) xout[d][r0 + row] = x;
+                                        }
+                                }
+                                ++flat;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (!resident) {
+                    __syncthreads();  // every warp is done with stage s
+                    if (tid == 0 && q + NS < Q) issue(q + NS);
+                    ++q;
+                }
+            }
+            first_pass = false;
+            if (pass == 0) {
+                // c = T w (upper triangular); the w fragments go through shared memory so that
+                // every lane can form its pass-1 A fragments -c[4s + t]
+                __syncwarp();
+#pragma unroll
+                for (int d = 0; d < DS; ++d)
+#pragma unroll
+                    for (int h = 0; h < NT0; ++h)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int j = 8 * h + 2 * t + e;
+                            if (j < KP) cw[(d * 8 + g) * KP + j] = wacc[d][h][e];
+                        }
+                __syncwarp();
+                double cf[DS][NS1];
+#pragma unroll
+                for (int d = 0; d < DS; ++d)
+#pragma unroll
+                    for (int s1 = 0; s1 < NS1; ++s1) {
+                        const int a = 4 * s1 + t;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int bcol = 0; bcol < KP; ++bcol)
+                            if (bcol >= a) acc = fma(sT[a * KP + bcol], cw[(d * 8 + g) * KP + bcol], acc);
+                        cf[d][s1] = acc;
+                    }
+                __syncwarp();
+#pragma unroll
+                for (int d = 0; d < DS; ++d)
+#pragma unroll
+                    for (int s1 = 0; s1 < NS1; ++s1) {
+                        cw[(d * 8 + g) * KP + 4 * s1 + t] = cf[d][s1];
+                        ncf[d][s1] = -cf[d][s1];
+                    }
+                __syncwarp();
+            }
+        }
+        // ---- per-draw results ---------------------------------------------------------------------
+#pragma unroll
+        for (int d = 0; d < DS; ++d) {
+            double us = unormsq[d];
+            us += __shfl_xor_sync(0xffffffffu, us, 1);
+            us += __shfl_xor_sync(0xffffffffu, us, 2);
+            macc[d].group_reduce();
+            if (t == 0 && active[d]) {
+                double logq = (fma((double)n, PFB_LOG2PI, logdet) + us) / -2.0;
+                if (!pd_ok) logq = NAN;
+                logp_out[(int64_t)slot * K + kd[d]] = macc[d].finish(n, mp);
+                logq_out[(int64_t)slot * K + kd[d]] = logq;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static size_t k3_smem_bytes(int KP, int NS, int NW) {
+    const int RS2 = pfb_rs2_of(KP);
+    return (size_t)NS * PFB_K3_RC * RS2 * 8 + (size_t)PF_ZIG_LAYERS * 8 * sizeof(pfb_zig_e) +
+           (size_t)2 * KP * KP * 8 + (size_t)NW * PFB_K3_DS * 8 * KP * 8 + (size_t)NW * sizeof(pfb_k3_warp_list) +
+           (size_t)(NS + 1) * 8;
+}
+
+template <int KP, int MODEL>
+static cudaError_t launch_k3_m(cudaStream_t st, int n, int K, int nslots, const int32_t* unit_list,
+                               const double* FR2, const double* HDR, const uint64_t* seeds,
+                               const double* u_host, pfb_model_params mp, double* logp, double* logq,
+                               double* draws) {
+    if (nslots <= 0) return cudaSuccess;
+    int dev = 0, nsm = 148, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    // warps: enough for K draws, at most 16 (256 draws per sweep)
+    int NW = (K + PFB_K3_DS * 8 - 1) / (PFB_K3_DS * 8);
+    NW = NW < 1 ? 1 : (NW > PFB_K3_MAXWARPS ? PFB_K3_MAXWARPS : NW);
+    const int DPS = NW * PFB_K3_DS * 8;
+    const int S = (K + DPS - 1) / DPS;
+    const int C = (pfb_npad8(n) + PFB_K3_RC - 1) / PFB_K3_RC;
+    int NS = C;
+    while (NS > 1 && k3_smem_bytes(KP, NS, NW) > (size_t)smem_max) --NS;
+    const size_t smem = k3_smem_bytes(KP, NS, NW);
+    if (smem > (size_t)smem_max) return cudaErrorInvalidConfiguration;
+    // split a unit's sweeps over several CTAs only when there are too few units to fill the GPU
+    int splits = (4 * nsm + nslots - 1) / nslots;
+    splits = splits < 1 ? 1 : (splits > S ? S : splits);
+    const int64_t grid = (int64_t)nslots * splits;
+    if (grid > 2147483647LL) return cudaErrorInvalidValue;
+    auto kern = pfb_k3_elbo_sample<KP, MODEL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)grid, NW * 32, smem, st>>>(n, K, splits, NS, unit_list, FR2, HDR, seeds, u_host, mp, logp,
+                                                logq, draws);
+    return cudaGetLastError();
+}
+
+template <int KP>
+static cudaError_t launch_k3_k(cudaStream_t st, int model, int n, int K, int nslots,
+                               const int32_t* unit_list, const double* FR2, const double* HDR,
+                               const uint64_t* seeds, const double* u_host, pfb_model_params mp,
+                               double* logp, double* logq, double* draws) {
+    switch (model) {
+        case PFB_MODEL_ISONORMAL:
+            return launch_k3_m<KP, PFB_MODEL_ISONORMAL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host,
+                                                        mp, logp, logq, draws);
+        case PFB_MODEL_FUNNEL:
+            return launch_k3_m<KP, PFB_MODEL_FUNNEL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host, mp,
+                                                     logp, logq, draws);
+        case PFB_MODEL_DIAGNORMAL:
+            return launch_k3_m<KP, PFB_MODEL_DIAGNORMAL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host,
+                                                         mp, logp, logq, draws);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// u_host != NULL: parity mode (normals [unit][K][n] supplied by the host).
+// draws != NULL: materialise x (mode M / K5), [slot][K][n] i.e. column-major n x K per slot.
+extern "C" cudaError_t PFB_K3_ENTRY(cudaStream_t st, int model, int n, int K, int nslots,
+                                    const int32_t* unit_list, const double* FR2, const double* HDR,
+                                    const uint64_t* seeds, const double* u_host, const double* mp0,
+                                    const double* mp1, double mc0, double* logp, double* logq,
+                                    double* draws) {
+    pfb_model_params mp{mp0, mp1, mc0};
+    return launch_k3_k<PFB_K3_KP>(st, model, n, K, nslots, unit_list, FR2, HDR, seeds, u_host, mp, logp, logq,
+                                  draws);
+}

@@ -4,20 +4,27 @@
 // iteration from a UInt64 seed (reference: src/elbo.jl:2-5, src/mvnormal.jl:30).  Julia's
 // generator cannot be reproduced outside Julia, so the engine fixes its own contract:
 //
-//   * bits:    Philox4x32-10 (Salmon et al., SC'11), key = the per-(path, iteration) UInt64
-//              seed, counter = (row_pair, draw, call, stream).
+//   * bits:    Philox4x32-10 (Salmon et al., SC'11) in counter mode with a FIXED key
+//              (PF_KEY0, PF_KEY1) and the counter
+//                  c0 = row_pair | stream << 28,  c1 = draw,
+//                  c2 = seed_lo + call,           c3 = seed_hi,
+//              seed = the per-(path, iteration) UInt64 seed.  A fixed key makes the ten round
+//              keys compile-time immediates (no per-call key schedule on the GPU's half-rate
+//              integer ALU); distinct seeds select disjoint counter sets.
 //   * normals: 256-layer ziggurat (Marsaglia & Tsang 2000) on 64 bits per variate
-//              (bits 0-7 layer, bit 8 sign, bits 12-63 a 52 bit mantissa j; x = j * 2^-52 * x_layer).  One Philox call at
-//              (row_pair = i/2, draw = k, call = 0, stream = 0) yields the fast-path words of
-//              elements (2*(i/2), k) and (2*(i/2)+1, k); an element that leaves the fast path
-//              (~1.2 %) continues on its private stream (stream = 1 + (i & 1), call = 0,1,...).
-//   * uniforms for resampling: stream = 3 (see pf_resample_bits).
+//              (bits 56-63 layer, bit 55 sign, bits 0-51 a 52-bit mantissa j; x = j 2^-52 x_layer).
+//              One Philox call (stream 0, call 0) yields the fast-path words of elements
+//              (2*row_pair, draw) and (2*row_pair + 1, draw); an element that leaves the fast
+//              path (1.5 %) continues on its private stream (1 + (row & 1), call = 0, 1, ...).
+//   * uniforms for resampling: stream 3 (see pf_resample_bits).
 //
 // The same function bodies are compiled by gcc (oracle helpers, tests) and nvcc (kernels).
 #pragma once
 #include "pf_math.h"
 #include "pf_zig_tables.h"
 
+#define PF_KEY0 0xA4093822u
+#define PF_KEY1 0x299F31D0u
 #define PF_PHILOX_M0 0xD2511F53u
 #define PF_PHILOX_M1 0xCD9E8D57u
 #define PF_PHILOX_W0 0x9E3779B9u
@@ -54,26 +61,48 @@ PF_HD void pf_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
     *b = (uint64_t)c2 | ((uint64_t)c3 << 32);
 }
 
+// Contract call: fixed key, (row_pair, stream, draw, seed, call) in the counter.
+PF_HD void pf_bits(uint32_t row_pair, uint32_t stream, uint32_t draw, uint32_t s_lo, uint32_t s_hi,
+                   uint32_t call, uint64_t* a, uint64_t* b) {
+    pf_philox4x32_10(row_pair | (stream << 28), draw, s_lo + call, s_hi, PF_KEY0, PF_KEY1, a, b);
+}
+
 // Uniform in the open interval (0,1) from the top 53 bits: (j + 0.5) * 2^-53.
 PF_HD double pf_u01(uint64_t bits) {
     return ((double)(bits >> 11) + 0.5) * 1.1102230246251565e-16;
 }
 
-// Exact conversion of a 52-bit integer to double without an int64->fp64 convert instruction:
-// (2^52 + j) - 2^52.
-PF_HD double pf_mant52(uint64_t j) {
-    return pf_u2d(0x4330000000000000ULL | j) - 4503599627370496.0;
+// ---- ziggurat word layout -------------------------------------------------------------------
+//   bits 56-63  layer i          bit 55  sign          bits 0-51  mantissa j  (52-54 unused)
+// x = j * w[i] (w[i] = x_i 2^-52).  The layout is chosen for the GPU: the mantissa is the low
+// word plus 20 bits of the high word, so (hi & 0xFFFFF) | 0x43300000 : lo is the double
+// 2^52 + j with one LOP3, and x = fma(2^52 + j, w, -2^52 w) is one DFMA (exactly j*w rounded
+// once: the product (2^52 + j) w is formed exactly inside the fma).
+#define PF_ZIG_MANT_MASK 0x000FFFFFFFFFFFFFULL
+#define PF_ZIG_2P52_BITS 0x4330000000000000ULL
+
+// High word of the fast-accept threshold: the fast test compares only the top 20 mantissa
+// bits, (j >> 32) < (kq >> 32) — conservative by < 2^-20; the exact test j < kq is the first
+// thing the slow path does, so the variate is the same as with an exact fast test.
+PF_HD uint32_t pf_zig_kqh(uint64_t kq) { return 0x43300000u | (uint32_t)(kq >> 32); }
+
+// -2^52 * w from the bits of w (exponent + 52, sign flipped): exact.
+PF_HD double pf_zig_negw52(double w) { return pf_u2d(pf_d2u(w) + 0x8340000000000000ULL); }
+
+// x = j * w with the sign of bit 55 (bit-identical on every path).
+PF_HD double pf_zig_value(uint64_t bits, double w) {
+    double m = pf_u2d((bits & PF_ZIG_MANT_MASK) | PF_ZIG_2P52_BITS);
+    double x = fma(m, w, pf_zig_negw52(w));
+    return pf_u2d(pf_d2u(x) ^ ((bits << 8) & 0x8000000000000000ULL));
 }
 
 // Ziggurat fast path.  Returns 1 and writes *z when the variate is accepted without
-// evaluating exp/log (98.8 % of calls).
+// evaluating exp/log (98.5 % of calls); *z is written (as if accepted) in either case.
 PF_HD int pf_zig_fast(uint64_t bits, const pf_zig_kw_t* kw, double* z) {
-    uint32_t i = (uint32_t)bits & 255u;
-    uint64_t j = bits >> 12;
-    pf_zig_kw_t e = kw[i];
-    double x = pf_mant52(j) * e.w;
-    *z = ((bits >> 8) & 1u) ? -x : x;
-    return j < e.kq;
+    pf_zig_kw_t e = kw[bits >> 56];
+    *z = pf_zig_value(bits, e.w);
+    uint32_t mh = 0x43300000u | ((uint32_t)(bits >> 32) & 0xFFFFFu);
+    return mh < pf_zig_kqh(e.kq);
 }
 
 // Full ziggurat continuation for an element whose first word `bits` failed the fast test.
@@ -82,14 +111,17 @@ PF_HD double pf_zig_slow(uint64_t bits, uint32_t row_pair, uint32_t draw, uint32
                          uint32_t k0, uint32_t k1, const pf_zig_kw_t* kw, const double* ftab) {
     uint32_t call = 0;
     for (;;) {
-        uint32_t i = (uint32_t)bits & 255u;
-        uint64_t j = bits >> 12;
-        int neg = (int)((bits >> 8) & 1u);
+        uint32_t i = (uint32_t)(bits >> 56);
+        uint64_t j = bits & PF_ZIG_MANT_MASK;
+        pf_zig_kw_t e = kw[i];
+        double z = pf_zig_value(bits, e.w);
+        if (j < e.kq) return z;  // exact core test (the fast test is conservative)
+        int neg = (int)((bits >> 55) & 1u);
         uint64_t a, b;
         if (i == 0) {
             // tail beyond r: Marsaglia's exponential-rejection method
             for (;;) {
-                pf_philox4x32_10(row_pair, draw, call++, stream, k0, k1, &a, &b);
+                pf_bits(row_pair, stream, draw, k0, k1, call++, &a, &b);
                 double xt = -pf_log(pf_u01(a)) / PF_ZIG_R;
                 double yt = -pf_log(pf_u01(b));
                 if (yt + yt > xt * xt) {
@@ -98,15 +130,12 @@ PF_HD double pf_zig_slow(uint64_t bits, uint32_t row_pair, uint32_t draw, uint32
                 }
             }
         }
-        double x = pf_mant52(j) * kw[i].w;
-        pf_philox4x32_10(row_pair, draw, call++, stream, k0, k1, &a, &b);
+        double x = neg ? -z : z;
+        pf_bits(row_pair, stream, draw, k0, k1, call++, &a, &b);
         double f_lo = ftab[i], f_hi = ftab[i + 1];
         double y = fma(pf_u01(a), f_hi - f_lo, f_lo);
-        if (y < pf_exp(-0.5 * x * x)) return neg ? -x : x;
-        // rejected: b is a fresh first word
-        bits = b;
-        double z;
-        if (pf_zig_fast(bits, kw, &z)) return z;
+        if (y < pf_exp(-0.5 * x * x)) return z;
+        bits = b;  // rejected: b is a fresh first word
     }
 }
 
@@ -114,7 +143,7 @@ PF_HD double pf_zig_slow(uint64_t bits, uint32_t row_pair, uint32_t draw, uint32
 PF_HD_NOINLINE void pf_normal_pair(uint32_t row_pair, uint32_t draw, uint32_t k0, uint32_t k1,
                           const pf_zig_kw_t* kw, const double* ftab, double* z0, double* z1) {
     uint64_t a, b;
-    pf_philox4x32_10(row_pair, draw, 0u, 0u, k0, k1, &a, &b);
+    pf_bits(row_pair, 0u, draw, k0, k1, 0u, &a, &b);
     if (!pf_zig_fast(a, kw, z0)) *z0 = pf_zig_slow(a, row_pair, draw, 1u, k0, k1, kw, ftab);
     if (!pf_zig_fast(b, kw, z1)) *z1 = pf_zig_slow(b, row_pair, draw, 2u, k0, k1, kw, ftab);
 }
@@ -125,7 +154,7 @@ PF_HD_NOINLINE void pf_normal_pair(uint32_t row_pair, uint32_t draw, uint32_t k0
 PF_HD_NOINLINE double pf_normal_finish_slow(uint32_t row, uint32_t draw, uint32_t k0, uint32_t k1,
                                             const pf_zig_kw_t* kw, const double* ftab) {
     uint64_t a, b;
-    pf_philox4x32_10(row >> 1, draw, 0u, 0u, k0, k1, &a, &b);
+    pf_bits(row >> 1, 0u, draw, k0, k1, 0u, &a, &b);
     return pf_zig_slow((row & 1u) ? b : a, row >> 1, draw, 1u + (row & 1u), k0, k1, kw, ftab);
 }
 
@@ -133,7 +162,7 @@ PF_HD_NOINLINE double pf_normal_finish_slow(uint32_t row, uint32_t draw, uint32_
 PF_HD uint64_t pf_resample_bits(uint64_t t, uint32_t k0, uint32_t k1) {
     uint64_t a, b;
     uint64_t q = t >> 1;
-    pf_philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), 0u, 3u, k0, k1, &a, &b);
+    pf_bits((uint32_t)q & 0x0FFFFFFFu, 3u, (uint32_t)(q >> 28), k0, k1, 0u, &a, &b);
     return (t & 1) ? b : a;
 }
 

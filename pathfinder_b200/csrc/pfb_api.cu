@@ -15,7 +15,7 @@ extern "C" {
 cudaError_t pfb_launch_k1(cudaStream_t, int, int, int, double, const double*, const double*, const int64_t*,
                           double*, int32_t*, int32_t*, int64_t*);
 cudaError_t pfb_launch_k2(cudaStream_t, int, int, int, int, const double*, const double*, const int32_t*,
-                          const double*, const int32_t*, const int32_t*, double*, double*);
+                          const double*, const int32_t*, const int32_t*, double*, double*, double*);
 #define PFB_DECL_K3(name)                                                                                  \
     cudaError_t name(cudaStream_t, int, int, int, int, const int32_t*, const double*, const double*,        \
                      const uint64_t*, const double*, const double*, const double*, double, double*, double*, \
@@ -81,7 +81,7 @@ struct pfb_engine {
     int launches = 0;
     std::vector<int64_t> h_off;
     DevBuf dX, dG, dOff, dSeeds, dUnitCol, dNormals;
-    DevBuf dAlpha, dHist, dHistCnt, dRej, dFR, dHDR, dLogp, dLogq, dElbo, dSe, dBestIter, dBestUnit, dSucc;
+    DevBuf dAlpha, dHist, dHistCnt, dRej, dFR, dFR2, dHDR, dLogp, dLogq, dElbo, dSe, dBestIter, dBestUnit, dSucc;
     DevBuf dPool, dPoolLogp, dPoolLogq, dAllDraws;
     DevBuf dFitMu, dFitAlpha, dFitVh, dFitT, dFitVc, dFitLogdet, dFitJeff;
     // psis
@@ -152,7 +152,7 @@ extern "C" int pfb_destroy(pfb_handle h) {
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->dModel, &h->dX, &h->dG, &h->dOff, &h->dSeeds, &h->dUnitCol, &h->dNormals, &h->dAlpha,
-                      &h->dHist, &h->dHistCnt, &h->dRej, &h->dFR, &h->dHDR, &h->dLogp, &h->dLogq, &h->dElbo,
+                      &h->dHist, &h->dHistCnt, &h->dRej, &h->dFR, &h->dFR2, &h->dHDR, &h->dLogp, &h->dLogq, &h->dElbo,
                       &h->dSe, &h->dBestIter, &h->dBestUnit, &h->dSucc, &h->dPool, &h->dPoolLogp,
                       &h->dPoolLogq, &h->dAllDraws, &h->dFitMu, &h->dFitAlpha, &h->dFitVh, &h->dFitT,
                       &h->dFitVc, &h->dFitLogdet, &h->dFitJeff, &h->dLogw, &h->dW, &h->dCum, &h->dScal,
@@ -233,6 +233,7 @@ extern "C" int pfb_batch_upload(pfb_handle h, int n, int P, const int64_t* offse
     PFB_CUDA(h, h->dHistCnt.ensure((size_t)U * 4 + 8));
     PFB_CUDA(h, h->dRej.ensure((size_t)P * 8 + 8));
     PFB_CUDA(h, h->dFR.ensure(nU * (size_t)pfb_rs_of(KP) * 8 + 16));
+    PFB_CUDA(h, h->dFR2.ensure((size_t)pfb_npad8(n) * (size_t)U * (size_t)pfb_rs2_of(KP) * 8 + 16));
     PFB_CUDA(h, h->dHDR.ensure((size_t)U * pfb_hs_of(KP) * 8 + 8));
     PFB_CUDA(h, h->dLogp.ensure((size_t)U * K * 8 + 8));
     PFB_CUDA(h, h->dLogq.ensure((size_t)U * K * 8 + 8));
@@ -271,7 +272,7 @@ static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list
     const double* mp1 = mp0 ? mp0 + h->model_n : nullptr;
     const double* un = h->have_normals ? h->dNormals.as<double>() : nullptr;
     auto fn = h->KP == 12 ? pfb_launch_k3_kp12 : (h->KP == 20 ? pfb_launch_k3_kp20 : pfb_launch_k3_kp24);
-    return fn(h->stream, h->model, h->n, h->K, nslots, unit_list, h->dFR.as<double>(), h->dHDR.as<double>(),
+    return fn(h->stream, h->model, h->n, h->K, nslots, unit_list, h->dFR2.as<double>(), h->dHDR.as<double>(),
               h->dSeeds.as<uint64_t>(), un, mp0, mp1, h->model_c0, logp, logq, draws);
 }
 
@@ -291,7 +292,7 @@ extern "C" int pfb_batch_run(pfb_handle h) {
     PFB_CUDA(h, cudaEventRecord(h->ev[1], st));
     PFB_CUDA(h, pfb_launch_k2(st, KP, n, U, J, h->dX.as<double>(), h->dG.as<double>(), h->dUnitCol.as<int32_t>(),
                               h->dAlpha.as<double>(), h->dHist.as<int32_t>(), h->dHistCnt.as<int32_t>(),
-                              h->dFR.as<double>(), h->dHDR.as<double>()));
+                              h->dFR.as<double>(), h->dHDR.as<double>(), h->dFR2.as<double>()));
     h->launches += (U > 0);
     PFB_CUDA(h, cudaEventRecord(h->ev[2], st));
     PFB_CUDA(h, launch_k3(h, U, nullptr, h->dLogp.as<double>(), h->dLogq.as<double>(),

@@ -8,8 +8,9 @@
 //   alpha       [n x U]   diagonal of H0 per unit                          (K1 -> K2)
 //   hist        [U x J]   point columns of the accepted (s,y) pairs, oldest first (int32)
 //   hist_cnt    [U]       J_eff (int32)
-//   FR          [U][n][RS]  "factor record" rows: RS = KP + 2 doubles per row =
-//                         { Vh[i][0..KP), sqrt(alpha_i), mu_i }           (K2 -> K3)
+//   FR          [U][n][RS]  K2's working rows: RS = KP + 2 doubles per row =
+//                         { Vh[i][0..KP), sqrt(alpha_i), mu_i }           (K2 scratch, fit export)
+//   FR2         [U][npad8(n)][RS2]  the same record in K3's swizzled tensor-core layout (K2 -> K3)
 //   HDR         [U][HS]   unit header: T[KP*KP] row-major, Vc[KP*KP] row-major (upper),
 //                         logdet, flag (1 = PD ok), k_eff
 //   logp, logq  [U x K]   per-draw log densities                            (K3 -> K4)
@@ -24,6 +25,16 @@
 __host__ __device__ inline int pfb_kp_of(int J) { return J <= 6 ? 12 : (J <= 10 ? 20 : (J <= 12 ? 24 : 0)); }
 __host__ __device__ inline int pfb_rs_of(int KP) { return KP + 2; }
 __host__ __device__ inline int pfb_hs_of(int KP) { return 2 * KP * KP + 4; }
+// K3's tensor-core record layout (FR2): per unit pfb_npad8(n) rows of RS2 doubles
+//   { Vh[i][0..KP), sqrt(alpha_i), mu_i, 0... }, rows >= n all zero, and inside a row the
+//   4-double groups XOR-swizzled: logical column c lives at c ^ pfb_swz(i).  pfb_swz takes 4
+//   distinct values both over rows {4q..4q+3} and over rows {r, r+2, r+4, r+6}, which makes the
+//   two DMMA fragment access patterns of K3 shared-memory bank-conflict free.
+__host__ __device__ inline int pfb_rs2_of(int KP) { return KP == 12 ? 16 : 32; }
+__host__ __device__ inline int pfb_npad8(int n) { return (n + 7) & ~7; }
+__host__ __device__ inline int pfb_swz(int row) {
+    return (((row >> 1) & 1) | (((row ^ (row >> 2)) & 1) << 1)) << 2;
+}
 #define PFB_HDR_LOGDET(KP) (2 * (KP) * (KP))
 #define PFB_HDR_FLAG(KP) (2 * (KP) * (KP) + 1)
 #define PFB_HDR_KEFF(KP) (2 * (KP) * (KP) + 2)
