@@ -43,6 +43,22 @@
 #define PFB_K3_RC 128    // record rows per TMA chunk (16 blocks of 8 rows)
 #define PFB_K3_DCAP 64   // deferred-list capacity per warp and round
 
+__device__ __forceinline__ double pfb_lds64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double2 pfb_lds128(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+// acc += x * x unless flag != 0 (one predicated DFMA)
+__device__ __forceinline__ void pfb_sqacc_unless(double& acc, double x, uint32_t flag) {
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p fma.rn.f64 %0, %1, %1, %0;\n\t}" : "+d"(acc) : "d"(x), "r"(flag));
+}
+
 struct pfb_model_params {
     const double* p0;  // DIAGNORMAL: mean[n]
     const double* p1;  // DIAGNORMAL: 1/sd[n]
@@ -68,6 +84,13 @@ struct pfb_model_acc {
     __device__ __forceinline__ void add_nz(int i, double x, const pfb_model_params& mp) {
         if (MODEL == PFB_MODEL_DIAGNORMAL) add(i, x, mp); else a = fma(x, x, a);
     }
+    __device__ __forceinline__ void add_nz_unless(int i, double x, const pfb_model_params& mp, uint32_t flag) {
+        if (MODEL == PFB_MODEL_DIAGNORMAL) {
+            if (!flag) add(i, x, mp);
+        } else {
+            pfb_sqacc_unless(a, x, flag);
+        }
+    }
     // combine the partial accumulators of the 4 lanes that share a draw
     __device__ __forceinline__ void group_reduce() {
         a += __shfl_xor_sync(0xffffffffu, a, 1);
@@ -87,9 +110,9 @@ struct pfb_model_acc {
     }
 };
 
-// replicated ziggurat table entry (16 B): w, high word of the fast-accept threshold
+// replicated ziggurat table entry (16 B): layer edge x_i, high word of the fast-accept threshold
 struct __align__(16) pfb_zig_e {
-    double w;
+    double xe;
     uint32_t kqh;
     uint32_t pad;
 };
@@ -107,19 +130,31 @@ __device__ __forceinline__ void pfb_dmma(double& d0, double& d1, double a, doubl
         : "d"(a), "d"(b));
 }
 
-// Fast ziggurat step on the replicated table: returns true when accepted; z is valid only then.
-__device__ __forceinline__ bool pfb_zig_fast_rep(uint64_t bits, const pfb_zig_e* __restrict__ zig_lane,
-                                                 double& z) {
-    const uint32_t hi = (uint32_t)(bits >> 32), lo = (uint32_t)bits;
-    const pfb_zig_e e = zig_lane[(hi >> 24) * 8];
-    const uint32_t mh = (hi & 0xFFFFFu) | 0x43300000u;
-    const double m = __hiloint2double((int)mh, (int)lo);
-    const double x = fma(m, e.w, pf_zig_negw52(e.w));
-    z = __hiloint2double(__double2hiint(x) ^ (int)((hi << 8) & 0x80000000u), __double2loint(x));
-    return mh < e.kqh;
+// Fast ziggurat step on the replicated table (zig_base = shared-memory byte address of this
+// lane's table copy; word layout: pf_rng.h).  Returns 0 and the variate in z when accepted,
+// 1 and z = 0 when the element has to take the slow path.
+__device__ __forceinline__ uint32_t pfb_zig_fast_rep(uint32_t lo, uint32_t hi, uint32_t zig_base, double& z) {
+    uint32_t elo, ehi, kqh, pad;
+    const uint32_t addr = ((hi >> 16) & 0x7F80u) + zig_base;  // layer (bits 23-30 of hi) * 128
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(elo), "=r"(ehi), "=r"(kqh), "=r"(pad) : "r"(addr));
+    uint32_t mh;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(mh) : "r"(hi), "r"(0xFFFFFu), "r"(0x3FF00000u));  // (a&b)|c
+    const double m = __hiloint2double((int)mh, (int)lo);    // 1 + j 2^-52
+    const double xe = __hiloint2double((int)ehi, (int)elo);
+    const double x = fma(m, xe, -xe);                       // j * w, rounded once
+    z = __hiloint2double(__double2hiint(x) ^ (int)(hi & 0x80000000u), __double2loint(x));
+    uint32_t bad;
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %2, %3;\n\tselp.u32 %1, 1, 0, p;\n\t@p mov.f64 %0, 0d0000000000000000;\n\t}"
+        : "+d"(z), "=r"(bad) : "r"(mh), "r"(kqh));
+    return bad;
 }
 
-template <int KP, int MODEL>
+template <int V>
+struct pfb_ic {
+    static constexpr int value = V;
+};
+
+template <int KP, int MODEL, bool MATERIALIZE>
 __global__ void __launch_bounds__(PFB_K3_MAXWARPS * 32, 1)
 pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__ unit_list,
                    const double* __restrict__ FR2, const double* __restrict__ HDR,
@@ -133,7 +168,8 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
     constexpr int NS1 = KP / 4;        // j steps of pass 1
     constexpr int HB = (KP + 7) / 8;   // head blocks (rows < KP get the Vc' multiply)
     constexpr int NHP = (KP / 2 + 3) / 4;  // head row pairs generated per lane
-    static_assert(RC / 8 * 2 * DS <= 64, "pending mask is 64 bits per chunk");
+    static_assert(DS == 2, "pending nibbles assume two draw sets");
+    static_assert(RC / 8 * 4 <= 64, "pending mask is 64 bits per chunk");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -166,7 +202,6 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
     const uint64_t seed = seeds[unit];
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const bool HOST_U = (u_host != nullptr);
-    const bool MATERIALIZE = (draws_out != nullptr);
 
     const int C = (npad + RC - 1) / RC;  // chunks per pass
     const bool resident = (C <= NS);
@@ -180,7 +215,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
     for (int e = tid; e < PF_ZIG_LAYERS * 8; e += blockDim.x) {
         const pf_zig_kw_t kw = PF_ZIG_KW_DEV[e >> 3];
         pfb_zig_e ze;
-        ze.w = kw.w;
+        ze.xe = pf_zig_edge(kw.w);
         ze.kqh = pf_zig_kqh(kw.kq);
         ze.pad = 0u;
         sZig[e] = ze;
@@ -208,99 +243,103 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
     const bool tail_special = (n & 7) != 0;
 
     // lane-constant fragment offsets (doubles) inside an 8-row block
-    int off0[2][NT0];  // pass 0: Vh[row 2t+e][j = 8h+g]
+    // (byte offsets)
+    uint32_t off0[2][NT0];  // pass 0: Vh[row 2t+e][j = 8h+g]
 #pragma unroll
     for (int e = 0; e < 2; ++e)
 #pragma unroll
-        for (int h = 0; h < NT0; ++h) off0[e][h] = (2 * t + e) * RS2 + ((8 * h + g) ^ pfb_swz(2 * t + e));
-    int off1[NS1];     // pass 1: Vh[row g][j = 4s+t]
+        for (int h = 0; h < NT0; ++h)
+            off0[e][h] = 8u * (uint32_t)((2 * t + e) * RS2 + ((8 * h + g) ^ pfb_swz(2 * t + e)));
+    uint32_t off1[NS1];     // pass 1: Vh[row g][j = 4s+t]
 #pragma unroll
-    for (int s = 0; s < NS1; ++s) off1[s] = g * RS2 + ((4 * s + t) ^ pfb_swz(g));
-    int offam[2];      // {sqrt(alpha), mu} of row 2t+e
+    for (int s = 0; s < NS1; ++s) off1[s] = 8u * (uint32_t)(g * RS2 + ((4 * s + t) ^ pfb_swz(g)));
+    uint32_t offam[2];      // {sqrt(alpha), mu} of row 2t+e
 #pragma unroll
-    for (int e = 0; e < 2; ++e) offam[e] = (2 * t + e) * RS2 + (KP ^ pfb_swz(2 * t + e));
+    for (int e = 0; e < 2; ++e) offam[e] = 8u * (uint32_t)((2 * t + e) * RS2 + (KP ^ pfb_swz(2 * t + e)));
 
-    const pfb_zig_e* zig_lane = sZig + (lane & 7);
+    const uint32_t zig_base = pfb_smem_u32(sZig + (lane & 7));
     pfb_k3_warp_list& wl = sList[warp];
-    double* cw = sC + (size_t)warp * DS * 8 * KP;  // this warp's [DS][8][KP]
+    double* cw = sC + (size_t)warp * DS * 8 * KP;  // this warp's [DS][8][KP]: w, then c = T w
 
     int q = 0;  // TMA load sequence number of the next chunk to consume (ring mode)
     bool first_pass = true;
 #pragma unroll 1
     for (int sw = split; sw < S; sw += splits) {
         uint32_t kd[DS];      // draw index (clamped)
-        bool active[DS];
-        const double* uh[DS];
-        double* xout[DS];
+        uint32_t actmask = 0u;  // pending-nibble mask of the active draw sets (bit d*2+e)
 #pragma unroll
         for (int d = 0; d < DS; ++d) {
             const int kraw = sw * DPS + (warp * DS + d) * 8 + g;
-            active[d] = kraw < K;
-            kd[d] = (uint32_t)(active[d] ? kraw : K - 1);
-            uh[d] = HOST_U ? u_host + ((int64_t)unit * K + kd[d]) * n : nullptr;
-            xout[d] = MATERIALIZE ? draws_out + ((int64_t)slot * K + kd[d]) * n : nullptr;
+            if (kraw < K) actmask |= 3u << (2 * d);
+            kd[d] = (uint32_t)(kraw < K ? kraw : K - 1);
         }
         double unormsq[DS];
         pfb_model_acc<MODEL> macc[DS];
-        double zhd[DS][HB][2];  // u~ of this lane's head rows
+        double wacc[DS][NT0][2];  // pass 0 accumulators: w[draw g][j = 8h + 2t + {0,1}]
+        double ncf[DS][NS1];      // pass 1 A fragments: -c[draw g][j = 4s + t]
 #pragma unroll
         for (int d = 0; d < DS; ++d) {
             unormsq[d] = 0.0;
             macc[d].init();
-        }
-        // ---- head: u~[0..H) = Vc' u[0..H)  (src/woodbury.jl:139) ------------------------------------
-#pragma unroll
-        for (int d = 0; d < DS; ++d) {
-            double own[NHP][2];
-#pragma unroll
-            for (int r = 0; r < NHP; ++r) {
-                const int jj = 4 * r + t;  // row pair generated by this lane
-                double z0 = 0.0, z1 = 0.0;
-                if (2 * jj < H) {
-                    if (HOST_U) {
-                        z0 = uh[d][2 * jj];
-                        if (2 * jj + 1 < H) z1 = uh[d][2 * jj + 1];
-                    } else {
-                        pf_normal_pair((uint32_t)jj, kd[d], k0, k1, PF_ZIG_KW_DEV, PF_ZIG_F_DEV, &z0, &z1);
-                        if (2 * jj + 1 >= H) z1 = 0.0;
-                    }
-                }
-                own[r][0] = z0;
-                own[r][1] = z1;
-                unormsq[d] = fma(z0, z0, unormsq[d]);
-                unormsq[d] = fma(z1, z1, unormsq[d]);
-            }
-            double zh[KP];
-#pragma unroll
-            for (int jj = 0; jj < KP / 2; ++jj) {
-                const int srcl = (lane & ~3) | (jj & 3);
-                zh[2 * jj] = __shfl_sync(0xffffffffu, own[jj >> 2][0], srcl);
-                zh[2 * jj + 1] = __shfl_sync(0xffffffffu, own[jj >> 2][1], srcl);
-            }
-#pragma unroll
-            for (int bb = 0; bb < HB; ++bb)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int j = 8 * bb + 2 * t + e;
-                    double acc = 0.0;
-                    if (j < KP) {
-#pragma unroll
-                        for (int m = 0; m < KP; ++m)
-                            if (m <= j) acc = fma(sVc[m * KP + j], zh[m], acc);
-                    }
-                    zhd[d][bb][e] = acc;
-                }
-        }
-
-        double wacc[DS][NT0][2];  // pass 0 accumulators: w[draw g][j = 8h + 2t + {0,1}]
-        double ncf[DS][NS1];      // pass 1 A fragments: -c[draw g][j = 4s + t]
-#pragma unroll
-        for (int d = 0; d < DS; ++d)
 #pragma unroll
             for (int h = 0; h < NT0; ++h) wacc[d][h][0] = wacc[d][h][1] = 0.0;
+#pragma unroll
+            for (int s1 = 0; s1 < NS1; ++s1) ncf[d][s1] = 0.0;
+        }
+        for (int e = lane; e < DS * 8 * KP; e += 32) cw[e] = 0.0;  // slow-path corrections of w
+        __syncwarp();
 
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
+        // One pass over all chunks.  PS::value = 0: accumulate w = Vh' u~;  1: x and the model sums.
+        auto run_pass = [&](auto PS) {
+            constexpr int PASS = decltype(PS)::value;
+            // ---- head: u~[0..H) = Vc' u[0..H)  (src/woodbury.jl:139); recomputed in each pass ------
+            double zhd[DS][HB][2];  // u~ of this lane's head rows
+#pragma unroll
+            for (int d = 0; d < DS; ++d) {
+                double own[NHP][2];
+#pragma unroll
+                for (int r = 0; r < NHP; ++r) {
+                    const int jj = 4 * r + t;  // row pair generated by this lane
+                    double z0 = 0.0, z1 = 0.0;
+                    if (2 * jj < H) {
+                        if (HOST_U) {
+                            const double* uh = u_host + ((int64_t)unit * K + kd[d]) * n;
+                            z0 = uh[2 * jj];
+                            if (2 * jj + 1 < H) z1 = uh[2 * jj + 1];
+                        } else {
+                            pf_normal_pair((uint32_t)jj, kd[d], k0, k1, PF_ZIG_KW_DEV, PF_ZIG_F_DEV, &z0, &z1);
+                            if (2 * jj + 1 >= H) z1 = 0.0;
+                        }
+                    }
+                    own[r][0] = z0;
+                    own[r][1] = z1;
+                    if (PASS == 0) {
+                        unormsq[d] = fma(z0, z0, unormsq[d]);
+                        unormsq[d] = fma(z1, z1, unormsq[d]);
+                    }
+                }
+                double zh[KP];
+#pragma unroll
+                for (int jj = 0; jj < KP / 2; ++jj) {
+                    const int srcl = (lane & ~3) | (jj & 3);
+                    zh[2 * jj] = __shfl_sync(0xffffffffu, own[jj >> 2][0], srcl);
+                    zh[2 * jj + 1] = __shfl_sync(0xffffffffu, own[jj >> 2][1], srcl);
+                }
+#pragma unroll
+                for (int bb = 0; bb < HB; ++bb)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = 8 * bb + 2 * t + e;
+                        double acc = 0.0;
+                        if (j < KP) {
+#pragma unroll
+                            for (int m = 0; m < KP; ++m)
+                                if (m <= j) acc = fma(sVc[m * KP + j], zh[m], acc);
+                        }
+                        zhd[d][bb][e] = acc;
+                    }
+            }
+
 #pragma unroll 1
             for (int c = 0; c < C; ++c) {
                 int s;
@@ -312,29 +351,32 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                     pfb_mbar_wait(&sBar[s], (uint32_t)((q / NS) & 1));
                 }
                 const double* st = sStage + (size_t)s * RC * RS2;
+                const uint32_t st_u32 = pfb_smem_u32(st);
                 const int r0 = c * RC;
                 const int nb = (min(npad, r0 + RC) - r0) >> 3;
-                unsigned long long pend = 0ull;  // bit ((o*2 + e)*DS + d): element deferred
-#pragma unroll 1
-                for (int o = 0; o < nb; ++o) {
+                // pending (deferred) elements: nibble per block, bit d*2+e; the first block of the
+                // chunk ends up in the highest of the nb nibbles
+                unsigned long long pend = 0ull;
+
+                auto block = [&](auto SP, int o) {
+                    constexpr bool SPECIAL = decltype(SP)::value != 0;
                     const int b = (r0 >> 3) + o;
-                    const double* blk = st + o * 8 * RS2;
+                    const uint32_t blk = st_u32 + (uint32_t)(o * 8 * RS2 * 8);
                     const int R = r0 + o * 8 + 2 * t;  // this lane's first row of the block
-                    const bool special = HOST_U || (b < HB) || (tail_special && b == nblk - 1);
                     double z[DS][2];
-                    bool ok[DS][2];
-                    if (!special) {
+                    uint32_t nib = 0u;
+                    if (!SPECIAL) {
 #pragma unroll
                         for (int d = 0; d < DS; ++d) {
                             uint64_t wa, wb;
                             pf_bits((uint32_t)(4 * b + t), 0u, kd[d], k0, k1, 0u, &wa, &wb);
-                            ok[d][0] = pfb_zig_fast_rep(wa, zig_lane, z[d][0]) || !active[d];
-                            ok[d][1] = pfb_zig_fast_rep(wb, zig_lane, z[d][1]) || !active[d];
+                            nib |= pfb_zig_fast_rep((uint32_t)wa, (uint32_t)(wa >> 32), zig_base, z[d][0]) << (2 * d);
+                            nib |= pfb_zig_fast_rep((uint32_t)wb, (uint32_t)(wb >> 32), zig_base, z[d][1])
+                                   << (2 * d + 1);
                         }
                     } else {
 #pragma unroll
                         for (int d = 0; d < DS; ++d) {
-                            ok[d][0] = ok[d][1] = true;
                             z[d][0] = z[d][1] = 0.0;
                             if (R < H) {
                                 // head rows come in pairs (H is a multiple of 4 unless n < KP, and
@@ -347,31 +389,28 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                                     }
                             } else if (R < n) {
                                 if (HOST_U) {
-                                    z[d][0] = uh[d][R];
-                                    if (R + 1 < n) z[d][1] = uh[d][R + 1];
+                                    const double* uh = u_host + ((int64_t)unit * K + kd[d]) * n;
+                                    z[d][0] = uh[R];
+                                    if (R + 1 < n) z[d][1] = uh[R + 1];
                                 } else {
                                     uint64_t wa, wb;
                                     pf_bits((uint32_t)(4 * b + t), 0u, kd[d], k0, k1, 0u, &wa, &wb);
-                                    ok[d][0] = pfb_zig_fast_rep(wa, zig_lane, z[d][0]) || !active[d];
-                                    ok[d][1] = pfb_zig_fast_rep(wb, zig_lane, z[d][1]) || !active[d];
-                                    if (R + 1 >= n) {
-                                        ok[d][1] = true;
+                                    nib |= pfb_zig_fast_rep((uint32_t)wa, (uint32_t)(wa >> 32), zig_base, z[d][0])
+                                           << (2 * d);
+                                    if (R + 1 < n) {
+                                        nib |= pfb_zig_fast_rep((uint32_t)wb, (uint32_t)(wb >> 32), zig_base,
+                                                                z[d][1]) << (2 * d + 1);
+                                    } else {
                                         z[d][1] = 0.0;
                                     }
                                 }
                             }
                         }
                     }
-#pragma unroll
-                    for (int d = 0; d < DS; ++d)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e)
-                            if (!ok[d][e]) {
-                                z[d][e] = 0.0;
-                                pend |= 1ull << ((o * 2 + e) * DS + d);
-                            }
-                    if (pass == 0) {
-                        if (!(special && R < H)) {  // head rows' |u|^2 was added with the raw normals
+                    nib &= actmask;  // (z of a rejected element is already 0)
+                    pend = (pend << 4) | nib;
+                    if (PASS == 0) {
+                        if (!(SPECIAL && R < H)) {  // head rows' |u|^2 was added with the raw normals
 #pragma unroll
                             for (int d = 0; d < DS; ++d) {
                                 unormsq[d] = fma(z[d][0], z[d][0], unormsq[d]);
@@ -382,7 +421,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 #pragma unroll
                         for (int e = 0; e < 2; ++e)
 #pragma unroll
-                            for (int h = 0; h < NT0; ++h) vf[e][h] = blk[off0[e][h]];
+                            for (int h = 0; h < NT0; ++h) vf[e][h] = pfb_lds64(blk + off0[e][h]);
 #pragma unroll
                         for (int e = 0; e < 2; ++e)
 #pragma unroll
@@ -393,10 +432,10 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                     } else {
                         double bf[NS1];
 #pragma unroll
-                        for (int s1 = 0; s1 < NS1; ++s1) bf[s1] = blk[off1[s1]];
+                        for (int s1 = 0; s1 < NS1; ++s1) bf[s1] = pfb_lds64(blk + off1[s1]);
                         double2 am[2];
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) am[e] = *reinterpret_cast<const double2*>(blk + offam[e]);
+                        for (int e = 0; e < 2; ++e) am[e] = pfb_lds128(blk + offam[e]);
 #pragma unroll
                         for (int d = 0; d < DS; ++d) {
                             double d0 = z[d][0], d1 = z[d][1];
@@ -404,31 +443,47 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                             for (int s1 = 0; s1 < NS1; ++s1) pfb_dmma(d0, d1, ncf[d][s1], bf[s1]);
                             const double x0 = fma(am[0].x, d0, am[0].y);
                             const double x1 = fma(am[1].x, d1, am[1].y);
-                            if (!special) {
-                                if (ok[d][0]) macc[d].add_nz(R, x0, mp);
-                                if (ok[d][1]) macc[d].add_nz(R + 1, x1, mp);
-                                if (MATERIALIZE && active[d]) {
+                            const bool act = (actmask >> (2 * d)) & 1u;
+                            double* xo = MATERIALIZE ? draws_out + ((int64_t)slot * K + kd[d]) * n : nullptr;
+                            if (!SPECIAL) {
+                                macc[d].add_nz_unless(R, x0, mp, nib & (1u << (2 * d)));
+                                macc[d].add_nz_unless(R + 1, x1, mp, nib & (2u << (2 * d)));
+                                if (MATERIALIZE && act) {
                                     if ((n & 1) == 0) {
                                         // both rows exist; a pending one is rewritten by the fix-up
-                                        *reinterpret_cast<double2*>(xout[d] + R) = make_double2(x0, x1);
+                                        *reinterpret_cast<double2*>(xo + R) = make_double2(x0, x1);
                                     } else {
-                                        xout[d][R] = x0;
-                                        xout[d][R + 1] = x1;
+                                        xo[R] = x0;
+                                        xo[R + 1] = x1;
                                     }
                                 }
                             } else {
                                 if (R < n) {
-                                    if (ok[d][0]) macc[d].add(R, x0, mp);
-                                    if (MATERIALIZE && active[d]) xout[d][R] = x0;
+                                    if (!(nib & (1u << (2 * d)))) macc[d].add(R, x0, mp);
+                                    if (MATERIALIZE && act) xo[R] = x0;
                                 }
                                 if (R + 1 < n) {
-                                    if (ok[d][1]) macc[d].add(R + 1, x1, mp);
-                                    if (MATERIALIZE && active[d]) xout[d][R + 1] = x1;
+                                    if (!(nib & (2u << (2 * d)))) macc[d].add(R + 1, x1, mp);
+                                    if (MATERIALIZE && act) xo[R + 1] = x1;
                                 }
                             }
                         }
                     }
-                }
+                };
+
+                // leading special blocks (head rows, or everything in parity mode), fast body,
+                // trailing special block (n not a multiple of 8)
+                int o_fast = HOST_U ? nb : max(0, min(nb, HB - (r0 >> 3)));
+                int o_end = nb;
+                if (tail_special && r0 + nb * 8 == npad && o_end > o_fast) --o_end;
+                int o = 0;
+#pragma unroll 1
+                for (; o < o_fast; ++o) block(pfb_ic<1>{}, o);
+#pragma unroll 1
+                for (; o < o_end; ++o) block(pfb_ic<0>{}, o);
+#pragma unroll 1
+                for (; o < nb; ++o) block(pfb_ic<1>{}, o);
+
                 // ---- deferred ziggurat slow path (warp-cooperative, deterministic order) -----------
                 if (!HOST_U) {
                     const int cnt = __popcll(pend);
@@ -440,6 +495,8 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                     }
                     const int excl = incl - cnt;
                     const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    // bit -> (block o, e, d): nibble index from the top, bit d*2+e inside
+                    auto row_of = [&](int bit) { return (nb - 1 - (bit >> 2)) * 8 + 2 * t + (bit & 1); };
 #pragma unroll 1
                     for (int base = 0; base < total; base += PFB_K3_DCAP) {
                         {
@@ -449,10 +506,9 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                                 const int bit = __ffsll((long long)a0) - 1;
                                 a0 &= a0 - 1;
                                 if (flat >= 0 && flat < PFB_K3_DCAP) {
-                                    const int oe = bit / DS;  // o*2 + e
-                                    wl.row[flat] = (uint16_t)((oe >> 1) * 8 + 2 * t + (oe & 1));
+                                    wl.row[flat] = (uint16_t)row_of(bit);
                                     wl.src[flat] = (uint8_t)lane;
-                                    wl.ds[flat] = (uint8_t)(bit % DS);
+                                    wl.ds[flat] = (uint8_t)((bit >> 1) & 1);
                                 }
                                 ++flat;
                             }
@@ -466,26 +522,33 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                                                              PF_ZIG_F_DEV);
                         }
                         __syncwarp();
-                        if (pass == 0) {
-                            // every lane folds the items of its draw group into its own w slots
-                            for (int it = 0; it < nitems; ++it) {
-                                const int srcl = wl.src[it];
-                                if ((srcl >> 2) != g) continue;
-                                const double zz = wl.z[it];
-                                const int row = wl.row[it];
-                                const int dsi = wl.ds[it];
-                                const double* rr = st + row * RS2;
-                                const int swz = pfb_swz(row);
+                        if (PASS == 0) {
+                            // the owner folds z * Vh[row][:] into the warp's w corrections; the four
+                            // lanes of a draw group take turns (fixed order => deterministic)
+#pragma unroll 1
+                            for (int ph = 0; ph < 4; ++ph) {
+                                if (t == ph) {
+                                    unsigned long long a0 = pend;
+                                    int flat = excl - base;
+                                    while (a0) {
+                                        const int bit = __ffsll((long long)a0) - 1;
+                                        a0 &= a0 - 1;
+                                        if (flat >= 0 && flat < PFB_K3_DCAP) {
+                                            const int row = row_of(bit), dsi = (bit >> 1) & 1;
+                                            const double zz = wl.z[flat];
+                                            const double* rr = st + row * RS2;
+                                            const int swz = pfb_swz(row);
+                                            double* cv = cw + (dsi * 8 + g) * KP;
 #pragma unroll
-                                for (int d = 0; d < DS; ++d)
-                                    if (d == dsi) {
-                                        if (srcl == lane) unormsq[d] = fma(zz, zz, unormsq[d]);
+                                            for (int j = 0; j < KP; ++j) cv[j] = fma(rr[j ^ swz], zz, cv[j]);
 #pragma unroll
-                                        for (int h = 0; h < NT0; ++h) {
-                                            wacc[d][h][0] = fma(rr[(8 * h + 2 * t) ^ swz], zz, wacc[d][h][0]);
-                                            wacc[d][h][1] = fma(rr[(8 * h + 2 * t + 1) ^ swz], zz, wacc[d][h][1]);
+                                            for (int d = 0; d < DS; ++d)
+                                                if (d == dsi) unormsq[d] = fma(zz, zz, unormsq[d]);
                                         }
+                                        ++flat;
                                     }
+                                }
+                                __syncwarp();
                             }
                         } else {
                             unsigned long long a0 = pend;
@@ -494,8 +557,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                                 const int bit = __ffsll((long long)a0) - 1;
                                 a0 &= a0 - 1;
                                 if (flat >= 0 && flat < PFB_K3_DCAP) {
-                                    const int oe = bit / DS, dsi = bit % DS;
-                                    const int row = (oe >> 1) * 8 + 2 * t + (oe & 1);
+                                    const int row = row_of(bit), dsi = (bit >> 1) & 1;
                                     const double* rr = st + row * RS2;
                                     const int swz = pfb_swz(row);
                                     const double* cv = cw + (dsi * 8 + g) * KP;
@@ -508,13 +570,14 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                                     for (int d = 0; d < DS; ++d)
                                         if (d == dsi) {
                                             macc[d].add(r0 + row, x, mp);
-                                            if (MATERIALIZE) xout[d][r0 + row] = x;
+                                            if (MATERIALIZE)
+                                                draws_out[((int64_t)slot * K + kd[d]) * n + r0 + row] = x;
                                         }
                                 }
                                 ++flat;
                             }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
                 }
                 if (!resident) {
@@ -523,44 +586,48 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                     ++q;
                 }
             }
-            first_pass = false;
-            if (pass == 0) {
-                // c = T w (upper triangular); the w fragments go through shared memory so that
-                // every lane can form its pass-1 A fragments -c[4s + t]
-                __syncwarp();
+        };
+
+        run_pass(pfb_ic<0>{});
+        first_pass = false;
+        {
+            // c = T w (upper triangular): the w fragments join the slow-path corrections in shared
+            // memory so that every lane can form its pass-1 A fragments -c[4s + t]
+            __syncwarp();
 #pragma unroll
-                for (int d = 0; d < DS; ++d)
+            for (int d = 0; d < DS; ++d)
 #pragma unroll
-                    for (int h = 0; h < NT0; ++h)
+                for (int h = 0; h < NT0; ++h)
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int j = 8 * h + 2 * t + e;
-                            if (j < KP) cw[(d * 8 + g) * KP + j] = wacc[d][h][e];
-                        }
-                __syncwarp();
-                double cf[DS][NS1];
-#pragma unroll
-                for (int d = 0; d < DS; ++d)
-#pragma unroll
-                    for (int s1 = 0; s1 < NS1; ++s1) {
-                        const int a = 4 * s1 + t;
-                        double acc = 0.0;
-#pragma unroll
-                        for (int bcol = 0; bcol < KP; ++bcol)
-                            if (bcol >= a) acc = fma(sT[a * KP + bcol], cw[(d * 8 + g) * KP + bcol], acc);
-                        cf[d][s1] = acc;
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = 8 * h + 2 * t + e;
+                        if (j < KP) cw[(d * 8 + g) * KP + j] += wacc[d][h][e];
                     }
-                __syncwarp();
+            __syncwarp();
+            double cf[DS][NS1];
 #pragma unroll
-                for (int d = 0; d < DS; ++d)
+            for (int d = 0; d < DS; ++d)
 #pragma unroll
-                    for (int s1 = 0; s1 < NS1; ++s1) {
-                        cw[(d * 8 + g) * KP + 4 * s1 + t] = cf[d][s1];
-                        ncf[d][s1] = -cf[d][s1];
-                    }
-                __syncwarp();
-            }
+                for (int s1 = 0; s1 < NS1; ++s1) {
+                    const int a = 4 * s1 + t;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int bcol = 0; bcol < KP; ++bcol)
+                        if (bcol >= a) acc = fma(sT[a * KP + bcol], cw[(d * 8 + g) * KP + bcol], acc);
+                    cf[d][s1] = acc;
+                }
+            __syncwarp();
+#pragma unroll
+            for (int d = 0; d < DS; ++d)
+#pragma unroll
+                for (int s1 = 0; s1 < NS1; ++s1) {
+                    cw[(d * 8 + g) * KP + 4 * s1 + t] = cf[d][s1];
+                    ncf[d][s1] = -cf[d][s1];
+                }
+            __syncwarp();
         }
+        run_pass(pfb_ic<1>{});
+
         // ---- per-draw results ---------------------------------------------------------------------
 #pragma unroll
         for (int d = 0; d < DS; ++d) {
@@ -568,7 +635,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
             us += __shfl_xor_sync(0xffffffffu, us, 1);
             us += __shfl_xor_sync(0xffffffffu, us, 2);
             macc[d].group_reduce();
-            if (t == 0 && active[d]) {
+            if (t == 0 && ((actmask >> (2 * d)) & 1u)) {
                 double logq = (fma((double)n, PFB_LOG2PI, logdet) + us) / -2.0;
                 if (!pd_ok) logq = NAN;
                 logp_out[(int64_t)slot * K + kd[d]] = macc[d].finish(n, mp);
@@ -611,7 +678,7 @@ static cudaError_t launch_k3_m(cudaStream_t st, int n, int K, int nslots, const 
     splits = splits < 1 ? 1 : (splits > S ? S : splits);
     const int64_t grid = (int64_t)nslots * splits;
     if (grid > 2147483647LL) return cudaErrorInvalidValue;
-    auto kern = pfb_k3_elbo_sample<KP, MODEL>;
+    auto kern = draws ? pfb_k3_elbo_sample<KP, MODEL, true> : pfb_k3_elbo_sample<KP, MODEL, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(unsigned)grid, NW * 32, smem, st>>>(n, K, splits, NS, unit_list, FR2, HDR, seeds, u_host, mp, logp,

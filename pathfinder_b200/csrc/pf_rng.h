@@ -12,7 +12,7 @@
 //              keys compile-time immediates (no per-call key schedule on the GPU's half-rate
 //              integer ALU); distinct seeds select disjoint counter sets.
 //   * normals: 256-layer ziggurat (Marsaglia & Tsang 2000) on 64 bits per variate
-//              (bits 56-63 layer, bit 55 sign, bits 0-51 a 52-bit mantissa j; x = j 2^-52 x_layer).
+//              (bit 63 sign, bits 55-62 layer, bits 0-51 a 52-bit mantissa j; x = j 2^-52 x_layer).
 //              One Philox call (stream 0, call 0) yields the fast-path words of elements
 //              (2*row_pair, draw) and (2*row_pair + 1, draw); an element that leaves the fast
 //              path (1.5 %) continues on its private stream (1 + (row & 1), call = 0, 1, ...).
@@ -32,8 +32,8 @@
 
 PF_HD void pf_mulhilo32(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
 #if defined(__CUDA_ARCH__)
-    *lo = a * b;
-    *hi = __umulhi(a, b);
+    asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}"
+        : "=r"(*lo), "=r"(*hi) : "r"(a), "r"(b));  // one IMAD.WIDE.U32
 #else
     uint64_t p = (uint64_t)a * (uint64_t)b;
     *lo = (uint32_t)p;
@@ -73,35 +73,37 @@ PF_HD double pf_u01(uint64_t bits) {
 }
 
 // ---- ziggurat word layout -------------------------------------------------------------------
-//   bits 56-63  layer i          bit 55  sign          bits 0-51  mantissa j  (52-54 unused)
+//   bit 63  sign        bits 55-62  layer i        bits 0-51  mantissa j       (52-54 unused)
 // x = j * w[i] (w[i] = x_i 2^-52).  The layout is chosen for the GPU: the mantissa is the low
-// word plus 20 bits of the high word, so (hi & 0xFFFFF) | 0x43300000 : lo is the double
-// 2^52 + j with one LOP3, and x = fma(2^52 + j, w, -2^52 w) is one DFMA (exactly j*w rounded
-// once: the product (2^52 + j) w is formed exactly inside the fma).
+// word plus 20 bits of the high word, so (hi & 0xFFFFF) | 0x3FF00000 : lo is the double
+// m = 1 + j 2^-52 with one LOP3, and x = fma(m, x_i, -x_i) is one DFMA — exactly j * w[i] rounded
+// once, because the product m * x_i is formed exactly inside the fma.  The sign is bit 31 of the
+// high word, so it is XORed into x without a shift.
 #define PF_ZIG_MANT_MASK 0x000FFFFFFFFFFFFFULL
-#define PF_ZIG_2P52_BITS 0x4330000000000000ULL
+#define PF_ZIG_ONE_BITS 0x3FF0000000000000ULL
 
 // High word of the fast-accept threshold: the fast test compares only the top 20 mantissa
 // bits, (j >> 32) < (kq >> 32) — conservative by < 2^-20; the exact test j < kq is the first
 // thing the slow path does, so the variate is the same as with an exact fast test.
-PF_HD uint32_t pf_zig_kqh(uint64_t kq) { return 0x43300000u | (uint32_t)(kq >> 32); }
+PF_HD uint32_t pf_zig_kqh(uint64_t kq) { return 0x3FF00000u | (uint32_t)(kq >> 32); }
 
-// -2^52 * w from the bits of w (exponent + 52, sign flipped): exact.
-PF_HD double pf_zig_negw52(double w) { return pf_u2d(pf_d2u(w) + 0x8340000000000000ULL); }
+// layer edge x_i = 2^52 * w[i] from the bits of w (exponent + 52): exact.
+PF_HD double pf_zig_edge(double w) { return pf_u2d(pf_d2u(w) + 0x0340000000000000ULL); }
 
-// x = j * w with the sign of bit 55 (bit-identical on every path).
+// x = j * w with the sign of bit 63 (bit-identical on every path).
 PF_HD double pf_zig_value(uint64_t bits, double w) {
-    double m = pf_u2d((bits & PF_ZIG_MANT_MASK) | PF_ZIG_2P52_BITS);
-    double x = fma(m, w, pf_zig_negw52(w));
-    return pf_u2d(pf_d2u(x) ^ ((bits << 8) & 0x8000000000000000ULL));
+    double m = pf_u2d((bits & PF_ZIG_MANT_MASK) | PF_ZIG_ONE_BITS);
+    double xe = pf_zig_edge(w);
+    double x = fma(m, xe, -xe);
+    return pf_u2d(pf_d2u(x) ^ (bits & 0x8000000000000000ULL));
 }
 
 // Ziggurat fast path.  Returns 1 and writes *z when the variate is accepted without
 // evaluating exp/log (98.5 % of calls); *z is written (as if accepted) in either case.
 PF_HD int pf_zig_fast(uint64_t bits, const pf_zig_kw_t* kw, double* z) {
-    pf_zig_kw_t e = kw[bits >> 56];
+    pf_zig_kw_t e = kw[(bits >> 55) & 255u];
     *z = pf_zig_value(bits, e.w);
-    uint32_t mh = 0x43300000u | ((uint32_t)(bits >> 32) & 0xFFFFFu);
+    uint32_t mh = 0x3FF00000u | ((uint32_t)(bits >> 32) & 0xFFFFFu);
     return mh < pf_zig_kqh(e.kq);
 }
 
@@ -111,12 +113,12 @@ PF_HD double pf_zig_slow(uint64_t bits, uint32_t row_pair, uint32_t draw, uint32
                          uint32_t k0, uint32_t k1, const pf_zig_kw_t* kw, const double* ftab) {
     uint32_t call = 0;
     for (;;) {
-        uint32_t i = (uint32_t)(bits >> 56);
+        uint32_t i = (uint32_t)(bits >> 55) & 255u;
         uint64_t j = bits & PF_ZIG_MANT_MASK;
         pf_zig_kw_t e = kw[i];
         double z = pf_zig_value(bits, e.w);
         if (j < e.kq) return z;  // exact core test (the fast test is conservative)
-        int neg = (int)((bits >> 55) & 1u);
+        int neg = (int)(bits >> 63);
         uint64_t a, b;
         if (i == 0) {
             // tail beyond r: Marsaglia's exponential-rejection method

