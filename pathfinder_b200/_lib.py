@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpfb200.so")
+LIB_PATH = os.environ.get("PFB200_LIB") or os.path.join(_HERE, "libpfb200.so")  # PFB200_LIB: A/B builds
 
 PFB_MODEL_ISONORMAL = 0
 PFB_MODEL_FUNNEL = 1

@@ -26,9 +26,9 @@
 // brought into shared memory by 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx) in chunks of
 // PFB_K3_RC rows: all chunks stay resident when they fit (n <= ~1150 at history 6), otherwise they
 // stream through a ring, twice per sweep.  A CTA loops over the sweeps (256 draws) of its unit so
-// the record is loaded once per unit.  The ziggurat layer table is replicated 8x in shared memory
-// (one copy per 16-byte bank) so the random layer lookups are conflict free.  Elements that leave
-// the ziggurat fast path (1.5 %) are deferred and finished warp-cooperatively per chunk.
+// the record is loaded once per unit.  The 1024-layer ziggurat table sits in shared memory twice
+// (even / odd lanes) to halve the bank conflicts of the random layer lookups.  Elements that leave
+// the ziggurat fast path (0.43 %) are deferred and finished warp-cooperatively per chunk.
 // Lean mode writes 16 B per draw (logp, logq); with a draws pointer x is written as well.
 #include "pfb_common.cuh"
 #include "pf_rng.h"
@@ -38,10 +38,15 @@
 #define PFB_K3_ENTRY pfb_launch_k3_kp12
 #endif
 
+#ifndef PFB_K3_SWP
+#define PFB_K3_SWP 0  // software-pipeline the normals of block o+1 under the DMMAs of block o
+#endif
 #define PFB_K3_MAXWARPS 16
 #define PFB_K3_DS 2      // draw sets (8 draws each) per warp
 #define PFB_K3_RC 128    // record rows per TMA chunk (16 blocks of 8 rows)
 #define PFB_K3_DCAP 64   // deferred-list capacity per warp and round
+#define PFB_K3_ZREP 2    // copies of the 1024-layer ziggurat table in shared memory (32 KB)
+static_assert(PF_ZIG_LAYERS == 1024 && PFB_K3_ZREP == 2, "pfb_zig_fast_rep address arithmetic");
 
 __device__ __forceinline__ double pfb_lds64(uint32_t addr) {
     double v;
@@ -135,7 +140,7 @@ __device__ __forceinline__ void pfb_dmma(double& d0, double& d1, double a, doubl
 // 1 and z = 0 when the element has to take the slow path.
 __device__ __forceinline__ uint32_t pfb_zig_fast_rep(uint32_t lo, uint32_t hi, uint32_t zig_base, double& z) {
     uint32_t elo, ehi, kqh, pad;
-    const uint32_t addr = ((hi >> 16) & 0x7F80u) + zig_base;  // layer (bits 23-30 of hi) * 128
+    const uint32_t addr = ((hi >> 16) & 0x7FE0u) + zig_base;  // layer (bits 21-30 of hi) * 32
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(elo), "=r"(ehi), "=r"(kqh), "=r"(pad) : "r"(addr));
     uint32_t mh;
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(mh) : "r"(hi), "r"(0xFFFFFu), "r"(0x3FF00000u));  // (a&b)|c
@@ -176,8 +181,8 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sStage = reinterpret_cast<double*>(smem_raw);                      // NS * RC * RS2
-    pfb_zig_e* sZig = reinterpret_cast<pfb_zig_e*>(sStage + (size_t)NS * RC * RS2);  // 256 * 8
-    double* sT = reinterpret_cast<double*>(sZig + PF_ZIG_LAYERS * 8);          // KP*KP
+    pfb_zig_e* sZig = reinterpret_cast<pfb_zig_e*>(sStage + (size_t)NS * RC * RS2);  // 1024 * 2
+    double* sT = reinterpret_cast<double*>(sZig + PF_ZIG_LAYERS * PFB_K3_ZREP);          // KP*KP
     double* sVc = sT + KP * KP;                                                // KP*KP
     double* sC = sVc + KP * KP;                                                // NW * DS * 8 * KP
     pfb_k3_warp_list* sList = reinterpret_cast<pfb_k3_warp_list*>(sC + (size_t)NW * DS * 8 * KP);
@@ -212,8 +217,8 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
         sT[e] = hdr[e];
         sVc[e] = hdr[KP * KP + e];
     }
-    for (int e = tid; e < PF_ZIG_LAYERS * 8; e += blockDim.x) {
-        const pf_zig_kw_t kw = PF_ZIG_KW_DEV[e >> 3];
+    for (int e = tid; e < PF_ZIG_LAYERS * PFB_K3_ZREP; e += blockDim.x) {
+        const pf_zig_kw_t kw = PF_ZIG_KW_DEV[e / PFB_K3_ZREP];
         pfb_zig_e ze;
         ze.xe = pf_zig_edge(kw.w);
         ze.kqh = pf_zig_kqh(kw.kq);
@@ -257,7 +262,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 #pragma unroll
     for (int e = 0; e < 2; ++e) offam[e] = 8u * (uint32_t)((2 * t + e) * RS2 + (KP ^ pfb_swz(2 * t + e)));
 
-    const uint32_t zig_base = pfb_smem_u32(sZig + (lane & 7));
+    const uint32_t zig_base = pfb_smem_u32(sZig + (lane & (PFB_K3_ZREP - 1)));
     pfb_k3_warp_list& wl = sList[warp];
     double* cw = sC + (size_t)warp * DS * 8 * KP;  // this warp's [DS][8][KP]: w, then c = T w
 
@@ -358,7 +363,20 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                 // chunk ends up in the highest of the nb nibbles
                 unsigned long long pend = 0ull;
 
-                auto block = [&](auto SP, int o) {
+                // normals of a body block (fast ziggurat step; rejected elements: z = 0, nibble bit)
+                auto gen = [&](int o, double (&z)[DS][2], uint32_t& nib) {
+                    const int b = (r0 >> 3) + o;
+                    nib = 0u;
+#pragma unroll
+                    for (int d = 0; d < DS; ++d) {
+                        uint64_t wa, wb;
+                        pf_bits((uint32_t)(4 * b + t), 0u, kd[d], k0, k1, 0u, &wa, &wb);
+                        nib |= pfb_zig_fast_rep((uint32_t)wa, (uint32_t)(wa >> 32), zig_base, z[d][0]) << (2 * d);
+                        nib |= pfb_zig_fast_rep((uint32_t)wb, (uint32_t)(wb >> 32), zig_base, z[d][1]) << (2 * d + 1);
+                    }
+                };
+                // SP = 0: consume the normals zin/nibin generated by gen();  SP = 1: special block
+                auto block = [&](auto SP, int o, const double (&zin)[DS][2], uint32_t nibin) {
                     constexpr bool SPECIAL = decltype(SP)::value != 0;
                     const int b = (r0 >> 3) + o;
                     const uint32_t blk = st_u32 + (uint32_t)(o * 8 * RS2 * 8);
@@ -368,12 +386,10 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                     if (!SPECIAL) {
 #pragma unroll
                         for (int d = 0; d < DS; ++d) {
-                            uint64_t wa, wb;
-                            pf_bits((uint32_t)(4 * b + t), 0u, kd[d], k0, k1, 0u, &wa, &wb);
-                            nib |= pfb_zig_fast_rep((uint32_t)wa, (uint32_t)(wa >> 32), zig_base, z[d][0]) << (2 * d);
-                            nib |= pfb_zig_fast_rep((uint32_t)wb, (uint32_t)(wb >> 32), zig_base, z[d][1])
-                                   << (2 * d + 1);
+                            z[d][0] = zin[d][0];
+                            z[d][1] = zin[d][1];
                         }
+                        nib = nibin;
                     } else {
 #pragma unroll
                         for (int d = 0; d < DS; ++d) {
@@ -477,12 +493,38 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                 int o_end = nb;
                 if (tail_special && r0 + nb * 8 == npad && o_end > o_fast) --o_end;
                 int o = 0;
+                double zc[DS][2] = {}, zn[DS][2];
+                uint32_t nibc = 0u, nibn;
 #pragma unroll 1
-                for (; o < o_fast; ++o) block(pfb_ic<1>{}, o);
+                for (; o < o_fast; ++o) block(pfb_ic<1>{}, o, zc, 0u);
+                // software pipeline: the normals of block o+1 are generated in the same basic block
+                // as the tensor-core work of block o, so the DMMAs interleave with the integer work
+#if PFB_K3_SWP
+                if (o < o_end) {
+                    gen(o, zc, nibc);
 #pragma unroll 1
-                for (; o < o_end; ++o) block(pfb_ic<0>{}, o);
+                    for (; o < o_end - 1; ++o) {
+                        gen(o + 1, zn, nibn);
+                        block(pfb_ic<0>{}, o, zc, nibc);
+#pragma unroll
+                        for (int d = 0; d < DS; ++d) {
+                            zc[d][0] = zn[d][0];
+                            zc[d][1] = zn[d][1];
+                        }
+                        nibc = nibn;
+                    }
+                    block(pfb_ic<0>{}, o, zc, nibc);
+                    ++o;
+                }
+#else
 #pragma unroll 1
-                for (; o < nb; ++o) block(pfb_ic<1>{}, o);
+                for (; o < o_end; ++o) {
+                    gen(o, zc, nibc);
+                    block(pfb_ic<0>{}, o, zc, nibc);
+                }
+#endif
+#pragma unroll 1
+                for (; o < nb; ++o) block(pfb_ic<1>{}, o, zc, 0u);
 
                 // ---- deferred ziggurat slow path (warp-cooperative, deterministic order) -----------
                 if (!HOST_U) {
@@ -648,7 +690,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 
 static size_t k3_smem_bytes(int KP, int NS, int NW) {
     const int RS2 = pfb_rs2_of(KP);
-    return (size_t)NS * PFB_K3_RC * RS2 * 8 + (size_t)PF_ZIG_LAYERS * 8 * sizeof(pfb_zig_e) +
+    return (size_t)NS * PFB_K3_RC * RS2 * 8 + (size_t)PF_ZIG_LAYERS * PFB_K3_ZREP * sizeof(pfb_zig_e) +
            (size_t)2 * KP * KP * 8 + (size_t)NW * PFB_K3_DS * 8 * KP * 8 + (size_t)NW * sizeof(pfb_k3_warp_list) +
            (size_t)(NS + 1) * 8;
 }

@@ -11,11 +11,11 @@
 //              seed = the per-(path, iteration) UInt64 seed.  A fixed key makes the ten round
 //              keys compile-time immediates (no per-call key schedule on the GPU's half-rate
 //              integer ALU); distinct seeds select disjoint counter sets.
-//   * normals: 256-layer ziggurat (Marsaglia & Tsang 2000) on 64 bits per variate
-//              (bit 63 sign, bits 55-62 layer, bits 0-51 a 52-bit mantissa j; x = j 2^-52 x_layer).
+//   * normals: 1024-layer ziggurat (Marsaglia & Tsang 2000) on 64 bits per variate
+//              (bit 63 sign, bits 53-62 layer, bits 0-51 a 52-bit mantissa j; x = j 2^-52 x_layer).
 //              One Philox call (stream 0, call 0) yields the fast-path words of elements
 //              (2*row_pair, draw) and (2*row_pair + 1, draw); an element that leaves the fast
-//              path (1.5 %) continues on its private stream (1 + (row & 1), call = 0, 1, ...).
+//              path (0.43 %) continues on its private stream (1 + (row & 1), call = 0, 1, ...).
 //   * uniforms for resampling: stream 3 (see pf_resample_bits).
 //
 // The same function bodies are compiled by gcc (oracle helpers, tests) and nvcc (kernels).
@@ -73,7 +73,7 @@ PF_HD double pf_u01(uint64_t bits) {
 }
 
 // ---- ziggurat word layout -------------------------------------------------------------------
-//   bit 63  sign        bits 55-62  layer i        bits 0-51  mantissa j       (52-54 unused)
+//   bit 63  sign        bits 53-62  layer i (10 bits)      bits 0-51  mantissa j       (52 unused)
 // x = j * w[i] (w[i] = x_i 2^-52).  The layout is chosen for the GPU: the mantissa is the low
 // word plus 20 bits of the high word, so (hi & 0xFFFFF) | 0x3FF00000 : lo is the double
 // m = 1 + j 2^-52 with one LOP3, and x = fma(m, x_i, -x_i) is one DFMA — exactly j * w[i] rounded
@@ -99,9 +99,9 @@ PF_HD double pf_zig_value(uint64_t bits, double w) {
 }
 
 // Ziggurat fast path.  Returns 1 and writes *z when the variate is accepted without
-// evaluating exp/log (98.5 % of calls); *z is written (as if accepted) in either case.
+// evaluating exp/log (99.57 % of calls); *z is written (as if accepted) in either case.
 PF_HD int pf_zig_fast(uint64_t bits, const pf_zig_kw_t* kw, double* z) {
-    pf_zig_kw_t e = kw[(bits >> 55) & 255u];
+    pf_zig_kw_t e = kw[(bits >> 53) & (PF_ZIG_LAYERS - 1)];
     *z = pf_zig_value(bits, e.w);
     uint32_t mh = 0x3FF00000u | ((uint32_t)(bits >> 32) & 0xFFFFFu);
     return mh < pf_zig_kqh(e.kq);
@@ -113,7 +113,7 @@ PF_HD double pf_zig_slow(uint64_t bits, uint32_t row_pair, uint32_t draw, uint32
                          uint32_t k0, uint32_t k1, const pf_zig_kw_t* kw, const double* ftab) {
     uint32_t call = 0;
     for (;;) {
-        uint32_t i = (uint32_t)(bits >> 55) & 255u;
+        uint32_t i = (uint32_t)(bits >> 53) & (PF_ZIG_LAYERS - 1);
         uint64_t j = bits & PF_ZIG_MANT_MASK;
         pf_zig_kw_t e = kw[i];
         double z = pf_zig_value(bits, e.w);
