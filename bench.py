@@ -226,8 +226,10 @@ def main():
     lib = _lib.load()
     import ctypes as C
     peak = C.c_double(0.0)
-    lib.pfb_measure_fp64_fma_tflops(local_rank, 5, C.byref(peak))
+    lib.pfb_measure_fp64_dmma_tflops(local_rank, 5, C.byref(peak))  # FP64 tensor-core (DMMA) peak
     fp64_peak = peak.value
+    peak2 = C.c_double(0.0)
+    lib.pfb_measure_fp64_fma_tflops(local_rank, 5, C.byref(peak2))  # DFMA peak, reported alongside
 
     eng = pf.Engine(n, model.family, model.blob, J, K, local_rank)
     eng.upload(offsets, X, G, seeds_cat)  # inputs resident in HBM before the timed region
@@ -352,15 +354,26 @@ def main():
     d2h = 16 * U + 20 * P + (n * P * 2 + n * KP * P + 2 * KP * KP * P + P) * 8 + 4 * P \
         + 16 * Npool + 16 * ndraws + (8 * n * ndraws if world == 1 else 0)
 
-    # ---- roofline of the dominant kernel (K3, lean mode: FP64-pipe bound) -------------------------
+    # ---- roofline of the dominant kernel (K3; its Q-apply runs on the FP64 tensor cores) -----------
     k3_avg_ms = float(np.mean(k3_ms))
     flops = algorithmic_flops(trajs, n, K, J)
     ach_tf = flops / (k3_avg_ms * 1e-3) / 1e12
-    roofline = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": ach_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
-                "kernel": "pfb_k3_elbo_sample (lean mode F)", "kernel_ms": k3_avg_ms,
-                "peak_source": "measured live: DFMA-chain microbenchmark pfb_measure_fp64_fma_tflops "
-                               "(MEASURED_PEAKS.json has no FP64 figure)",
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic.json")))
+        if tj.get("workload") == name:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": ach_tf / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
+                "kernel": "pfb_k3_elbo_sample (lean mode F: FP64 DMMA Q-apply + Philox/ziggurat normals)",
+                "kernel_ms": k3_avg_ms, "algorithmic_flops_per_launch": flops,
+                "peak_source": "measured live: pfb_measure_fp64_dmma_tflops (mma.sync m8n8k4 f64 chains); "
+                               "MEASURED_PEAKS.json has bf16 and HBM figures only",
+                "dfma_peak_tflops": peak2.value,
+                "note": "the kernel is limited by the half-rate integer path (Philox4x32-10 + ziggurat), not by "
+                        "FP64 math or HBM: see DESIGN.md section 4 and profiles/",
                 "k3_share_of_step": k3_avg_ms * args.steps / max_ms}
 
     line = {

@@ -147,6 +147,9 @@ int pfb_get_timings(pfb_handle h, double* ms6);
 
 /* Measurement utility: FP64 FMA peak of `device` in TFLOP/s (DFMA chains, best of reps). */
 int pfb_measure_fp64_fma_tflops(int device, int reps, double* tflops);
+/* The same for the FP64 tensor cores (mma.sync m8n8k4 f64, SASS DMMA): the roofline denominator
+ * of K3, whose Q-apply runs on them. */
+int pfb_measure_fp64_dmma_tflops(int device, int reps, double* tflops);
 
 #ifdef __cplusplus
 }

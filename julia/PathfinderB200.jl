@@ -1,0 +1,227 @@
+# PathfinderB200.jl — the Julia side of the drop-in boundary: a thin `ccall` shim over
+# libpfb200.so (C ABI: include/pfb200.h).
+#
+# STATUS: source only.  Julia is not installed in the build container, so this file has never been
+# executed; the same ABI is exercised end to end by the Python ctypes twin
+# (pathfinder_b200/_lib.py, engine.py, api.py), which the GPU parity tests call.
+#
+# What stays in Julia (unchanged Pathfinder.jl code): `optimize_with_trace` (src/optimize.jl:35),
+# init sampling, retry policy, result structs.  What moves to the GPU, batched over
+# (path x iteration):
+#     fit_mvnormals          src/singlepath.jl:301-303
+#     maximize_elbo          src/singlepath.jl:306-308
+#     success / draws        src/singlepath.jl:309-314, 224-233
+#     _compute_psis_result   src/multipath.jl:220-224
+#     _resample              src/multipath.jl:225
+module PathfinderB200
+
+using Random
+
+const LIB = Ref{String}(get(ENV, "PFB200_LIB", "libpfb200.so"))
+
+const PFB_MODEL_ISONORMAL = Cint(0)
+const PFB_MODEL_FUNNEL = Cint(1)
+const PFB_MODEL_DIAGNORMAL = Cint(2)
+
+# mirrors `pfb_config` (include/pfb200.h); defaults = src/Pathfinder.jl:24-27
+struct PfbConfig
+    device::Int32
+    history_length::Int32
+    ndraws_elbo::Int32
+    materialize_all::Int32
+    eps::Float64
+end
+
+# mirrors `pfb_elbo_out`: 18 pointers, NULL = skip
+mutable struct PfbElboOut
+    elbo::Ptr{Float64}
+    elbo_se::Ptr{Float64}
+    logp::Ptr{Float64}
+    logq::Ptr{Float64}
+    best_iter::Ptr{Int64}
+    success::Ptr{Int32}
+    n_rejected::Ptr{Int64}
+    draws::Ptr{Float64}
+    draws_logp::Ptr{Float64}
+    draws_logq::Ptr{Float64}
+    fit_mu::Ptr{Float64}
+    fit_alpha::Ptr{Float64}
+    fit_vh::Ptr{Float64}
+    fit_T::Ptr{Float64}
+    fit_Vc::Ptr{Float64}
+    fit_logdet::Ptr{Float64}
+    fit_jeff::Ptr{Int32}
+    all_draws::Ptr{Float64}
+end
+PfbElboOut() = PfbElboOut(ntuple(_ -> C_NULL, 18)...)
+
+# mirrors `pfb_resample_out`
+mutable struct PfbResampleOut
+    log_weights::Ptr{Float64}
+    weights::Ptr{Float64}
+    pareto_k::Ptr{Float64}
+    tail_len::Ptr{Int64}
+    inds::Ptr{Int64}
+    ids::Ptr{Int64}
+    draws::Ptr{Float64}
+end
+PfbResampleOut() = PfbResampleOut(ntuple(_ -> C_NULL, 7)...)
+
+mutable struct Engine
+    handle::Ptr{Cvoid}
+    n::Int
+    K::Int
+    J::Int
+    function Engine(n::Integer, family::Integer, blob::Vector{Float64}=Float64[];
+                    history_length::Integer=6, ndraws_elbo::Integer=5, device::Integer=0,
+                    materialize_all::Bool=false, eps::Float64=1e-12)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        cfg = Ref(PfbConfig(device, history_length, ndraws_elbo, materialize_all, eps))
+        rc = ccall((:pfb_create, LIB[]), Cint, (Ref{Ptr{Cvoid}}, Ref{PfbConfig}), h, cfg)
+        rc == 0 || throw(ErrorException("pfb_create failed ($rc): " * last_error(C_NULL)))
+        e = new(h[], n, ndraws_elbo, history_length)
+        finalizer(close, e)
+        rc = ccall((:pfb_register_model, LIB[]), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Csize_t),
+                   e.handle, family, n, isempty(blob) ? C_NULL : pointer(blob), length(blob))
+        check(e, rc)
+        return e
+    end
+end
+
+function Base.close(e::Engine)
+    if e.handle != C_NULL
+        ccall((:pfb_destroy, LIB[]), Cint, (Ptr{Cvoid},), e.handle)
+        e.handle = C_NULL
+    end
+    return nothing
+end
+
+last_error(h) = unsafe_string(ccall((:pfb_last_error, LIB[]), Cstring, (Ptr{Cvoid},), h))
+
+# error convention of include/pfb200.h: < 0 argument / shape error, > 0 CUDA runtime error
+function check(e::Engine, rc::Integer)
+    rc == 0 && return nothing
+    msg = last_error(e.handle)
+    rc == -2 && throw(DimensionMismatch(msg))
+    rc < 0 && throw(ArgumentError(msg))
+    throw(ErrorException("CUDA error $rc: $msg"))
+end
+
+"""
+    elbo_batch(engine, traces, seeds; normals=nothing)
+
+`traces`: vector of `(points, gradients)` with `points::Vector{Vector{Float64}}` exactly as
+`OptimizationTrace` holds them (src/optimize.jl:110-114); `seeds[p]`: the `UInt64` seeds
+`rand!(rng, Vector{UInt64}(undef, L_p))` of src/elbo.jl:2.  Returns a NamedTuple with, per
+(path, iteration): `elbo`, `elbo_se`; per path: `fit_iteration`, `success`,
+`num_bfgs_updates_rejected`, `draws[n, K, P]`, `logp`, `logq`, and the best-iteration
+`WoodburyPDMat` ingredients (`mu, alpha, vh, T, Vc, logdet, jeff`).
+"""
+function elbo_batch(e::Engine, traces, seeds::Vector{Vector{UInt64}}; normals=nothing)
+    P = length(traces)
+    n, K = e.n, e.K
+    offsets = zeros(Int64, P + 1)
+    for (p, (pts, _)) in enumerate(traces)
+        offsets[p + 1] = offsets[p] + length(pts)
+    end
+    T = offsets[end]
+    U = T - P
+    X = Matrix{Float64}(undef, n, T)      # column-major, what the ABI expects
+    G = Matrix{Float64}(undef, n, T)
+    for (p, (pts, grads)) in enumerate(traces), (l, (x, g)) in enumerate(zip(pts, grads))
+        X[:, offsets[p] + l] .= x
+        G[:, offsets[p] + l] .= g
+    end
+    sd = reduce(vcat, seeds; init=UInt64[])
+    length(sd) == U || throw(DimensionMismatch("need one seed per (path, iteration)"))
+    kp = ccall((:pfb_kp, LIB[]), Cint, (Ptr{Cvoid},), e.handle)
+    elbo = Vector{Float64}(undef, U); se = similar(elbo)
+    best = Vector{Int64}(undef, P); succ = Vector{Int32}(undef, P); rej = Vector{Int64}(undef, P)
+    draws = Array{Float64}(undef, n, K, P); lp = Matrix{Float64}(undef, K, P); lq = similar(lp)
+    mu = Matrix{Float64}(undef, n, P); alpha = similar(mu); vh = Array{Float64}(undef, n, kp, P)
+    Tm = Array{Float64}(undef, kp, kp, P); Vc = similar(Tm)  # row-major per path: transpose on use
+    logdet = Vector{Float64}(undef, P); jeff = Vector{Int32}(undef, P)
+    out = PfbElboOut()
+    GC.@preserve offsets X G sd normals elbo se best succ rej draws lp lq mu alpha vh Tm Vc logdet jeff begin
+        out.elbo = pointer(elbo); out.elbo_se = pointer(se)
+        out.best_iter = pointer(best); out.success = pointer(succ); out.n_rejected = pointer(rej)
+        out.draws = pointer(draws); out.draws_logp = pointer(lp); out.draws_logq = pointer(lq)
+        out.fit_mu = pointer(mu); out.fit_alpha = pointer(alpha); out.fit_vh = pointer(vh)
+        out.fit_T = pointer(Tm); out.fit_Vc = pointer(Vc)
+        out.fit_logdet = pointer(logdet); out.fit_jeff = pointer(jeff)
+        rc = ccall((:pfb_elbo_batch, LIB[]), Cint,
+                   (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt64},
+                    Ptr{Float64}, Ref{PfbElboOut}),
+                   e.handle, n, P, offsets, X, G, sd, normals === nothing ? C_NULL : pointer(normals), out)
+        check(e, rc)
+    end
+    return (; offsets, elbo, elbo_se=se, fit_iteration=best, success=succ .!= 0,
+            num_bfgs_updates_rejected=rej, draws, logp=lp, logq=lq, mu, alpha, vh,
+            T=permutedims(Tm, (2, 1, 3)), Vc=permutedims(Vc, (2, 1, 3)), logdet, jeff)
+end
+
+"""
+    psis_resample(engine, seed, ndraws; importance=true)
+
+`_compute_psis_result` + `_resample` (src/multipath.jl:220-225) on the pool left on the device
+by the last `elbo_batch` (N = P * K draws, draw-fastest / component-slowest).
+"""
+function psis_resample(e::Engine, P::Integer, seed::UInt64, ndraws::Integer; importance::Bool=true)
+    N = P * e.K
+    lw = Vector{Float64}(undef, N); w = similar(lw)
+    k = Ref(NaN); tl = Ref(Int64(0))
+    inds = Vector{Int64}(undef, ndraws); ids = similar(inds)
+    draws = Matrix{Float64}(undef, e.n, ndraws)
+    out = PfbResampleOut()
+    GC.@preserve lw w inds ids draws begin
+        if importance
+            out.log_weights = pointer(lw); out.weights = pointer(w)
+        end
+        out.pareto_k = Base.unsafe_convert(Ptr{Float64}, k)
+        out.tail_len = Base.unsafe_convert(Ptr{Int64}, tl)
+        out.inds = pointer(inds); out.ids = pointer(ids); out.draws = pointer(draws)
+        rc = ccall((:pfb_psis_resample, LIB[]), Cint,
+                   (Ptr{Cvoid}, UInt64, Cint, Cint, Ref{PfbResampleOut}), e.handle, seed, ndraws, importance, out)
+        check(e, rc)
+    end
+    return (; log_weights=lw, weights=w, pareto_shape=k[], tail_length=tl[], sample_inds=inds,
+            draw_component_ids=ids, draws)
+end
+
+"""
+    multipathfinder_b200(optimize_one, model_family, dim, ndraws; nruns, ndraws_elbo, rng, ...)
+
+Drop-in for the ELBO-and-resample part of `multipathfinder` (src/multipath.jl:118-245).
+`optimize_one(init) -> (points, gradients)` is the caller's unchanged trajectory producer, e.g.
+
+    optimize_one(x0) = let (_, tr) = Pathfinder.optimize_with_trace(SciMLBase.remake(prob; u0=x0), optimizer)
+        (tr.points, tr.gradients)
+    end
+
+Seeds are drawn exactly where the reference draws them (`run_seeds`, src/multipath.jl:162; per
+iteration, src/elbo.jl:2), so the run is reproducible under `Random.seed!` like the reference's.
+"""
+function multipathfinder_b200(optimize_one, family::Integer, dim::Integer, ndraws::Integer;
+                              nruns::Integer, ndraws_elbo::Integer=5, history_length::Integer=6,
+                              init_scale::Real=2, rng::AbstractRNG=Random.default_rng(),
+                              importance::Bool=true, blob::Vector{Float64}=Float64[], device::Integer=0)
+    run_seeds = rand(rng, UInt64, nruns)                       # src/multipath.jl:162
+    eng = Engine(dim, family, blob; history_length, ndraws_elbo, device)
+    try
+        traces = Vector{Any}(undef, nruns)
+        seeds = Vector{Vector{UInt64}}(undef, nruns)
+        for p in 1:nruns                                       # host phase A; use @threads / ntasks freely
+            prng = copy(rng); Random.seed!(prng, run_seeds[p]) # src/multipath.jl:191-193
+            x0 = (rand(prng, dim) .* 2 .- 1) .* init_scale     # UniformSampler, src/singlepath.jl:340-344
+            traces[p] = optimize_one(x0)
+            seeds[p] = rand(prng, UInt64, length(traces[p][1]) - 1)   # src/elbo.jl:2
+        end
+        fit = elbo_batch(eng, traces, seeds)
+        res = psis_resample(eng, nruns, rand(rng, UInt64), ndraws; importance)
+        return (; fit, res...)
+    finally
+        close(eng)
+    end
+end
+
+end # module

@@ -240,8 +240,13 @@ def pdfactorize(alpha, B, D) -> WoodburyPD:
     return W
 
 
-def lbfgs_inverse_hessians(thetas, grads, history_length=6, eps=1e-12):
-    """reference: src/inverse_hessian.jl:25-66.  thetas, grads: (n, L+1) arrays (columns = points;
+def nocedal_wright_scaling(alpha, s, y):
+    """Hinit used by test/inverse_hessian.jl:50: fill(y's / y'y)."""
+    return np.full_like(alpha, np.dot(y, s) / np.dot(y, y))
+
+
+def lbfgs_inverse_hessians(thetas, grads, history_length=6, eps=1e-12, hinit=None):
+    """reference: src/inverse_hessian.jl:25-66 (hinit = Hinit keyword, default gilbert_init).  thetas, grads: (n, L+1) arrays (columns = points;
     grads are gradients of the log density).  Returns (list of WoodburyPD length L+1,
     num_bfgs_updates_rejected, per-point state list)."""
     thetas = np.asarray(thetas, dtype=np.float64)
@@ -271,7 +276,7 @@ def lbfgs_inverse_hessians(thetas, grads, history_length=6, eps=1e-12):
             history_eff = max(history_ind, history_eff)
             S[:, history_ind - 1] = s
             Y[:, history_ind - 1] = y
-            alpha = gilbert_init(alpha, s, y)  # :55
+            alpha = (hinit or gilbert_init)(alpha, s, y)  # :55
         else:
             rejected += 1
         theta, g = theta1, g1

@@ -77,6 +77,7 @@ SYMBOLS = {
                                            C.c_uint64, C.c_int, C.c_int, C.POINTER(pfb_resample_out)]),
     "pfb_get_timings": (C.c_int, [C.c_void_p, _dp]),
     "pfb_measure_fp64_fma_tflops": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "pfb_measure_fp64_dmma_tflops": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 
 _lib = None

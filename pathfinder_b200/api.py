@@ -21,6 +21,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+from . import distributed as D
 from .engine import Engine
 from .optimize import OptimizationTrace, optimize_with_trace
 
@@ -180,8 +181,13 @@ def pathfinder(model, *, init=None, init_scale=2.0, ndraws_elbo=DEFAULT_NDRAWS_E
 
 def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT_NDRAWS_ELBO,
                     ndraws_per_run=None, importance=True, rng=None, history_length=DEFAULT_HISTORY_LENGTH,
-                    init_scale=2.0, ntries=1000, maxiters=1000, device=0, engine=None):
-    """Multi-path Pathfinder (src/multipath.jl:94-245)."""
+                    init_scale=2.0, ntries=1000, maxiters=1000, device=0, engine=None, group=None):
+    """Multi-path Pathfinder (src/multipath.jl:94-245).
+
+    Under an initialised ``torch.distributed`` process group (one process per GPU) the runs shard
+    across the ranks (distributed.py): every rank must call with the same arguments and an
+    identically seeded ``rng``; every rank returns the same draws / ids / PSIS result, and
+    ``pathfinder_results`` holds the rank's own runs."""
     rng = np.random.default_rng() if rng is None else rng
     if init is None:
         if nruns is None or nruns <= 0:
@@ -199,22 +205,41 @@ def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT
     run_seeds = _draw_seeds(rng, nruns)  # src/multipath.jl:162
     path_rngs = [np.random.Generator(np.random.Philox(key=int(s))) for s in run_seeds]
     inits = [(_uniform_init(path_rngs[p], model.n, init_scale) if x is None else x) for p, x in enumerate(inits)]
+    seed = int(_draw_seeds(rng, 1)[0])
+    dist_on = D.is_distributed(group)
+    lo, hi = 0, nruns
+    if dist_on:
+        import torch.distributed as dist
+
+        lo, hi = D.shard_range(nruns, dist.get_rank(group), dist.get_world_size(group))
     own = engine is None
     if own:
         engine = Engine(model.n, model.family, model.blob, history_length, ndraws_elbo, device)
-    final, last = _run_paths(engine, model, inits, path_rngs, history_length=history_length, maxiters=maxiters,
-                             ntries=ntries, init_scale=init_scale)
-    results = [_assemble_path(model, path_rngs[p], final[p], ndraws_per_run, ndraws_elbo) for p in range(nruns)]
+    final, last = _run_paths(engine, model, inits[lo:hi], path_rngs[lo:hi], history_length=history_length,
+                             maxiters=maxiters, ntries=ntries, init_scale=init_scale)
+    results = [_assemble_path(model, path_rngs[lo + j], final[j], ndraws_per_run, ndraws_elbo)
+               for j in range(hi - lo)]
     # PSIS pool: draw-fastest, component-slowest (test/resample.jl:81-88)
     K_run = ndraws_per_run
-    single_batch = last is not None and len(last[0]) == nruns and K_run == ndraws_elbo
-    seed = int(_draw_seeds(rng, 1)[0])
-    if single_batch:
-        r = engine.psis_resample(seed, ndraws, importance)  # pool still resident on the device
+    if dist_on:
+        import torch.distributed as dist
+
+        dev = f"cuda:{device}" if dist.get_backend(group) == "nccl" else "cpu"
+        pool = np.concatenate([pr.draws for pr in results], axis=1) if results else np.zeros((model.n, 0))
+        lp = np.concatenate([pr.draws_logp for pr in results]) if results else np.zeros(0)
+        lq = np.concatenate([pr.draws_logq for pr in results]) if results else np.zeros(0)
+        r = D.pooled_resample(
+            lp, lq, pool, K_run, nruns,
+            lambda logr, N: engine.psis_resample_host(logr, K_run, seed, ndraws, importance, N=N),
+            seed, ndraws, importance, group, dev)
     else:
-        pool = np.concatenate([pr.draws for pr in results], axis=1)
-        logr = np.concatenate([pr.draws_logp - pr.draws_logq for pr in results])
-        r = engine.psis_resample_host(logr if importance else None, K_run, seed, ndraws, importance, pool=pool)
+        single_batch = last is not None and len(last[0]) == nruns and K_run == ndraws_elbo
+        if single_batch:
+            r = engine.psis_resample(seed, ndraws, importance)  # pool still resident on the device
+        else:
+            pool = np.concatenate([pr.draws for pr in results], axis=1)
+            logr = np.concatenate([pr.draws_logp - pr.draws_logq for pr in results])
+            r = engine.psis_resample_host(logr if importance else None, K_run, seed, ndraws, importance, pool=pool)
     psis = PSISResult(r["log_weights"], r["weights"], r["pareto_k"], r["tail_len"]) if importance else None
     return MultiPathfinderResult(model, rng, r["draws"], r["ids"], results, psis, r["inds"],
                                  engine if not own else _close_and_none(engine))

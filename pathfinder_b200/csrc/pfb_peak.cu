@@ -52,3 +52,56 @@ extern "C" int pfb_measure_fp64_fma_tflops(int device, int reps, double* tflops)
     *tflops = best;
     return e == cudaSuccess ? 0 : (int)e;
 }
+
+// FP64 tensor-core peak (mma.sync m8n8k4 f64 = SASS DMMA.8x8x4): 8 independent accumulator pairs per
+// warp, 2 CTAs of 256 threads per SM.  256 FMAs per warp-level instruction.
+__global__ void __launch_bounds__(256) pfb_dmma_chain(double* out, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-3; c[i][1] = i; }
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int pfb_measure_fp64_dmma_tflops(int device, int reps, double* tflops) {
+    if (!tflops) return -1;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return (int)e;
+    const int blocks = prop.multiProcessorCount * 2, threads = 256, iters = 4096;
+    double* d = nullptr;
+    e = cudaMalloc(&d, (size_t)blocks * threads * 8);
+    if (e != cudaSuccess) return (int)e;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    double best = 0.0;
+    for (int r = 0; r < reps + 2; ++r) {
+        cudaEventRecord(a);
+        pfb_dmma_chain<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(b);
+        e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        double fl = 2.0 * 256.0 * 8.0 * iters * (double)blocks * (threads / 32);
+        double tf = fl / (ms * 1e-3) / 1e12;
+        if (r >= 2 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = best;
+    return e == cudaSuccess ? 0 : (int)e;
+}

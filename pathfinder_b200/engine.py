@@ -194,13 +194,15 @@ class Engine:
                                                       int(bool(importance)), C.byref(out)))
         return self._finish(r)
 
-    def psis_resample_host(self, log_ratios, K_run, seed, ndraws, importance=True, pool=None):
+    def psis_resample_host(self, log_ratios, K_run, seed, ndraws, importance=True, pool=None, N=None):
         lr = None if log_ratios is None else np.ascontiguousarray(log_ratios, dtype=np.float64)
         if pool is not None:
             pool = np.asfortranarray(pool, dtype=np.float64)
             N = pool.shape[1]
-        else:
+        elif lr is not None:
             N = lr.size
+        elif N is None:
+            raise ValueError("pool size N is needed when neither log_ratios nor pool is given")
         out, r = self._resample_out(N, ndraws, importance, pool is not None)
         _lib.check(self.h, self.lib.pfb_psis_resample_host(
             self.h, self.n, N, int(K_run), _ptr(lr), _ptr(pool), C.c_uint64(int(seed)), int(ndraws),

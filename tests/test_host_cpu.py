@@ -1,0 +1,193 @@
+"""CPU tests (no GPU) of the host side: the C ABI surface, the loud failure without a device, the
+trajectory producer, batch packing, and the multi-rank pool exchange over gloo (world size 2)."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _have_gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+# ---- C ABI ------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    """include/pfb200.h is the contract: every function it declares is exported by libpfb200.so
+    and bound by the ctypes layer (no compute calls here)."""
+    from pathfinder_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "pfb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pfb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    lib = _lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_struct_layouts_match_header():
+    import ctypes as C
+
+    from pathfinder_b200 import _lib
+
+    assert C.sizeof(_lib.pfb_config) == 24
+    assert C.sizeof(_lib.pfb_elbo_out) == 18 * C.sizeof(C.c_void_p)
+    assert C.sizeof(_lib.pfb_resample_out) == 7 * C.sizeof(C.c_void_p)
+    assert C.sizeof(_lib.pfb_device_view) == 5 * C.sizeof(C.c_void_p) + 4 * 8
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-device behaviour")
+def test_no_device_fails_loudly():
+    """There is no CPU fallback: without a CUDA device the engine raises, with the CUDA error text."""
+    import pathfinder_b200 as pf
+
+    with pytest.raises(pf.PfbError) as ei:
+        pf.Engine(4, pf.PFB_MODEL_ISONORMAL, None, 6, 5, 0)
+    assert ei.value.code != 0
+    with pytest.raises(pf.PfbError):
+        pf.pathfinder(pf.IsoNormal(3), rng=np.random.default_rng(0))
+
+
+def test_argument_errors_do_not_need_a_device():
+    import ctypes as C
+
+    from pathfinder_b200 import _lib
+
+    lib = _lib.load()
+    h = C.c_void_p()
+    bad = _lib.pfb_config(0, 0, 5, 0, 1e-12)  # history_length = 0
+    assert lib.pfb_create(C.byref(h), C.byref(bad)) == -1
+    bad = _lib.pfb_config(0, 13, 5, 0, 1e-12)  # history_length > 12 unsupported
+    assert lib.pfb_create(C.byref(h), C.byref(bad)) == -3
+    assert lib.pfb_create(None, None) == -1
+    assert lib.pfb_batch_run(None) == -1 and lib.pfb_destroy(None) == 0
+
+
+# ---- host logic ---------------------------------------------------------------------------------
+def test_optimize_with_trace_records_points_and_gradients():
+    """src/optimize.jl:86-108: every iterate with its log density and gradient of the LOG density;
+    the run ends at a non-finite value."""
+    import pathfinder_b200 as pf
+
+    model = pf.Funnel(6)
+    x0 = np.array([1.0, 0.5, -0.5, 0.2, 0.1, -0.3])
+    tr = pf.optimize_with_trace(model, x0, 6, 50)
+    assert tr.points.shape == tr.gradients.shape and tr.points.shape[0] == 6
+    assert np.array_equal(tr.points[:, 0], x0)
+    for l in range(len(tr)):
+        assert np.isclose(tr.log_densities[l], model.logp(tr.points[:, l]))
+        np.testing.assert_allclose(tr.gradients[:, l], model.grad(tr.points[:, l]))
+    assert tr.log_densities[-1] >= tr.log_densities[0]
+
+    class Bad(pf.IsoNormal):
+        def logp(self, x):
+            return float("nan")
+
+    assert len(pf.optimize_with_trace(Bad(3), np.ones(3))) == 0  # non-finite at the initial point
+
+
+def test_model_gradients_match_finite_differences():
+    import pathfinder_b200 as pf
+
+    rng = np.random.default_rng(0)
+    for model in (pf.IsoNormal(5), pf.Funnel(5), pf.DiagNormal(rng.normal(size=5), rng.random(5) + 0.5)):
+        x = rng.normal(size=5)
+        g = model.grad(x)
+        for i in range(5):
+            e = np.zeros(5); e[i] = 1e-6
+            assert abs((model.logp(x + e) - model.logp(x - e)) / 2e-6 - g[i]) < 1e-5 * max(1, abs(g[i]))
+
+
+def test_pack_layout():
+    import pathfinder_b200 as pf
+
+    a = (np.arange(6.0).reshape(2, 3), -np.arange(6.0).reshape(2, 3))
+    b = (np.ones((2, 1)), np.zeros((2, 1)))
+    off, X, G = pf.Engine.pack([a, b])
+    assert off.tolist() == [0, 3, 4] and X.flags.f_contiguous and X.shape == (2, 4)
+    assert np.array_equal(X[:, :3], a[0]) and np.array_equal(G[:, 3:], b[1])
+
+
+def test_shard_ranges_cover_all_runs():
+    from pathfinder_b200 import distributed as D
+
+    for nruns in (1, 7, 8, 64, 65):
+        for world in (1, 2, 3, 8):
+            got = []
+            for r in range(world):
+                lo, hi = D.shard_range(nruns, r, world)
+                got += list(range(lo, hi))
+            assert got == list(range(nruns))
+            c = D.shard_counts(nruns, world)
+            assert sum(c) == nruns and max(c) - min(c) <= 1
+
+
+# ---- multi-rank pool exchange over gloo ----------------------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nruns, K_run, n, ndraws, importance, q):
+    import torch.distributed as dist
+
+    from oracle import psis as OP
+    from pathfinder_b200 import distributed as D
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(123)  # every rank builds the same global pool, keeps its block
+    logp = rng.standard_t(4, size=nruns * K_run)
+    logq = rng.normal(size=nruns * K_run)
+    pool = np.asfortranarray(rng.normal(size=(n, nruns * K_run)))
+    lo, hi = D.shard_range(nruns, rank, world)
+    sl = slice(lo * K_run, hi * K_run)
+
+    def psis_fn(logr, N):  # stand-in for the engine's K6/K7 (the oracle computes the same contract)
+        if logr is None:
+            return dict(inds=OP.resample_indices(5, None, N, ndraws))
+        res = OP.psis(logr)
+        return dict(inds=OP.resample_indices(5, res["weights"], N, ndraws), weights=res["weights"],
+                    log_weights=res["log_weights"], pareto_k=res["pareto_k"], tail_len=res["tail_length"])
+
+    r = D.pooled_resample(logp[sl], logq[sl], pool[:, sl], K_run, nruns, psis_fn, 5, ndraws, importance)
+    # single-process answer on the whole pool
+    ref = psis_fn(logp - logq if importance else None, nruns * K_run)
+    ok = (np.array_equal(r["inds"], ref["inds"]) and np.array_equal(r["draws"], pool[:, ref["inds"] - 1])
+          and np.array_equal(r["ids"], -(-ref["inds"] // K_run)))
+    if importance:
+        ok = ok and np.array_equal(r["weights"], ref["weights"])
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nruns,importance", [(4, True), (5, True), (3, False)])
+def test_pool_exchange_world_size_2_gloo(nruns, importance):
+    """Two ranks, ragged shards (5 runs -> 2 + 3): the gathered log ratios, the replicated index
+    draw and the owner-contributed columns equal the single-process result bit for bit."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, nruns, 10, 3, 25, importance, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]

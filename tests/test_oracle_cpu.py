@@ -1,0 +1,353 @@
+"""CPU tests (no GPU): pin the oracle against every fixture / known answer the reference's own
+tests hold for the hot path, and the RNG / math contract against published vectors.
+
+Each test names the reference test it mirrors (paths relative to the reference repo).
+"""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+from scipy import stats
+
+from oracle import pf_oracle as O
+from oracle import psis as OP
+
+# test/inverse_hessian.jl:19-20 — the reference's literal fixture
+S0 = np.array([
+    [1.719573, 3.294037, -2.008877, 3.901275, 0.214324, 0.400382, 0.113598, -1.804262, 0.465563, 2.465748],
+    [-0.445476, -0.514915, 1.069617, -1.505506, -0.036535, -0.11386, -0.029737, 0.579662, -0.118694, -1.726258],
+    [-0.013354, 0.1981, 0.081886, -0.194172, 0.010499, -0.007944, -0.001039, 0.061604, -0.002621, 0.11145],
+    [0.00648, 0.255961, -0.011901, -0.059042, 0.013587, -0.002064, 0.000302, 0.023457, 0.00257, -0.002343],
+    [-0.016408, 0.015005, 0.009654, 0.016735, -0.000245, -0.002825, -0.00106, 0.004272, -0.004578, 0.002275],
+]).T
+Y0 = -np.array([
+    [-2.357935, -3.343312, 4.659008, -7.065433, -0.228045, -0.584164, -0.156837, 2.863289, -0.631753, -7.152021],
+    [0.610851, 0.522617, -2.480668, 2.726559, 0.038874, 0.166123, 0.041055, -0.9199, 0.161064, 5.007094],
+    [0.018312, -0.201064, -0.189911, 0.351657, -0.011171, 0.011591, 0.001434, -0.097763, 0.003557, -0.323265],
+    [-0.008886, -0.25979, 0.027601, 0.106929, -0.014456, 0.003011, -0.000418, -0.037225, -0.003488, 0.006795],
+    [0.022499, -0.015229, -0.02239, -0.030308, 0.00026, 0.004122, 0.001463, -0.00678, 0.006212, -0.006598],
+]).T
+
+
+def explicit_inverse_hessian(alpha, S, Y):
+    """lbfgs_inverse_hessian_explicit, test/inverse_hessian.jl:8-14."""
+    H0 = np.diag(alpha)
+    B = np.hstack([H0 @ Y, S])
+    R = np.triu(S.T @ Y)
+    E = np.diag(np.diag(R))
+    Rinv = np.linalg.inv(R)
+    J = S.shape[1]
+    D = np.block([[np.zeros((J, J)), -Rinv], [-Rinv.T, np.linalg.solve(R.T, E + Y.T @ H0 @ Y) @ Rinv]])
+    return H0 + B @ D @ B.T
+
+
+# ---- RNG / math contract --------------------------------------------------------------------
+def test_philox4x32_10_known_answers():
+    """Random123 kat_vectors (Salmon et al., SC'11) for philox4x32-10."""
+    lib = O.clib()
+    lib.pfo_philox.argtypes = [ctypes.c_uint32] * 6 + [ctypes.c_void_p]
+    out = np.zeros(2, dtype=np.uint64)
+
+    def call(c, k):
+        lib.pfo_philox(*c, *k, out.ctypes.data)
+        a, b = int(out[0]), int(out[1])
+        return [a & 0xFFFFFFFF, a >> 32, b & 0xFFFFFFFF, b >> 32]
+
+    assert call([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert call([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert call([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == \
+        [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def _ulps(a, b):
+    return np.abs(a - b) / np.spacing(np.abs(b))
+
+
+def test_pf_math_against_libm():
+    """pf_math.h stays within 2 ulp of libm on the ranges the PSIS stage uses."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-700, 700, 20000), rng.normal(size=20000), [0.0, -0.0, 1e-300, -745.0, 709.0]])
+    assert _ulps(O.pf_exp(x), np.exp(x)).max() <= 2
+    y = np.concatenate([np.exp(rng.uniform(-700, 700, 20000)), rng.uniform(0.5, 2, 20000), [5e-324, 1.0]])
+    assert _ulps(O.pf_log(y), np.log(y))[np.log(y) != 0].max() <= 2
+    z = np.concatenate([rng.uniform(-0.999, 10, 20000), rng.normal(size=20000) * 1e-8])
+    assert _ulps(O.pf_log1p(z), np.log1p(z))[z != 0].max() <= 4
+    assert _ulps(O.pf_expm1(z), np.expm1(z))[z != 0].max() <= 4
+    assert np.isnan(O.pf_log(np.array([-1.0]))[0]) and O.pf_log(np.array([0.0]))[0] == -np.inf
+    assert O.pf_exp(np.array([1000.0]))[0] == np.inf and O.pf_exp(np.array([-1000.0]))[0] == 0.0
+
+
+def test_contract_normals_are_standard_normal():
+    """Moment / KS check of the engine's own normal stream (test/mvnormal.jl:71-107 checks the
+    same of Julia's)."""
+    u = np.asarray(O.contract_normals(2024, 1000, 1000)).ravel()
+    n = u.size
+    assert abs(u.mean()) < 5 / math.sqrt(n)
+    assert abs(u.var() - 1) < 5 * math.sqrt(2 / n)
+    assert abs(stats.kurtosis(u)) < 5 * math.sqrt(24 / n)
+    assert stats.kstest(u[:200000], "norm").pvalue > 1e-4
+    # tail beyond the ziggurat base strip edge has the right mass
+    r = 4.038849846109505
+    p = 2 * stats.norm.sf(r)
+    big = np.asarray(O.contract_normals(7, 2000, 4000)).ravel()
+    k = np.sum(np.abs(big) > r)
+    assert abs(k - p * big.size) < 6 * math.sqrt(p * big.size)
+    # seeds select independent streams; same seed reproduces
+    v = np.asarray(O.contract_normals(2025, 1000, 100)).ravel()
+    assert abs(np.corrcoef(u[:100000], v)[0, 1]) < 0.02
+    assert np.array_equal(O.contract_normals(2024, 33, 7), O.contract_normals(2024, 33, 7))
+
+
+# ---- inverse Hessian / Woodbury ---------------------------------------------------------------
+def test_lbfgs_inverse_hessian_reference_fixture():
+    """test/inverse_hessian.jl:16-44 (literal S0/Y0; J_eff in {0, 3, 5}; rotated ring buffer)."""
+    rng = np.random.default_rng(1)
+    N, J = S0.shape
+    alpha = rng.random(N)
+    B, D = O.lbfgs_inverse_hessian(alpha, S0, Y0, 0, 0)
+    assert B.shape[1] == 0 or np.allclose(np.diag(alpha) + B @ D @ B.T, np.diag(alpha))
+    B, D = O.lbfgs_inverse_hessian(alpha, S0, Y0, 3, 3)
+    np.testing.assert_allclose(np.diag(alpha) + B @ D @ B.T, explicit_inverse_hessian(alpha, S0[:, :3], Y0[:, :3]),
+                               rtol=1e-9, atol=1e-12)
+    perm = [3, 4, 0, 1, 2]  # [4:J; 1:3] (1-based) — newest column (5) now sits at position 2
+    S2, Y2 = S0[:, perm], Y0[:, perm]
+    ilast = int(np.argmax(perm)) + 1
+    B, D = O.lbfgs_inverse_hessian(alpha, S2, Y2, ilast, J)
+    Hexp = explicit_inverse_hessian(alpha, S0, Y0)
+    np.testing.assert_allclose(np.diag(alpha) + B @ D @ B.T, Hexp, rtol=1e-8, atol=1e-11)
+    B, D = O.lbfgs_inverse_hessian(alpha, S0, Y0, J, J)
+    np.testing.assert_allclose(np.diag(alpha) + B @ D @ B.T, Hexp, rtol=1e-8, atol=1e-11)
+
+
+def test_inverse_hessians_reproduce_lbfgs_directions():
+    """test/inverse_hessian.jl:46-76: with Hinit = y's/y'y the reconstructed H_l g_l is parallel to the
+    step the optimiser actually took, and no update is rejected."""
+    from scipy.optimize import minimize
+
+    n, J = 10, 5
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(n, n))
+    P = A @ A.T / n + np.eye(n)
+
+    def f(x):
+        return 0.5 * x @ P @ x + 0.05 * np.sum(x**4), P @ x + 0.2 * x**3
+
+    pts, grads = [], []
+    x0 = 3 * rng.normal(size=n)
+    pts.append(x0.copy()); grads.append(-f(x0)[1])
+
+    def cb(xk):
+        pts.append(xk.copy()); grads.append(-f(xk)[1])
+
+    minimize(f, x0, jac=True, method="L-BFGS-B", callback=cb, options=dict(maxcor=J, maxiter=25, gtol=1e-12))
+    X, G = np.stack(pts, 1), np.stack(grads, 1)
+    Hs, rejected, _ = O.lbfgs_inverse_hessians(X, G, history_length=J, hinit=O.nocedal_wright_scaling)
+    assert rejected == 0
+    for l in range(1, X.shape[1] - 1):
+        step = X[:, l + 1] - X[:, l]
+        p = Hs[l].mul(G[:, l])
+        cos = step @ p / np.linalg.norm(step) / np.linalg.norm(p)
+        assert cos > 1 - 1e-6, (l, cos)
+
+
+def _rand_pd_diag(rng, n):
+    return rng.random(n) + 0.05
+
+
+@pytest.mark.parametrize("n,m", [(5, 8), (10, 8), (30, 12), (12, 12)])
+def test_woodbury_identities_against_dense(n, m):
+    """test/woodbury.jl:155-404 for A = Diagonal: dense reconstruction, logdet, mul, factor products,
+    solves, invquad; right-factor structure [V 0; 0 I] Q' U (:26-36)."""
+    rng = np.random.default_rng(n * 100 + m)
+    alpha = _rand_pd_diag(rng, n)
+    B = rng.normal(size=(n, m))
+    Dh = rng.normal(size=(m, m))
+    D = Dh @ Dh.T / m  # PSD => W is PD
+    W = O.pdfactorize(alpha, np.asfortranarray(B), D)
+    assert W.pd_ok
+    Wmat = np.diag(alpha) + B @ D @ B.T
+    np.testing.assert_allclose(W.dense(), Wmat)
+    k = min(n, m)
+    # R'R = W with R = diag(Vc, I) Q' U
+    R = W.lmul_R(np.eye(n))
+    np.testing.assert_allclose(R.T @ R, Wmat, rtol=1e-9, atol=1e-10)
+    L = W.lmul_L(np.eye(n))
+    np.testing.assert_allclose(L, R.T, rtol=1e-9, atol=1e-10)
+    # structure of the right factor
+    Q = W._q_apply(np.eye(n), trans=False)
+    np.testing.assert_allclose(Q.T @ Q, np.eye(n), atol=1e-12)
+    blk = np.eye(n)
+    blk[:k, :k] = W.Vc
+    np.testing.assert_allclose(R, blk @ Q.T @ np.diag(np.sqrt(alpha)), rtol=1e-9, atol=1e-10)
+    # compact WY: Q = I - Vh T Vh'
+    np.testing.assert_allclose(Q, np.eye(n) - W.Vh @ W.T[:k, :k] @ W.Vh.T, atol=1e-12)
+    sign, ld = np.linalg.slogdet(Wmat)
+    assert sign > 0 and abs(W.logdet() - ld) < 1e-9 * max(1, abs(ld))
+    for shape in [(n,), (n, 3)]:
+        x = rng.normal(size=shape)
+        np.testing.assert_allclose(W.mul(x), Wmat @ x, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(W.ldiv_L(W.lmul_L(x)), x, rtol=1e-8, atol=1e-9)
+        z = W.ldiv_L(x)  # whiten: dot(z, z) = x' W^-1 x   (test/woodbury.jl:311-355)
+        ref = np.sum(x * np.linalg.solve(Wmat, x), axis=0)
+        np.testing.assert_allclose(np.sum(z * z, axis=0), ref, rtol=1e-8)
+    X = rng.normal(size=(n, 4))
+    np.testing.assert_allclose(W.invquad(X), np.sum(X * np.linalg.solve(Wmat, X), axis=0), rtol=1e-8)
+
+
+def test_fit_mvnormals_mean_and_covariances():
+    """test/mvnormal.jl:8-29: Sigma_l == lbfgs_inverse_hessians output, mu = theta + Sigma g."""
+    from tests.helpers import synthetic_trajectory
+
+    X, G = synthetic_trajectory(10, 8, 5)
+    mus, Hs, rej = O.fit_mvnormals(X, G, history_length=5)
+    Hs2, rej2, _ = O.lbfgs_inverse_hessians(X, G, history_length=5)
+    assert rej == rej2 and len(Hs) == X.shape[1]
+    for l, (W, W2) in enumerate(zip(Hs, Hs2)):
+        np.testing.assert_allclose(W.dense(), W2.dense())
+        np.testing.assert_allclose(mus[:, l], X[:, l] + W.dense() @ G[:, l], rtol=1e-9, atol=1e-10)
+    assert Hs[0].k == 0 and np.all(Hs[0].alpha == 1)  # H_0 = I (src/inverse_hessian.jl:38-40)
+
+
+def test_rand_and_logpdf_matches_dense_mvn():
+    """test/mvnormal.jl:31-68: x = mu + L u has logq == logpdf(MvNormal(mu, Sigma), x)."""
+    from tests.helpers import synthetic_trajectory
+
+    X, G = synthetic_trajectory(8, 6, 9)
+    mus, Hs, _ = O.fit_mvnormals(X, G, history_length=4)
+    u = np.random.default_rng(0).normal(size=(8, 50))
+    for l in (0, 2, 6):
+        x, logq = O.rand_and_logpdf(u, mus[:, l], Hs[l])
+        Sig = Hs[l].dense()
+        ref = stats.multivariate_normal(mus[:, l], Sig).logpdf(x.T)
+        np.testing.assert_allclose(logq, ref, rtol=1e-9, atol=1e-9)
+        # and the draws have the right covariance structure: L L' = Sigma
+        L = Hs[l].lmul_L(np.eye(8))
+        np.testing.assert_allclose(L @ L.T, Sig, rtol=1e-9, atol=1e-10)
+
+
+# ---- ELBO ------------------------------------------------------------------------------------
+def test_elbo_known_answer():
+    """test/elbo.jl:7-28: target N(0, 0.08), fit N(0, sigma): ELBO = (1 - r^2)/2 + log r."""
+    st = 0.08
+    K = 200_000
+
+    def logp(x):
+        return stats.norm(0, st).logpdf(x[0])
+
+    for i, sigma in enumerate([1e-3, 0.05, 0.8, 1.0, 5.0]):
+        W = O.pdfactorize(np.array([sigma**2]), np.zeros((1, 0)), np.zeros((0, 0)))
+        u = O.contract_normals(100 + i, 1, K)
+        est = O.elbo_and_samples(u, logp, np.zeros(1), W)
+        r = sigma / st
+        assert abs(est["value"] - ((1 - r**2) / 2 + math.log(r))) < 4 * est["std_err"] + 1e-12
+        np.testing.assert_array_equal(est["logr"], est["logp"] - est["logq"])
+        assert np.isclose(est["value"], est["logr"].mean())
+        assert np.isclose(est["std_err"], est["logr"].std(ddof=1) / math.sqrt(K))
+
+
+def test_maximize_elbo_picks_matching_scale():
+    """test/elbo.jl:30-54: among fits with sigma in [1e-3, .05, .08, 1, 5] the argmax is the third,
+    ELBO ~ 0; reseeding reproduces; empty input -> (0, [])."""
+    st = 0.08
+
+    def logp(x):
+        return stats.norm(0, st).logpdf(x[0])
+
+    sig = [1e-3, 0.05, st, 1.0, 5.0]
+    Hs = [None] + [O.pdfactorize(np.array([s**2]), np.zeros((1, 0)), np.zeros((0, 0))) for s in sig]
+    mus = np.zeros((1, len(Hs)))
+    seeds = np.arange(5, dtype=np.uint64) + 11
+    lopt, ests = O.maximize_elbo(seeds, logp, mus, Hs, 100)
+    assert lopt == 3 and abs(ests[2]["value"]) < 1e-12
+    lopt2, ests2 = O.maximize_elbo(seeds, logp, mus, Hs, 100)
+    assert lopt2 == lopt and all(np.array_equal(a["draws"], b["draws"]) for a, b in zip(ests, ests2))
+    assert O.maximize_elbo(seeds[:0], logp, mus[:, :1], Hs[:1], 100) == (0, [])
+
+
+def test_findmax_skipnan_table():
+    """test/utils.jl:6-13."""
+    nan = float("nan")
+    assert O.findmax_skipnan([nan, 3.0, 1.0]) == (3.0, 2)
+    v, i = O.findmax_skipnan([nan, nan])
+    assert math.isnan(v) and i == 1
+    assert O.findmax_skipnan([2.0, nan, 4.0]) == (4.0, 3)
+    assert O.findmax_skipnan([1.0, 1.0]) == (1.0, 1)  # ties keep the earliest
+    v, i = O.findmax_skipnan([])
+    assert math.isnan(v) and i == 0
+    assert not O.path_success(0, [], 0)
+    assert not O.path_success(2, [dict(value=nan), dict(value=-math.inf)], 1)
+    assert not O.path_success(2, [dict(value=nan), dict(value=-math.inf)], 2)
+    assert O.path_success(2, [dict(value=nan), dict(value=-3.0)], 2)
+
+
+# ---- PSIS / resample -------------------------------------------------------------------------
+def test_log_importance_ratio_ordering():
+    """test/resample.jl:62-89: ratios are draw-fastest, component-slowest."""
+    from tests.helpers import synthetic_trajectory
+
+    n, K_run, P = 4, 6, 3
+    rng = np.random.default_rng(5)
+    mus, Ws = [], []
+    for p in range(P):
+        X, G = synthetic_trajectory(n, 5, 40 + p)
+        m, Hs, _ = O.fit_mvnormals(X, G, history_length=3)
+        mus.append(m[:, -1]); Ws.append(Hs[-1])
+    draws = rng.normal(size=(n, K_run, P))
+    lr = O  # noqa
+    ratios = OP.log_importance_ratios(O.logp_isonormal, mus, Ws, draws)
+    for k in range(P):
+        ref = stats.multivariate_normal(mus[k], Ws[k].dense())
+        for j in range(K_run):
+            x = draws[:, j, k]
+            assert np.isclose(ratios[k * K_run + j], -0.5 * x @ x - ref.logpdf(x), rtol=1e-8, atol=1e-8)
+
+
+def test_resample_membership_ids_and_degenerate_weights():
+    """test/resample.jl:8-60."""
+    dim, K_run, P, ndraws = 3, 10, 4, 20
+    rng = np.random.default_rng(42)
+    dpc = rng.normal(size=(dim, K_run, P))
+    allc = dpc.reshape(dim, -1, order="F")
+    draws, ids, inds = OP.resample(1, dpc, None, ndraws)  # uniform (psis_result === nothing)
+    assert draws.shape == (dim, ndraws) and ids.shape == (ndraws,)
+    assert ids.min() >= 1 and ids.max() <= P
+    for c, cid in zip(draws.T, ids):
+        assert any(np.array_equal(c, a) for a in allc.T)
+        assert any(np.array_equal(c, a) for a in dpc[:, :, cid - 1].T)
+    lw = np.full((K_run, P), -1000.0)
+    lw[:, 0] = 0.0
+    res = OP.psis(lw.reshape(-1, order="F"))
+    draws, ids, _ = OP.resample(2, dpc, res, ndraws)
+    assert np.all(ids == 1)
+    for c in draws.T:
+        assert any(np.array_equal(c, a) for a in dpc[:, :, 0].T)
+
+
+def test_psis_result_properties_and_gpd_fit():
+    """test/resample.jl:91-109 (length, sum(weights) ~ 1) + the Zhang-Stephens fit recovers the shape
+    of a generalized-Pareto sample, and PSIS k-hat grows with the tail weight of the ratios."""
+    rng = np.random.default_rng(7)
+    lr = rng.normal(size=5000)
+    r = OP.psis(lr)
+    assert r["log_weights"].shape == (5000,) and abs(r["weights"].sum() - 1) < 1e-12
+    assert r["tail_length"] == min(1000, math.ceil(3 * math.sqrt(5000)))
+    for k_true in (-0.3, 0.2, 0.7):
+        x = np.sort(stats.genpareto(k_true, scale=1.5).rvs(size=4000, random_state=rng))
+        k, sigma = OP.fit_gpd(x)
+        assert abs(k - k_true) < 0.08 and abs(sigma - 1.5) < 0.15
+    k_light = OP.psis(rng.normal(size=20000) * 0.3)["pareto_k"]
+    k_heavy = OP.psis(rng.standard_t(2, size=20000) * 2)["pareto_k"]
+    assert k_light < 0.3 < 0.7 < k_heavy
+    # too few draws for a tail fit: plain self-normalisation, k = NaN
+    small = OP.psis(np.array([0.1, -0.2, 0.3, 0.0]))
+    assert math.isnan(small["pareto_k"]) and abs(small["weights"].sum() - 1) < 1e-12
+
+
+def test_resample_indices_follow_weights():
+    w = np.array([0.5, 0.25, 0.125, 0.125])
+    inds = OP.resample_indices(9, w, 4, 40000)
+    freq = np.bincount(inds, minlength=5)[1:] / 40000
+    assert np.abs(freq - w).max() < 0.01
+    assert np.array_equal(inds, OP.resample_indices(9, w, 4, 40000))  # reproducible under reseed
+    assert not np.array_equal(inds, OP.resample_indices(10, w, 4, 40000))
