@@ -45,6 +45,10 @@ typedef struct {
     int32_t ndraws_elbo;     /* K, DEFAULT_NDRAWS_ELBO = 5                                    */
     int32_t materialize_all; /* 1: keep the draws of every iteration on the device (mode M,
                                 the ELBOEstimate.draws payload of src/elbo.jl:19); 0: lean    */
+    int32_t elbo_mode;       /* 0: auto — the lean ELBO stage generates each normal once and gets
+                                log p from quadratic-form statistics (all registered families are
+                                diagonal-quadratic); 1: always the generic two-pass kernel     */
+    int32_t reserved;        /* 0                                                              */
     double eps;              /* curvature tolerance, 1e-12                                    */
 } pfb_config;
 

@@ -29,6 +29,8 @@ struct PfbConfig
     history_length::Int32
     ndraws_elbo::Int32
     materialize_all::Int32
+    elbo_mode::Int32
+    reserved::Int32
     eps::Float64
 end
 
@@ -76,7 +78,7 @@ mutable struct Engine
                     history_length::Integer=6, ndraws_elbo::Integer=5, device::Integer=0,
                     materialize_all::Bool=false, eps::Float64=1e-12)
         h = Ref{Ptr{Cvoid}}(C_NULL)
-        cfg = Ref(PfbConfig(device, history_length, ndraws_elbo, materialize_all, eps))
+        cfg = Ref(PfbConfig(device, history_length, ndraws_elbo, materialize_all, 0, 0, eps))
         rc = ccall((:pfb_create, LIB[]), Cint, (Ref{Ptr{Cvoid}}, Ref{PfbConfig}), h, cfg)
         rc == 0 || throw(ErrorException("pfb_create failed ($rc): " * last_error(C_NULL)))
         e = new(h[], n, ndraws_elbo, history_length)

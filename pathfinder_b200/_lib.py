@@ -29,6 +29,8 @@ class pfb_config(C.Structure):
         ("history_length", C.c_int32),
         ("ndraws_elbo", C.c_int32),
         ("materialize_all", C.c_int32),
+        ("elbo_mode", C.c_int32),
+        ("reserved", C.c_int32),
         ("eps", C.c_double),
     ]
 

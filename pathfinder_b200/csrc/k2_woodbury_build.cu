@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(PFB_K2_THREADS)
 pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* __restrict__ G,
                       const int32_t* __restrict__ unit_col, const double* __restrict__ alpha_all,
                       const int32_t* __restrict__ hist, const int32_t* __restrict__ hist_cnt,
-                      double* __restrict__ FR, double* __restrict__ HDR, double* __restrict__ FR2) {
+                      double* __restrict__ FR, double* __restrict__ HDR, double* __restrict__ FR2,
+                      int model, const double* __restrict__ mp0, const double* __restrict__ mp1) {
     constexpr int RS = KP + 2;
     constexpr int JM = KP / 2;
     __shared__ double scratch[KP * 32];
@@ -328,19 +329,34 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
             }
         }
     }
+    // ---- mu, and the diagonal-quadratic statistics of K3's single-pass mode (pfb_common.cuh) --------
+    // weights d_i and centres m_i of the registered model family
+    auto model_d = [&](int i) -> double {
+        if (model == PFB_MODEL_FUNNEL) return i == 0 ? 0.0 : 1.0;
+        if (model == PFB_MODEL_DIAGNORMAL) { double is = mp1[i]; return is * is; }  // mp1 = 1 / sd
+        return 1.0;
+    };
+    auto model_m = [&](int i) -> double { return model == PFB_MODEL_DIAGNORMAL ? mp0[i] : 0.0; };
+    double e0acc[1] = {0.0};
     for (int i = tid; i < n; i += nt) {
         double* row = fr + (int64_t)i * RS;
         // kq == 0: Sigma = diag(alpha): t = sqrt(alpha) g, mu = theta + sqrt(alpha) t
-        row[KP + 1] = fma(row[KP], row[KP + 1], theta[i]);
+        const double sa = row[KP];
+        const double mu = fma(sa, row[KP + 1], theta[i]);
+        row[KP + 1] = mu;
+        const double d = model_d(i), e = mu - model_m(i);
+        e0acc[0] = fma(d * e, e, e0acc[0]);
         if (FR2 != nullptr) {
             // second copy in the tensor-core layout of K3 (pfb_common.cuh): RS2 doubles per row,
             // 4-double groups XOR-swizzled by pfb_swz(row)
             constexpr int RS2 = (KP == 12) ? 16 : 32;
             double* r2 = FR2 + ((int64_t)u * pfb_npad8(n) + i) * RS2;
             const int sw = pfb_swz(i);
+            const double pi_ = d * alpha[i], ri_ = d * sa * e;
 #pragma unroll
             for (int c = 0; c < RS2; ++c) {
-                double v = (c < KP) ? row[c] : (c == KP ? row[KP] : (c == KP + 1 ? row[KP + 1] : 0.0));
+                double v = (c < KP) ? row[c]
+                                    : (c == KP ? sa : (c == KP + 1 ? mu : (c == KP + 2 ? pi_ : (c == KP + 3 ? ri_ : 0.0))));
                 r2[c ^ sw] = v;
             }
         }
@@ -349,6 +365,30 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
         constexpr int RS2 = (KP == 12) ? 16 : 32;
         const int npad = pfb_npad8(n);
         for (int e = n * RS2 + tid; e < npad * RS2; e += nt) FR2[(int64_t)u * npad * RS2 + e] = 0.0;
+    }
+    pfb_block_sum<1>(e0acc, scratch);
+    // M = Vh' diag(p) Vh (row a per round), rv = Vh' r
+    for (int a = 0; a <= KP; ++a) {
+        double acc[KP];
+#pragma unroll
+        for (int b = 0; b < KP; ++b) acc[b] = 0.0;
+        if (a < kq || a == KP) {
+            for (int i = tid; i < n; i += nt) {
+                const double* row = fr + (int64_t)i * RS;
+                const double d = model_d(i);
+                const double wgt = (a < KP) ? d * alpha[i] * row[a] : d * row[KP] * (row[KP + 1] - model_m(i));
+#pragma unroll
+                for (int b = 0; b < KP; ++b) acc[b] = fma(wgt, row[b], acc[b]);
+            }
+            pfb_block_sum<KP>(acc, scratch);
+        }
+        if (tid == 0) {
+#pragma unroll
+            for (int b = 0; b < KP; ++b) {
+                if (a < KP) hdr[PFB_HDR_M(KP) + a * KP + b] = acc[b];
+                else hdr[PFB_HDR_RV(KP) + b] = acc[b];
+            }
+        }
     }
     // ---- header ---------------------------------------------------------------------------------
     for (int e = tid; e < KP * KP; e += nt) {
@@ -359,27 +399,31 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
         hdr[PFB_HDR_LOGDET(KP)] = logdet;
         hdr[PFB_HDR_FLAG(KP)] = (double)sFlag;
         hdr[PFB_HDR_KEFF(KP)] = (double)kq;
+        hdr[PFB_HDR_E0(KP)] = e0acc[0];
     }
 }
 
 template <int KP>
 static cudaError_t launch_k2(cudaStream_t st, int n, int U, int J, const double* X, const double* G,
                              const int32_t* unit_col, const double* alpha, const int32_t* hist,
-                             const int32_t* hist_cnt, double* FR, double* HDR, double* FR2) {
+                             const int32_t* hist_cnt, double* FR, double* HDR, double* FR2, int model,
+                             const double* mp0, const double* mp1) {
     int threads = n >= PFB_K2_THREADS ? PFB_K2_THREADS : ((n + 31) / 32) * 32;
     if (threads < 64) threads = 64;  // >= KP threads are needed by the small-matrix phases
-    pfb_k2_woodbury_build<KP><<<U, threads, 0, st>>>(n, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR, FR2);
+    pfb_k2_woodbury_build<KP><<<U, threads, 0, st>>>(n, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR, FR2,
+                                                     model, mp0, mp1);
     return cudaGetLastError();
 }
 
 extern "C" cudaError_t pfb_launch_k2(cudaStream_t st, int KP, int n, int U, int J, const double* X,
                                      const double* G, const int32_t* unit_col, const double* alpha,
                                      const int32_t* hist, const int32_t* hist_cnt, double* FR,
-                                     double* HDR, double* FR2) {
+                                     double* HDR, double* FR2, int model, const double* mp0,
+                                     const double* mp1) {
     if (U <= 0) return cudaSuccess;
     switch (KP) {
 #define PFB_K2_CASE(k) \
-    case k: return launch_k2<k>(st, n, U, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR, FR2);
+    case k: return launch_k2<k>(st, n, U, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR, FR2, model, mp0, mp1);
         PFB_K2_CASE(12)
         PFB_K2_CASE(20)
         PFB_K2_CASE(24)

@@ -44,7 +44,7 @@
 #define PFB_K3_MAXWARPS 16
 #define PFB_K3_DS 2      // draw sets (8 draws each) per warp
 #define PFB_K3_RC 128    // record rows per TMA chunk (16 blocks of 8 rows)
-#define PFB_K3_DCAP 64   // deferred-list capacity per warp and round
+#define PFB_K3_DCAP 32   // deferred-list capacity per warp and round
 #define PFB_K3_ZREP 2    // copies of the 1024-layer ziggurat table in shared memory (32 KB)
 static_assert(PF_ZIG_LAYERS == 1024 && PFB_K3_ZREP == 2, "pfb_zig_fast_rep address arithmetic");
 
@@ -159,20 +159,28 @@ struct pfb_ic {
     static constexpr int value = V;
 };
 
-template <int KP, int MODEL, bool MATERIALIZE>
+// MODE 0: two passes, lean (logp, logq only)      MODE 1: two passes, x materialised (K5 / mode M)
+// MODE 2: single pass for the diagonal-quadratic target family (pfb_common.cuh, PFB_HDR_M): the
+//         normals are generated ONCE; S = sum d (x - m)^2 and x_0 follow from linear functionals of
+//         u~ (w = Vh' u~, Vh' (p u~), r' u~ — all DMMA columns) and sum p u~^2, so the second
+//         Philox/ziggurat sweep (the kernel's bottleneck) disappears.
+template <int KP, int MODEL, int MODE>
 __global__ void __launch_bounds__(PFB_K3_MAXWARPS * 32, 1)
 pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__ unit_list,
                    const double* __restrict__ FR2, const double* __restrict__ HDR,
                    const uint64_t* __restrict__ seeds, const double* __restrict__ u_host,
                    pfb_model_params mp, double* __restrict__ logp_out, double* __restrict__ logq_out,
                    double* __restrict__ draws_out) {
+    constexpr bool MATERIALIZE = (MODE == 1);
+    constexpr bool QUAD = (MODE == 2);
     constexpr int RS2 = (KP == 12) ? 16 : 32;
     constexpr int RC = PFB_K3_RC;
     constexpr int DS = PFB_K3_DS;
-    constexpr int NT0 = (KP + 7) / 8;  // j tiles of pass 0
+    constexpr int NT0 = QUAD ? (2 * KP + 7) / 8 : (KP + 7) / 8;  // column tiles of pass 0
     constexpr int NS1 = KP / 4;        // j steps of pass 1
     constexpr int HB = (KP + 7) / 8;   // head blocks (rows < KP get the Vc' multiply)
     constexpr int NHP = (KP / 2 + 3) / 4;  // head row pairs generated per lane
+    constexpr int CWW = QUAD ? 2 * KP : KP;  // per-draw shared accumulators: w (and Vh'(p u~))
     static_assert(DS == 2, "pending nibbles assume two draw sets");
     static_assert(RC / 8 * 4 <= 64, "pending mask is 64 bits per chunk");
 
@@ -182,10 +190,11 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sStage = reinterpret_cast<double*>(smem_raw);                      // NS * RC * RS2
     pfb_zig_e* sZig = reinterpret_cast<pfb_zig_e*>(sStage + (size_t)NS * RC * RS2);  // 1024 * 2
-    double* sT = reinterpret_cast<double*>(sZig + PF_ZIG_LAYERS * PFB_K3_ZREP);          // KP*KP
+    double* sT = reinterpret_cast<double*>(sZig + PF_ZIG_LAYERS * PFB_K3_ZREP);  // KP*KP
     double* sVc = sT + KP * KP;                                                // KP*KP
-    double* sC = sVc + KP * KP;                                                // NW * DS * 8 * KP
-    pfb_k3_warp_list* sList = reinterpret_cast<pfb_k3_warp_list*>(sC + (size_t)NW * DS * 8 * KP);
+    double* sM = sVc + KP * KP;                                                // KP*KP + KP (QUAD)
+    double* sC = sM + (QUAD ? KP * KP + KP : 0);                               // NW * DS * 8 * CWW
+    pfb_k3_warp_list* sList = reinterpret_cast<pfb_k3_warp_list*>(sC + (size_t)NW * DS * 8 * CWW);
     uint64_t* sBar = reinterpret_cast<uint64_t*>(sList + NW);                  // NS
 
     const int slot = blockIdx.x / splits;
@@ -211,12 +220,14 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
     const int C = (npad + RC - 1) / RC;  // chunks per pass
     const bool resident = (C <= NS);
     const int nsweeps_cta = (S - split + splits - 1) / splits;
-    const int Q = resident ? C : 2 * C * nsweeps_cta;  // TMA loads issued by this CTA
+    const int Q = resident ? C : (QUAD ? 1 : 2) * C * nsweeps_cta;  // TMA loads issued by this CTA
 
     for (int e = tid; e < KP * KP; e += blockDim.x) {
         sT[e] = hdr[e];
         sVc[e] = hdr[KP * KP + e];
     }
+    if (QUAD)
+        for (int e = tid; e < KP * KP + KP; e += blockDim.x) sM[e] = hdr[PFB_HDR_M(KP) + e];  // M, then rv
     for (int e = tid; e < PF_ZIG_LAYERS * PFB_K3_ZREP; e += blockDim.x) {
         const pf_zig_kw_t kw = PF_ZIG_KW_DEV[e / PFB_K3_ZREP];
         pfb_zig_e ze;
@@ -244,27 +255,32 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
     const double logdet = hdr[PFB_HDR_LOGDET(KP)];
     const bool pd_ok = hdr[PFB_HDR_FLAG(KP)] != 0.0;
     const int H = min(KP, n);          // head rows
-    const int nblk = npad >> 3;        // 8-row blocks
     const bool tail_special = (n & 7) != 0;
 
-    // lane-constant fragment offsets (doubles) inside an 8-row block
-    // (byte offsets)
-    uint32_t off0[2][NT0];  // pass 0: Vh[row 2t+e][j = 8h+g]
+    // lane-constant fragment offsets (bytes) inside an 8-row block.
+    // pass 0: column cc = 8h + g of row 2t+e;  two-pass: cc = j (Vh[row][j]);  single pass: cc < KP
+    // is Vh[row][cc], cc >= KP is p_row * Vh[row][cc - KP].
+    uint32_t off0[2][NT0];
+    bool scaled[NT0];  // this lane's column of tile h is a p-scaled one (QUAD)
 #pragma unroll
-    for (int e = 0; e < 2; ++e)
+    for (int h = 0; h < NT0; ++h) {
+        const int cc = 8 * h + g;
+        scaled[h] = QUAD && cc >= KP;
+        const int j = scaled[h] ? cc - KP : cc;
 #pragma unroll
-        for (int h = 0; h < NT0; ++h)
-            off0[e][h] = 8u * (uint32_t)((2 * t + e) * RS2 + ((8 * h + g) ^ pfb_swz(2 * t + e)));
+        for (int e = 0; e < 2; ++e)
+            off0[e][h] = 8u * (uint32_t)((2 * t + e) * RS2 + ((j < RS2 ? j : 0) ^ pfb_swz(2 * t + e)));
+    }
     uint32_t off1[NS1];     // pass 1: Vh[row g][j = 4s+t]
 #pragma unroll
     for (int s = 0; s < NS1; ++s) off1[s] = 8u * (uint32_t)(g * RS2 + ((4 * s + t) ^ pfb_swz(g)));
-    uint32_t offam[2];      // {sqrt(alpha), mu} of row 2t+e
+    uint32_t offam[2];      // {sqrt(alpha), mu} of row 2t+e;  {p, r} sit 16 bytes further
 #pragma unroll
     for (int e = 0; e < 2; ++e) offam[e] = 8u * (uint32_t)((2 * t + e) * RS2 + (KP ^ pfb_swz(2 * t + e)));
 
     const uint32_t zig_base = pfb_smem_u32(sZig + (lane & (PFB_K3_ZREP - 1)));
     pfb_k3_warp_list& wl = sList[warp];
-    double* cw = sC + (size_t)warp * DS * 8 * KP;  // this warp's [DS][8][KP]: w, then c = T w
+    double* cw = sC + (size_t)warp * DS * 8 * CWW;  // this warp's [DS][8][CWW]: w (| Vh'(p u~)), then c = T w
 
     int q = 0;  // TMA load sequence number of the next chunk to consume (ring mode)
     bool first_pass = true;
@@ -280,21 +296,24 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
         }
         double unormsq[DS];
         pfb_model_acc<MODEL> macc[DS];
-        double wacc[DS][NT0][2];  // pass 0 accumulators: w[draw g][j = 8h + 2t + {0,1}]
+        double wacc[DS][NT0][2];  // pass 0 accumulators: column cc = 8h + 2t + {0,1} of draw g
         double ncf[DS][NS1];      // pass 1 A fragments: -c[draw g][j = 4s + t]
+        double qsum[DS], s1sum[DS], u0[DS];  // QUAD: sum p u~^2, sum r u~, u~_0 (lane t = 0)
 #pragma unroll
         for (int d = 0; d < DS; ++d) {
             unormsq[d] = 0.0;
+            qsum[d] = s1sum[d] = u0[d] = 0.0;
             macc[d].init();
 #pragma unroll
             for (int h = 0; h < NT0; ++h) wacc[d][h][0] = wacc[d][h][1] = 0.0;
 #pragma unroll
             for (int s1 = 0; s1 < NS1; ++s1) ncf[d][s1] = 0.0;
         }
-        for (int e = lane; e < DS * 8 * KP; e += 32) cw[e] = 0.0;  // slow-path corrections of w
+        for (int e = lane; e < DS * 8 * CWW; e += 32) cw[e] = 0.0;  // slow-path corrections of w
         __syncwarp();
 
-        // One pass over all chunks.  PS::value = 0: accumulate w = Vh' u~;  1: x and the model sums.
+        // One pass over all chunks.  PS::value = 0: accumulate w = Vh' u~ (QUAD: and the other
+        // statistics);  1: x and the model sums.
         auto run_pass = [&](auto PS) {
             constexpr int PASS = decltype(PS)::value;
             // ---- head: u~[0..H) = Vc' u[0..H)  (src/woodbury.jl:139); recomputed in each pass ------
@@ -343,6 +362,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                         }
                         zhd[d][bb][e] = acc;
                     }
+                if (QUAD) u0[d] = zhd[d][0][0];  // u~ of row 0 (meaningful in lane t = 0)
             }
 
 #pragma unroll 1
@@ -426,18 +446,34 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                     nib &= actmask;  // (z of a rejected element is already 0)
                     pend = (pend << 4) | nib;
                     if (PASS == 0) {
-                        if (!(SPECIAL && R < H)) {  // head rows' |u|^2 was added with the raw normals
+                        const bool headrow = SPECIAL && R < H;  // |u|^2 of head rows: added with the raw normals
+                        double2 pr[2];
+                        if (QUAD) {
 #pragma unroll
-                            for (int d = 0; d < DS; ++d) {
-                                unormsq[d] = fma(z[d][0], z[d][0], unormsq[d]);
-                                unormsq[d] = fma(z[d][1], z[d][1], unormsq[d]);
-                            }
+                            for (int e = 0; e < 2; ++e) pr[e] = pfb_lds128(blk + offam[e] + 16u);  // {p, r}
                         }
+#pragma unroll
+                        for (int d = 0; d < DS; ++d)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                if (QUAD) {
+                                    const double zz = z[d][e] * z[d][e];
+                                    if (!headrow) unormsq[d] += zz;
+                                    qsum[d] = fma(pr[e].x, zz, qsum[d]);
+                                    s1sum[d] = fma(pr[e].y, z[d][e], s1sum[d]);
+                                } else if (!headrow) {
+                                    unormsq[d] = fma(z[d][e], z[d][e], unormsq[d]);
+                                }
+                            }
                         double vf[2][NT0];
 #pragma unroll
                         for (int e = 0; e < 2; ++e)
 #pragma unroll
-                            for (int h = 0; h < NT0; ++h) vf[e][h] = pfb_lds64(blk + off0[e][h]);
+                            for (int h = 0; h < NT0; ++h) {
+                                vf[e][h] = pfb_lds64(blk + off0[e][h]);
+                                if (QUAD && 8 * h + 7 >= KP)  // tile holds p-scaled columns
+                                    vf[e][h] *= (8 * h >= KP || scaled[h]) ? pr[e].x : 1.0;
+                            }
 #pragma unroll
                         for (int e = 0; e < 2; ++e)
 #pragma unroll
@@ -493,36 +529,15 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                 int o_end = nb;
                 if (tail_special && r0 + nb * 8 == npad && o_end > o_fast) --o_end;
                 int o = 0;
-                double zc[DS][2] = {}, zn[DS][2];
-                uint32_t nibc = 0u, nibn;
+                double zc[DS][2] = {};
+                uint32_t nibc = 0u;
 #pragma unroll 1
                 for (; o < o_fast; ++o) block(pfb_ic<1>{}, o, zc, 0u);
-                // software pipeline: the normals of block o+1 are generated in the same basic block
-                // as the tensor-core work of block o, so the DMMAs interleave with the integer work
-#if PFB_K3_SWP
-                if (o < o_end) {
-                    gen(o, zc, nibc);
-#pragma unroll 1
-                    for (; o < o_end - 1; ++o) {
-                        gen(o + 1, zn, nibn);
-                        block(pfb_ic<0>{}, o, zc, nibc);
-#pragma unroll
-                        for (int d = 0; d < DS; ++d) {
-                            zc[d][0] = zn[d][0];
-                            zc[d][1] = zn[d][1];
-                        }
-                        nibc = nibn;
-                    }
-                    block(pfb_ic<0>{}, o, zc, nibc);
-                    ++o;
-                }
-#else
 #pragma unroll 1
                 for (; o < o_end; ++o) {
                     gen(o, zc, nibc);
                     block(pfb_ic<0>{}, o, zc, nibc);
                 }
-#endif
 #pragma unroll 1
                 for (; o < nb; ++o) block(pfb_ic<1>{}, o, zc, 0u);
 
@@ -580,12 +595,23 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                                             const double zz = wl.z[flat];
                                             const double* rr = st + row * RS2;
                                             const int swz = pfb_swz(row);
-                                            double* cv = cw + (dsi * 8 + g) * KP;
+                                            double* cv = cw + (dsi * 8 + g) * CWW;
+                                            const double pz = QUAD ? rr[(KP + 2) ^ swz] * zz : 0.0;
 #pragma unroll
-                                            for (int j = 0; j < KP; ++j) cv[j] = fma(rr[j ^ swz], zz, cv[j]);
+                                            for (int j = 0; j < KP; ++j) {
+                                                const double v = rr[j ^ swz];
+                                                cv[j] = fma(v, zz, cv[j]);
+                                                if (QUAD) cv[KP + j] = fma(v, pz, cv[KP + j]);
+                                            }
 #pragma unroll
                                             for (int d = 0; d < DS; ++d)
-                                                if (d == dsi) unormsq[d] = fma(zz, zz, unormsq[d]);
+                                                if (d == dsi) {
+                                                    unormsq[d] = fma(zz, zz, unormsq[d]);
+                                                    if (QUAD) {
+                                                        qsum[d] = fma(pz, zz, qsum[d]);
+                                                        s1sum[d] = fma(rr[(KP + 3) ^ swz], zz, s1sum[d]);
+                                                    }
+                                                }
                                         }
                                         ++flat;
                                     }
@@ -602,7 +628,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                                     const int row = row_of(bit), dsi = (bit >> 1) & 1;
                                     const double* rr = st + row * RS2;
                                     const int swz = pfb_swz(row);
-                                    const double* cv = cw + (dsi * 8 + g) * KP;
+                                    const double* cv = cw + (dsi * 8 + g) * CWW;
                                     double zz = wl.z[flat];
 #pragma unroll
                                     for (int j = 0; j < KP; ++j) zz = fma(-rr[j ^ swz], cv[j], zz);
@@ -642,8 +668,8 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                 for (int h = 0; h < NT0; ++h)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int j = 8 * h + 2 * t + e;
-                        if (j < KP) cw[(d * 8 + g) * KP + j] += wacc[d][h][e];
+                        const int cc = 8 * h + 2 * t + e;
+                        if (cc < CWW) cw[(d * 8 + g) * CWW + cc] += wacc[d][h][e];
                     }
             __syncwarp();
             double cf[DS][NS1];
@@ -655,7 +681,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                     double acc = 0.0;
 #pragma unroll
                     for (int bcol = 0; bcol < KP; ++bcol)
-                        if (bcol >= a) acc = fma(sT[a * KP + bcol], cw[(d * 8 + g) * KP + bcol], acc);
+                        if (bcol >= a) acc = fma(sT[a * KP + bcol], cw[(d * 8 + g) * CWW + bcol], acc);
                     cf[d][s1] = acc;
                 }
             __syncwarp();
@@ -663,12 +689,39 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
             for (int d = 0; d < DS; ++d)
 #pragma unroll
                 for (int s1 = 0; s1 < NS1; ++s1) {
-                    cw[(d * 8 + g) * KP + 4 * s1 + t] = cf[d][s1];
+                    cw[(d * 8 + g) * CWW + 4 * s1 + t] = cf[d][s1];
                     ncf[d][s1] = -cf[d][s1];
                 }
             __syncwarp();
+            if (QUAD) {
+                // S = q + 2 s1 + e0 + sum_a c_a (-2 (Vh'(p u~))_a - 2 rv_a + (M c)_a);  x_0 from row 0
+                const double e0 = hdr[PFB_HDR_E0(KP)];
+                const double* sRv = sM + KP * KP;
+#pragma unroll
+                for (int d = 0; d < DS; ++d) {
+                    const double* cv = cw + (d * 8 + g) * CWW;
+                    double part = 0.0, v0c = 0.0;
+#pragma unroll
+                    for (int s1 = 0; s1 < NS1; ++s1) {
+                        const int a = 4 * s1 + t;
+                        double mc = 0.0;
+#pragma unroll
+                        for (int kk = 0; kk < KP; ++kk) mc = fma(sM[a * KP + kk], cv[kk], mc);
+                        part = fma(cf[d][s1], mc - 2.0 * (cv[KP + a] + sRv[a]), part);
+                        v0c = fma(fr[a], cf[d][s1], v0c);  // Vh[0][a] c_a (row 0: swizzle 0)
+                    }
+                    part += qsum[d] + 2.0 * s1sum[d];
+                    part += __shfl_xor_sync(0xffffffffu, part, 1);
+                    part += __shfl_xor_sync(0xffffffffu, part, 2);
+                    v0c += __shfl_xor_sync(0xffffffffu, v0c, 1);
+                    v0c += __shfl_xor_sync(0xffffffffu, v0c, 2);
+                    const double ut0 = __shfl_sync(0xffffffffu, u0[d], lane & ~3);  // u~_0 lives in lane t = 0
+                    macc[d].a = part + e0;
+                    macc[d].b = fma(fr[KP], ut0 - v0c, fr[KP + 1]);  // x_0 = a_0 (u~_0 - v_0'c) + mu_0
+                }
+            }
         }
-        run_pass(pfb_ic<1>{});
+        if (!QUAD) run_pass(pfb_ic<1>{});
 
         // ---- per-draw results ---------------------------------------------------------------------
 #pragma unroll
@@ -676,7 +729,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
             double us = unormsq[d];
             us += __shfl_xor_sync(0xffffffffu, us, 1);
             us += __shfl_xor_sync(0xffffffffu, us, 2);
-            macc[d].group_reduce();
+            if (!QUAD) macc[d].group_reduce();
             if (t == 0 && ((actmask >> (2 * d)) & 1u)) {
                 double logq = (fma((double)n, PFB_LOG2PI, logdet) + us) / -2.0;
                 if (!pd_ok) logq = NAN;
@@ -688,10 +741,11 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
     }
 }
 
-static size_t k3_smem_bytes(int KP, int NS, int NW) {
+static size_t k3_smem_bytes(int KP, int NS, int NW, bool quad) {
     const int RS2 = pfb_rs2_of(KP);
     return (size_t)NS * PFB_K3_RC * RS2 * 8 + (size_t)PF_ZIG_LAYERS * PFB_K3_ZREP * sizeof(pfb_zig_e) +
-           (size_t)2 * KP * KP * 8 + (size_t)NW * PFB_K3_DS * 8 * KP * 8 + (size_t)NW * sizeof(pfb_k3_warp_list) +
+           (size_t)2 * KP * KP * 8 + (quad ? (size_t)(KP * KP + KP) * 8 : 0) +
+           (size_t)NW * PFB_K3_DS * 8 * (quad ? 2 * KP : KP) * 8 + (size_t)NW * sizeof(pfb_k3_warp_list) +
            (size_t)(NS + 1) * 8;
 }
 
@@ -699,8 +753,11 @@ template <int KP, int MODEL>
 static cudaError_t launch_k3_m(cudaStream_t st, int n, int K, int nslots, const int32_t* unit_list,
                                const double* FR2, const double* HDR, const uint64_t* seeds,
                                const double* u_host, pfb_model_params mp, double* logp, double* logq,
-                               double* draws) {
+                               double* draws, int two_pass) {
     if (nslots <= 0) return cudaSuccess;
+    // every registered family is diagonal-quadratic, so the lean path runs single pass unless
+    // the caller asks for the generic two-pass kernel (or wants x written out)
+    const bool quad = (draws == nullptr) && !two_pass;
     int dev = 0, nsm = 148, smem_max = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -712,15 +769,16 @@ static cudaError_t launch_k3_m(cudaStream_t st, int n, int K, int nslots, const 
     const int S = (K + DPS - 1) / DPS;
     const int C = (pfb_npad8(n) + PFB_K3_RC - 1) / PFB_K3_RC;
     int NS = C;
-    while (NS > 1 && k3_smem_bytes(KP, NS, NW) > (size_t)smem_max) --NS;
-    const size_t smem = k3_smem_bytes(KP, NS, NW);
+    while (NS > 1 && k3_smem_bytes(KP, NS, NW, quad) > (size_t)smem_max) --NS;
+    const size_t smem = k3_smem_bytes(KP, NS, NW, quad);
     if (smem > (size_t)smem_max) return cudaErrorInvalidConfiguration;
     // split a unit's sweeps over several CTAs only when there are too few units to fill the GPU
     int splits = (4 * nsm + nslots - 1) / nslots;
     splits = splits < 1 ? 1 : (splits > S ? S : splits);
     const int64_t grid = (int64_t)nslots * splits;
     if (grid > 2147483647LL) return cudaErrorInvalidValue;
-    auto kern = draws ? pfb_k3_elbo_sample<KP, MODEL, true> : pfb_k3_elbo_sample<KP, MODEL, false>;
+    auto kern = draws ? pfb_k3_elbo_sample<KP, MODEL, 1>
+                      : (quad ? pfb_k3_elbo_sample<KP, MODEL, 2> : pfb_k3_elbo_sample<KP, MODEL, 0>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(unsigned)grid, NW * 32, smem, st>>>(n, K, splits, NS, unit_list, FR2, HDR, seeds, u_host, mp, logp,
@@ -732,17 +790,17 @@ template <int KP>
 static cudaError_t launch_k3_k(cudaStream_t st, int model, int n, int K, int nslots,
                                const int32_t* unit_list, const double* FR2, const double* HDR,
                                const uint64_t* seeds, const double* u_host, pfb_model_params mp,
-                               double* logp, double* logq, double* draws) {
+                               double* logp, double* logq, double* draws, int two_pass) {
     switch (model) {
         case PFB_MODEL_ISONORMAL:
             return launch_k3_m<KP, PFB_MODEL_ISONORMAL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host,
-                                                        mp, logp, logq, draws);
+                                                        mp, logp, logq, draws, two_pass);
         case PFB_MODEL_FUNNEL:
             return launch_k3_m<KP, PFB_MODEL_FUNNEL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host, mp,
-                                                     logp, logq, draws);
+                                                     logp, logq, draws, two_pass);
         case PFB_MODEL_DIAGNORMAL:
             return launch_k3_m<KP, PFB_MODEL_DIAGNORMAL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host,
-                                                         mp, logp, logq, draws);
+                                                         mp, logp, logq, draws, two_pass);
     }
     return cudaErrorInvalidValue;
 }
@@ -753,8 +811,8 @@ extern "C" cudaError_t PFB_K3_ENTRY(cudaStream_t st, int model, int n, int K, in
                                     const int32_t* unit_list, const double* FR2, const double* HDR,
                                     const uint64_t* seeds, const double* u_host, const double* mp0,
                                     const double* mp1, double mc0, double* logp, double* logq,
-                                    double* draws) {
+                                    double* draws, int two_pass) {
     pfb_model_params mp{mp0, mp1, mc0};
     return launch_k3_k<PFB_K3_KP>(st, model, n, K, nslots, unit_list, FR2, HDR, seeds, u_host, mp, logp, logq,
-                                  draws);
+                                  draws, two_pass);
 }

@@ -15,11 +15,12 @@ extern "C" {
 cudaError_t pfb_launch_k1(cudaStream_t, int, int, int, double, const double*, const double*, const int64_t*,
                           double*, int32_t*, int32_t*, int64_t*);
 cudaError_t pfb_launch_k2(cudaStream_t, int, int, int, int, const double*, const double*, const int32_t*,
-                          const double*, const int32_t*, const int32_t*, double*, double*, double*);
+                          const double*, const int32_t*, const int32_t*, double*, double*, double*, int,
+                          const double*, const double*);
 #define PFB_DECL_K3(name)                                                                                  \
     cudaError_t name(cudaStream_t, int, int, int, int, const int32_t*, const double*, const double*,        \
                      const uint64_t*, const double*, const double*, const double*, double, double*, double*, \
-                     double*);
+                     double*, int);
 PFB_DECL_K3(pfb_launch_k3_kp12)
 PFB_DECL_K3(pfb_launch_k3_kp20)
 PFB_DECL_K3(pfb_launch_k3_kp24)
@@ -273,7 +274,7 @@ static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list
     const double* un = h->have_normals ? h->dNormals.as<double>() : nullptr;
     auto fn = h->KP == 12 ? pfb_launch_k3_kp12 : (h->KP == 20 ? pfb_launch_k3_kp20 : pfb_launch_k3_kp24);
     return fn(h->stream, h->model, h->n, h->K, nslots, unit_list, h->dFR2.as<double>(), h->dHDR.as<double>(),
-              h->dSeeds.as<uint64_t>(), un, mp0, mp1, h->model_c0, logp, logq, draws);
+              h->dSeeds.as<uint64_t>(), un, mp0, mp1, h->model_c0, logp, logq, draws, h->cfg.elbo_mode == 1);
 }
 
 extern "C" int pfb_batch_run(pfb_handle h) {
@@ -292,7 +293,8 @@ extern "C" int pfb_batch_run(pfb_handle h) {
     PFB_CUDA(h, cudaEventRecord(h->ev[1], st));
     PFB_CUDA(h, pfb_launch_k2(st, KP, n, U, J, h->dX.as<double>(), h->dG.as<double>(), h->dUnitCol.as<int32_t>(),
                               h->dAlpha.as<double>(), h->dHist.as<int32_t>(), h->dHistCnt.as<int32_t>(),
-                              h->dFR.as<double>(), h->dHDR.as<double>(), h->dFR2.as<double>()));
+                              h->dFR.as<double>(), h->dHDR.as<double>(), h->dFR2.as<double>(), h->model,
+                              h->dModel.as<double>(), h->dModel.p ? h->dModel.as<double>() + h->model_n : nullptr));
     h->launches += (U > 0);
     PFB_CUDA(h, cudaEventRecord(h->ev[2], st));
     PFB_CUDA(h, launch_k3(h, U, nullptr, h->dLogp.as<double>(), h->dLogq.as<double>(),
@@ -329,7 +331,7 @@ __global__ void pfb_gather_fit(int n, int KP, const int32_t* __restrict__ best_u
                                int32_t* jeff) {
     const int p = blockIdx.x;
     const int u = best_unit[p];
-    const int RS = KP + 2, HS = 2 * KP * KP + 4;
+    const int RS = KP + 2, HS = pfb_hs_of(KP);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         if (u >= 0) {
             const double* row = FR + ((int64_t)u * n + i) * RS;

@@ -44,12 +44,12 @@ class ElboBatchResult:
 
 class Engine:
     def __init__(self, n, model_family, model_blob=None, history_length=6, ndraws_elbo=5,
-                 device=0, materialize_all=False, eps=1e-12):
+                 device=0, materialize_all=False, eps=1e-12, two_pass=False):
         self.lib = _lib.load()
         self.n = int(n)
         self.K = int(ndraws_elbo)
         self.J = int(history_length)
-        cfg = pfb_config(int(device), self.J, self.K, int(bool(materialize_all)), float(eps))
+        cfg = pfb_config(int(device), self.J, self.K, int(bool(materialize_all)), int(bool(two_pass)), 0, float(eps))
         h = C.c_void_p()
         rc = self.lib.pfb_create(C.byref(h), C.byref(cfg))
         if rc != 0:

@@ -280,3 +280,69 @@ def test_multipathfinder_end_to_end_matches_oracle_pipeline():
     from oracle import pf_oracle as O
     for pr in res.pathfinder_results:
         np.testing.assert_allclose(pr.draws_logp, O.logp_funnel(pr.draws), rtol=1e-9, atol=1e-9)
+
+
+def _lean_vs_oracle(model, trajs, K, J, normals=False, rtol=RTOL):
+    """The lean ELBO stage (single pass: log p from quadratic-form statistics, the normals generated
+    once) against the oracle and against the generic two-pass kernel."""
+    import pathfinder_b200 as pf
+    from tests.helpers import oracle_batch
+
+    seeds = _seeds(trajs, 3)
+    offsets, X, G = pf.Engine.pack(trajs)
+    U = int(offsets[-1]) - len(trajs)
+    nrm = None
+    if normals:
+        nrm = np.asfortranarray(np.random.default_rng(5).normal(size=(model.n, K, U)))
+    sd = np.concatenate(seeds) if U else np.zeros(0, np.uint64)
+    orc = oracle_batch(model, trajs, seeds, K, J, normals=nrm)
+    out = {}
+    for two_pass in (False, True):
+        eng = _engine(model, K, J, two_pass=two_pass)
+        out[two_pass] = eng.elbo_batch(offsets, X, G, sd, nrm, draws=True, per_draw=True)
+        eng.close()
+    a, b = out[False], out[True]
+    for p, o in enumerate(orc):
+        sl = a.unit_slice(p)
+        for l, e in enumerate(o["ests"]):
+            u = sl.start + l
+            scale = max(1.0, float(np.max(np.abs(e["logp"]))))
+            np.testing.assert_allclose(a.logq[:, u], e["logq"], rtol=rtol, atol=rtol)
+            np.testing.assert_allclose(a.logp[:, u], e["logp"], rtol=rtol, atol=rtol * scale)
+            assert abs(a.elbo[u] - e["value"]) <= rtol * max(1.0, abs(e["value"]))
+            # the two device formulations agree far below the parity tolerance
+            np.testing.assert_allclose(a.logp[:, u], b.logp[:, u], rtol=1e-9, atol=1e-9 * scale)
+            np.testing.assert_allclose(a.logq[:, u], b.logq[:, u], rtol=1e-13, atol=1e-12)  # |u|^2 rounding
+        assert a.best_iter[p] == o["lopt"] == b.best_iter[p]
+    assert np.array_equal(a.draws, b.draws)  # K5 is the same kernel in both engines
+
+
+@pytest.mark.parametrize("n", [1, 7, 12, 16, 100, 257])
+def test_lean_single_pass_isonormal(n):
+    import pathfinder_b200 as pf
+    from tests.helpers import synthetic_trajectory
+
+    _lean_vs_oracle(pf.IsoNormal(n), [synthetic_trajectory(n, L, 60 + n + L) for L in (1, 5, 11)], K=48, J=6)
+
+
+def test_lean_single_pass_funnel_diagnormal_history10_host_normals():
+    import pathfinder_b200 as pf
+    from tests.helpers import synthetic_trajectory
+
+    rng = np.random.default_rng(8)
+    n = 40
+    trajs = [synthetic_trajectory(n, L, 80 + L, scale=0.3) for L in (2, 9)]
+    _lean_vs_oracle(pf.Funnel(n), trajs, K=64, J=6)
+    _lean_vs_oracle(pf.DiagNormal(rng.normal(size=n), rng.random(n) + 0.5), trajs, K=64, J=6)
+    _lean_vs_oracle(pf.IsoNormal(n), [synthetic_trajectory(n, 14, 91)], K=40, J=10)
+    _lean_vs_oracle(pf.IsoNormal(n), [synthetic_trajectory(n, 14, 92)], K=40, J=12)
+    _lean_vs_oracle(pf.Funnel(n), trajs, K=24, J=6, normals=True)
+
+
+def test_lean_single_pass_ring_mode_large_n():
+    """n = 1500 does not fit the shared-memory stage: the factor record streams through the ring."""
+    import pathfinder_b200 as pf
+    from tests.helpers import synthetic_trajectory
+
+    n = 1500
+    _lean_vs_oracle(pf.Funnel(n), [synthetic_trajectory(n, 4, 77, scale=0.2)], K=300, J=6)

@@ -40,7 +40,7 @@ def test_struct_layouts_match_header():
 
     from pathfinder_b200 import _lib
 
-    assert C.sizeof(_lib.pfb_config) == 24
+    assert C.sizeof(_lib.pfb_config) == 32
     assert C.sizeof(_lib.pfb_elbo_out) == 18 * C.sizeof(C.c_void_p)
     assert C.sizeof(_lib.pfb_resample_out) == 7 * C.sizeof(C.c_void_p)
     assert C.sizeof(_lib.pfb_device_view) == 5 * C.sizeof(C.c_void_p) + 4 * 8
@@ -65,9 +65,9 @@ def test_argument_errors_do_not_need_a_device():
 
     lib = _lib.load()
     h = C.c_void_p()
-    bad = _lib.pfb_config(0, 0, 5, 0, 1e-12)  # history_length = 0
+    bad = _lib.pfb_config(0, 0, 5, 0, 0, 0, 1e-12)  # history_length = 0
     assert lib.pfb_create(C.byref(h), C.byref(bad)) == -1
-    bad = _lib.pfb_config(0, 13, 5, 0, 1e-12)  # history_length > 12 unsupported
+    bad = _lib.pfb_config(0, 13, 5, 0, 0, 0, 1e-12)  # history_length > 12 unsupported
     assert lib.pfb_create(C.byref(h), C.byref(bad)) == -3
     assert lib.pfb_create(None, None) == -1
     assert lib.pfb_batch_run(None) == -1 and lib.pfb_destroy(None) == 0
