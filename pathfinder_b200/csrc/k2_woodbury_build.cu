@@ -15,9 +15,14 @@
 #include "pfb_common.cuh"
 
 #define PFB_K2_THREADS 256
+#define PFB_K2_THREADS_SMEM 512
+#define PFB_K2_SCRATCH(KP) ((KP) * 16 * 8 + (KP) + 1)  // doubles; keeps the panel 16-byte aligned for even KP
 
-template <int KP>
-__global__ void __launch_bounds__(PFB_K2_THREADS)
+// The unit's n x (KP+2) panel { A~ -> Vh, sqrt(alpha), t -> mu } lives in shared memory, column-major
+// (conflict-free for thread-per-row access), when it fits (SMEM_PANEL: n (KP+2) 8 bytes <= ~200 KB,
+// i.e. n <= 1800 at history 6); otherwise in the FR rows in global memory (L2 resident).
+template <int KP, bool SMEM_PANEL>
+__global__ void __launch_bounds__(SMEM_PANEL ? PFB_K2_THREADS_SMEM : PFB_K2_THREADS)
 pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* __restrict__ G,
                       const int32_t* __restrict__ unit_col, const double* __restrict__ alpha_all,
                       const int32_t* __restrict__ hist, const int32_t* __restrict__ hist_cnt,
@@ -25,7 +30,6 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
                       int model, const double* __restrict__ mp0, const double* __restrict__ mp1) {
     constexpr int RS = KP + 2;
     constexpr int JM = KP / 2;
-    __shared__ double scratch[KP * 32];
     __shared__ double sStY[JM][JM], sYaY[JM][JM], sNRinv[JM][JM], sM[JM][JM];
     __shared__ double sD[KP][KP], sRq[KP][KP], sE[KP][KP], sC[KP][KP], sVc[KP][KP], sT[KP][KP];
     __shared__ double sVtV[KP][KP];
@@ -38,7 +42,13 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
     const int jeff = hist_cnt[u];
     const int kc = 2 * jeff;
     const int kq = min(n, kc);
-    double* fr = FR + (int64_t)u * n * RS;
+    extern __shared__ __align__(16) double s_dyn[];  // scratch of pfb_block_sum_fast, then the panel
+    double* scratch = s_dyn;                          // KP * 16 * 8 + KP (<= 16 warps)
+    double* s_panel = s_dyn + PFB_K2_SCRATCH(KP);     // SMEM_PANEL: [KP+2][ldp]
+    const int ldp = (n + 1) | 1;  // odd leading dimension
+    double* fr = SMEM_PANEL ? nullptr : FR + (int64_t)u * n * RS;
+    // element (row i, column c) of the panel
+#define PNL(i, c) (*(SMEM_PANEL ? (s_panel + (c) * ldp + (i)) : (fr + (int64_t)(i) * RS + (c))))
     double* hdr = HDR + (int64_t)u * pfb_hs_of(KP);
     const double* alpha = alpha_all + (int64_t)u * n;
     const int64_t col = unit_col[u];
@@ -50,17 +60,16 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
     for (int i = tid; i < n; i += nt) {
         double a = alpha[i];
         double sa = sqrt(a);
-        double* row = fr + (int64_t)i * RS;
         for (int j = 0; j < jeff; ++j) {
             int64_t c = hu[j];
             double s = X[(c + 1) * n + i] - X[c * n + i];
             double y = G[c * n + i] - G[(c + 1) * n + i];
-            row[j] = (a * y) / sa;
-            row[jeff + j] = s / sa;
+            PNL(i, j) = (a * y) / sa;
+            PNL(i, jeff + j) = s / sa;
         }
-        for (int j = kc; j < KP; ++j) row[j] = 0.0;
-        row[KP] = sa;
-        row[KP + 1] = sa * g[i];  // scratch for phase H: t = U g
+        for (int j = kc; j < KP; ++j) PNL(i, j) = 0.0;
+        PNL(i, KP) = sa;
+        PNL(i, KP + 1) = sa * g[i];  // scratch for phase H: t = U g
     }
     if (tid == 0) sFlag = 1;
     // zero-init small matrices
@@ -74,28 +83,28 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
     __syncthreads();
 
     if (jeff > 0) {
-        // ---- Gram blocks of A~: S'Y = A2' A1, Y' diag(alpha) Y = A1' A1 ------------------------
+        // ---- Gram blocks of A~: S'Y = A2' A1, Y' diag(alpha) Y = A1' A1 (upper triangles) ---------
         for (int a = 0; a < jeff; ++a) {
             double acc[KP];
 #pragma unroll
             for (int b = 0; b < KP; ++b) acc[b] = 0.0;
             for (int i = tid; i < n; i += nt) {
-                const double* row = fr + (int64_t)i * RS;
-                double sa_ = row[jeff + a], ya_ = row[a];
+                double sa_ = PNL(i, jeff + a), ya_ = PNL(i, a);
 #pragma unroll
                 for (int b = 0; b < JM; ++b) {
-                    if (b < jeff) {
-                        double yb = row[b];
+                    if (b >= a && b < jeff) {
+                        double yb = PNL(i, b);
                         acc[b] = fma(sa_, yb, acc[b]);
                         acc[JM + b] = fma(ya_, yb, acc[JM + b]);
                     }
                 }
             }
-            pfb_block_sum<KP>(acc, scratch);
+            const unsigned tri = ((1u << jeff) - 1u) & ~((1u << a) - 1u);  // b in [a, jeff)
+            pfb_block_sum_fast<KP>(acc, scratch, tri | (tri << JM));
             if (tid == 0) {
 #pragma unroll
                 for (int b = 0; b < JM; ++b) {
-                    if (b < jeff) {
+                    if (b >= a && b < jeff) {
                         sStY[a][b] = acc[b];
                         sYaY[a][b] = acc[JM + b];
                     }
@@ -141,53 +150,49 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
 
         // ---- Phase C: Householder QR in place (dgeqr2 / dlarfg / dlarf conventions) ------------
         for (int j = 0; j < kq; ++j) {
-            double ss[1] = {0.0};
-            for (int i = tid; i < n; i += nt) {
-                if (i > j) {
-                    double x = fr[(int64_t)i * RS + j];
-                    ss[0] = fma(x, x, ss[0]);
-                }
-                if (i == j) sBcast[0] = fr[(int64_t)i * RS + j];
-            }
-            pfb_block_sum<1>(ss, scratch);
-            const double ajj = sBcast[0];
-            double tau = 0.0, beta = ajj, scale = 0.0;
-            if (ss[0] != 0.0) {
-                beta = -copysign(sqrt(fma(ajj, ajj, ss[0])), ajj);
-                tau = (beta - ajj) / beta;
-                scale = 1.0 / (ajj - beta);
-            }
+            // one reduction per reflector: acc[j] = sum_{i>j} a_ij^2, acc[c] = sum_{i>j} a_ij a_ic on
+            // the unscaled column; v = scale * a_j (v_j = 1) then gives v'a_c = scale acc[c] + a_jc
             double acc[KP];
 #pragma unroll
             for (int c = 0; c < KP; ++c) acc[c] = 0.0;
+            for (int i = tid; i < n; i += nt) {
+                if (i > j) {
+                    const double x = PNL(i, j);
+#pragma unroll
+                    for (int c = 0; c < KP; ++c)
+                        if (c < kc) acc[c] = fma(x, (c == j) ? x : PNL(i, c), acc[c]);
+                }
+            }
+            pfb_block_sum_fast<KP>(acc, scratch, (kc >= 32) ? 0xffffffffu : ((1u << kc) - 1u));
+            double ss = 0.0;
+#pragma unroll
+            for (int c = 0; c < KP; ++c)
+                if (c == j) ss = acc[c];
+            const double ajj = PNL(j, j);
+            double tau = 0.0, beta = ajj, scale = 0.0;
+            if (ss != 0.0) {
+                beta = -copysign(sqrt(fma(ajj, ajj, ss)), ajj);
+                tau = (beta - ajj) / beta;
+                scale = 1.0 / (ajj - beta);
+            }
+            // v'a_c for c != j (row j contributes a_jc because v_j = 1); 0 when tau == 0
+#pragma unroll
+            for (int c = 0; c < KP; ++c)
+                acc[c] = (tau != 0.0 && c < kc && c != j) ? fma(scale, acc[c], PNL(j, c)) : 0.0;
+            __syncthreads();  // every thread has read row j before it is updated
             if (tau != 0.0) {
                 for (int i = tid; i < n; i += nt) {
-                    double* row = fr + (int64_t)i * RS;
                     if (i > j) {
-                        double v = row[j] * scale;
-                        row[j] = v;
+                        const double v = PNL(i, j) * scale;
+                        PNL(i, j) = v;
 #pragma unroll
                         for (int c = 0; c < KP; ++c)
-                            if (c < kc && c != j) acc[c] = fma(v, row[c], acc[c]);
+                            if (c > j && c < kc) PNL(i, c) = fma(v, -tau * acc[c], PNL(i, c));
                     } else if (i == j) {
 #pragma unroll
                         for (int c = 0; c < KP; ++c)
-                            if (c < kc && c != j) acc[c] += row[c];
-                    }
-                }
-                pfb_block_sum<KP>(acc, scratch);
-                for (int i = tid; i < n; i += nt) {
-                    double* row = fr + (int64_t)i * RS;
-                    if (i > j) {
-                        double v = row[j];
-#pragma unroll
-                        for (int c = 0; c < KP; ++c)
-                            if (c > j && c < kc) row[c] = fma(v, -tau * acc[c], row[c]);
-                    } else if (i == j) {
-#pragma unroll
-                        for (int c = 0; c < KP; ++c)
-                            if (c > j && c < kc) row[c] = row[c] - tau * acc[c];
-                        row[j] = beta;
+                            if (c > j && c < kc) PNL(i, c) = PNL(i, c) - tau * acc[c];
+                        PNL(i, j) = beta;
                     }
                 }
             }
@@ -217,13 +222,12 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
         }
         // ---- Phase E: Rq to smem, fix up Vh (unit diagonal, zeros above / in padded columns) ----
         for (int i = tid; i < n; i += nt) {
-            double* row = fr + (int64_t)i * RS;
             if (i < kq) {
-                for (int c = i; c < kc; ++c) sRq[i][c] = row[c];
-                row[i] = 1.0;
-                for (int c = i + 1; c < KP; ++c) row[c] = 0.0;
+                for (int c = i; c < kc; ++c) sRq[i][c] = PNL(i, c);
+                PNL(i, i) = 1.0;
+                for (int c = i + 1; c < KP; ++c) PNL(i, c) = 0.0;
             } else {
-                for (int c = kq; c < kc; ++c) row[c] = 0.0;
+                for (int c = kq; c < kc; ++c) PNL(i, c) = 0.0;
             }
         }
         __syncthreads();
@@ -266,8 +270,8 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
 
     // ---- Phase G: logdet = 2 (logdet U + logdet V) ---------------------------------------------
     double ld[1] = {0.0};
-    for (int i = tid; i < n; i += nt) ld[0] += log(fr[(int64_t)i * RS + KP]);
-    pfb_block_sum<1>(ld, scratch);
+    for (int i = tid; i < n; i += nt) ld[0] += log(PNL(i, KP));
+    pfb_block_sum_fast<1>(ld, scratch, 1u);
     double ldv = 0.0;
     for (int j = 0; j < kq; ++j) ldv += log(sVc[j][j]);
     const double logdet = 2.0 * (ld[0] + ldv);
@@ -280,12 +284,12 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
 #pragma unroll
             for (int c = 0; c < KP; ++c) acc[c] = 0.0;
             for (int i = tid; i < n; i += nt) {
-                const double* row = fr + (int64_t)i * RS;
-                double t = row[KP + 1];
+                double t = PNL(i, KP + 1);
 #pragma unroll
-                for (int c = 0; c < KP; ++c) acc[c] = fma(row[c], t, acc[c]);
+                for (int c = 0; c < KP; ++c)
+                    if (c < kq) acc[c] = fma(PNL(i, c), t, acc[c]);
             }
-            pfb_block_sum<KP>(acc, scratch);
+            pfb_block_sum_fast<KP>(acc, scratch, (1u << kq) - 1u);
             if (tid == 0) {
 #pragma unroll
                 for (int c = 0; c < KP; ++c) sW2[c] = acc[c];
@@ -303,12 +307,11 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
             }
             __syncthreads();
             for (int i = tid; i < n; i += nt) {
-                double* row = fr + (int64_t)i * RS;
-                double t = row[KP + 1];
+                double t = PNL(i, KP + 1);
 #pragma unroll
                 for (int c = 0; c < KP; ++c)
-                    if (c < kq) t = fma(-row[c], sW[c], t);
-                row[KP + 1] = t;
+                    if (c < kq) t = fma(-PNL(i, c), sW[c], t);
+                PNL(i, KP + 1) = t;
                 if (pass == 0 && i < kq) sHead[i] = t;
             }
             __syncthreads();
@@ -323,7 +326,7 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
                 if (tid < kq) {
                     double s = 0.0;
                     for (int c = 0; c <= tid; ++c) s = fma(sVc[c][tid], sW2[c], s);
-                    fr[(int64_t)tid * RS + KP + 1] = s;
+                    PNL(tid, KP + 1) = s;
                 }
                 __syncthreads();
             }
@@ -339,11 +342,10 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
     auto model_m = [&](int i) -> double { return model == PFB_MODEL_DIAGNORMAL ? mp0[i] : 0.0; };
     double e0acc[1] = {0.0};
     for (int i = tid; i < n; i += nt) {
-        double* row = fr + (int64_t)i * RS;
         // kq == 0: Sigma = diag(alpha): t = sqrt(alpha) g, mu = theta + sqrt(alpha) t
-        const double sa = row[KP];
-        const double mu = fma(sa, row[KP + 1], theta[i]);
-        row[KP + 1] = mu;
+        const double sa = PNL(i, KP);
+        const double mu = fma(sa, PNL(i, KP + 1), theta[i]);
+        PNL(i, KP + 1) = mu;
         const double d = model_d(i), e = mu - model_m(i);
         e0acc[0] = fma(d * e, e, e0acc[0]);
         if (FR2 != nullptr) {
@@ -355,7 +357,7 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
             const double pi_ = d * alpha[i], ri_ = d * sa * e;
 #pragma unroll
             for (int c = 0; c < RS2; ++c) {
-                double v = (c < KP) ? row[c]
+                double v = (c < KP) ? PNL(i, c)
                                     : (c == KP ? sa : (c == KP + 1 ? mu : (c == KP + 2 ? pi_ : (c == KP + 3 ? ri_ : 0.0))));
                 r2[c ^ sw] = v;
             }
@@ -366,27 +368,34 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
         const int npad = pfb_npad8(n);
         for (int e = n * RS2 + tid; e < npad * RS2; e += nt) FR2[(int64_t)u * npad * RS2 + e] = 0.0;
     }
-    pfb_block_sum<1>(e0acc, scratch);
-    // M = Vh' diag(p) Vh (row a per round), rv = Vh' r
+    pfb_block_sum_fast<1>(e0acc, scratch, 1u);
+    // M = Vh' diag(p) Vh (upper triangle, row a per round; mirrored on store), rv = Vh' r
     for (int a = 0; a <= KP; ++a) {
         double acc[KP];
 #pragma unroll
         for (int b = 0; b < KP; ++b) acc[b] = 0.0;
-        if (a < kq || a == KP) {
+        const unsigned msk = (a < KP) ? (((1u << kq) - 1u) & ~((1u << a) - 1u)) : ((1u << kq) - 1u);
+        if (msk) {
             for (int i = tid; i < n; i += nt) {
-                const double* row = fr + (int64_t)i * RS;
                 const double d = model_d(i);
-                const double wgt = (a < KP) ? d * alpha[i] * row[a] : d * row[KP] * (row[KP + 1] - model_m(i));
+                const double wgt = (a < KP) ? d * alpha[i] * PNL(i, a) : d * PNL(i, KP) * (PNL(i, KP + 1) - model_m(i));
 #pragma unroll
-                for (int b = 0; b < KP; ++b) acc[b] = fma(wgt, row[b], acc[b]);
+                for (int b = 0; b < KP; ++b)
+                    if ((msk >> b) & 1u) acc[b] = fma(wgt, PNL(i, b), acc[b]);
             }
-            pfb_block_sum<KP>(acc, scratch);
+            pfb_block_sum_fast<KP>(acc, scratch, msk);
         }
         if (tid == 0) {
 #pragma unroll
             for (int b = 0; b < KP; ++b) {
-                if (a < KP) hdr[PFB_HDR_M(KP) + a * KP + b] = acc[b];
-                else hdr[PFB_HDR_RV(KP) + b] = acc[b];
+                if (a < KP) {
+                    if (b >= a) {
+                        hdr[PFB_HDR_M(KP) + a * KP + b] = acc[b];
+                        hdr[PFB_HDR_M(KP) + b * KP + a] = acc[b];
+                    }
+                } else {
+                    hdr[PFB_HDR_RV(KP) + b] = acc[b];
+                }
             }
         }
     }
@@ -403,15 +412,39 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
     }
 }
 
+static size_t k2_panel_bytes(int KP, int n) { return (size_t)(KP + 2) * (size_t)((n + 1) | 1) * 8; }
+static size_t k2_scratch_bytes(int KP) { return (size_t)PFB_K2_SCRATCH(KP) * 8; }
+
+// The panel goes to shared memory when it fits next to the kernel's static arrays.
+extern "C" int pfb_k2_uses_smem_panel(int KP, int n) {
+    int dev = 0, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const size_t stat = (size_t)(9 * KP * KP + 4 * KP + 8) * 8 + 1024;  // static arrays (upper bound)
+    return k2_panel_bytes(KP, n) + k2_scratch_bytes(KP) + stat <= (size_t)smem_max;
+}
+
 template <int KP>
 static cudaError_t launch_k2(cudaStream_t st, int n, int U, int J, const double* X, const double* G,
                              const int32_t* unit_col, const double* alpha, const int32_t* hist,
                              const int32_t* hist_cnt, double* FR, double* HDR, double* FR2, int model,
                              const double* mp0, const double* mp1) {
+    if (pfb_k2_uses_smem_panel(KP, n)) {
+        int threads = n >= PFB_K2_THREADS_SMEM ? PFB_K2_THREADS_SMEM : ((n + 31) / 32) * 32;
+        if (threads < 64) threads = 64;  // >= KP threads are needed by the small-matrix phases
+        auto kern = pfb_k2_woodbury_build<KP, true>;
+        const size_t smem = k2_panel_bytes(KP, n) + k2_scratch_bytes(KP);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<U, threads, smem, st>>>(n, J, X, G, unit_col, alpha, hist, hist_cnt, nullptr, HDR, FR2, model, mp0, mp1);
+        return cudaGetLastError();
+    }
+    if (FR == nullptr) return cudaErrorInvalidValue;
     int threads = n >= PFB_K2_THREADS ? PFB_K2_THREADS : ((n + 31) / 32) * 32;
-    if (threads < 64) threads = 64;  // >= KP threads are needed by the small-matrix phases
-    pfb_k2_woodbury_build<KP><<<U, threads, 0, st>>>(n, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR, FR2,
-                                                     model, mp0, mp1);
+    if (threads < 64) threads = 64;
+    pfb_k2_woodbury_build<KP, false><<<U, threads, k2_scratch_bytes(KP), st>>>(n, J, X, G, unit_col, alpha, hist,
+                                                                              hist_cnt, FR, HDR, FR2, model, mp0,
+                                                                              mp1);
     return cudaGetLastError();
 }
 

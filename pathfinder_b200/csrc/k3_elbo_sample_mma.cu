@@ -41,6 +41,9 @@
 #ifndef PFB_K3_SWP
 #define PFB_K3_SWP 0  // software-pipeline the normals of block o+1 under the DMMAs of block o
 #endif
+#ifndef PFB_K3_STAGGER
+#define PFB_K3_STAGGER 0  // ns of start delay for every other warp of a scheduler
+#endif
 #define PFB_K3_MAXWARPS 16
 #define PFB_K3_DS 2      // draw sets (8 draws each) per warp
 #define PFB_K3_RC 128    // record rows per TMA chunk (16 blocks of 8 rows)
@@ -375,6 +378,13 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                     s = q % NS;
                     pfb_mbar_wait(&sBar[s], (uint32_t)((q / NS) & 1));
                 }
+#if PFB_K3_STAGGER
+                // warps of one scheduler alternate between an integer phase (Philox / ziggurat) and an
+                // FP64 phase (DMMA); left alone they run in lock-step and the two pipes take turns
+                // idling.  Delaying every other warp of a scheduler by half a block period locks the
+                // pairs in anti-phase.
+                if (c == 0 && ((warp >> 2) & 1)) __nanosleep(PFB_K3_STAGGER);
+#endif
                 const double* st = sStage + (size_t)s * RC * RS2;
                 const uint32_t st_u32 = pfb_smem_u32(st);
                 const int r0 = c * RC;
@@ -533,11 +543,34 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                 uint32_t nibc = 0u;
 #pragma unroll 1
                 for (; o < o_fast; ++o) block(pfb_ic<1>{}, o, zc, 0u);
+#if PFB_K3_SWP
+                // software pipeline: the normals of block o+1 are generated in the same basic block
+                // as the tensor-core work of block o
+                if (o < o_end) {
+                    double zn[DS][2];
+                    uint32_t nibn;
+                    gen(o, zc, nibc);
+#pragma unroll 1
+                    for (; o < o_end - 1; ++o) {
+                        gen(o + 1, zn, nibn);
+                        block(pfb_ic<0>{}, o, zc, nibc);
+#pragma unroll
+                        for (int d = 0; d < DS; ++d) {
+                            zc[d][0] = zn[d][0];
+                            zc[d][1] = zn[d][1];
+                        }
+                        nibc = nibn;
+                    }
+                    block(pfb_ic<0>{}, o, zc, nibc);
+                    ++o;
+                }
+#else
 #pragma unroll 1
                 for (; o < o_end; ++o) {
                     gen(o, zc, nibc);
                     block(pfb_ic<0>{}, o, zc, nibc);
                 }
+#endif
 #pragma unroll 1
                 for (; o < nb; ++o) block(pfb_ic<1>{}, o, zc, 0u);
 

@@ -26,6 +26,7 @@ PFB_DECL_K3(pfb_launch_k3_kp20)
 PFB_DECL_K3(pfb_launch_k3_kp24)
 cudaError_t pfb_launch_k4(cudaStream_t, int, int, const int64_t*, const double*, const double*, double*,
                           double*, int64_t*, int32_t*, int32_t*);
+int pfb_k2_uses_smem_panel(int KP, int n);
 size_t pfb_psis_scalars_size();
 cudaError_t pfb_launch_k6(cudaStream_t, int, int, int, const double*, const double*, const double*, double*,
                           double*, uint64_t*, void*);
@@ -233,7 +234,8 @@ extern "C" int pfb_batch_upload(pfb_handle h, int n, int P, const int64_t* offse
     PFB_CUDA(h, h->dHist.ensure((size_t)U * J * 4 + 8));
     PFB_CUDA(h, h->dHistCnt.ensure((size_t)U * 4 + 8));
     PFB_CUDA(h, h->dRej.ensure((size_t)P * 8 + 8));
-    PFB_CUDA(h, h->dFR.ensure(nU * (size_t)pfb_rs_of(KP) * 8 + 16));
+    if (!pfb_k2_uses_smem_panel(KP, n))  // K2's global-memory workspace (large n only)
+        PFB_CUDA(h, h->dFR.ensure(nU * (size_t)pfb_rs_of(KP) * 8 + 16));
     PFB_CUDA(h, h->dFR2.ensure((size_t)pfb_npad8(n) * (size_t)U * (size_t)pfb_rs2_of(KP) * 8 + 16));
     PFB_CUDA(h, h->dHDR.ensure((size_t)U * pfb_hs_of(KP) * 8 + 8));
     PFB_CUDA(h, h->dLogp.ensure((size_t)U * K * 8 + 8));
@@ -323,21 +325,23 @@ extern "C" int pfb_batch_sync(pfb_handle h) {
     return PFB_OK;
 }
 
-// gather of the best-iteration factor in the reference's WoodburyPDMat form
+// gather of the best-iteration factor in the reference's WoodburyPDMat form (from the swizzled
+// FR2 record, pfb_common.cuh)
 __global__ void pfb_gather_fit(int n, int KP, const int32_t* __restrict__ best_unit,
-                               const double* __restrict__ FR, const double* __restrict__ HDR,
+                               const double* __restrict__ FR2, const double* __restrict__ HDR,
                                const double* __restrict__ alpha, const int32_t* __restrict__ hist_cnt,
                                double* mu, double* al, double* vh, double* Tm, double* Vc, double* logdet,
                                int32_t* jeff) {
     const int p = blockIdx.x;
     const int u = best_unit[p];
-    const int RS = KP + 2, HS = pfb_hs_of(KP);
+    const int RS2 = pfb_rs2_of(KP), HS = pfb_hs_of(KP), npad = pfb_npad8(n);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         if (u >= 0) {
-            const double* row = FR + ((int64_t)u * n + i) * RS;
-            mu[(int64_t)p * n + i] = row[KP + 1];
+            const double* row = FR2 + ((int64_t)u * npad + i) * RS2;
+            const int sw = pfb_swz(i);
+            mu[(int64_t)p * n + i] = row[(KP + 1) ^ sw];
             al[(int64_t)p * n + i] = alpha[(int64_t)u * n + i];
-            for (int j = 0; j < KP; ++j) vh[((int64_t)p * KP + j) * n + i] = row[j];
+            for (int j = 0; j < KP; ++j) vh[((int64_t)p * KP + j) * n + i] = row[j ^ sw];
         } else {
             mu[(int64_t)p * n + i] = NAN;
             al[(int64_t)p * n + i] = NAN;
@@ -390,7 +394,7 @@ extern "C" int pfb_batch_download(pfb_handle h, pfb_elbo_out* o) {
         PFB_CUDA(h, h->dFitLogdet.ensure(P * 8));
         PFB_CUDA(h, h->dFitJeff.ensure(P * 4));
         pfb_gather_fit<<<(unsigned)P, 256, 0, st>>>((int)n, (int)KP, h->dBestUnit.as<int32_t>(),
-                                                    h->dFR.as<double>(), h->dHDR.as<double>(),
+                                                    h->dFR2.as<double>(), h->dHDR.as<double>(),
                                                     h->dAlpha.as<double>(), h->dHistCnt.as<int32_t>(),
                                                     h->dFitMu.as<double>(), h->dFitAlpha.as<double>(),
                                                     h->dFitVh.as<double>(), h->dFitT.as<double>(),

@@ -81,6 +81,42 @@ __device__ __forceinline__ void pfb_block_sum(double (&v)[NV], double* scratch) 
     }
 }
 
+// Cheaper block-wide sum of the values selected by `mask` (bit a = v[a] takes part; must be the
+// same in every thread): the warps fold their 32 lanes to 8 partials with two shuffle steps, park
+// them in shared memory, and then ONE warp per value finishes it (instead of every warp
+// butterfly-reducing every value).  ~3x fewer instructions than pfb_block_sum for NV = 12.
+// `scratch` needs NV * nwarp * 8 + NV doubles.  Fixed order => deterministic.  Result broadcast.
+template <int NV>
+__device__ __forceinline__ void pfb_block_sum_fast(double (&v)[NV], double* scratch, unsigned mask) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    double* totals = scratch + NV * nwarp * 8;
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+        if ((mask >> a) & 1u) {
+            v[a] += __shfl_xor_sync(0xffffffffu, v[a], 16);
+            v[a] += __shfl_xor_sync(0xffffffffu, v[a], 8);
+        }
+    __syncthreads();  // scratch may still be read from a previous call
+    if (lane < 8) {
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+            if ((mask >> a) & 1u) scratch[(a * nwarp + warp) * 8 + lane] = v[a];
+    }
+    __syncthreads();
+    for (int a = warp; a < NV; a += nwarp) {
+        if ((mask >> a) & 1u) {
+            double t = 0.0;
+            for (int k = lane; k < nwarp * 8; k += 32) t += scratch[a * nwarp * 8 + k];
+            t = pfb_warp_sum(t);
+            if (lane == 0) totals[a] = t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+        if ((mask >> a) & 1u) v[a] = totals[a];
+}
+
 // Runtime-count variant: values live in shared memory vals[t * stride + a]? No — each thread
 // passes a pointer to its private array of `nv` values (nv <= NVMAX, loops fully unrolled).
 template <int NVMAX>
