@@ -35,6 +35,13 @@ extern "C" {
 #define PFB_MODEL_ISONORMAL 0 /* logp(x) = -|x|^2/2          test/singlepath.jl:15          */
 #define PFB_MODEL_FUNNEL 1    /* Neal's funnel               docs/src/examples/quickstart.md:229-234 */
 #define PFB_MODEL_DIAGNORMAL 2 /* independent normals; blob = { mean[n], sd[n] }  test/elbo.jl:8-12 */
+#define PFB_MODEL_DENSENORMAL 3 /* logp = -(x-m)'P(x-m)/2; blob = { m[n], P[n x n] column-major }
+                                   docs/src/examples/quickstart.md:17-24 (BASELINE config 5)         */
+#define PFB_MODEL_HLOGISTIC 4  /* hierarchical logistic regression, theta = (log tau, b0, b[n-2]):
+                                   log tau ~ N(0,1), b0 ~ N(0,2.5^2), b_j ~ N(0,tau^2),
+                                   y_i ~ Bernoulli(sigmoid(b0 + x_i'b)); blob = { nobs,
+                                   X[nobs x (n-2)] column-major, y[nobs] }   (BASELINE config 4)     */
+#define PFB_MODEL_EXTERNAL 100 /* internal: log p evaluated outside the sampling kernel             */
 
 typedef struct pfb_engine* pfb_handle;
 

@@ -380,3 +380,23 @@ def make_logp_dense_gaussian(mean, prec):
         return -0.5 * np.sum(z * (prec @ z), axis=0)
 
     return f
+
+
+def make_logp_hier_logistic(X, y):
+    """SURVEY §8d config 4 (not in the reference; spec fixed there): theta = (log tau, b0, b),
+    log tau ~ N(0,1), b0 ~ N(0, 2.5^2), b_j ~ N(0, tau^2), y_i ~ Bernoulli(sigmoid(b0 + x_i'b))."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+
+    def f(th):
+        lt, b0, b = th[0], th[1], th[2:]
+        eta = b0[None, :] + X @ b
+        ll = np.sum(y[:, None] * eta - np.logaddexp(0.0, eta), axis=0)
+        h = 0.5 * LOG2PI
+        nb = b.shape[0]
+        lp = -0.5 * lt * lt - h
+        lp = lp + (-0.5 * (b0 / 2.5) ** 2 - math.log(2.5) - h)
+        lp = lp + (-0.5 * np.sum(b * b, axis=0) * np.exp(-2 * lt) - nb * lt - nb * h)
+        return lp + ll
+
+    return f

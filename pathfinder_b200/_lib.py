@@ -15,6 +15,8 @@ LIB_PATH = os.environ.get("PFB200_LIB") or os.path.join(_HERE, "libpfb200.so")  
 PFB_MODEL_ISONORMAL = 0
 PFB_MODEL_FUNNEL = 1
 PFB_MODEL_DIAGNORMAL = 2
+PFB_MODEL_DENSENORMAL = 3
+PFB_MODEL_HLOGISTIC = 4
 
 
 class PfbError(RuntimeError):

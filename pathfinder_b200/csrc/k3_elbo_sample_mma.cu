@@ -107,6 +107,7 @@ struct pfb_model_acc {
         b += __shfl_xor_sync(0xffffffffu, b, 2);
     }
     __device__ __forceinline__ double finish(int n, const pfb_model_params& mp) const {
+        if (MODEL == PFB_MODEL_EXTERNAL) return 0.0;  // log p comes from K8 (GEMM over the draws)
         if (MODEL == PFB_MODEL_ISONORMAL) return a / -2.0;
         if (MODEL == PFB_MODEL_FUNNEL) {
             // ((tau/3)^2 + (n-1) tau + exp(-tau) * sum beta^2) / -2
@@ -810,8 +811,14 @@ static cudaError_t launch_k3_m(cudaStream_t st, int n, int K, int nslots, const 
     splits = splits < 1 ? 1 : (splits > S ? S : splits);
     const int64_t grid = (int64_t)nslots * splits;
     if (grid > 2147483647LL) return cudaErrorInvalidValue;
-    auto kern = draws ? pfb_k3_elbo_sample<KP, MODEL, 1>
-                      : (quad ? pfb_k3_elbo_sample<KP, MODEL, 2> : pfb_k3_elbo_sample<KP, MODEL, 0>);
+    void (*kern)(int, int, int, int, const int32_t*, const double*, const double*, const uint64_t*, const double*,
+                 pfb_model_params, double*, double*, double*);
+    if constexpr (MODEL == PFB_MODEL_EXTERNAL) {
+        kern = pfb_k3_elbo_sample<KP, MODEL, 1>;
+    } else {
+        kern = draws ? pfb_k3_elbo_sample<KP, MODEL, 1>
+                     : (quad ? pfb_k3_elbo_sample<KP, MODEL, 2> : pfb_k3_elbo_sample<KP, MODEL, 0>);
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(unsigned)grid, NW * 32, smem, st>>>(n, K, splits, NS, unit_list, FR2, HDR, seeds, u_host, mp, logp,
@@ -834,6 +841,11 @@ static cudaError_t launch_k3_k(cudaStream_t st, int model, int n, int K, int nsl
         case PFB_MODEL_DIAGNORMAL:
             return launch_k3_m<KP, PFB_MODEL_DIAGNORMAL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host,
                                                          mp, logp, logq, draws, two_pass);
+        case PFB_MODEL_DENSENORMAL:
+        case PFB_MODEL_HLOGISTIC:
+            if (draws == nullptr) return cudaErrorInvalidValue;  // these families need x written out (K8)
+            return launch_k3_m<KP, PFB_MODEL_EXTERNAL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host, mp,
+                                                       logp, logq, draws, 1);
     }
     return cudaErrorInvalidValue;
 }

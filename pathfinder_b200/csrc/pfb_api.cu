@@ -1,10 +1,12 @@
 // pfb_api.cu — the C ABI of libpfb200.so (declared in include/pfb200.h): engine handle,
 // device workspace (grow-only, engine-owned), and the orchestration of K1..K7 on one stream.
+#include <cublas_v2.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -27,6 +29,10 @@ PFB_DECL_K3(pfb_launch_k3_kp24)
 cudaError_t pfb_launch_k4(cudaStream_t, int, int, const int64_t*, const double*, const double*, double*,
                           double*, int64_t*, int32_t*, int32_t*);
 int pfb_k2_uses_smem_panel(int KP, int n);
+cudaError_t pfb_launch_k8_dense(cudaStream_t, int, int64_t, int, const int32_t*, const double*, const double*,
+                                const double*, double, double*);
+cudaError_t pfb_launch_k8_logistic(cudaStream_t, int, int, int64_t, int, const int32_t*, const double*,
+                                   const double*, const double*, double*);
 size_t pfb_psis_scalars_size();
 cudaError_t pfb_launch_k6(cudaStream_t, int, int, int, const double*, const double*, const double*, double*,
                           double*, uint64_t*, void*);
@@ -76,6 +82,9 @@ struct pfb_engine {
     int model = -1, model_n = 0;
     DevBuf dModel;
     double model_c0 = 0.0;
+    int model_nobs = 0;                 // HLOGISTIC
+    cublasHandle_t cublas = nullptr;    // families whose log p needs a GEMM over the draws (K8)
+    DevBuf dGenX, dGenY, dIota;
     // batch state
     int n = 0, P = 0, K = 0;
     int64_t T = 0, U = 0;
@@ -158,8 +167,9 @@ extern "C" int pfb_destroy(pfb_handle h) {
                       &h->dSe, &h->dBestIter, &h->dBestUnit, &h->dSucc, &h->dPool, &h->dPoolLogp,
                       &h->dPoolLogq, &h->dAllDraws, &h->dFitMu, &h->dFitAlpha, &h->dFitVh, &h->dFitT,
                       &h->dFitVc, &h->dFitLogdet, &h->dFitJeff, &h->dLogw, &h->dW, &h->dCum, &h->dScal,
-                      &h->dInds, &h->dIds, &h->dOutDraws, &h->dTmpLogr, &h->dTmpPool};
+                      &h->dInds, &h->dIds, &h->dOutDraws, &h->dTmpLogr, &h->dTmpPool, &h->dGenX, &h->dGenY, &h->dIota};
     for (auto* b : bufs) b->release();
+    if (h->cublas) cublasDestroy(h->cublas);
     for (auto& ev : h->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -193,8 +203,48 @@ extern "C" int pfb_register_model(pfb_handle h, int family, int n, const double*
             h->model_c0 = c0;
             break;
         }
+        case PFB_MODEL_DENSENORMAL: {
+            const size_t nn = (size_t)n;
+            if (!blob || ndoubles != nn + nn * nn) PFB_FAIL(h, PFB_ERR_SHAPE, "DENSENORMAL blob = {m[n], P[n x n]}");
+            // device: { m[n], P m [n], P[n x n] };  c0 = m' P m
+            std::vector<double> pm(nn, 0.0);
+            const double* m = blob;
+            const double* P = blob + nn;
+            for (size_t j = 0; j < nn; ++j) {
+                const double mj = m[j];
+                const double* col = P + j * nn;
+                for (size_t i = 0; i < nn; ++i) pm[i] += col[i] * mj;
+            }
+            double mPm = 0.0;
+            for (size_t i = 0; i < nn; ++i) mPm += m[i] * pm[i];
+            PFB_CUDA(h, h->dModel.ensure((2 * nn + nn * nn) * 8));
+            double* d = h->dModel.as<double>();
+            PFB_CUDA(h, cudaMemcpyAsync(d, m, nn * 8, cudaMemcpyHostToDevice, h->stream));
+            PFB_CUDA(h, cudaMemcpyAsync(d + nn, pm.data(), nn * 8, cudaMemcpyHostToDevice, h->stream));
+            PFB_CUDA(h, cudaMemcpyAsync(d + 2 * nn, P, nn * nn * 8, cudaMemcpyHostToDevice, h->stream));
+            PFB_CUDA(h, cudaStreamSynchronize(h->stream));
+            h->model_c0 = mPm;
+            break;
+        }
+        case PFB_MODEL_HLOGISTIC: {
+            if (n < 3 || !blob || ndoubles < 1) PFB_FAIL(h, PFB_ERR_SHAPE, "HLOGISTIC needs n >= 3 and a blob");
+            const long long nobs = (long long)blob[0];
+            const size_t nb = (size_t)n - 2;
+            if (nobs < 1 || ndoubles != 1 + (size_t)nobs * nb + (size_t)nobs)
+                PFB_FAIL(h, PFB_ERR_SHAPE, "HLOGISTIC blob = {nobs, X[nobs x (n-2)], y[nobs]}");
+            // device: { X[nobs x (n-2)], y[nobs] }
+            PFB_CUDA(h, h->dModel.ensure((ndoubles - 1) * 8));
+            PFB_CUDA(h, cudaMemcpyAsync(h->dModel.p, blob + 1, (ndoubles - 1) * 8, cudaMemcpyHostToDevice, h->stream));
+            PFB_CUDA(h, cudaStreamSynchronize(h->stream));
+            h->model_nobs = (int)nobs;
+            break;
+        }
         default:
             PFB_FAIL(h, PFB_ERR_UNSUPPORTED, "unknown model family");
+    }
+    if ((family == PFB_MODEL_DENSENORMAL || family == PFB_MODEL_HLOGISTIC) && !h->cublas) {
+        if (cublasCreate(&h->cublas) != CUBLAS_STATUS_SUCCESS) PFB_FAIL(h, 1, "cublasCreate failed");
+        cublasSetStream(h->cublas, h->stream);
     }
     h->model = family;
     h->model_n = n;
@@ -269,9 +319,39 @@ extern "C" int pfb_batch_upload(pfb_handle h, int n, int P, const int64_t* offse
     return PFB_OK;
 }
 
+static bool model_is_external(const pfb_engine* h) {
+    return h->model == PFB_MODEL_DENSENORMAL || h->model == PFB_MODEL_HLOGISTIC;
+}
+
+// K8: log p of M = nslots * K materialised draws X [n x M] for the GEMM-shaped families.
+static int generic_logp(pfb_engine* h, const double* X, int64_t M, const int32_t* slot_unit, double* logp) {
+    if (M <= 0) return PFB_OK;
+    const int n = h->n, K = h->K;
+    const double one = 1.0, zero = 0.0;
+    if (h->model == PFB_MODEL_DENSENORMAL) {
+        const double* d = h->dModel.as<double>();
+        PFB_CUDA(h, h->dGenY.ensure((size_t)n * (size_t)M * 8));
+        if (cublasDgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_N, n, (int)M, n, &one, d + 2 * (size_t)n, n, X, n, &zero,
+                        h->dGenY.as<double>(), n) != CUBLAS_STATUS_SUCCESS)
+            PFB_FAIL(h, 1, "cublasDgemm failed");
+        PFB_CUDA(h, pfb_launch_k8_dense(h->stream, n, M, K, slot_unit, X, h->dGenY.as<double>(), d + n, h->model_c0,
+                                        logp));
+    } else {
+        const int nobs = h->model_nobs, nb = n - 2;
+        const double* Xm = h->dModel.as<double>();
+        const double* yobs = Xm + (size_t)nobs * nb;
+        PFB_CUDA(h, h->dGenY.ensure((size_t)nobs * (size_t)M * 8));
+        if (cublasDgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_N, nobs, (int)M, nb, &one, Xm, nobs, X + 2, n, &zero,
+                        h->dGenY.as<double>(), nobs) != CUBLAS_STATUS_SUCCESS)
+            PFB_FAIL(h, 1, "cublasDgemm failed");
+        PFB_CUDA(h, pfb_launch_k8_logistic(h->stream, n, nobs, M, K, slot_unit, X, h->dGenY.as<double>(), yobs, logp));
+    }
+    return PFB_OK;
+}
+
 static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list, double* logp, double* logq,
                              double* draws) {
-    const double* mp0 = h->dModel.as<double>();
+    const double* mp0 = model_is_external(h) ? nullptr : h->dModel.as<double>();
     const double* mp1 = mp0 ? mp0 + h->model_n : nullptr;
     const double* un = h->have_normals ? h->dNormals.as<double>() : nullptr;
     auto fn = h->KP == 12 ? pfb_launch_k3_kp12 : (h->KP == 20 ? pfb_launch_k3_kp20 : pfb_launch_k3_kp24);
@@ -295,13 +375,41 @@ extern "C" int pfb_batch_run(pfb_handle h) {
     PFB_CUDA(h, cudaEventRecord(h->ev[1], st));
     PFB_CUDA(h, pfb_launch_k2(st, KP, n, U, J, h->dX.as<double>(), h->dG.as<double>(), h->dUnitCol.as<int32_t>(),
                               h->dAlpha.as<double>(), h->dHist.as<int32_t>(), h->dHistCnt.as<int32_t>(),
-                              h->dFR.as<double>(), h->dHDR.as<double>(), h->dFR2.as<double>(), h->model,
-                              h->dModel.as<double>(), h->dModel.p ? h->dModel.as<double>() + h->model_n : nullptr));
+                              h->dFR.as<double>(), h->dHDR.as<double>(), h->dFR2.as<double>(),
+                              model_is_external(h) ? PFB_MODEL_ISONORMAL : h->model,
+                              model_is_external(h) ? nullptr : h->dModel.as<double>(),
+                              (h->dModel.p && !model_is_external(h)) ? h->dModel.as<double>() + h->model_n : nullptr));
     h->launches += (U > 0);
     PFB_CUDA(h, cudaEventRecord(h->ev[2], st));
-    PFB_CUDA(h, launch_k3(h, U, nullptr, h->dLogp.as<double>(), h->dLogq.as<double>(),
-                          h->cfg.materialize_all ? h->dAllDraws.as<double>() : nullptr));
-    h->launches += (U > 0);
+    if (!model_is_external(h)) {
+        PFB_CUDA(h, launch_k3(h, U, nullptr, h->dLogp.as<double>(), h->dLogq.as<double>(),
+                              h->cfg.materialize_all ? h->dAllDraws.as<double>() : nullptr));
+        h->launches += (U > 0);
+    } else if (U > 0) {
+        // GEMM-shaped log p: materialise the draws of a chunk of units (K3), then K8 (cuBLAS + epilogue)
+        const size_t per_unit = (size_t)n * (size_t)K * 8;
+        int chunk = (int)std::max<size_t>(1, ((size_t)1 << 30) / per_unit);
+        if (h->cfg.materialize_all || chunk > U) chunk = U;
+        if (!h->cfg.materialize_all) PFB_CUDA(h, h->dGenX.ensure(per_unit * (size_t)chunk));
+        PFB_CUDA(h, h->dIota.ensure((size_t)U * 4));
+        {
+            std::vector<int32_t> iota((size_t)U);
+            for (int u = 0; u < U; ++u) iota[(size_t)u] = u;
+            PFB_CUDA(h, cudaMemcpyAsync(h->dIota.p, iota.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
+            PFB_CUDA(h, cudaStreamSynchronize(st));
+        }
+        for (int u0 = 0; u0 < U; u0 += chunk) {
+            const int cnt = std::min(chunk, U - u0);
+            double* xbuf = h->cfg.materialize_all ? h->dAllDraws.as<double>() + (size_t)u0 * n * K
+                                                  : h->dGenX.as<double>();
+            double* lp = h->dLogp.as<double>() + (size_t)u0 * K;
+            PFB_CUDA(h, launch_k3(h, cnt, h->dIota.as<int32_t>() + u0, lp, h->dLogq.as<double>() + (size_t)u0 * K,
+                                  xbuf));
+            int rc = generic_logp(h, xbuf, (int64_t)cnt * K, nullptr, lp);
+            if (rc) return rc;
+            h->launches += 3;
+        }
+    }
     PFB_CUDA(h, cudaEventRecord(h->ev[3], st));
     PFB_CUDA(h, pfb_launch_k4(st, P, K, h->dOff.as<int64_t>(), h->dLogp.as<double>(), h->dLogq.as<double>(),
                               h->dElbo.as<double>(), h->dSe.as<double>(), h->dBestIter.as<int64_t>(),
@@ -313,6 +421,12 @@ extern "C" int pfb_batch_run(pfb_handle h) {
     PFB_CUDA(h, launch_k3(h, P, h->dBestUnit.as<int32_t>(), h->dPoolLogp.as<double>(), h->dPoolLogq.as<double>(),
                           h->dPool.as<double>()));
     h->launches += (P > 0);
+    if (model_is_external(h) && P > 0) {
+        int rc = generic_logp(h, h->dPool.as<double>(), (int64_t)P * K, h->dBestUnit.as<int32_t>(),
+                              h->dPoolLogp.as<double>());
+        if (rc) return rc;
+        h->launches += 2;
+    }
     PFB_CUDA(h, cudaEventRecord(h->ev[5], st));
     h->ran = true;
     return PFB_OK;

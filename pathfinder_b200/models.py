@@ -10,7 +10,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from ._lib import PFB_MODEL_DIAGNORMAL, PFB_MODEL_FUNNEL, PFB_MODEL_ISONORMAL
+from ._lib import (PFB_MODEL_DENSENORMAL, PFB_MODEL_DIAGNORMAL, PFB_MODEL_FUNNEL, PFB_MODEL_HLOGISTIC,
+                   PFB_MODEL_ISONORMAL)
 
 
 class IsoNormal:
@@ -72,3 +73,60 @@ class DiagNormal:
 
     def grad(self, x):
         return -(x - self.mean) / self.sd**2
+
+
+class DenseNormal:
+    """logp(x) = -(x - m)' P (x - m) / 2   (docs/src/examples/quickstart.md:17-24; BASELINE config 5).
+    The device evaluates it as a GEMM over the materialised draws (K8)."""
+
+    family = PFB_MODEL_DENSENORMAL
+
+    def __init__(self, mean, prec):
+        self.mean = np.asarray(mean, dtype=np.float64)
+        self.prec = np.asarray(prec, dtype=np.float64)
+        self.n = self.mean.size
+        if self.prec.shape != (self.n, self.n):
+            raise ValueError("prec must be n x n")
+        self.blob = np.concatenate([self.mean, np.asfortranarray(self.prec).reshape(-1, order="F")])
+
+    def logp(self, x):
+        z = x - self.mean
+        return -0.5 * float(z @ (self.prec @ z))
+
+    def grad(self, x):
+        return -(self.prec @ (x - self.mean))
+
+
+class HierLogistic:
+    """Hierarchical logistic regression: theta = (log tau, b0, b_1..b_p),
+    log tau ~ N(0, 1), b0 ~ N(0, 2.5^2), b_j ~ N(0, tau^2), y_i ~ Bernoulli(sigmoid(b0 + x_i'b))."""
+
+    family = PFB_MODEL_HLOGISTIC
+
+    def __init__(self, X, y):
+        self.X = np.asarray(X, dtype=np.float64)
+        self.y = np.asarray(y, dtype=np.float64)
+        self.nobs, p = self.X.shape
+        self.n = p + 2
+        self.blob = np.concatenate([[float(self.nobs)], np.asfortranarray(self.X).reshape(-1, order="F"), self.y])
+
+    def logp(self, th):
+        lt, b0, b = th[0], th[1], th[2:]
+        eta = b0 + self.X @ b
+        ll = float(np.sum(self.y * eta - np.logaddexp(0.0, eta)))
+        h = 0.5 * np.log(2 * np.pi)
+        lp = -0.5 * lt * lt - h
+        lp += -0.5 * (b0 / 2.5) ** 2 - np.log(2.5) - h
+        lp += -0.5 * float(b @ b) * np.exp(-2 * lt) - b.size * lt - b.size * h
+        return lp + ll
+
+    def grad(self, th):
+        lt, b0, b = th[0], th[1], th[2:]
+        eta = b0 + self.X @ b
+        r = self.y - 1.0 / (1.0 + np.exp(-eta))
+        g = np.empty_like(th)
+        e2 = np.exp(-2 * lt)
+        g[0] = -lt + float(b @ b) * e2 - b.size
+        g[1] = -b0 / 6.25 + float(np.sum(r))
+        g[2:] = -b * e2 + self.X.T @ r
+        return g

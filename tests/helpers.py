@@ -33,7 +33,12 @@ def synthetic_trajectory(n, L, seed, scale=1.0):
 
 
 def oracle_logp_fn(model):
-    from pathfinder_b200 import DiagNormal, Funnel, IsoNormal
+    from pathfinder_b200 import DenseNormal, DiagNormal, Funnel, HierLogistic, IsoNormal
+
+    if isinstance(model, DenseNormal):
+        return O.make_logp_dense_gaussian(model.mean, model.prec)
+    if isinstance(model, HierLogistic):
+        return O.make_logp_hier_logistic(model.X, model.y)
 
     if isinstance(model, IsoNormal):
         return O.logp_isonormal

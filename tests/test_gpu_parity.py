@@ -346,3 +346,55 @@ def test_lean_single_pass_ring_mode_large_n():
 
     n = 1500
     _lean_vs_oracle(pf.Funnel(n), [synthetic_trajectory(n, 4, 77, scale=0.2)], K=300, J=6)
+
+
+def _rand_pd(rng, n):
+    """rand_pd_mat of test/test_utils.jl:7-11: Q diag(U(0,1)) Q'."""
+    Q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    return Q @ np.diag(rng.random(n) + 0.05) @ Q.T
+
+
+def test_dense_normal_config5_shape():
+    """BASELINE config 5 at reduced size: correlated Gaussian (docs quickstart :17-24), history 10;
+    log p goes through K8 (cuBLAS DGEMM + epilogue) on the materialised draws."""
+    import pathfinder_b200 as pf
+    from tests.helpers import make_trajectories
+
+    rng = np.random.default_rng(6)
+    n = 48
+    Sigma = _rand_pd(rng, n)
+    model = pf.DenseNormal(rng.normal(size=n), np.linalg.inv(Sigma))
+    trajs = make_trajectories(model, 2, seed=7, init_scale=2.0, history_length=10, maxiters=30, min_len=4)
+    _compare_batch(model, trajs, K=64, J=10, cond_aware=True)
+    # lean mode (chunked K3 + K8, draws not kept) gives the same ELBO table
+    seeds = _seeds(trajs, 1)
+    offsets, X, G = pf.Engine.pack(trajs)
+    eng = _engine(model, 64, 10)
+    lean = eng.elbo_batch(offsets, X, G, np.concatenate(seeds), per_draw=True)
+    eng.close()
+    eng = _engine(model, 64, 10, materialize_all=True)
+    full = eng.elbo_batch(offsets, X, G, np.concatenate(seeds), per_draw=True)
+    eng.close()
+    assert np.array_equal(lean.logp, full.logp) and np.array_equal(lean.elbo, full.elbo)
+
+
+def test_hier_logistic_config4_shape():
+    """BASELINE config 4 at reduced size: hierarchical logistic regression on synthetic X."""
+    import pathfinder_b200 as pf
+    from tests.helpers import make_trajectories
+
+    rng = np.random.default_rng(4)
+    p, nobs = 14, 96
+    Xm = rng.normal(size=(nobs, p))
+    beta = rng.normal(size=p) * 0.5
+    y = (rng.random(nobs) < 1 / (1 + np.exp(-(0.3 + Xm @ beta)))).astype(np.float64)
+    model = pf.HierLogistic(Xm, y)
+    trajs = make_trajectories(model, 2, seed=9, init_scale=1.0, maxiters=40, min_len=4)
+    _compare_batch(model, trajs, K=80, J=6, cond_aware=True)
+    res = pf.multipathfinder(model, 30, nruns=3, ndraws_elbo=40, rng=np.random.default_rng(2), init_scale=1.0,
+                             maxiters=40)
+    assert res.draws.shape == (p + 2, 30)
+    from oracle import pf_oracle as O
+    f = O.make_logp_hier_logistic(Xm, y)
+    for pr in res.pathfinder_results:
+        np.testing.assert_allclose(pr.draws_logp, f(pr.draws), rtol=1e-9, atol=1e-9)
