@@ -34,17 +34,41 @@ METRIC = "elbo_mc_samples_per_sec"
 UNIT = "samples/s"
 
 CONFIGS = {
-    # name: (n, paths per GPU, K, J, init_scale, ndraws)
-    "cfg3_funnel1024_p64_k1000_j6": (1024, 64, 1000, 6, 10.0, 1000),
-    "cfg2_funnel100_p8_k1000_j6": (100, 8, 1000, 6, 10.0, 1000),
+    # name: (model kind, n, paths per GPU, K, J, init_scale, ndraws)
+    "cfg3_funnel1024_p64_k1000_j6": ("funnel", 1024, 64, 1000, 6, 10.0, 1000),
+    "cfg2_funnel100_p8_k1000_j6": ("funnel", 100, 8, 1000, 6, 10.0, 1000),
+    # hierarchical logistic regression, 254 features + (log tau, b0), 2048 rows
+    "cfg4_hlogistic256_p32_k2000_j6": ("hlogistic", 256, 32, 2000, 6, 2.0, 1000),
+    # 4096-dim correlated Gaussian, history 10 (16 paths per GPU = 128 on 8 GPUs)
+    "cfg5_dense4096_p16_k500_j10": ("dense", 4096, 16, 500, 10, 2.0, 1000),
 }
+
+
+def make_model(kind, n):
+    import pathfinder_b200 as pf
+
+    if kind == "funnel":
+        return pf.Funnel(n), 3.0 * n
+    if kind == "hlogistic":
+        nobs, p = 2048, n - 2
+        Xm = np.random.default_rng(4).normal(size=(nobs, p))
+        beta = np.random.default_rng(5).normal(size=p) * 0.5
+        y = (np.random.default_rng(55).random(nobs) < 1.0 / (1.0 + np.exp(-(Xm @ beta)))).astype(np.float64)
+        return pf.HierLogistic(Xm, y), 2.0 * nobs * p + 30.0 * nobs
+    if kind == "dense":
+        rng = np.random.default_rng(6)
+        Q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+        lam = rng.random(n) * 0.95 + 0.05
+        prec = (Q / lam) @ Q.T  # Sigma = Q diag(lam) Q' (test/test_utils.jl:7-10)
+        return pf.DenseNormal(np.random.default_rng(7).normal(size=n), 0.5 * (prec + prec.T)), 2.0 * n * n
+    raise ValueError(kind)
 
 
 def build_workload(name, rank, world):
     import pathfinder_b200 as pf
 
-    n, P, K, J, scale, ndraws = CONFIGS[name]
-    model = pf.Funnel(n)
+    kind, n, P, K, J, scale, ndraws = CONFIGS[name]
+    model, model_flops = make_model(kind, n)
     trajs, seeds = [], []
     for p in range(P):
         gp = rank * P + p
@@ -53,17 +77,17 @@ def build_workload(name, rank, world):
         tr = pf.optimize_with_trace(model, x0, J, 1000)
         trajs.append((tr.points, tr.gradients))
         seeds.append(rng.integers(0, 2**64, size=len(tr) - 1, dtype=np.uint64))
-    return model, trajs, seeds, (n, P, K, J, ndraws)
+    return model, trajs, seeds, (n, P, K, J, ndraws, model_flops)
 
 
-def algorithmic_flops(trajs, n, K, J):
+def algorithmic_flops(trajs, n, K, J, model_flops):
     """SURVEY §8(d) mode-F count per sample: 2n (|u|^2) + k^2 (Vc') + 4nk (Vh'u, Vh w) +
-    2k^2 (T) + 2n (scale, shift) + 3n (funnel), k = 2 min(l, J)."""
+    2k^2 (T) + 2n (scale, shift) + F_model (3n funnel, 2n^2 dense normal, ...), k = 2 min(l, J)."""
     total = 0.0
     for X, _ in trajs:
         for l in range(1, X.shape[1]):
             k = 2 * min(l, J)
-            total += K * (2 * n + k * k + 4 * n * k + 2 * k * k + 2 * n + 3 * n)
+            total += K * (2 * n + k * k + 4 * n * k + 2 * k * k + 2 * n + model_flops)
     return total
 
 
@@ -121,11 +145,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_elbo_stage(model_n, trajs, seeds, K, J, budget_s, max_paths=None):
+def oracle_logp(kind, model):
+    from oracle import pf_oracle as O
+
+    if kind == "funnel":
+        return O.logp_funnel
+    if kind == "dense":
+        return O.make_logp_dense_gaussian(model.mean, model.prec)
+    return O.make_logp_hier_logistic(model.X, model.y)
+
+
+def oracle_elbo_stage(model_n, trajs, seeds, K, J, budget_s, max_paths=None, logp_fn=None):
     """The CPU restatement (oracle) of the ELBO stage on a bounded sample; returns
     (samples done, seconds)."""
     from oracle import pf_oracle as O
 
+    logp_fn = logp_fn or O.logp_funnel
     done, t0 = 0, time.perf_counter()
     for p, (X, G) in enumerate(trajs):
         if max_paths is not None and p >= max_paths:
@@ -134,7 +169,7 @@ def oracle_elbo_stage(model_n, trajs, seeds, K, J, budget_s, max_paths=None):
         L = X.shape[1] - 1
         for l in range(1, L + 1):
             u = O.contract_normals(int(seeds[p][l - 1]), model_n, K)
-            O.elbo_and_samples(u, O.logp_funnel, mus[:, l], Hs[l])
+            O.elbo_and_samples(u, logp_fn, mus[:, l], Hs[l])
             done += K
             if time.perf_counter() - t0 > budget_s:
                 return done, time.perf_counter() - t0
@@ -144,9 +179,10 @@ def oracle_elbo_stage(model_n, trajs, seeds, K, J, budget_s, max_paths=None):
 def _ref_worker(args):
     from threadpoolctl import threadpool_limits
 
-    n, X, G, sd, K, J, budget = args
+    n, X, G, sd, K, J, budget, kind = args
+    model, _ = make_model(kind, n)
     with threadpool_limits(limits=1):  # one BLAS thread per worker process, one process per core
-        return oracle_elbo_stage(n, [(X, G)], [sd], K, J, budget)
+        return oracle_elbo_stage(n, [(X, G)], [sd], K, J, budget, logp_fn=oracle_logp(kind, model))
 
 
 def run_reference(args, rank, world):
@@ -157,14 +193,15 @@ def run_reference(args, rank, world):
     import multiprocessing as mp
 
     name = args.config
-    model, trajs, seeds, (n, P, K, J, ndraws) = build_workload(name, 0, 1)
+    model, trajs, seeds, (n, P, K, J, ndraws, model_flops) = build_workload(name, 0, 1)
     cores = os.cpu_count() or 1
     per_step_budget = 6.0
     ctx = mp.get_context("fork")
     vals = []
     with ctx.Pool(cores) as pool:
         for step in range(args.warmup + args.steps):
-            jobs = [(n, trajs[c % P][0], trajs[c % P][1], seeds[c % P], K, J, per_step_budget) for c in range(cores)]
+            jobs = [(n, trajs[c % P][0], trajs[c % P][1], seeds[c % P], K, J, per_step_budget, CONFIGS[name][0])
+                    for c in range(cores)]
             t0 = time.perf_counter()
             out = pool.map(_ref_worker, jobs)
             dt = time.perf_counter() - t0
@@ -218,7 +255,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     name = args.config
-    model, trajs, seeds, (n, P, K, J, ndraws) = build_workload(name, rank, world)
+    model, trajs, seeds, (n, P, K, J, ndraws, model_flops) = build_workload(name, rank, world)
     U = sum(X.shape[1] - 1 for X, _ in trajs)
     offsets, X, G = pf.Engine.pack(trajs)
     seeds_cat = np.concatenate(seeds)
@@ -356,7 +393,7 @@ def main():
 
     # ---- roofline of the dominant kernel (K3; its Q-apply runs on the FP64 tensor cores) -----------
     k3_avg_ms = float(np.mean(k3_ms))
-    flops = algorithmic_flops(trajs, n, K, J)
+    flops = algorithmic_flops(trajs, n, K, J, model_flops)
     ach_tf = flops / (k3_avg_ms * 1e-3) / 1e12
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch
@@ -367,7 +404,8 @@ def main():
         pass
     roofline = {"bound": "tensor", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": ach_tf / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
-                "kernel": "pfb_k3_elbo_sample (lean mode F: FP64 DMMA Q-apply + Philox/ziggurat normals)",
+                "kernel": "pfb_k3_elbo_sample (lean: FP64 DMMA Q-apply, Philox/ziggurat normals; single pass for the "
+                          "diagonal-quadratic families, K3 + cuBLAS DGEMM epilogue K8 for the GEMM-shaped ones)",
                 "kernel_ms": k3_avg_ms, "algorithmic_flops_per_launch": flops,
                 "peak_source": "measured live: pfb_measure_fp64_dmma_tflops (mma.sync m8n8k4 f64 chains); "
                                "MEASURED_PEAKS.json has bf16 and HBM figures only",
@@ -392,7 +430,7 @@ def main():
         "wall_s_timed_region": wall,
     }
 
-    if rank == 0 and world == 1 and not args.no_mode_m:
+    if rank == 0 and world == 1 and not args.no_mode_m and float(U) * n * K * 8 < 40e9:
         # secondary accounting: reference-faithful mode M (every iteration's draws written to HBM)
         engm = pf.Engine(n, model.family, model.blob, J, K, local_rank, materialize_all=True)
         engm.upload(offsets, X, G, seeds_cat)
@@ -421,7 +459,8 @@ def main():
         from threadpoolctl import threadpool_limits
 
         with threadpool_limits(limits=1):
-            done, secs = oracle_elbo_stage(n, trajs, seeds, K, J, args.cpu_budget)
+            done, secs = oracle_elbo_stage(n, trajs, seeds, K, J, args.cpu_budget,
+                                           logp_fn=oracle_logp(CONFIGS[name][0], model))
         line["cpu_baseline"] = {"value": done / secs, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"oracle ELBO stage on the first {done // K} (path, iteration) units of "
                                           f"this workload, {secs:.1f} s, single thread"}
