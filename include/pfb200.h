@@ -123,6 +123,20 @@ int pfb_batch_run(pfb_handle h);  /* K1..K5, asynchronous on the engine stream *
 int pfb_batch_sync(pfb_handle h);
 int pfb_batch_download(pfb_handle h, pfb_elbo_out* out);
 
+/* K1 + K2 only, the best iteration of every path given by the caller (1-based, 0 = none): rebuilds
+ * the fitted normals of a stored result for resample() re-entry (src/resample.jl:20-46) without
+ * an ELBO stage.  Needs pfb_batch_upload first. */
+int pfb_batch_fit_only(pfb_handle h, const int64_t* best_iter);
+
+/* K_new fresh draws per path from its best-iteration normal, one UInt64 seed per path:
+ * rand(rng, fit_distribution, K_new) of src/singlepath.jl:228-230 (top-up draws when ndraws >
+ * ndraws_elbo) and src/resample.jl:102-109 (resample with ndraws_per_run), together with logp(x)
+ * and logq = logpdf(fit, x) (src/resample.jl:81-95).  Host outputs draws[n x K_new x P],
+ * logp / logq[K_new x P] may be NULL.  keep_as_pool != 0 makes these draws the device pool of
+ * pfb_psis_resample (N = P * K_new). */
+int pfb_draw_from_fits(pfb_handle h, int K_new, const uint64_t* seeds, double* draws, double* logp,
+                       double* logq, int keep_as_pool);
+
 /* Replaces _compute_psis_result + _resample (src/multipath.jl:220-225, src/resample.jl:58-95)
  * on the pool produced by the last batch (N = P * K draws; log ratios reuse the ELBO stage's
  * logp - logq, which src/resample.jl:81-95 recomputes).  importance = 0: uniform resampling

@@ -72,6 +72,8 @@ SYMBOLS = {
     "pfb_batch_run": (C.c_int, [C.c_void_p]),
     "pfb_batch_sync": (C.c_int, [C.c_void_p]),
     "pfb_batch_download": (C.c_int, [C.c_void_p, C.POINTER(pfb_elbo_out)]),
+    "pfb_batch_fit_only": (C.c_int, [C.c_void_p, _dp]),
+    "pfb_draw_from_fits": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, C.c_int]),
     "pfb_psis_resample": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int,
                                     C.POINTER(pfb_resample_out)]),
     "pfb_psis_resample_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, _dp, _dp,

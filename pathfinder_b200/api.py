@@ -96,7 +96,7 @@ def _draw_seeds(rng, m):
     return rng.integers(0, 2**64, size=m, dtype=np.uint64)
 
 
-def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntries, init_scale):
+def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntries, init_scale, ndraws_run=None):
     """Optimise every path on the host, run the ELBO stage as one batch, retry failures."""
     P = len(inits)
     final = [None] * P
@@ -117,6 +117,14 @@ def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntr
         offsets, X, G = Engine.pack([(t.points, t.gradients) for t in traces])
         res = engine.elbo_batch(offsets, X, G, np.concatenate(seeds) if seeds else np.zeros(0, np.uint64),
                                 draws=True, fit=True)
+        if ndraws_run is not None and ndraws_run > engine.K:
+            # top-up draws from the fitted normal with the path's rng (src/singlepath.jl:228-230)
+            top_seeds = np.array([int(_draw_seeds(path_rngs[p], 1)[0]) for p in todo], dtype=np.uint64)
+            xd, lp, lq = engine.draw_from_fits(ndraws_run - engine.K, top_seeds)
+            res.draws = np.asfortranarray(np.concatenate([res.draws, xd], axis=1))
+            res.draws_logp = np.asfortranarray(np.concatenate([res.draws_logp, lp], axis=0))
+            res.draws_logq = np.asfortranarray(np.concatenate([res.draws_logq, lq], axis=0))
+            res.topped_up = True
         last = (todo[:], res, traces)
         retry = []
         for j, p in enumerate(todo):
@@ -161,9 +169,6 @@ def pathfinder(model, *, init=None, init_scale=2.0, ndraws_elbo=DEFAULT_NDRAWS_E
     """Single-path Pathfinder (src/singlepath.jl:101-139)."""
     rng = np.random.default_rng() if rng is None else rng
     ndraws = ndraws_elbo if ndraws is None else ndraws
-    if ndraws > ndraws_elbo:
-        raise NotImplementedError("ndraws > ndraws_elbo (top-up draws, src/singlepath.jl:228-230) is not "
-                                  "accelerated yet; raise ndraws_elbo")
     x0 = _uniform_init(rng, model.n, init_scale) if init is None else np.asarray(init, dtype=np.float64)
     if x0.shape != (model.n,):
         raise ValueError("init has the wrong dimension")
@@ -172,7 +177,7 @@ def pathfinder(model, *, init=None, init_scale=2.0, ndraws_elbo=DEFAULT_NDRAWS_E
         engine = Engine(model.n, model.family, model.blob, history_length, ndraws_elbo, device)
     try:
         final, _ = _run_paths(engine, model, [x0], [rng], history_length=history_length, maxiters=maxiters,
-                              ntries=ntries, init_scale=init_scale)
+                              ntries=ntries, init_scale=init_scale, ndraws_run=ndraws)
         return _assemble_path(model, rng, final[0], ndraws, ndraws_elbo)
     finally:
         if own:
@@ -198,8 +203,6 @@ def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT
     nruns = len(inits)
     if ndraws_per_run is None:
         ndraws_per_run = max(ndraws_elbo, -(-ndraws // max(nruns, 1)))  # src/multipath.jl:138
-    if ndraws_per_run > ndraws_elbo:
-        raise NotImplementedError("ndraws_per_run > ndraws_elbo (top-up draws) is not accelerated yet")
     if ndraws > ndraws_per_run * nruns:
         warnings.warn("More draws requested than total number of draws across replicas. Draws will not be unique.")
     run_seeds = _draw_seeds(rng, nruns)  # src/multipath.jl:162
@@ -216,7 +219,7 @@ def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT
     if own:
         engine = Engine(model.n, model.family, model.blob, history_length, ndraws_elbo, device)
     final, last = _run_paths(engine, model, inits[lo:hi], path_rngs[lo:hi], history_length=history_length,
-                             maxiters=maxiters, ntries=ntries, init_scale=init_scale)
+                             maxiters=maxiters, ntries=ntries, init_scale=init_scale, ndraws_run=ndraws_per_run)
     results = [_assemble_path(model, path_rngs[lo + j], final[j], ndraws_per_run, ndraws_elbo)
                for j in range(hi - lo)]
     # PSIS pool: draw-fastest, component-slowest (test/resample.jl:81-88)
@@ -233,7 +236,8 @@ def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT
             lambda logr, N: engine.psis_resample_host(logr, K_run, seed, ndraws, importance, N=N),
             seed, ndraws, importance, group, dev)
     else:
-        single_batch = last is not None and len(last[0]) == nruns and K_run == ndraws_elbo
+        single_batch = (last is not None and len(last[0]) == nruns and K_run == ndraws_elbo
+                        and not getattr(last[1], "topped_up", False))
         if single_batch:
             r = engine.psis_resample(seed, ndraws, importance)  # pool still resident on the device
         else:
@@ -251,29 +255,50 @@ def _close_and_none(engine):
 
 
 def resample(result: MultiPathfinderResult, ndraws, *, rng=None, replace=True, importance=True,
-             ndraws_per_run=None, device=0):
-    """Re-resample a fitted result (src/resample.jl:20-46) from its stored draws."""
+             ndraws_per_run=None, device=0, history_length=DEFAULT_HISTORY_LENGTH):
+    """Re-resample a fitted result (src/resample.jl:20-46): from its stored draws, or — with
+    `ndraws_per_run` — from fresh draws of every path's fitted normal (src/resample.jl:102-109),
+    rebuilt on the device from the stored trajectories without an ELBO stage."""
     if not replace:
         raise NotImplementedError("replace=false is not accelerated yet")
-    if ndraws_per_run is not None:
-        raise NotImplementedError("fresh draws per run (src/resample.jl:102-109) are not accelerated yet")
     rng = result.rng if rng is None else rng
     prs = result.pathfinder_results
     model = result.input
-    pool = np.concatenate([pr.draws for pr in prs], axis=1)
-    K_run = prs[0].draws.shape[1]
-    seed = int(_draw_seeds(rng, 1)[0])
-    eng = Engine(model.n, model.family, model.blob, DEFAULT_HISTORY_LENGTH, K_run, device)
+    if ndraws_per_run is None:
+        pool = np.concatenate([pr.draws for pr in prs], axis=1)
+        K_run = prs[0].draws.shape[1]
+        seed = int(_draw_seeds(rng, 1)[0])
+        eng = Engine(model.n, model.family, model.blob, history_length, K_run, device)
+        try:
+            if importance:
+                # the log ratios of the stored draws are the ELBO stage's logp - logq (what
+                # _compute_log_importance_ratios, src/resample.jl:81-95, recomputes)
+                logr = np.concatenate([pr.draws_logp - pr.draws_logq for pr in prs])
+                r = eng.psis_resample_host(logr, K_run, seed, ndraws, True, pool=pool)
+                psis = PSISResult(r["log_weights"], r["weights"], r["pareto_k"], r["tail_len"])
+            else:
+                r = eng.psis_resample_host(None, K_run, seed, ndraws, False, pool=pool)
+                psis = None
+        finally:
+            eng.close()
+        return MultiPathfinderResult(model, rng, r["draws"], r["ids"], prs, psis, r["inds"], None)
+    K_run = int(ndraws_per_run)
+    eng = Engine(model.n, model.family, model.blob, history_length, K_run, device)
     try:
-        if importance:
-            # the log ratios of the stored draws are the ELBO stage's logp - logq (what
-            # _compute_log_importance_ratios, src/resample.jl:81-95, recomputes)
-            logr = np.concatenate([pr.draws_logp - pr.draws_logq for pr in prs])
-            r = eng.psis_resample_host(logr, K_run, seed, ndraws, True, pool=pool)
-            psis = PSISResult(r["log_weights"], r["weights"], r["pareto_k"], r["tail_len"])
-        else:
-            r = eng.psis_resample_host(None, K_run, seed, ndraws, False, pool=pool)
-            psis = None
+        offsets, X, G = Engine.pack([(pr.optim_trace.points, pr.optim_trace.gradients) for pr in prs])
+        U = int(offsets[-1]) - len(prs)
+        eng.upload(offsets, X, G, np.zeros(U, dtype=np.uint64))
+        eng.fit_only([pr.fit_iteration for pr in prs])
+        seeds = _draw_seeds(rng, len(prs))
+        xd, lp, lq = eng.draw_from_fits(K_run, seeds, keep_as_pool=True)
+        r = eng.psis_resample(int(_draw_seeds(rng, 1)[0]), ndraws, importance)
     finally:
         eng.close()
-    return MultiPathfinderResult(model, rng, r["draws"], r["ids"], prs, psis, r["inds"], None)
+    new_prs = []
+    for j, pr in enumerate(prs):
+        q = PathfinderResult(pr.input, pr.rng, pr.fit_distribution, xd[:, :, j].copy(), pr.fit_iteration,
+                             pr.num_tries, pr.optim_trace, pr.elbo_estimates, pr.num_bfgs_updates_rejected,
+                             pr.success, lp[:, j].copy(), lq[:, j].copy())
+        new_prs.append(q)
+    psis = PSISResult(r["log_weights"], r["weights"], r["pareto_k"], r["tail_len"]) if importance else None
+    return MultiPathfinderResult(model, rng, r["draws"], r["ids"], new_prs, psis, r["inds"], None)

@@ -84,11 +84,12 @@ struct pfb_engine {
     double model_c0 = 0.0;
     int model_nobs = 0;                 // HLOGISTIC
     cublasHandle_t cublas = nullptr;    // families whose log p needs a GEMM over the draws (K8)
-    DevBuf dGenX, dGenY, dIota;
+    DevBuf dGenX, dGenY, dIota, dTopSeeds;
     // batch state
     int n = 0, P = 0, K = 0;
     int64_t T = 0, U = 0;
     bool have_batch = false, ran = false, have_normals = false;
+    int poolK = 0;  // draws per path in the device pool (K, or the count of the last pfb_draw_from_fits)
     int launches = 0;
     std::vector<int64_t> h_off;
     DevBuf dX, dG, dOff, dSeeds, dUnitCol, dNormals;
@@ -167,7 +168,7 @@ extern "C" int pfb_destroy(pfb_handle h) {
                       &h->dSe, &h->dBestIter, &h->dBestUnit, &h->dSucc, &h->dPool, &h->dPoolLogp,
                       &h->dPoolLogq, &h->dAllDraws, &h->dFitMu, &h->dFitAlpha, &h->dFitVh, &h->dFitT,
                       &h->dFitVc, &h->dFitLogdet, &h->dFitJeff, &h->dLogw, &h->dW, &h->dCum, &h->dScal,
-                      &h->dInds, &h->dIds, &h->dOutDraws, &h->dTmpLogr, &h->dTmpPool, &h->dGenX, &h->dGenY, &h->dIota};
+                      &h->dInds, &h->dIds, &h->dOutDraws, &h->dTmpLogr, &h->dTmpPool, &h->dGenX, &h->dGenY, &h->dIota, &h->dTopSeeds};
     for (auto* b : bufs) b->release();
     if (h->cublas) cublasDestroy(h->cublas);
     for (auto& ev : h->ev) cudaEventDestroy(ev);
@@ -324,9 +325,10 @@ static bool model_is_external(const pfb_engine* h) {
 }
 
 // K8: log p of M = nslots * K materialised draws X [n x M] for the GEMM-shaped families.
-static int generic_logp(pfb_engine* h, const double* X, int64_t M, const int32_t* slot_unit, double* logp) {
+static int generic_logp(pfb_engine* h, const double* X, int64_t M, const int32_t* slot_unit, double* logp,
+                        int K_over = 0) {
     if (M <= 0) return PFB_OK;
-    const int n = h->n, K = h->K;
+    const int n = h->n, K = K_over > 0 ? K_over : h->K;
     const double one = 1.0, zero = 0.0;
     if (h->model == PFB_MODEL_DENSENORMAL) {
         const double* d = h->dModel.as<double>();
@@ -349,14 +351,16 @@ static int generic_logp(pfb_engine* h, const double* X, int64_t M, const int32_t
     return PFB_OK;
 }
 
+// K_over > 0 / seeds_over != NULL: fresh draws from the fitted normals (top-up draws, resample()).
 static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list, double* logp, double* logq,
-                             double* draws) {
+                             double* draws, int K_over = 0, const uint64_t* seeds_over = nullptr) {
     const double* mp0 = model_is_external(h) ? nullptr : h->dModel.as<double>();
     const double* mp1 = mp0 ? mp0 + h->model_n : nullptr;
-    const double* un = h->have_normals ? h->dNormals.as<double>() : nullptr;
+    const double* un = (h->have_normals && !seeds_over) ? h->dNormals.as<double>() : nullptr;
     auto fn = h->KP == 12 ? pfb_launch_k3_kp12 : (h->KP == 20 ? pfb_launch_k3_kp20 : pfb_launch_k3_kp24);
-    return fn(h->stream, h->model, h->n, h->K, nslots, unit_list, h->dFR2.as<double>(), h->dHDR.as<double>(),
-              h->dSeeds.as<uint64_t>(), un, mp0, mp1, h->model_c0, logp, logq, draws, h->cfg.elbo_mode == 1);
+    return fn(h->stream, h->model, h->n, K_over > 0 ? K_over : h->K, nslots, unit_list, h->dFR2.as<double>(),
+              h->dHDR.as<double>(), seeds_over ? seeds_over : h->dSeeds.as<uint64_t>(), un, mp0, mp1, h->model_c0,
+              logp, logq, draws, h->cfg.elbo_mode == 1);
 }
 
 extern "C" int pfb_batch_run(pfb_handle h) {
@@ -429,6 +433,88 @@ extern "C" int pfb_batch_run(pfb_handle h) {
     }
     PFB_CUDA(h, cudaEventRecord(h->ev[5], st));
     h->ran = true;
+    h->poolK = K;
+    return PFB_OK;
+}
+
+// K1 + K2 only, with the best iteration of every path given by the caller: rebuilds the fitted
+// normals of a stored result (resample() re-entry, src/resample.jl:20-46) without an ELBO stage.
+extern "C" int pfb_batch_fit_only(pfb_handle h, const int64_t* best_iter) {
+    if (!h || !best_iter) return PFB_ERR_ARG;
+    if (!h->have_batch) PFB_FAIL(h, PFB_ERR_STATE, "pfb_batch_upload has not been called");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const int n = h->n, P = h->P, J = h->cfg.history_length, KP = h->KP;
+    const int U = (int)h->U;
+    std::vector<int32_t> bu((size_t)P);
+    std::vector<int32_t> ok((size_t)P);
+    for (int p = 0; p < P; ++p) {
+        const int64_t L = h->h_off[(size_t)p + 1] - h->h_off[(size_t)p] - 1;
+        if (best_iter[p] < 0 || best_iter[p] > L) PFB_FAIL(h, PFB_ERR_ARG, "best_iter out of range");
+        bu[(size_t)p] = best_iter[p] > 0 ? (int32_t)(h->h_off[(size_t)p] - p + best_iter[p] - 1) : -1;
+        ok[(size_t)p] = best_iter[p] > 0;
+    }
+    PFB_CUDA(h, pfb_launch_k1(st, n, P, J, h->cfg.eps, h->dX.as<double>(), h->dG.as<double>(),
+                              h->dOff.as<int64_t>(), h->dAlpha.as<double>(), h->dHist.as<int32_t>(),
+                              h->dHistCnt.as<int32_t>(), h->dRej.as<int64_t>()));
+    PFB_CUDA(h, pfb_launch_k2(st, KP, n, U, J, h->dX.as<double>(), h->dG.as<double>(), h->dUnitCol.as<int32_t>(),
+                              h->dAlpha.as<double>(), h->dHist.as<int32_t>(), h->dHistCnt.as<int32_t>(),
+                              h->dFR.as<double>(), h->dHDR.as<double>(), h->dFR2.as<double>(),
+                              model_is_external(h) ? PFB_MODEL_ISONORMAL : h->model,
+                              model_is_external(h) ? nullptr : h->dModel.as<double>(),
+                              (h->dModel.p && !model_is_external(h)) ? h->dModel.as<double>() + h->model_n : nullptr));
+    PFB_CUDA(h, cudaMemcpyAsync(h->dBestUnit.p, bu.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
+    PFB_CUDA(h, cudaMemcpyAsync(h->dBestIter.p, best_iter, (size_t)P * 8, cudaMemcpyHostToDevice, st));
+    PFB_CUDA(h, cudaMemcpyAsync(h->dSucc.p, ok.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    for (int i = 0; i <= 5; ++i) PFB_CUDA(h, cudaEventRecord(h->ev[i], st));
+    h->launches = 2;
+    h->ran = true;
+    h->poolK = 0;
+    return PFB_OK;
+}
+
+// K_new fresh draws from the best-iteration normal of every path, seeded per path:
+//   rand(rng, fit_distribution, K_new)  of src/singlepath.jl:228-230 (top-up draws) and
+//   src/resample.jl:102-109 (resample with ndraws_per_run), with their logp and logq = logpdf(fit, x)
+//   (what _compute_log_importance_ratios, src/resample.jl:81-95, evaluates for fresh draws).
+// keep_as_pool != 0: the device pool becomes these draws (N = P * K_new for pfb_psis_resample).
+extern "C" int pfb_draw_from_fits(pfb_handle h, int K_new, const uint64_t* seeds, double* draws, double* logp,
+                                  double* logq, int keep_as_pool) {
+    if (!h || !seeds) return PFB_ERR_ARG;
+    if (K_new < 1) PFB_FAIL(h, PFB_ERR_ARG, "K_new must be positive");
+    if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "no fitted batch (pfb_batch_run / pfb_batch_fit_only)");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const size_t n = h->n, P = h->P, U = (size_t)h->U;
+    if (P == 0) return PFB_OK;
+    // K3 reads seeds[unit]: scatter the per-path seeds to their best units
+    std::vector<int32_t> bu(P);
+    PFB_CUDA(h, cudaMemcpyAsync(bu.data(), h->dBestUnit.p, P * 4, cudaMemcpyDeviceToHost, st));
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    std::vector<uint64_t> sd(U > 0 ? U : 1, 0);
+    for (size_t p = 0; p < P; ++p)
+        if (bu[p] >= 0) sd[(size_t)bu[p]] = seeds[p];
+    PFB_CUDA(h, h->dTopSeeds.ensure(sd.size() * 8));
+    PFB_CUDA(h, cudaMemcpyAsync(h->dTopSeeds.p, sd.data(), sd.size() * 8, cudaMemcpyHostToDevice, st));
+    DevBuf* X = keep_as_pool ? &h->dPool : &h->dGenX;
+    DevBuf* Lp = keep_as_pool ? &h->dPoolLogp : &h->dTmpLogr;
+    DevBuf* Lq = keep_as_pool ? &h->dPoolLogq : &h->dTmpPool;
+    PFB_CUDA(h, X->ensure(n * (size_t)K_new * P * 8 + 8));
+    PFB_CUDA(h, Lp->ensure((size_t)K_new * P * 8 + 8));
+    PFB_CUDA(h, Lq->ensure((size_t)K_new * P * 8 + 8));
+    PFB_CUDA(h, launch_k3(h, (int)P, h->dBestUnit.as<int32_t>(), Lp->as<double>(), Lq->as<double>(), X->as<double>(),
+                          K_new, h->dTopSeeds.as<uint64_t>()));
+    if (model_is_external(h)) {
+        int rc = generic_logp(h, X->as<double>(), (int64_t)P * K_new, h->dBestUnit.as<int32_t>(), Lp->as<double>(),
+                              K_new);
+        if (rc) return rc;
+    }
+    if (draws) PFB_CUDA(h, cudaMemcpyAsync(draws, X->p, n * (size_t)K_new * P * 8, cudaMemcpyDeviceToHost, st));
+    if (logp) PFB_CUDA(h, cudaMemcpyAsync(logp, Lp->p, (size_t)K_new * P * 8, cudaMemcpyDeviceToHost, st));
+    if (logq) PFB_CUDA(h, cudaMemcpyAsync(logq, Lq->p, (size_t)K_new * P * 8, cudaMemcpyDeviceToHost, st));
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    if (keep_as_pool) h->poolK = K_new;
     return PFB_OK;
 }
 
@@ -592,9 +678,9 @@ static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const 
 
 extern "C" int pfb_psis_resample(pfb_handle h, uint64_t seed, int ndraws, int importance, pfb_resample_out* o) {
     if (!h || !o) return PFB_ERR_ARG;
-    if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "pfb_batch_run has not been called");
+    if (!h->ran || h->poolK <= 0) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
-    return psis_resample_impl(h, h->n, (int64_t)h->P * h->K, h->K, h->dPoolLogp.as<double>(),
+    return psis_resample_impl(h, h->n, (int64_t)h->P * h->poolK, h->poolK, h->dPoolLogp.as<double>(),
                               h->dPoolLogq.as<double>(), nullptr, h->dPool.as<double>(), seed, ndraws,
                               importance, o);
 }

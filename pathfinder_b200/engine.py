@@ -63,6 +63,7 @@ class Engine:
         self._P = 0
         self._U = 0
         self._offsets = None
+        self._poolK = self.K
 
     def close(self):
         if getattr(self, "h", None):
@@ -112,6 +113,7 @@ class Engine:
 
     def run(self):
         _lib.check(self.h, self.lib.pfb_batch_run(self.h))
+        self._poolK = self.K
 
     def sync(self):
         _lib.check(self.h, self.lib.pfb_batch_sync(self.h))
@@ -154,6 +156,28 @@ class Engine:
         self.run()
         return self.download(**kw)
 
+    def fit_only(self, best_iter):
+        """K1 + K2 with caller-given best iterations (resample() re-entry)."""
+        bi = np.ascontiguousarray(best_iter, dtype=np.int64)
+        if bi.size != self._P:
+            raise ValueError("need one best_iter per path")
+        _lib.check(self.h, self.lib.pfb_batch_fit_only(self.h, _ptr(bi)))
+
+    def draw_from_fits(self, K_new, seeds, keep_as_pool=False, want_draws=True):
+        """K_new fresh draws per path from its best-iteration normal: (draws [n, K_new, P], logp, logq)."""
+        sd = np.ascontiguousarray(seeds, dtype=np.uint64)
+        if sd.size != self._P:
+            raise ValueError("need one seed per path")
+        P = self._P
+        draws = np.empty((self.n, int(K_new), P), order="F") if want_draws else None
+        lp = np.empty((int(K_new), P), order="F")
+        lq = np.empty((int(K_new), P), order="F")
+        _lib.check(self.h, self.lib.pfb_draw_from_fits(self.h, int(K_new), _ptr(sd), _ptr(draws), _ptr(lp), _ptr(lq),
+                                                       int(bool(keep_as_pool))))
+        if keep_as_pool:
+            self._poolK = int(K_new)
+        return draws, lp, lq
+
     def timings(self):
         ms = np.zeros(6)
         nl = self.lib.pfb_get_timings(self.h, _ptr(ms))
@@ -187,8 +211,8 @@ class Engine:
         return r
 
     def psis_resample(self, seed, ndraws, importance=True):
-        """On the pool of the last batch (device resident)."""
-        N = self._P * self.K
+        """On the pool of the last batch / the last draw_from_fits(keep_as_pool=True) (device resident)."""
+        N = self._P * self._poolK
         out, r = self._resample_out(N, ndraws, importance, True)
         _lib.check(self.h, self.lib.pfb_psis_resample(self.h, C.c_uint64(int(seed)), int(ndraws),
                                                       int(bool(importance)), C.byref(out)))

@@ -398,3 +398,74 @@ def test_hier_logistic_config4_shape():
     f = O.make_logp_hier_logistic(Xm, y)
     for pr in res.pathfinder_results:
         np.testing.assert_allclose(pr.draws_logp, f(pr.draws), rtol=1e-9, atol=1e-9)
+
+
+def test_topup_draws_and_resample_with_fresh_draws():
+    """ndraws > ndraws_elbo tops the draws up from the fitted normal (src/singlepath.jl:228-230);
+    resample(result; ndraws_per_run) redraws from the stored fits (src/resample.jl:102-109).
+    Fresh draws must be x = mu + L u for the contract normals of their seed, with logq = logpdf."""
+    from oracle import pf_oracle as O
+    from oracle import psis as OP
+    import pathfinder_b200 as pf
+
+    model = pf.Funnel(12)
+    rng = np.random.default_rng(77)
+    res = pf.multipathfinder(model, 100, nruns=3, ndraws_elbo=16, rng=rng, init_scale=3.0, maxiters=30)
+    # ndraws_per_run = max(16, cld(100, 3)) = 34 > 16: top-up happened
+    assert all(pr.draws.shape == (12, 34) for pr in res.pathfinder_results)
+    for pr in res.pathfinder_results:
+        np.testing.assert_allclose(pr.draws_logp, O.logp_funnel(pr.draws), rtol=1e-9, atol=1e-9)
+        mus, Hs, _ = O.fit_mvnormals(pr.optim_trace.points, pr.optim_trace.gradients, history_length=6)
+        W, mu = Hs[pr.fit_iteration], mus[:, pr.fit_iteration]
+        logq = -(12 * O.LOG2PI + W.logdet()) / 2.0 - W.invquad(pr.draws - mu[:, None]) / 2.0
+        np.testing.assert_allclose(pr.draws_logq, logq, rtol=1e-6, atol=1e-6)
+    pool = np.concatenate([pr.draws for pr in res.pathfinder_results], axis=1)
+    logr = np.concatenate([pr.draws_logp - pr.draws_logq for pr in res.pathfinder_results])
+    assert np.array_equal(res.psis_result.weights, OP.psis(logr)["weights"], equal_nan=True)
+    assert np.array_equal(res.draws, pool[:, res.sample_inds - 1])
+    assert np.array_equal(res.draw_component_ids, -(-res.sample_inds // 34))
+
+    # resample with fresh draws: consistent with the stored fits, reproducible under reseed
+    r2 = pf.resample(res, 40, rng=np.random.default_rng(5), ndraws_per_run=50)
+    r3 = pf.resample(res, 40, rng=np.random.default_rng(5), ndraws_per_run=50)
+    for j, pr in enumerate(r2.pathfinder_results):
+        assert pr.draws.shape == (12, 50)
+        assert np.array_equal(pr.draws, r3.pathfinder_results[j].draws)
+        assert not np.array_equal(pr.draws[:, :16], res.pathfinder_results[j].draws[:, :16])
+        mus, Hs, _ = O.fit_mvnormals(pr.optim_trace.points, pr.optim_trace.gradients, history_length=6)
+        W, mu = Hs[pr.fit_iteration], mus[:, pr.fit_iteration]
+        logq = -(12 * O.LOG2PI + W.logdet()) / 2.0 - W.invquad(pr.draws - mu[:, None]) / 2.0
+        np.testing.assert_allclose(pr.draws_logq, logq, rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(pr.draws_logp, O.logp_funnel(pr.draws), rtol=1e-9, atol=1e-9)
+    assert np.array_equal(r2.sample_inds, r3.sample_inds)
+    pool2 = np.concatenate([pr.draws for pr in r2.pathfinder_results], axis=1)
+    assert r2.draws.shape == (12, 40) and np.array_equal(r2.draws, pool2[:, r2.sample_inds - 1])
+    assert abs(r2.psis_result.weights.sum() - 1) < 1e-12
+    # single path with ndraws > ndraws_elbo
+    one = pf.pathfinder(model, ndraws_elbo=8, ndraws=20, rng=np.random.default_rng(1), init_scale=3.0, maxiters=30)
+    assert one.draws.shape == (12, 20)
+    np.testing.assert_allclose(one.draws_logp, O.logp_funnel(one.draws), rtol=1e-9, atol=1e-9)
+
+
+def test_fresh_draws_match_oracle_on_a_well_conditioned_fit():
+    """pfb_draw_from_fits: x = mu + L u for the contract normals of the given seed."""
+    from oracle import pf_oracle as O
+    import pathfinder_b200 as pf
+    from tests.helpers import synthetic_trajectory
+
+    n, K = 20, 8
+    trajs = [synthetic_trajectory(n, L, 300 + L) for L in (4, 9)]
+    offsets, X, G = pf.Engine.pack(trajs)
+    eng = _engine(pf.IsoNormal(n), K)
+    eng.upload(offsets, X, G, np.zeros(13, dtype=np.uint64))
+    best = [3, 9]
+    eng.fit_only(best)
+    seeds = np.array([11, 2**63 + 5], dtype=np.uint64)
+    xd, lp, lq = eng.draw_from_fits(37, seeds)
+    for p, (Xp, Gp) in enumerate(trajs):
+        mus, Hs, _ = O.fit_mvnormals(Xp, Gp, history_length=6)
+        x, logq = O.rand_and_logpdf(O.contract_normals(int(seeds[p]), n, 37), mus[:, best[p]], Hs[best[p]])
+        assert _rel(xd[:, :, p], x) < RTOL
+        np.testing.assert_allclose(lq[:, p], logq, rtol=RTOL, atol=RTOL)
+        np.testing.assert_allclose(lp[:, p], O.logp_isonormal(x), rtol=RTOL, atol=RTOL)
+    eng.close()
