@@ -50,6 +50,64 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
     // element (row i, column c) of the panel
 #define PNL(i, c) (*(SMEM_PANEL ? (s_panel + (c) * ldp + (i)) : (fr + (int64_t)(i) * RS + (c))))
     double* hdr = HDR + (int64_t)u * pfb_hs_of(KP);
+
+    // Weighted Gram matrix of the panel's first KP columns on the FP64 tensor cores:
+    //   Gm[a][b] = sum_i wgt(i) P(i, a) P(i, b),  a, b < KP  (row-major, KP x KP, shared memory).
+    // Each warp takes a slice of rows (4 per DMMA k-step); A[m = col][k = row] and B[k = row][n = col]
+    // are the same panel element, B scaled by the weight.  Warp partials are summed in warp order
+    // through `scratch` (one 8 x 8 tile at a time) => deterministic.
+    constexpr int GT = (KP + 7) / 8;
+    auto gram = [&](auto wgt, double* Gm) {
+        const int lane = tid & 31, warp = tid >> 5, nwarp = (nt + 31) >> 5;
+        const int g = lane >> 2, t = lane & 3;
+        double acc[GT][GT][2];
+#pragma unroll
+        for (int ta = 0; ta < GT; ++ta)
+#pragma unroll
+            for (int tb = 0; tb < GT; ++tb) acc[ta][tb][0] = acc[ta][tb][1] = 0.0;
+        const int ksteps = (n + 3) >> 2;
+        for (int ks = warp; ks < ksteps; ks += nwarp) {
+            const int row = 4 * ks + t;
+            const bool rok = row < n;
+            const double w = rok ? wgt(row) : 0.0;
+            double fa[GT], fb[GT];
+#pragma unroll
+            for (int ta = 0; ta < GT; ++ta) {
+                const int col = 8 * ta + g;
+                fa[ta] = (rok && col < KP) ? PNL(row, col) : 0.0;
+                fb[ta] = fa[ta] * w;
+            }
+#pragma unroll
+            for (int ta = 0; ta < GT; ++ta)
+#pragma unroll
+                for (int tb = 0; tb < GT; ++tb)
+                    if (tb >= ta)  // upper block triangle; mirrored below
+                        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                            : "+d"(acc[ta][tb][0]), "+d"(acc[ta][tb][1])
+                            : "d"(fa[ta]), "d"(fb[tb]));
+        }
+#pragma unroll
+        for (int ta = 0; ta < GT; ++ta)
+#pragma unroll
+            for (int tb = 0; tb < GT; ++tb) {
+                if (tb < ta) continue;
+                __syncthreads();  // scratch free
+                // D fragment: rows 8 ta + g, columns 8 tb + 2 t + {0, 1}
+                scratch[(warp * 8 + g) * 8 + 2 * t] = acc[ta][tb][0];
+                scratch[(warp * 8 + g) * 8 + 2 * t + 1] = acc[ta][tb][1];
+                __syncthreads();
+                if (tid < 64) {
+                    double sum = 0.0;
+                    for (int wq = 0; wq < nwarp; ++wq) sum += scratch[wq * 64 + tid];
+                    const int a = 8 * ta + (tid >> 3), b = 8 * tb + (tid & 7);
+                    if (a < KP && b < KP) {
+                        Gm[a * KP + b] = sum;
+                        Gm[b * KP + a] = sum;
+                    }
+                }
+            }
+        __syncthreads();
+    };
     const double* alpha = alpha_all + (int64_t)u * n;
     const int64_t col = unit_col[u];
     const double* theta = X + col * n;
@@ -83,33 +141,12 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
     __syncthreads();
 
     if (jeff > 0) {
-        // ---- Gram blocks of A~: S'Y = A2' A1, Y' diag(alpha) Y = A1' A1 (upper triangles) ---------
-        for (int a = 0; a < jeff; ++a) {
-            double acc[KP];
-#pragma unroll
-            for (int b = 0; b < KP; ++b) acc[b] = 0.0;
-            for (int i = tid; i < n; i += nt) {
-                double sa_ = PNL(i, jeff + a), ya_ = PNL(i, a);
-#pragma unroll
-                for (int b = 0; b < JM; ++b) {
-                    if (b >= a && b < jeff) {
-                        double yb = PNL(i, b);
-                        acc[b] = fma(sa_, yb, acc[b]);
-                        acc[JM + b] = fma(ya_, yb, acc[JM + b]);
-                    }
-                }
-            }
-            const unsigned tri = ((1u << jeff) - 1u) & ~((1u << a) - 1u);  // b in [a, jeff)
-            pfb_block_sum_fast<KP>(acc, scratch, tri | (tri << JM));
-            if (tid == 0) {
-#pragma unroll
-                for (int b = 0; b < JM; ++b) {
-                    if (b >= a && b < jeff) {
-                        sStY[a][b] = acc[b];
-                        sYaY[a][b] = acc[JM + b];
-                    }
-                }
-            }
+        // ---- Gram blocks of A~ (DMMA): S'Y = A2' A1, Y' diag(alpha) Y = A1' A1 ---------------------
+        gram([](int) { return 1.0; }, &sE[0][0]);
+        for (int e = tid; e < jeff * jeff; e += nt) {
+            const int a = e / jeff, b = e % jeff;
+            sStY[a][b] = sE[jeff + a][b];
+            sYaY[a][b] = sE[a][b];
         }
         __syncthreads();
         // ---- D  (src/inverse_hessian.jl:119-130) ----------------------------------------------
@@ -369,34 +406,23 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
         for (int e = n * RS2 + tid; e < npad * RS2; e += nt) FR2[(int64_t)u * npad * RS2 + e] = 0.0;
     }
     pfb_block_sum_fast<1>(e0acc, scratch, 1u);
-    // M = Vh' diag(p) Vh (upper triangle, row a per round; mirrored on store), rv = Vh' r
-    for (int a = 0; a <= KP; ++a) {
+    // M = Vh' diag(p) Vh on the tensor cores (sE is free by now), rv = Vh' r by one reduction round
+    gram([&](int i) { return model_d(i) * alpha[i]; }, &sE[0][0]);
+    for (int e = tid; e < KP * KP; e += nt) hdr[PFB_HDR_M(KP) + e] = (&sE[0][0])[e];
+    {
         double acc[KP];
 #pragma unroll
         for (int b = 0; b < KP; ++b) acc[b] = 0.0;
-        const unsigned msk = (a < KP) ? (((1u << kq) - 1u) & ~((1u << a) - 1u)) : ((1u << kq) - 1u);
-        if (msk) {
-            for (int i = tid; i < n; i += nt) {
-                const double d = model_d(i);
-                const double wgt = (a < KP) ? d * alpha[i] * PNL(i, a) : d * PNL(i, KP) * (PNL(i, KP + 1) - model_m(i));
+        for (int i = tid; i < n; i += nt) {
+            const double wgt = model_d(i) * PNL(i, KP) * (PNL(i, KP + 1) - model_m(i));
 #pragma unroll
-                for (int b = 0; b < KP; ++b)
-                    if ((msk >> b) & 1u) acc[b] = fma(wgt, PNL(i, b), acc[b]);
-            }
-            pfb_block_sum_fast<KP>(acc, scratch, msk);
+            for (int b = 0; b < KP; ++b)
+                if (b < kq) acc[b] = fma(wgt, PNL(i, b), acc[b]);
         }
+        if (kq > 0) pfb_block_sum_fast<KP>(acc, scratch, (1u << kq) - 1u);
         if (tid == 0) {
 #pragma unroll
-            for (int b = 0; b < KP; ++b) {
-                if (a < KP) {
-                    if (b >= a) {
-                        hdr[PFB_HDR_M(KP) + a * KP + b] = acc[b];
-                        hdr[PFB_HDR_M(KP) + b * KP + a] = acc[b];
-                    }
-                } else {
-                    hdr[PFB_HDR_RV(KP) + b] = acc[b];
-                }
-            }
+            for (int b = 0; b < KP; ++b) hdr[PFB_HDR_RV(KP) + b] = acc[b];
         }
     }
     // ---- header ---------------------------------------------------------------------------------
