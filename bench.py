@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--config", default="cfg3_funnel1024_p64_k1000_j6", choices=list(CONFIGS))
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-mode-m", action="store_true", help="skip the secondary mode-M (materialise) timing")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -458,9 +459,12 @@ def main():
         # ---- cpu_baseline: the oracle port on one host core, bounded sample -----------------------
         from threadpoolctl import threadpool_limits
 
-        with threadpool_limits(limits=1):
-            done, secs = oracle_elbo_stage(n, trajs, seeds, K, J, args.cpu_budget,
-                                           logp_fn=oracle_logp(CONFIGS[name][0], model))
+        if args.no_cpu_baseline:
+            done, secs = 0, 1.0
+        else:
+            with threadpool_limits(limits=1):
+                done, secs = oracle_elbo_stage(n, trajs, seeds, K, J, args.cpu_budget,
+                                               logp_fn=oracle_logp(CONFIGS[name][0], model))
         line["cpu_baseline"] = {"value": done / secs, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"oracle ELBO stage on the first {done // K} (path, iteration) units of "
                                           f"this workload, {secs:.1f} s, single thread"}
