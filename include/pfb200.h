@@ -123,6 +123,33 @@ int pfb_batch_run(pfb_handle h);  /* K1..K5, asynchronous on the engine stream *
 int pfb_batch_sync(pfb_handle h);
 int pfb_batch_download(pfb_handle h, pfb_elbo_out* out);
 
+/* Row f1 — batched device L-BFGS for the closed-form families (iso-normal, funnel, independent
+ * normals).  Replaces the per-path trajectory producer
+ *   optimize_with_trace(prob, optimizer; maxiters)                src/optimize.jl:35-59
+ *   (default_optimizer = Optim.LBFGS(m = history_length, ...),    src/Pathfinder.jl:29-35)
+ * mapped over the runs by _chunk_tmap (src/multipath.jl:190-208): one CTA per path runs the whole
+ * optimisation (contract: pathfinder_b200/csrc/pf_lbfgs.h) and leaves the trace
+ * (OptimizationTrace points / log_densities / gradients, src/optimize.jl:110-114) resident on the
+ * device.  x0[n x P]: initial points.  npoints[P] = L_p + 1 trace points; status[P] = PF_LBFGS_*
+ * (0 gradient tolerance, 1 objective tolerance, 2 maxiters, 3 line search failed, 4 non-finite:
+ * the point is recorded and the run stops, src/optimize.jl:103-105); nevals[P] density evaluations
+ * (may be NULL).  PFB_ERR_UNSUPPORTED for the GEMM-shaped families (optimise those on the host). */
+typedef struct {
+    int32_t maxiters;   /* 1000, src/optimize.jl:40                                       */
+    int32_t max_points; /* capacity of the per-path trace on the device (<= maxiters + 1) */
+    double gtol;        /* max |gradient| tolerance, 1e-8 (Optim g_abstol)                */
+    double ftol;        /* relative objective decrease tolerance                          */
+} pfb_lbfgs_opts;
+int pfb_lbfgs_batch(pfb_handle h, int n, int P, const double* x0, const pfb_lbfgs_opts* opts,
+                    int64_t* npoints, int32_t* status, int32_t* nevals);
+/* Makes the traces of the last pfb_lbfgs_batch the current batch (device-to-device pack into the
+ * n x T layout; what pfb_batch_upload does from host buffers).  seeds[U], U = sum(npoints) - P. */
+int pfb_batch_from_lbfgs(pfb_handle h, const uint64_t* seeds);
+/* The traces of the last pfb_lbfgs_batch, packed path after path: positions / gradients
+ * [n x T] column-major, log_densities[T], T = sum(npoints).  Any pointer may be NULL. */
+int pfb_lbfgs_download(pfb_handle h, double* positions, double* gradients, double* log_densities);
+int pfb_lbfgs_ms(pfb_handle h, double* ms); /* kernel time of the last pfb_lbfgs_batch */
+
 /* K1 + K2 only, the best iteration of every path given by the caller (1-based, 0 = none): rebuilds
  * the fitted normals of a stored result for resample() re-entry (src/resample.jl:20-46) without
  * an ELBO stage.  Needs pfb_batch_upload first. */

@@ -52,6 +52,10 @@ class pfb_resample_out(C.Structure):
         "log_weights", "weights", "pareto_k", "tail_len", "inds", "ids", "draws")]
 
 
+class pfb_lbfgs_opts(C.Structure):
+    _fields_ = [("maxiters", C.c_int32), ("max_points", C.c_int32), ("gtol", C.c_double), ("ftol", C.c_double)]
+
+
 class pfb_device_view(C.Structure):
     _fields_ = [
         ("pool_draws", _dp), ("pool_logp", _dp), ("pool_logq", _dp), ("elbo", _dp), ("stream", _dp),
@@ -72,6 +76,10 @@ SYMBOLS = {
     "pfb_batch_run": (C.c_int, [C.c_void_p]),
     "pfb_batch_sync": (C.c_int, [C.c_void_p]),
     "pfb_batch_download": (C.c_int, [C.c_void_p, C.POINTER(pfb_elbo_out)]),
+    "pfb_lbfgs_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, C.POINTER(pfb_lbfgs_opts), _dp, _dp, _dp]),
+    "pfb_batch_from_lbfgs": (C.c_int, [C.c_void_p, _dp]),
+    "pfb_lbfgs_download": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
+    "pfb_lbfgs_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "pfb_batch_fit_only": (C.c_int, [C.c_void_p, _dp]),
     "pfb_draw_from_fits": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, C.c_int]),
     "pfb_psis_resample": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int,

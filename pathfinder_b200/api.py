@@ -96,8 +96,22 @@ def _draw_seeds(rng, m):
     return rng.integers(0, 2**64, size=m, dtype=np.uint64)
 
 
-def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntries, init_scale, ndraws_run=None):
-    """Optimise every path on the host, run the ELBO stage as one batch, retry failures."""
+DEVICE_LBFGS_FAMILIES = (0, 1, 2)  # iso-normal, funnel, independent normals (include/pfb200.h)
+
+
+def _use_device_optimizer(model, optimizer):
+    if optimizer not in ("auto", "device", "host"):
+        raise ValueError("optimizer must be 'auto', 'device' or 'host'")
+    if optimizer == "device" and model.family not in DEVICE_LBFGS_FAMILIES:
+        raise ValueError("the device L-BFGS covers the closed-form families only; use optimizer='host'")
+    return optimizer == "device" or (optimizer == "auto" and model.family in DEVICE_LBFGS_FAMILIES)
+
+
+def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntries, init_scale, ndraws_run=None,
+               optimizer="host", gtol=1e-8, ftol=1e-14):
+    """Optimise every path (host L-BFGS, or kernel K0 for the closed-form families), run the ELBO
+    stage as one batch, retry failures."""
+    device_opt = _use_device_optimizer(model, optimizer)
     P = len(inits)
     final = [None] * P
     todo = list(range(P))
@@ -106,17 +120,31 @@ def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntr
     last = None
     while todo:
         traces, seeds = [], []
-        for p in todo:
-            tries[p] += 1
-            tr = optimize_with_trace(model, cur_init[p], history_length, maxiters)
-            if len(tr) == 0:  # non-finite at the initial point: an empty trace, L = 0
-                x0 = np.asarray(cur_init[p], dtype=np.float64)[:, None]
-                tr = OptimizationTrace(x0, np.array([np.nan]), np.zeros_like(x0))
-            traces.append(tr)
-            seeds.append(_draw_seeds(path_rngs[p], len(tr) - 1))  # src/elbo.jl:2
-        offsets, X, G = Engine.pack([(t.points, t.gradients) for t in traces])
-        res = engine.elbo_batch(offsets, X, G, np.concatenate(seeds) if seeds else np.zeros(0, np.uint64),
-                                draws=True, fit=True)
+        if device_opt:
+            # K0: all trajectories in one launch; they stay on the device for K1/K2
+            for p in todo:
+                tries[p] += 1
+            x0s = np.stack([np.asarray(cur_init[p], dtype=np.float64) for p in todo], axis=1)
+            npts, _, _ = engine.lbfgs_batch(x0s, maxiters, None, gtol, ftol)
+            seeds = [_draw_seeds(path_rngs[p], int(npts[j]) - 1) for j, p in enumerate(todo)]  # src/elbo.jl:2
+            engine.batch_from_lbfgs(np.concatenate(seeds) if seeds else np.zeros(0, np.uint64))
+            engine.run()
+            res = engine.download(draws=True, fit=True)
+            off, Xd, FXd, Gd = engine.lbfgs_download()
+            traces = [OptimizationTrace(Xd[:, off[j]:off[j + 1]], FXd[off[j]:off[j + 1]], Gd[:, off[j]:off[j + 1]])
+                      for j in range(len(todo))]
+        else:
+            for p in todo:
+                tries[p] += 1
+                tr = optimize_with_trace(model, cur_init[p], history_length, maxiters)
+                if len(tr) == 0:  # non-finite at the initial point: an empty trace, L = 0
+                    x0 = np.asarray(cur_init[p], dtype=np.float64)[:, None]
+                    tr = OptimizationTrace(x0, np.array([np.nan]), np.zeros_like(x0))
+                traces.append(tr)
+                seeds.append(_draw_seeds(path_rngs[p], len(tr) - 1))  # src/elbo.jl:2
+            offsets, X, G = Engine.pack([(t.points, t.gradients) for t in traces])
+            res = engine.elbo_batch(offsets, X, G, np.concatenate(seeds) if seeds else np.zeros(0, np.uint64),
+                                    draws=True, fit=True)
         if ndraws_run is not None and ndraws_run > engine.K:
             # top-up draws from the fitted normal with the path's rng (src/singlepath.jl:228-230)
             top_seeds = np.array([int(_draw_seeds(path_rngs[p], 1)[0]) for p in todo], dtype=np.uint64)
@@ -165,8 +193,10 @@ def _assemble_path(model, rng, entry, ndraws, K):
 
 
 def pathfinder(model, *, init=None, init_scale=2.0, ndraws_elbo=DEFAULT_NDRAWS_ELBO, ndraws=None, rng=None,
-               history_length=DEFAULT_HISTORY_LENGTH, ntries=1000, maxiters=1000, device=0, engine=None):
-    """Single-path Pathfinder (src/singlepath.jl:101-139)."""
+               history_length=DEFAULT_HISTORY_LENGTH, ntries=1000, maxiters=1000, device=0, engine=None,
+               optimizer="host"):
+    """Single-path Pathfinder (src/singlepath.jl:101-139).  optimizer: 'host' (SciPy L-BFGS on the
+    CPU, like src/optimize.jl), 'device' (kernel K0, closed-form families) or 'auto'."""
     rng = np.random.default_rng() if rng is None else rng
     ndraws = ndraws_elbo if ndraws is None else ndraws
     x0 = _uniform_init(rng, model.n, init_scale) if init is None else np.asarray(init, dtype=np.float64)
@@ -177,7 +207,7 @@ def pathfinder(model, *, init=None, init_scale=2.0, ndraws_elbo=DEFAULT_NDRAWS_E
         engine = Engine(model.n, model.family, model.blob, history_length, ndraws_elbo, device)
     try:
         final, _ = _run_paths(engine, model, [x0], [rng], history_length=history_length, maxiters=maxiters,
-                              ntries=ntries, init_scale=init_scale, ndraws_run=ndraws)
+                              ntries=ntries, init_scale=init_scale, ndraws_run=ndraws, optimizer=optimizer)
         return _assemble_path(model, rng, final[0], ndraws, ndraws_elbo)
     finally:
         if own:
@@ -186,7 +216,8 @@ def pathfinder(model, *, init=None, init_scale=2.0, ndraws_elbo=DEFAULT_NDRAWS_E
 
 def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT_NDRAWS_ELBO,
                     ndraws_per_run=None, importance=True, rng=None, history_length=DEFAULT_HISTORY_LENGTH,
-                    init_scale=2.0, ntries=1000, maxiters=1000, device=0, engine=None, group=None):
+                    init_scale=2.0, ntries=1000, maxiters=1000, device=0, engine=None, group=None,
+                    optimizer="host"):
     """Multi-path Pathfinder (src/multipath.jl:94-245).
 
     Under an initialised ``torch.distributed`` process group (one process per GPU) the runs shard
@@ -219,7 +250,8 @@ def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT
     if own:
         engine = Engine(model.n, model.family, model.blob, history_length, ndraws_elbo, device)
     final, last = _run_paths(engine, model, inits[lo:hi], path_rngs[lo:hi], history_length=history_length,
-                             maxiters=maxiters, ntries=ntries, init_scale=init_scale, ndraws_run=ndraws_per_run)
+                             maxiters=maxiters, ntries=ntries, init_scale=init_scale, ndraws_run=ndraws_per_run,
+                             optimizer=optimizer)
     results = [_assemble_path(model, path_rngs[lo + j], final[j], ndraws_per_run, ndraws_elbo)
                for j in range(hi - lo)]
     # PSIS pool: draw-fastest, component-slowest (test/resample.jl:81-88)

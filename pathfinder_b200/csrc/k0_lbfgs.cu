@@ -1,0 +1,102 @@
+// K0 lbfgs_trajectories — batched device L-BFGS for the registered closed-form families
+// (SURVEY §8 row f1).  Replaces the per-path host optimiser
+//   optimize_with_trace (src/optimize.jl:35-59) under _chunk_tmap (src/multipath.jl:190-208)
+// by ONE launch: one CTA of PF_LBFGS_T threads per path runs the whole trajectory (pf_lbfgs.h:
+// two-loop recursion + strong-Wolfe line search) and writes the points / log-density gradients the
+// callback records (src/optimize.jl:94-101) straight into HBM slabs, from where a pack kernel
+// gathers them into the contiguous n x T layout K1/K2 read — the trajectories never visit the host.
+//
+// Every vector (direction, S/Y history, the slab columns) is touched with the fixed ownership
+// i = tid + k * PF_LBFGS_T, so after the first pass it is L1/L2 resident; the sequential part is
+// the ~20 block-wide reductions per iteration (2 J for the two-loop recursion, 2 per density
+// evaluation, 2 for the curvature pair).  The reduction order is the contract of pf_lbfgs.h, which
+// the CPU oracle emulates, so trajectories are bit-identical to the oracle's.
+#include "pfb_common.cuh"
+#include "pf_lbfgs.h"
+
+struct pfb_lbfgs_dev_ctx {
+    int n;
+    double* scratch;  // 64 doubles of shared memory
+    template <class F>
+    __device__ __forceinline__ void each(F f) {
+        for (int i = threadIdx.x; i < n; i += PF_LBFGS_T) f(i);
+    }
+    template <class F>
+    __device__ __forceinline__ double sum(F f) {
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < n; i += PF_LBFGS_T) acc = f(i, acc);
+        double v[1] = {acc};
+        pfb_block_sum<1>(v, scratch);
+        return v[0];
+    }
+    template <class F>
+    __device__ __forceinline__ void sum2(F f, double& a, double& b) {
+        double v[2] = {0.0, 0.0};
+        for (int i = threadIdx.x; i < n; i += PF_LBFGS_T) f(i, v[0], v[1]);
+        pfb_block_sum<2>(v, scratch);
+        a = v[0];
+        b = v[1];
+    }
+    template <class F>
+    __device__ __forceinline__ double maxv(F f) {
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < n; i += PF_LBFGS_T) acc = fmax(acc, f(i));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc = fmax(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        __syncthreads();
+        if (lane == 0) scratch[warp] = acc;
+        __syncthreads();
+        double t = (lane < PF_LBFGS_T / 32) ? scratch[lane] : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, off));
+        return t;
+    }
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+
+__global__ void __launch_bounds__(PF_LBFGS_T)
+pfb_k0_lbfgs(pf_lbfgs_model m, pf_lbfgs_opts o, const double* __restrict__ x0, double* X, double* G, double* FX,
+             double* ws, int64_t* npoints, int32_t* status, int32_t* nevals) {
+    __shared__ double scratch[64];
+    const int p = blockIdx.x;
+    const size_t slab = (size_t)m.n * (size_t)o.max_points;
+    pfb_lbfgs_dev_ctx c{m.n, scratch};
+    int st = 0, nev = 0;
+    const int np = pf_lbfgs_run(c, m, o, x0 + (size_t)p * m.n, X + (size_t)p * slab, G + (size_t)p * slab,
+                                FX + (size_t)p * o.max_points, ws + (size_t)p * (2 * o.J + 1) * m.n, &st, &nev);
+    if (threadIdx.x == 0) {
+        npoints[p] = np;
+        status[p] = st;
+        nevals[p] = nev;
+    }
+}
+
+// dst[:, t] = slab[:, src[t]] for the points and the gradients; one CTA per packed column
+__global__ void pfb_k0_pack(int n, const int64_t* __restrict__ src, const double* __restrict__ sX,
+                            const double* __restrict__ sG, double* __restrict__ dX, double* __restrict__ dG) {
+    const int64_t t = blockIdx.x;
+    const int64_t s = src[t];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        dX[t * n + i] = sX[s * n + i];
+        dG[t * n + i] = sG[s * n + i];
+    }
+}
+
+extern "C" cudaError_t pfb_launch_k0(cudaStream_t st, int family, int n, int P, const double* mp0, const double* mp1,
+                                     double mc0, int J, int maxiters, int max_points, double gtol, double ftol,
+                                     const double* x0, double* X, double* G, double* FX, double* ws,
+                                     int64_t* npoints, int32_t* status, int32_t* nevals) {
+    if (P <= 0) return cudaSuccess;
+    pf_lbfgs_model m{family, n, mp0, mp1, mc0};
+    pf_lbfgs_opts o{J, maxiters, max_points, gtol, ftol};
+    pfb_k0_lbfgs<<<P, PF_LBFGS_T, 0, st>>>(m, o, x0, X, G, FX, ws, npoints, status, nevals);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t pfb_launch_k0_pack(cudaStream_t st, int n, int64_t T, const int64_t* src, const double* sX,
+                                          const double* sG, double* dX, double* dG) {
+    if (T <= 0) return cudaSuccess;
+    pfb_k0_pack<<<(unsigned)T, 256, 0, st>>>(n, src, sX, sG, dX, dG);
+    return cudaGetLastError();
+}

@@ -100,7 +100,10 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
                     double sum = 0.0;
                     for (int wq = 0; wq < nwarp; ++wq) sum += scratch[wq * 64 + tid];
                     const int a = 8 * ta + (tid >> 3), b = 8 * tb + (tid & 7);
-                    if (a < KP && b < KP) {
+                    // diagonal tiles: (a, b) and (b, a) are both computed but round differently when the
+                    // weight is not 1 (a (b w) vs b (a w)) — only the upper triangle writes, so the result
+                    // is symmetric and deterministic
+                    if (a < KP && b < KP && (ta != tb || a <= b)) {
                         Gm[a * KP + b] = sum;
                         Gm[b * KP + a] = sum;
                     }

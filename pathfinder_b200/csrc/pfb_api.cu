@@ -33,6 +33,10 @@ cudaError_t pfb_launch_k8_dense(cudaStream_t, int, int64_t, int, const int32_t*,
                                 const double*, double, double*);
 cudaError_t pfb_launch_k8_logistic(cudaStream_t, int, int, int64_t, int, const int32_t*, const double*,
                                    const double*, const double*, double*);
+cudaError_t pfb_launch_k0(cudaStream_t, int, int, int, const double*, const double*, double, int, int, int, double,
+                          double, const double*, double*, double*, double*, double*, int64_t*, int32_t*, int32_t*);
+cudaError_t pfb_launch_k0_pack(cudaStream_t, int, int64_t, const int64_t*, const double*, const double*, double*,
+                               double*);
 size_t pfb_psis_scalars_size();
 cudaError_t pfb_launch_k6(cudaStream_t, int, int, int, const double*, const double*, const double*, double*,
                           double*, uint64_t*, void*);
@@ -96,6 +100,13 @@ struct pfb_engine {
     DevBuf dAlpha, dHist, dHistCnt, dRej, dFR, dFR2, dHDR, dLogp, dLogq, dElbo, dSe, dBestIter, dBestUnit, dSucc;
     DevBuf dPool, dPoolLogp, dPoolLogq, dAllDraws;
     DevBuf dFitMu, dFitAlpha, dFitVh, dFitT, dFitVc, dFitLogdet, dFitJeff;
+    // device L-BFGS (K0): trajectory slabs [n x max_points] per path
+    DevBuf dLbX0, dLbX, dLbG, dLbFX, dLbWs, dLbNp, dLbSt, dLbNev, dLbSrc;
+    std::vector<int64_t> lb_np;
+    int lb_P = 0, lb_n = 0, lb_maxpts = 0;
+    bool lb_ok = false;
+    float lb_ms = 0.f;
+    cudaEvent_t lb_ev[2] = {};
     // psis
     DevBuf dLogw, dW, dCum, dScal, dInds, dIds, dOutDraws, dTmpLogr, dTmpPool;
 };
@@ -155,6 +166,7 @@ extern "C" int pfb_create(pfb_handle* out, const pfb_config* cfg) {
         return (int)e;
     }
     for (auto& ev : h->ev) cudaEventCreate(&ev);
+    for (auto& ev : h->lb_ev) cudaEventCreate(&ev);
     *out = h;
     return PFB_OK;
 }
@@ -168,10 +180,12 @@ extern "C" int pfb_destroy(pfb_handle h) {
                       &h->dSe, &h->dBestIter, &h->dBestUnit, &h->dSucc, &h->dPool, &h->dPoolLogp,
                       &h->dPoolLogq, &h->dAllDraws, &h->dFitMu, &h->dFitAlpha, &h->dFitVh, &h->dFitT,
                       &h->dFitVc, &h->dFitLogdet, &h->dFitJeff, &h->dLogw, &h->dW, &h->dCum, &h->dScal,
-                      &h->dInds, &h->dIds, &h->dOutDraws, &h->dTmpLogr, &h->dTmpPool, &h->dGenX, &h->dGenY, &h->dIota, &h->dTopSeeds};
+                      &h->dInds, &h->dIds, &h->dOutDraws, &h->dTmpLogr, &h->dTmpPool, &h->dGenX, &h->dGenY, &h->dIota, &h->dTopSeeds,
+                      &h->dLbX0, &h->dLbX, &h->dLbG, &h->dLbFX, &h->dLbWs, &h->dLbNp, &h->dLbSt, &h->dLbNev, &h->dLbSrc};
     for (auto* b : bufs) b->release();
     if (h->cublas) cublasDestroy(h->cublas);
     for (auto& ev : h->ev) cudaEventDestroy(ev);
+    for (auto& ev : h->lb_ev) cudaEventDestroy(ev);
     cudaStreamDestroy(h->stream);
     delete h;
     return PFB_OK;
@@ -252,9 +266,9 @@ extern "C" int pfb_register_model(pfb_handle h, int family, int n, const double*
     return PFB_OK;
 }
 
-extern "C" int pfb_batch_upload(pfb_handle h, int n, int P, const int64_t* offsets, const double* positions,
-                                const double* gradients, const uint64_t* seeds, const double* normals) {
-    if (!h) return PFB_ERR_ARG;
+// Validates the batch shape, sizes every device buffer (grow-only) and uploads the small index
+// arrays (offsets, unit -> point column).  Shared by pfb_batch_upload and pfb_batch_from_lbfgs.
+static int batch_prepare(pfb_engine* h, int n, int P, const int64_t* offsets) {
     if (n < 1 || P < 0 || !offsets) PFB_FAIL(h, PFB_ERR_ARG, "bad n / P / offsets");
     if (h->model < 0) PFB_FAIL(h, PFB_ERR_STATE, "no model registered");
     if (h->model_n != n) PFB_FAIL(h, PFB_ERR_SHAPE, "dimension differs from the registered model's");
@@ -263,8 +277,6 @@ extern "C" int pfb_batch_upload(pfb_handle h, int n, int P, const int64_t* offse
         if (offsets[p + 1] < offsets[p] + 1) PFB_FAIL(h, PFB_ERR_SHAPE, "every path needs at least one point");
     const int64_t T = offsets[P], U = T - P;
     if (T > 2147483647LL) PFB_FAIL(h, PFB_ERR_UNSUPPORTED, "too many trajectory points");
-    if (T > 0 && (!positions || !gradients)) PFB_FAIL(h, PFB_ERR_ARG, "positions / gradients are NULL");
-    if (U > 0 && !seeds) PFB_FAIL(h, PFB_ERR_ARG, "seeds is NULL");
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
     const int K = h->cfg.ndraws_elbo, J = h->cfg.history_length, KP = h->KP;
     h->n = n; h->P = P; h->K = K; h->T = T; h->U = U;
@@ -301,22 +313,151 @@ extern "C" int pfb_batch_upload(pfb_handle h, int n, int P, const int64_t* offse
     PFB_CUDA(h, h->dPoolLogq.ensure((size_t)K * P * 8 + 8));
     if (h->cfg.materialize_all) PFB_CUDA(h, h->dAllDraws.ensure(nU * (size_t)K * 8 + 8));
     cudaStream_t st = h->stream;
+    PFB_CUDA(h, cudaMemcpyAsync(h->dOff.p, offsets, (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (U > 0)
+        PFB_CUDA(h, cudaMemcpyAsync(h->dUnitCol.p, unit_col.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
+    PFB_CUDA(h, cudaStreamSynchronize(st));  // unit_col is a stack-owned staging vector
+    return PFB_OK;
+}
+
+extern "C" int pfb_batch_upload(pfb_handle h, int n, int P, const int64_t* offsets, const double* positions,
+                                const double* gradients, const uint64_t* seeds, const double* normals) {
+    if (!h) return PFB_ERR_ARG;
+    if (n >= 1 && P >= 0 && offsets) {
+        const int64_t T = offsets[P], U = T - P;
+        if (T > 0 && (!positions || !gradients)) PFB_FAIL(h, PFB_ERR_ARG, "positions / gradients are NULL");
+        if (U > 0 && !seeds) PFB_FAIL(h, PFB_ERR_ARG, "seeds is NULL");
+    }
+    int rc = batch_prepare(h, n, P, offsets);
+    if (rc) return rc;
+    const int64_t T = h->T, U = h->U;
+    const int K = h->K;
+    const size_t nT = (size_t)n * (size_t)T, nU = (size_t)n * (size_t)U;
+    cudaStream_t st = h->stream;
     if (T > 0) {
         PFB_CUDA(h, cudaMemcpyAsync(h->dX.p, positions, nT * 8, cudaMemcpyHostToDevice, st));
         PFB_CUDA(h, cudaMemcpyAsync(h->dG.p, gradients, nT * 8, cudaMemcpyHostToDevice, st));
     }
-    PFB_CUDA(h, cudaMemcpyAsync(h->dOff.p, offsets, (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (U > 0) {
-        PFB_CUDA(h, cudaMemcpyAsync(h->dSeeds.p, seeds, (size_t)U * 8, cudaMemcpyHostToDevice, st));
-        PFB_CUDA(h, cudaMemcpyAsync(h->dUnitCol.p, unit_col.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
-    }
+    if (U > 0) PFB_CUDA(h, cudaMemcpyAsync(h->dSeeds.p, seeds, (size_t)U * 8, cudaMemcpyHostToDevice, st));
     h->have_normals = (normals != nullptr);
     if (normals && U > 0) {
         PFB_CUDA(h, h->dNormals.ensure(nU * (size_t)K * 8));
         PFB_CUDA(h, cudaMemcpyAsync(h->dNormals.p, normals, nU * (size_t)K * 8, cudaMemcpyHostToDevice, st));
     }
-    PFB_CUDA(h, cudaStreamSynchronize(st));  // unit_col is a stack-owned staging vector
+    PFB_CUDA(h, cudaStreamSynchronize(st));
     h->have_batch = true;
+    return PFB_OK;
+}
+
+// ---- K0: batched device L-BFGS ---------------------------------------------
+static bool model_has_device_lbfgs(const pfb_engine* h) {
+    return h->model == PFB_MODEL_ISONORMAL || h->model == PFB_MODEL_FUNNEL || h->model == PFB_MODEL_DIAGNORMAL;
+}
+
+extern "C" int pfb_lbfgs_batch(pfb_handle h, int n, int P, const double* x0, const pfb_lbfgs_opts* o,
+                               int64_t* npoints, int32_t* status, int32_t* nevals) {
+    if (!h) return PFB_ERR_ARG;
+    if (n < 1 || P < 0 || (P > 0 && !x0) || !o) PFB_FAIL(h, PFB_ERR_ARG, "bad n / P / x0 / opts");
+    if (h->model < 0) PFB_FAIL(h, PFB_ERR_STATE, "no model registered");
+    if (h->model_n != n) PFB_FAIL(h, PFB_ERR_SHAPE, "dimension differs from the registered model's");
+    if (!model_has_device_lbfgs(h))
+        PFB_FAIL(h, PFB_ERR_UNSUPPORTED, "device L-BFGS covers the closed-form families (iso-normal, funnel, "
+                                         "independent normals); optimise this family on the host");
+    if (o->maxiters < 0 || o->max_points < 1) PFB_FAIL(h, PFB_ERR_ARG, "maxiters >= 0 and max_points >= 1 required");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const int J = h->cfg.history_length;
+    const int maxpts = std::min(o->max_points, o->maxiters + 1);
+    const size_t slab = (size_t)n * (size_t)maxpts * (size_t)P;
+    h->lb_ok = false;
+    PFB_CUDA(h, h->dLbX0.ensure((size_t)n * P * 8 + 8));
+    PFB_CUDA(h, h->dLbX.ensure(slab * 8 + 8));
+    PFB_CUDA(h, h->dLbG.ensure(slab * 8 + 8));
+    PFB_CUDA(h, h->dLbFX.ensure((size_t)maxpts * P * 8 + 8));
+    PFB_CUDA(h, h->dLbWs.ensure((size_t)(2 * J + 1) * n * P * 8 + 8));
+    PFB_CUDA(h, h->dLbNp.ensure((size_t)P * 8 + 8));
+    PFB_CUDA(h, h->dLbSt.ensure((size_t)P * 4 + 8));
+    PFB_CUDA(h, h->dLbNev.ensure((size_t)P * 4 + 8));
+    h->lb_np.assign((size_t)P, 0);
+    h->lb_P = P; h->lb_n = n; h->lb_maxpts = maxpts;
+    if (P == 0) {
+        h->lb_ok = true;
+        return PFB_OK;
+    }
+    PFB_CUDA(h, cudaMemcpyAsync(h->dLbX0.p, x0, (size_t)n * P * 8, cudaMemcpyHostToDevice, st));
+    const double* mp0 = h->model == PFB_MODEL_DIAGNORMAL ? h->dModel.as<double>() : nullptr;
+    PFB_CUDA(h, cudaEventRecord(h->lb_ev[0], st));
+    PFB_CUDA(h, pfb_launch_k0(st, h->model, n, P, mp0, mp0 ? mp0 + n : nullptr, h->model_c0, J, o->maxiters, maxpts,
+                              o->gtol, o->ftol, h->dLbX0.as<double>(), h->dLbX.as<double>(), h->dLbG.as<double>(),
+                              h->dLbFX.as<double>(), h->dLbWs.as<double>(), h->dLbNp.as<int64_t>(),
+                              h->dLbSt.as<int32_t>(), h->dLbNev.as<int32_t>()));
+    PFB_CUDA(h, cudaEventRecord(h->lb_ev[1], st));
+    PFB_CUDA(h, cudaMemcpyAsync(h->lb_np.data(), h->dLbNp.p, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+    if (status) PFB_CUDA(h, cudaMemcpyAsync(status, h->dLbSt.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    if (nevals) PFB_CUDA(h, cudaMemcpyAsync(nevals, h->dLbNev.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    PFB_CUDA(h, cudaEventElapsedTime(&h->lb_ms, h->lb_ev[0], h->lb_ev[1]));
+    if (npoints) memcpy(npoints, h->lb_np.data(), (size_t)P * 8);
+    h->lb_ok = true;
+    return PFB_OK;
+}
+
+extern "C" int pfb_batch_from_lbfgs(pfb_handle h, const uint64_t* seeds) {
+    if (!h) return PFB_ERR_ARG;
+    if (!h->lb_ok) PFB_FAIL(h, PFB_ERR_STATE, "pfb_lbfgs_batch has not been called");
+    const int n = h->lb_n, P = h->lb_P;
+    std::vector<int64_t> off((size_t)P + 1, 0);
+    for (int p = 0; p < P; ++p) off[(size_t)p + 1] = off[(size_t)p] + h->lb_np[(size_t)p];
+    const int64_t T = off[(size_t)P], U = T - P;
+    if (U > 0 && !seeds) PFB_FAIL(h, PFB_ERR_ARG, "seeds is NULL");
+    int rc = batch_prepare(h, n, P, off.data());
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    std::vector<int64_t> src((size_t)T);
+    for (int p = 0; p < P; ++p)
+        for (int64_t l = 0; l < h->lb_np[(size_t)p]; ++l)
+            src[(size_t)(off[(size_t)p] + l)] = (int64_t)p * h->lb_maxpts + l;
+    PFB_CUDA(h, h->dLbSrc.ensure((size_t)T * 8 + 8));
+    if (T > 0) {
+        PFB_CUDA(h, cudaMemcpyAsync(h->dLbSrc.p, src.data(), (size_t)T * 8, cudaMemcpyHostToDevice, st));
+        PFB_CUDA(h, pfb_launch_k0_pack(st, n, T, h->dLbSrc.as<int64_t>(), h->dLbX.as<double>(), h->dLbG.as<double>(),
+                                       h->dX.as<double>(), h->dG.as<double>()));
+    }
+    if (U > 0) PFB_CUDA(h, cudaMemcpyAsync(h->dSeeds.p, seeds, (size_t)U * 8, cudaMemcpyHostToDevice, st));
+    h->have_normals = false;
+    PFB_CUDA(h, cudaStreamSynchronize(st));  // src is a stack-owned staging vector
+    h->have_batch = true;
+    return PFB_OK;
+}
+
+extern "C" int pfb_lbfgs_download(pfb_handle h, double* positions, double* gradients, double* log_densities) {
+    if (!h) return PFB_ERR_ARG;
+    if (!h->lb_ok) PFB_FAIL(h, PFB_ERR_STATE, "pfb_lbfgs_batch has not been called");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const size_t n = (size_t)h->lb_n, mp = (size_t)h->lb_maxpts;
+    int64_t off = 0;
+    for (int p = 0; p < h->lb_P; ++p) {
+        const size_t np = (size_t)h->lb_np[(size_t)p];
+        if (positions)
+            PFB_CUDA(h, cudaMemcpyAsync(positions + (size_t)off * n, h->dLbX.as<double>() + (size_t)p * mp * n,
+                                        np * n * 8, cudaMemcpyDeviceToHost, st));
+        if (gradients)
+            PFB_CUDA(h, cudaMemcpyAsync(gradients + (size_t)off * n, h->dLbG.as<double>() + (size_t)p * mp * n,
+                                        np * n * 8, cudaMemcpyDeviceToHost, st));
+        if (log_densities)
+            PFB_CUDA(h, cudaMemcpyAsync(log_densities + off, h->dLbFX.as<double>() + (size_t)p * mp, np * 8,
+                                        cudaMemcpyDeviceToHost, st));
+        off += (int64_t)np;
+    }
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    return PFB_OK;
+}
+
+extern "C" int pfb_lbfgs_ms(pfb_handle h, double* ms) {
+    if (!h || !ms) return PFB_ERR_ARG;
+    if (!h->lb_ok) PFB_FAIL(h, PFB_ERR_STATE, "pfb_lbfgs_batch has not been called");
+    *ms = h->lb_ms;
     return PFB_OK;
 }
 

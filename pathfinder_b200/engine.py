@@ -12,7 +12,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import pfb_config, pfb_device_view, pfb_elbo_out, pfb_resample_out
+from ._lib import pfb_config, pfb_device_view, pfb_elbo_out, pfb_lbfgs_opts, pfb_resample_out
 
 
 def _ptr(a):
@@ -110,6 +110,55 @@ class Engine:
         _lib.check(self.h, self.lib.pfb_batch_upload(self.h, self.n, P, _ptr(offsets), _ptr(X), _ptr(G),
                                                      _ptr(seeds), _ptr(normals)))
         self._P, self._U, self._offsets = P, U, offsets.copy()
+
+    # ---- device L-BFGS (K0) ----------------------------------------------
+    def lbfgs_batch(self, x0, maxiters=1000, max_points=None, gtol=1e-8, ftol=1e-14):
+        """Run the L-BFGS trajectories of P paths on the device (one CTA per path; replaces
+        optimize_with_trace, src/optimize.jl:35-59).  x0: [n, P].  Returns (npoints [P], status [P],
+        nevals [P]); the traces stay resident (batch_from_lbfgs / lbfgs_download)."""
+        x0 = np.asfortranarray(x0, dtype=np.float64)
+        if x0.ndim != 2 or x0.shape[0] != self.n:
+            raise ValueError("x0 must be n x P")
+        P = x0.shape[1]
+        o = pfb_lbfgs_opts(int(maxiters), int(max_points or maxiters + 1), float(gtol), float(ftol))
+        npts = np.zeros(P, dtype=np.int64)
+        st = np.zeros(P, dtype=np.int32)
+        nev = np.zeros(P, dtype=np.int32)
+        _lib.check(self.h, self.lib.pfb_lbfgs_batch(self.h, self.n, P, _ptr(x0), C.byref(o), _ptr(npts), _ptr(st),
+                                                    _ptr(nev)))
+        self._lb_npts = npts
+        return npts, st, nev
+
+    def batch_from_lbfgs(self, seeds):
+        """Make the device-resident traces of the last lbfgs_batch the current batch (what upload()
+        does from host buffers); seeds: one per (path, iteration)."""
+        npts = self._lb_npts
+        P = npts.size
+        offsets = np.zeros(P + 1, dtype=np.int64)
+        np.cumsum(npts, out=offsets[1:])
+        U = int(offsets[-1]) - P
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        if seeds.size != U:
+            raise ValueError("need one seed per (path, iteration)")
+        _lib.check(self.h, self.lib.pfb_batch_from_lbfgs(self.h, _ptr(seeds)))
+        self._P, self._U, self._offsets = P, U, offsets
+
+    def lbfgs_download(self):
+        """(offsets [P+1], points [n, T], log_densities [T], gradients [n, T]) of the last lbfgs_batch."""
+        npts = self._lb_npts
+        offsets = np.zeros(npts.size + 1, dtype=np.int64)
+        np.cumsum(npts, out=offsets[1:])
+        T = int(offsets[-1])
+        X = np.empty((self.n, T), order="F")
+        G = np.empty((self.n, T), order="F")
+        FX = np.empty(T)
+        _lib.check(self.h, self.lib.pfb_lbfgs_download(self.h, _ptr(X), _ptr(G), _ptr(FX)))
+        return offsets, X, FX, G
+
+    def lbfgs_ms(self):
+        ms = C.c_double(0.0)
+        _lib.check(self.h, self.lib.pfb_lbfgs_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def run(self):
         _lib.check(self.h, self.lib.pfb_batch_run(self.h))

@@ -469,3 +469,107 @@ def test_fresh_draws_match_oracle_on_a_well_conditioned_fit():
         np.testing.assert_allclose(lq[:, p], logq, rtol=RTOL, atol=RTOL)
         np.testing.assert_allclose(lp[:, p], O.logp_isonormal(x), rtol=RTOL, atol=RTOL)
     eng.close()
+
+
+# ---- K0: device L-BFGS (row f1) ------------------------------------------------------------------
+def _oracle_traces(model, x0s, J, maxiters, max_points=None, gtol=1e-8, ftol=1e-14):
+    from oracle import lbfgs as OL
+
+    kw = {}
+    if model.family == OL.FAMILY_DIAGNORMAL:
+        kw = dict(mean=model.mean, sd=model.sd)
+    return [OL.lbfgs_path(model.family, x0s[:, p], J, maxiters, max_points, gtol, ftol, **kw)
+            for p in range(x0s.shape[1])]
+
+
+@pytest.mark.parametrize("kind,n,J,scale,maxiters", [
+    ("iso", 10, 6, 2.0, 1000), ("funnel", 5, 6, 3.0, 60), ("funnel", 100, 6, 10.0, 80),
+    ("funnel", 1024, 6, 10.0, 40), ("funnel", 257, 10, 10.0, 50), ("diag", 333, 6, 2.0, 1000),
+])
+def test_device_lbfgs_trajectories_bit_exact(kind, n, J, scale, maxiters):
+    """Kernel K0 against the CPU restatement of the same contract (pf_lbfgs.h): points, gradients,
+    log densities, lengths, status and evaluation counts are bit-identical."""
+    import pathfinder_b200 as pf
+
+    rng = np.random.default_rng(n + J)
+    if kind == "iso":
+        model = pf.IsoNormal(n)
+    elif kind == "funnel":
+        model = pf.Funnel(n)
+    else:
+        model = pf.DiagNormal(rng.normal(size=n) * 3, rng.uniform(0.05, 20.0, size=n))
+    P = 7
+    x0s = np.asfortranarray(rng.uniform(-scale, scale, size=(n, P)))
+    eng = _engine(model, 16, J)
+    npts, st, nev = eng.lbfgs_batch(x0s, maxiters)
+    off, X, FX, G = eng.lbfgs_download()
+    ref = _oracle_traces(model, x0s, J, maxiters)
+    for p, (Xo, FXo, Go, sto, nevo) in enumerate(ref):
+        assert npts[p] == Xo.shape[1] and st[p] == sto and nev[p] == nevo, (p, npts[p], Xo.shape[1], st[p], sto)
+        sl = slice(off[p], off[p + 1])
+        assert np.array_equal(X[:, sl], Xo, equal_nan=True)
+        assert np.array_equal(G[:, sl], Go, equal_nan=True)
+        assert np.array_equal(FX[sl], FXo, equal_nan=True)
+    eng.close()
+
+
+def test_device_lbfgs_capacity_nonfinite_and_unsupported_family():
+    import pathfinder_b200 as pf
+
+    n = 16
+    model = pf.Funnel(n)
+    x0s = np.asfortranarray(np.random.default_rng(3).uniform(-5, 5, size=(n, 3)))
+    x0s[0, 1], x0s[1:, 1] = -800.0, 1.0  # exp(800) = Inf: recorded, then the run stops (src/optimize.jl:103-105)
+    eng = _engine(model, 8)
+    npts, st, nev = eng.lbfgs_batch(x0s, 1000, max_points=9)
+    assert list(npts) == [9, 1, 9] and st[1] == 4 and st[0] == 2
+    ref = _oracle_traces(model, x0s, 6, 1000, 9)
+    off, X, FX, G = eng.lbfgs_download()
+    assert np.array_equal(X[:, :9], ref[0][0]) and np.array_equal(G[:, 10:], ref[2][2])
+    # the failed path has L = 0: no ELBO units, success = False, the others run normally
+    seeds = np.arange(16, dtype=np.uint64) + 1
+    eng.batch_from_lbfgs(seeds)
+    eng.run()
+    res = eng.download()
+    assert list(res.success) == [True, False, True] and res.best_iter[1] == 0
+    eng.close()
+    dense = pf.DenseNormal(np.zeros(4), np.eye(4))
+    eng = _engine(dense, 8)
+    with pytest.raises(pf.PfbError) as ei:
+        eng.lbfgs_batch(np.zeros((4, 2)), 10)
+    assert ei.value.code == -3
+    eng.close()
+
+
+def test_device_optimizer_pipeline_equals_host_fed_pipeline():
+    """multipathfinder(optimizer='device') == the engine fed, through the host upload path, with the
+    oracle's trajectories for the same inits: K0's traces never leave the device, yet every
+    downstream number (ELBO table, best iterations, PSIS weights, indices, draws) is identical."""
+    import pathfinder_b200 as pf
+    from pathfinder_b200.api import _draw_seeds, _uniform_init
+
+    n, P, K, ndraws, maxiters = 48, 5, 64, 100, 30
+    model = pf.Funnel(n)
+    r = pf.multipathfinder(model, ndraws, nruns=P, ndraws_elbo=K, rng=np.random.default_rng(11), init_scale=4.0,
+                           maxiters=maxiters, optimizer="device")
+    # replay: same rng protocol on the host
+    rng = np.random.default_rng(11)
+    run_seeds = _draw_seeds(rng, P)
+    prngs = [np.random.Generator(np.random.Philox(key=int(s))) for s in run_seeds]
+    inits = np.stack([_uniform_init(prngs[p], n, 4.0) for p in range(P)], axis=1)
+    seed = int(_draw_seeds(rng, 1)[0])
+    ref = _oracle_traces(model, inits, 6, maxiters)
+    seeds = [_draw_seeds(prngs[p], ref[p][0].shape[1] - 1) for p in range(P)]
+    eng = _engine(model, K)
+    offsets, X, G = pf.Engine.pack([(t[0], t[2]) for t in ref])
+    res = eng.elbo_batch(offsets, X, G, np.concatenate(seeds), draws=True, fit=True)
+    rr = eng.psis_resample(seed, ndraws, True)
+    assert all(pr.num_tries == 1 for pr in r.pathfinder_results)
+    for p, pr in enumerate(r.pathfinder_results):
+        assert np.array_equal(pr.optim_trace.points, ref[p][0])
+        assert np.array_equal(pr.optim_trace.log_densities, ref[p][1])
+        assert np.array_equal([e.value for e in pr.elbo_estimates], res.elbo[res.unit_slice(p)], equal_nan=True)
+        assert pr.fit_iteration == res.best_iter[p]
+    assert np.array_equal(r.sample_inds, rr["inds"]) and np.array_equal(r.draws, rr["draws"])
+    assert np.array_equal(r.psis_result.weights, rr["weights"])
+    eng.close()

@@ -44,6 +44,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.pfb_elbo_out) == 18 * C.sizeof(C.c_void_p)
     assert C.sizeof(_lib.pfb_resample_out) == 7 * C.sizeof(C.c_void_p)
     assert C.sizeof(_lib.pfb_device_view) == 5 * C.sizeof(C.c_void_p) + 4 * 8
+    assert C.sizeof(_lib.pfb_lbfgs_opts) == 24
 
 
 @pytest.mark.skipif(_have_gpu(), reason="checks the no-device behaviour")

@@ -351,3 +351,70 @@ def test_resample_indices_follow_weights():
     assert np.abs(freq - w).max() < 0.01
     assert np.array_equal(inds, OP.resample_indices(9, w, 4, 40000))  # reproducible under reseed
     assert not np.array_equal(inds, OP.resample_indices(10, w, 4, 40000))
+
+
+# ---- L-BFGS trajectory contract (row f1; src/optimize.jl:35-59, src/Pathfinder.jl:29-35) ----------
+def test_lbfgs_isonormal_is_solved_in_one_newton_like_step():
+    """test/singlepath.jl:13-41: on the iso-normal target the optimiser lands on the mode at once
+    (history_length_effective == 1 there), the trace has the initial point plus few iterations."""
+    from oracle import lbfgs as OL
+
+    x0 = np.random.default_rng(0).uniform(-2, 2, size=10)
+    X, FX, G, st, nev = OL.lbfgs_path(OL.FAMILY_ISONORMAL, x0)
+    assert OL.STATUS[st] in ("gtol", "ftol")
+    assert 2 <= X.shape[1] <= 4
+    np.testing.assert_allclose(X[:, 0], x0)
+    np.testing.assert_allclose(X[:, -1], 0.0, atol=1e-8)
+    np.testing.assert_allclose(G, -X)                       # gradient of the LOG density (src/optimize.jl:96)
+    np.testing.assert_allclose(FX, -0.5 * np.sum(X * X, axis=0))
+
+
+def test_lbfgs_diag_normal_reaches_the_mean_and_matches_scipy():
+    from scipy.optimize import minimize
+
+    from oracle import lbfgs as OL
+
+    rng = np.random.default_rng(1)
+    n = 37
+    mean, sd = rng.normal(size=n) * 3, rng.uniform(0.05, 20.0, size=n)
+    x0 = rng.uniform(-2, 2, size=n)
+    X, FX, G, st, nev = OL.lbfgs_path(OL.FAMILY_DIAGNORMAL, x0, mean=mean, sd=sd)
+    assert OL.STATUS[st] in ("gtol", "ftol")
+    np.testing.assert_allclose(X[:, -1], mean, atol=1e-5 * np.max(sd) ** 2)
+    assert np.all(np.diff(FX) > 0)                          # monotone ascent of log p (Armijo)
+    z = (X - mean[:, None]) / sd[:, None]
+    np.testing.assert_allclose(G, -z / sd[:, None], rtol=1e-12, atol=1e-300)
+    c0 = -np.sum(np.log(sd)) - 0.5 * n * np.log(2 * np.pi)
+    np.testing.assert_allclose(FX, -0.5 * np.sum(z * z, axis=0) + c0, rtol=1e-12)
+    ref = minimize(lambda x: (0.5 * np.sum(((x - mean) / sd) ** 2), (x - mean) / sd**2), x0, jac=True,
+                   method="L-BFGS-B", options=dict(maxcor=6, gtol=1e-10, ftol=1e-15))
+    assert abs((FX[-1] - c0) + ref.fun) < 1e-8
+    assert X.shape[1] - 1 <= 3 * ref.nit + 10              # comparable iteration count
+
+
+def test_lbfgs_funnel_trace_satisfies_wolfe_and_stops_on_caps():
+    """Every recorded step satisfies the strong-Wolfe conditions the line search promises
+    (=> s'y > 0, so lbfgs_inverse_hessians never has to reject an update for curvature)."""
+    from oracle import lbfgs as OL
+
+    n = 64
+    x0 = np.random.default_rng(5).uniform(-10, 10, size=n)
+    X, FX, G, st, nev = OL.lbfgs_path(OL.FAMILY_FUNNEL, x0, maxiters=40)
+    assert X.shape[1] == 41 and OL.STATUS[st] == "maxiters"
+    np.testing.assert_allclose(FX, O.logp_funnel(X), rtol=1e-12)
+    S, Y = np.diff(X, axis=1), -np.diff(G, axis=1)
+    assert np.all(np.sum(S * Y, axis=0) > 0)
+    assert np.all(np.diff(FX) > 0)
+    Xc, FXc, Gc, stc, _ = OL.lbfgs_path(OL.FAMILY_FUNNEL, x0, maxiters=1000, max_points=8)
+    assert Xc.shape[1] == 8 and np.array_equal(Xc, X[:, :8]) and np.array_equal(Gc, G[:, :8])
+
+
+def test_lbfgs_nonfinite_start_is_recorded_and_stops():
+    """src/optimize.jl:94-105: the point is pushed, then the run stops."""
+    from oracle import lbfgs as OL
+
+    x0 = np.zeros(8)
+    x0[0] = -800.0  # exp(800) = Inf
+    x0[1:] = 1.0
+    X, FX, G, st, nev = OL.lbfgs_path(OL.FAMILY_FUNNEL, x0)
+    assert X.shape[1] == 1 and OL.STATUS[st] == "nonfinite" and nev == 1
