@@ -431,6 +431,33 @@ def main():
         "wall_s_timed_region": wall,
     }
 
+    # ---- whole multipathfinder() call, trajectories included (north_star's wall-clock target) ----------
+    # K0 runs the L-BFGS of all paths on the device (closed-form families), so nothing but the inits
+    # goes up and only the result struct comes back.  maxiters = 64 keeps the unit count close to the
+    # host-trajectory workload above (SURVEY §8d "fixed-L stress input").
+    mpf = None
+    if rank == 0 and world == 1 and model.family in (0, 1, 2):
+        MAXIT = 64
+        engw = pf.Engine(n, model.family, model.blob, J, K, local_rank)
+        walls, units_w = [], 0
+        for rep in range(4):
+            t0 = time.perf_counter()
+            rw = pf.multipathfinder(model, ndraws, nruns=P, ndraws_elbo=K, rng=np.random.default_rng(MASTER_SEED),
+                                    init_scale=CONFIGS[name][5], maxiters=MAXIT, optimizer="device", engine=engw,
+                                    ntries=1, history_length=J)
+            walls.append(time.perf_counter() - t0)
+            units_w = sum(len(pr.elbo_estimates) for pr in rw.pathfinder_results)
+        k0_ms = engw.lbfgs_ms()
+        engw.close()
+        t0 = time.perf_counter()
+        tr_host = [pf.optimize_with_trace(model, (np.random.default_rng(MASTER_SEED + p).random(n) * 2 - 1)
+                                          * CONFIGS[name][5], J, 1000) for p in range(min(P, 8))]
+        host_lbfgs_s = (time.perf_counter() - t0) * P / max(1, min(P, 8))
+        mpf = {"ours_s": float(min(walls[1:])), "ours_first_call_s": float(walls[0]), "optimizer": f"device K0, "
+               f"maxiters {MAXIT}", "units": int(units_w), "k0_ms": float(k0_ms),
+               "host_scipy_lbfgs_s_for_the_same_paths": float(host_lbfgs_s), "paths": P, "K": K, "ndraws": ndraws}
+        line["multipathfinder_wall"] = mpf
+
     if rank == 0 and world == 1 and not args.no_mode_m and float(U) * n * K * 8 < 40e9:
         # secondary accounting: reference-faithful mode M (every iteration's draws written to HBM)
         engm = pf.Engine(n, model.family, model.blob, J, K, local_rank, materialize_all=True)
@@ -468,6 +495,20 @@ def main():
         line["cpu_baseline"] = {"value": done / secs, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"oracle ELBO stage on the first {done // K} (path, iteration) units of "
                                           f"this workload, {secs:.1f} s, single thread"}
+        if mpf is not None and done > 0:
+            # the same multipathfinder() on one CPU core: the oracle's L-BFGS (C++, measured on a sample
+            # of the paths) + its ELBO stage at the rate just measured (PSIS/resample: negligible)
+            from oracle import lbfgs as OL
+
+            t0 = time.perf_counter()
+            for p in range(min(P, 8)):
+                x0 = (np.random.default_rng(MASTER_SEED + 1000 + p).random(n) * 2 - 1) * CONFIGS[name][5]
+                kw = dict(mean=model.mean, sd=model.sd) if model.family == 2 else {}
+                OL.lbfgs_path(model.family, x0, J, 64, **kw)
+            cpu_lbfgs_s = (time.perf_counter() - t0) * P / max(1, min(P, 8))
+            cpu_s = cpu_lbfgs_s + mpf["units"] * K / (done / secs)
+            mpf["cpu_port_single_thread_est_s"] = float(cpu_s)
+            mpf["speedup_vs_cpu_port_est"] = float(cpu_s / mpf["ours_s"])
         print(json.dumps(line))
     eng.close()
     if world > 1:

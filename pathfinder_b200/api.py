@@ -187,9 +187,10 @@ def _assemble_path(model, rng, entry, ndraws, K):
         f = res.fit
         fit = FitDistribution(f["mu"][:, j].copy(), f["alpha"][:, j].copy(), f["vh"][:, :, j].copy(),
                               f["T"][j].copy(), f["Vc"][j].copy(), float(f["logdet"][j]), int(f["jeff"][j]))
-    draws = res.draws[:, :ndraws, j].copy()
+    # views into the batch's download buffers (F-order, so each path's slab is contiguous): no copies
+    draws = res.draws[:, :ndraws, j]
     return PathfinderResult(model, rng, fit, draws, int(res.best_iter[j]), ntry, trace, ests, rej, ok,
-                            res.draws_logp[:ndraws, j].copy(), res.draws_logq[:ndraws, j].copy())
+                            res.draws_logp[:ndraws, j], res.draws_logq[:ndraws, j])
 
 
 def pathfinder(model, *, init=None, init_scale=2.0, ndraws_elbo=DEFAULT_NDRAWS_ELBO, ndraws=None, rng=None,
