@@ -41,6 +41,7 @@ extern "C" {
                                    log tau ~ N(0,1), b0 ~ N(0,2.5^2), b_j ~ N(0,tau^2),
                                    y_i ~ Bernoulli(sigmoid(b0 + x_i'b)); blob = { nobs,
                                    X[nobs x (n-2)] column-major, y[nobs] }   (BASELINE config 4)     */
+#define PFB_MODEL_HOSTCALLBACK 5 /* arbitrary target evaluated by a HOST callback (pfb_register_host_model) */
 #define PFB_MODEL_EXTERNAL 100 /* internal: log p evaluated outside the sampling kernel             */
 
 typedef struct pfb_engine* pfb_handle;
@@ -103,6 +104,17 @@ int pfb_kp(pfb_handle h); /* padded reflector count KP (12, 20 or 24) for histor
 /* Target density: replaces the Julia closure logp(x) (src/singlepath.jl:186, src/multipath.jl:159)
  * by a registered device-side family + parameter blob (doubles). */
 int pfb_register_model(pfb_handle h, int family, int n, const double* blob, size_t ndoubles);
+
+/* Row f2 — arbitrary target density: the Julia closure `logp` itself (src/singlepath.jl:186,
+ * src/multipath.jl:159; any LogDensityProblems / Turing model) evaluated on the HOST.  The ELBO
+ * stage then materialises the draws of a chunk of (path, iteration) units on the device, streams
+ * them to pinned host memory, and calls `cb(user, x, n, m, logp_out)` with x = n x m column-major
+ * draws (what `logp.(eachcol(x))` consumes, src/elbo.jl:15; src/resample.jl:90-92) while the next
+ * chunk is being sampled and copied; logp_out[m] goes back to the device for the ELBO reduction.
+ * The callback runs on the thread that called pfb_batch_run / pfb_draw_from_fits, never
+ * concurrently with itself.  Non-finite values propagate as in src/elbo.jl:16-17. */
+typedef void (*pfb_logp_callback)(void* user, const double* x, int64_t n, int64_t m, double* logp_out);
+int pfb_register_host_model(pfb_handle h, int n, pfb_logp_callback cb, void* user);
 
 /* One call for the whole ELBO stage of P paths.  Replaces, batched over (path x iteration):
  *   fit_mvnormals(optim_trace.points, optim_trace.gradients; history_length)   src/singlepath.jl:301-303
@@ -167,14 +179,17 @@ int pfb_draw_from_fits(pfb_handle h, int K_new, const uint64_t* seeds, double* d
 /* Replaces _compute_psis_result + _resample (src/multipath.jl:220-225, src/resample.jl:58-95)
  * on the pool produced by the last batch (N = P * K draws; log ratios reuse the ELBO stage's
  * logp - logq, which src/resample.jl:81-95 recomputes).  importance = 0: uniform resampling
- * (psis_result === nothing, src/resample.jl:61). */
-int pfb_psis_resample(pfb_handle h, uint64_t seed, int ndraws, int importance, pfb_resample_out* out);
+ * (psis_result === nothing, src/resample.jl:61).  replace = 0: sampling without replacement
+ * (the `replace` keyword of resample, src/resample.jl:25 -> StatsBase.sample(...; replace),
+ * src/resample.jl:61-66); ndraws > N is then an argument error like StatsBase's. */
+int pfb_psis_resample(pfb_handle h, uint64_t seed, int ndraws, int importance, int replace,
+                      pfb_resample_out* out);
 
 /* PSIS + resampling on caller-supplied log ratios (host): log_ratios[N]; pool_or_null[n x N].
  * Used by resample() re-entry (src/resample.jl:20-46) and by the parity tests. */
 int pfb_psis_resample_host(pfb_handle h, int n, int64_t N, int K_run, const double* log_ratios,
                            const double* pool_or_null, uint64_t seed, int ndraws, int importance,
-                           pfb_resample_out* out);
+                           int replace, pfb_resample_out* out);
 
 /* Device views for multi-GPU plumbing (NCCL all-gather of the pool by the host layer). */
 typedef struct {
@@ -191,7 +206,7 @@ int pfb_batch_device_view(pfb_handle h, pfb_device_view* view);
  * outputs in `out` are HOST pointers. */
 int pfb_psis_resample_device(pfb_handle h, int n, int64_t N, int K_run, const void* d_logp,
                              const void* d_logq, const void* d_pool, uint64_t seed, int ndraws,
-                             int importance, pfb_resample_out* out);
+                             int importance, int replace, pfb_resample_out* out);
 
 /* Timings of the last batch in milliseconds (CUDA events on the engine stream):
  * ms[0..5] = K1, K2, K3, K4, K5, total; returns the number of kernels launched. */

@@ -163,12 +163,13 @@ function elbo_batch(e::Engine, traces, seeds::Vector{Vector{UInt64}}; normals=no
 end
 
 """
-    psis_resample(engine, seed, ndraws; importance=true)
+    psis_resample(engine, seed, ndraws; importance=true, replace=true)
 
 `_compute_psis_result` + `_resample` (src/multipath.jl:220-225) on the pool left on the device
 by the last `elbo_batch` (N = P * K draws, draw-fastest / component-slowest).
 """
-function psis_resample(e::Engine, P::Integer, seed::UInt64, ndraws::Integer; importance::Bool=true)
+function psis_resample(e::Engine, P::Integer, seed::UInt64, ndraws::Integer; importance::Bool=true,
+                       replace::Bool=true)
     N = P * e.K
     lw = Vector{Float64}(undef, N); w = similar(lw)
     k = Ref(NaN); tl = Ref(Int64(0))
@@ -183,7 +184,8 @@ function psis_resample(e::Engine, P::Integer, seed::UInt64, ndraws::Integer; imp
         out.tail_len = Base.unsafe_convert(Ptr{Int64}, tl)
         out.inds = pointer(inds); out.ids = pointer(ids); out.draws = pointer(draws)
         rc = ccall((:pfb_psis_resample, LIB[]), Cint,
-                   (Ptr{Cvoid}, UInt64, Cint, Cint, Ref{PfbResampleOut}), e.handle, seed, ndraws, importance, out)
+                   (Ptr{Cvoid}, UInt64, Cint, Cint, Cint, Ref{PfbResampleOut}), e.handle, seed, ndraws, importance,
+                   replace, out)
         check(e, rc)
     end
     return (; log_weights=lw, weights=w, pareto_shape=k[], tail_length=tl[], sample_inds=inds,

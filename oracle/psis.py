@@ -165,12 +165,41 @@ def resample_indices(seed, weights, N, ndraws):
     return np.searchsorted(cum, targets, side="right").astype(np.int64) + 1
 
 
-def resample(seed, draws_per_component, psis_result, ndraws):
+def resample_indices_norep(seed, log_weights, N, ndraws):
+    """1-based indices WITHOUT replacement (replace=false, src/resample.jl:61-66).  StatsBase's
+    A-ExpJ runs on Julia's RNG stream (third party, parity unpinned); the engine contract is the
+    same design as order statistics: key_i = log(E_i) - log w_i with E_i = -log(u_i) ~ Exp(1) from
+    53 Philox bits of counter i; the ndraws smallest keys in ascending order, ties to the smaller
+    index.  log_weights=None -> uniform (importance=false)."""
+    if ndraws > N:
+        raise ValueError("Cannot draw more samples without replacement.")
+    bits = np.empty(N, dtype=np.uint64)
+    O.clib().pfo_resample_bits(int(seed) & (2**64 - 1), N, bits.ctypes.data)
+    u = ((bits >> np.uint64(11)).astype(np.float64) + 0.5) * 1.1102230246251565e-16
+    e = -O.pf_log(u)
+    lw = np.zeros(N) if log_weights is None else np.asarray(log_weights, dtype=np.float64)
+    with np.errstate(invalid="ignore"):
+        key = np.where(np.isfinite(lw) | (lw == np.inf), O.pf_log(e) - lw, np.inf)
+    key = np.where(np.isnan(lw), np.inf, key)
+    # the device sorts the order-preserving integer image of the keys (NaN last), stable in the index
+    b = key.view(np.uint64)
+    neg = (b >> np.uint64(63)).astype(bool)
+    ordered = np.where(neg, ~b, b | np.uint64(1 << 63))
+    ordered = np.where(np.isnan(key), np.uint64(0xFFFFFFFFFFFFFFFF), ordered)
+    order = np.argsort(ordered, kind="stable")
+    return order[:ndraws].astype(np.int64) + 1
+
+
+def resample(seed, draws_per_component, psis_result, ndraws, replace=True):
     """reference: src/resample.jl:58-72.  draws_per_component: (n, K_run, P)."""
     n, K_run, P = draws_per_component.shape
     draws_all = draws_per_component.reshape(n, K_run * P, order="F")
     w = None if psis_result is None else psis_result["weights"]
-    inds = resample_indices(seed, w, K_run * P, ndraws)
+    if replace:
+        inds = resample_indices(seed, w, K_run * P, ndraws)
+    else:
+        lw = None if psis_result is None else psis_result["log_weights"]
+        inds = resample_indices_norep(seed, lw, K_run * P, ndraws)
     draws = draws_all[:, inds - 1]
     ids = -(-inds // K_run)  # cld
     return draws, ids, inds

@@ -6,9 +6,9 @@ the C ABI, built into libpfb200.so) and the host-side mirror of the reference's
 There is no CPU fallback: without the CUDA library and a GPU every compute call raises.
 """
 from ._lib import (PFB_MODEL_DENSENORMAL, PFB_MODEL_DIAGNORMAL, PFB_MODEL_FUNNEL, PFB_MODEL_HLOGISTIC,  # noqa: F401
-                   PFB_MODEL_ISONORMAL, PfbError)
+                   PFB_MODEL_HOSTCALLBACK, PFB_MODEL_ISONORMAL, PfbError)
 from .api import (DEFAULT_HISTORY_LENGTH, DEFAULT_NDRAWS_ELBO, ELBOEstimate, FitDistribution,  # noqa: F401
                   MultiPathfinderResult, PathfinderResult, PSISResult, multipathfinder, pathfinder, resample)
 from .engine import ElboBatchResult, Engine  # noqa: F401
-from .models import DenseNormal, DiagNormal, Funnel, HierLogistic, IsoNormal  # noqa: F401
+from .models import DenseNormal, DiagNormal, Funnel, HierLogistic, HostModel, IsoNormal  # noqa: F401
 from .optimize import OptimizationTrace, optimize_with_trace  # noqa: F401

@@ -17,6 +17,7 @@ PFB_MODEL_FUNNEL = 1
 PFB_MODEL_DIAGNORMAL = 2
 PFB_MODEL_DENSENORMAL = 3
 PFB_MODEL_HLOGISTIC = 4
+PFB_MODEL_HOSTCALLBACK = 5
 
 
 class PfbError(RuntimeError):
@@ -38,6 +39,8 @@ class pfb_config(C.Structure):
 
 
 _dp = C.c_void_p
+# void cb(void* user, const double* x /* n x m column-major */, int64_t n, int64_t m, double* logp_out)
+pfb_logp_callback = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.c_int64, C.POINTER(C.c_double))
 
 
 class pfb_elbo_out(C.Structure):
@@ -70,6 +73,7 @@ SYMBOLS = {
     "pfb_last_error": (C.c_char_p, [C.c_void_p]),
     "pfb_kp": (C.c_int, [C.c_void_p]),
     "pfb_register_model": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, C.c_size_t]),
+    "pfb_register_host_model": (C.c_int, [C.c_void_p, C.c_int, pfb_logp_callback, C.c_void_p]),
     "pfb_elbo_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp,
                                  C.POINTER(pfb_elbo_out)]),
     "pfb_batch_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]),
@@ -82,13 +86,13 @@ SYMBOLS = {
     "pfb_lbfgs_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "pfb_batch_fit_only": (C.c_int, [C.c_void_p, _dp]),
     "pfb_draw_from_fits": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, C.c_int]),
-    "pfb_psis_resample": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int,
+    "pfb_psis_resample": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(pfb_resample_out)]),
     "pfb_psis_resample_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, _dp, _dp,
-                                         C.c_uint64, C.c_int, C.c_int, C.POINTER(pfb_resample_out)]),
+                                         C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(pfb_resample_out)]),
     "pfb_batch_device_view": (C.c_int, [C.c_void_p, C.POINTER(pfb_device_view)]),
     "pfb_psis_resample_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, _dp, _dp, _dp,
-                                           C.c_uint64, C.c_int, C.c_int, C.POINTER(pfb_resample_out)]),
+                                           C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(pfb_resample_out)]),
     "pfb_get_timings": (C.c_int, [C.c_void_p, _dp]),
     "pfb_measure_fp64_fma_tflops": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "pfb_measure_fp64_dmma_tflops": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),

@@ -205,7 +205,7 @@ def pathfinder(model, *, init=None, init_scale=2.0, ndraws_elbo=DEFAULT_NDRAWS_E
         raise ValueError("init has the wrong dimension")
     own = engine is None
     if own:
-        engine = Engine(model.n, model.family, model.blob, history_length, ndraws_elbo, device)
+        engine = Engine.for_model(model, history_length, ndraws_elbo, device)
     try:
         final, _ = _run_paths(engine, model, [x0], [rng], history_length=history_length, maxiters=maxiters,
                               ntries=ntries, init_scale=init_scale, ndraws_run=ndraws, optimizer=optimizer)
@@ -249,7 +249,7 @@ def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT
         lo, hi = D.shard_range(nruns, dist.get_rank(group), dist.get_world_size(group))
     own = engine is None
     if own:
-        engine = Engine(model.n, model.family, model.blob, history_length, ndraws_elbo, device)
+        engine = Engine.for_model(model, history_length, ndraws_elbo, device)
     final, last = _run_paths(engine, model, inits[lo:hi], path_rngs[lo:hi], history_length=history_length,
                              maxiters=maxiters, ntries=ntries, init_scale=init_scale, ndraws_run=ndraws_per_run,
                              optimizer=optimizer)
@@ -292,8 +292,6 @@ def resample(result: MultiPathfinderResult, ndraws, *, rng=None, replace=True, i
     """Re-resample a fitted result (src/resample.jl:20-46): from its stored draws, or — with
     `ndraws_per_run` — from fresh draws of every path's fitted normal (src/resample.jl:102-109),
     rebuilt on the device from the stored trajectories without an ELBO stage."""
-    if not replace:
-        raise NotImplementedError("replace=false is not accelerated yet")
     rng = result.rng if rng is None else rng
     prs = result.pathfinder_results
     model = result.input
@@ -301,22 +299,22 @@ def resample(result: MultiPathfinderResult, ndraws, *, rng=None, replace=True, i
         pool = np.concatenate([pr.draws for pr in prs], axis=1)
         K_run = prs[0].draws.shape[1]
         seed = int(_draw_seeds(rng, 1)[0])
-        eng = Engine(model.n, model.family, model.blob, history_length, K_run, device)
+        eng = Engine.for_model(model, history_length, K_run, device)
         try:
             if importance:
                 # the log ratios of the stored draws are the ELBO stage's logp - logq (what
                 # _compute_log_importance_ratios, src/resample.jl:81-95, recomputes)
                 logr = np.concatenate([pr.draws_logp - pr.draws_logq for pr in prs])
-                r = eng.psis_resample_host(logr, K_run, seed, ndraws, True, pool=pool)
+                r = eng.psis_resample_host(logr, K_run, seed, ndraws, True, pool=pool, replace=replace)
                 psis = PSISResult(r["log_weights"], r["weights"], r["pareto_k"], r["tail_len"])
             else:
-                r = eng.psis_resample_host(None, K_run, seed, ndraws, False, pool=pool)
+                r = eng.psis_resample_host(None, K_run, seed, ndraws, False, pool=pool, replace=replace)
                 psis = None
         finally:
             eng.close()
         return MultiPathfinderResult(model, rng, r["draws"], r["ids"], prs, psis, r["inds"], None)
     K_run = int(ndraws_per_run)
-    eng = Engine(model.n, model.family, model.blob, history_length, K_run, device)
+    eng = Engine.for_model(model, history_length, K_run, device)
     try:
         offsets, X, G = Engine.pack([(pr.optim_trace.points, pr.optim_trace.gradients) for pr in prs])
         U = int(offsets[-1]) - len(prs)
@@ -324,7 +322,7 @@ def resample(result: MultiPathfinderResult, ndraws, *, rng=None, replace=True, i
         eng.fit_only([pr.fit_iteration for pr in prs])
         seeds = _draw_seeds(rng, len(prs))
         xd, lp, lq = eng.draw_from_fits(K_run, seeds, keep_as_pool=True)
-        r = eng.psis_resample(int(_draw_seeds(rng, 1)[0]), ndraws, importance)
+        r = eng.psis_resample(int(_draw_seeds(rng, 1)[0]), ndraws, importance, replace)
     finally:
         eng.close()
     new_prs = []

@@ -843,6 +843,7 @@ static cudaError_t launch_k3_k(cudaStream_t st, int model, int n, int K, int nsl
                                                          mp, logp, logq, draws, two_pass);
         case PFB_MODEL_DENSENORMAL:
         case PFB_MODEL_HLOGISTIC:
+        case PFB_MODEL_HOSTCALLBACK:
             if (draws == nullptr) return cudaErrorInvalidValue;  // these families need x written out (K8)
             return launch_k3_m<KP, PFB_MODEL_EXTERNAL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host, mp,
                                                        logp, logq, draws, 1);

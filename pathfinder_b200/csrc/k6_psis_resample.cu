@@ -347,3 +347,66 @@ extern "C" cudaError_t pfb_launch_k7(cudaStream_t st, int n, int N, int K_run, u
                                                    pool, inds, ids, draws_out);
     return cudaGetLastError();
 }
+
+// ---- K7b: weighted sampling WITHOUT replacement (replace = false, src/resample.jl:58-72) -----------
+// StatsBase.sample(rng, 1:N, pweights, ndraws; replace = false) is third-party (parity unpinned,
+// it runs Efraimidis-Spirakis A-ExpJ on Julia's RNG stream).  The engine's contract is
+// the same sampling design in its order-statistics form: every pool entry i gets the key
+//     key_i = log(E_i) - log w_i,   E_i = -log(u_i) ~ Exp(1),  u_i from 53 Philox bits of counter i,
+// and the ndraws smallest keys are the sample, in ascending key order (= the order sequential
+// weighted sampling without replacement would have drawn them); ties break towards the smaller
+// index.  importance = false: log w = 0 (a uniform random subset in random order).  Zero / NaN
+// weights get key = +Inf and are taken only when nothing else is left.  pf_log makes the keys
+// bit-identical to the oracle's (oracle/psis.py::resample_indices_norep).
+#include <cub/device/device_radix_sort.cuh>
+
+__global__ void pfb_k7b_keys(int N, uint64_t seed, const double* __restrict__ logw, uint64_t* __restrict__ keys,
+                             int32_t* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint64_t bits = pf_resample_bits((uint64_t)i, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u = ((double)(bits >> 11) + 0.5) * 1.1102230246251565e-16;  // (0, 1), 2^-53 grid
+    const double e = -pf_log(u);
+    double lw = logw ? logw[i] : 0.0;
+    double key = (lw == lw && lw > -INFINITY) ? pf_log(e) - lw : (double)INFINITY;
+    keys[i] = pfb_ordered_key(key);
+    idx[i] = i;
+}
+
+__global__ void __launch_bounds__(128)
+pfb_k7b_gather(int n, int K_run, const int32_t* __restrict__ order, const double* __restrict__ pool,
+               int64_t* __restrict__ inds, int64_t* __restrict__ ids, double* __restrict__ draws_out) {
+    const int t = blockIdx.x;
+    const int64_t idx = order[t];
+    if (threadIdx.x == 0) {
+        inds[t] = idx + 1;
+        ids[t] = idx / K_run + 1;
+    }
+    if (pool != nullptr && draws_out != nullptr) {
+        const double* src = pool + idx * (int64_t)n;
+        double* dst = draws_out + (int64_t)t * n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+// temp_bytes == NULL-query convention of CUB: call once with tmp = NULL to get the size.
+extern "C" cudaError_t pfb_k7b_temp_bytes(int N, size_t* bytes) {
+    *bytes = 0;
+    return cub::DeviceRadixSort::SortPairs(nullptr, *bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                           (const int32_t*)nullptr, (int32_t*)nullptr, N);
+}
+
+// work: 2 N uint64 keys + 2 N int32 indices (in / out) laid out by the caller; tmp: CUB scratch.
+extern "C" cudaError_t pfb_launch_k7b(cudaStream_t st, int n, int N, int K_run, uint64_t seed, int ndraws,
+                                      const double* logw, const double* pool, uint64_t* keys_in, uint64_t* keys_out,
+                                      int32_t* idx_in, int32_t* idx_out, void* tmp, size_t tmp_bytes, int64_t* inds,
+                                      int64_t* ids, double* draws_out) {
+    if (ndraws <= 0 || N <= 0) return cudaSuccess;
+    pfb_k7b_keys<<<(N + 255) / 256, 256, 0, st>>>(N, seed, logw, keys_in, idx_in);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, idx_in, idx_out, N, 0, 64, st);
+    if (e != cudaSuccess) return e;
+    pfb_k7b_gather<<<ndraws, 128, 0, st>>>(n, K_run, idx_out, pool, inds, ids, draws_out);
+    return cudaGetLastError();
+}

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -38,6 +39,9 @@ cudaError_t pfb_launch_k0(cudaStream_t, int, int, int, const double*, const doub
 cudaError_t pfb_launch_k0_pack(cudaStream_t, int, int64_t, const int64_t*, const double*, const double*, double*,
                                double*);
 size_t pfb_psis_scalars_size();
+cudaError_t pfb_k7b_temp_bytes(int, size_t*);
+cudaError_t pfb_launch_k7b(cudaStream_t, int, int, int, uint64_t, int, const double*, const double*, uint64_t*,
+                           uint64_t*, int32_t*, int32_t*, void*, size_t, int64_t*, int64_t*, double*);
 cudaError_t pfb_launch_k6(cudaStream_t, int, int, int, const double*, const double*, const double*, double*,
                           double*, uint64_t*, void*);
 cudaError_t pfb_launch_k7(cudaStream_t, int, int, int, uint64_t, int, const uint64_t*, const void*,
@@ -100,6 +104,16 @@ struct pfb_engine {
     DevBuf dAlpha, dHist, dHistCnt, dRej, dFR, dFR2, dHDR, dLogp, dLogq, dElbo, dSe, dBestIter, dBestUnit, dSucc;
     DevBuf dPool, dPoolLogp, dPoolLogq, dAllDraws;
     DevBuf dFitMu, dFitAlpha, dFitVh, dFitT, dFitVc, dFitLogdet, dFitJeff;
+    // host-callback target (row f2): pinned staging, copy stream
+    pfb_logp_callback host_cb = nullptr;
+    void* host_user = nullptr;
+    double* hX[2] = {nullptr, nullptr};
+    size_t hX_cap = 0;
+    double* hLp = nullptr;
+    size_t hLp_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t hc_k[2] = {}, hc_c[2] = {};
+    double host_cb_s = 0.0;  // seconds spent inside the callback during the last run
     // device L-BFGS (K0): trajectory slabs [n x max_points] per path
     DevBuf dLbX0, dLbX, dLbG, dLbFX, dLbWs, dLbNp, dLbSt, dLbNev, dLbSrc;
     std::vector<int64_t> lb_np;
@@ -108,7 +122,7 @@ struct pfb_engine {
     float lb_ms = 0.f;
     cudaEvent_t lb_ev[2] = {};
     // psis
-    DevBuf dLogw, dW, dCum, dScal, dInds, dIds, dOutDraws, dTmpLogr, dTmpPool;
+    DevBuf dLogw, dW, dCum, dScal, dInds, dIds, dOutDraws, dTmpLogr, dTmpPool, dSortWork, dSortTmp;
 };
 
 #define PFB_FAIL(h, code, msg)     \
@@ -181,9 +195,16 @@ extern "C" int pfb_destroy(pfb_handle h) {
                       &h->dPoolLogq, &h->dAllDraws, &h->dFitMu, &h->dFitAlpha, &h->dFitVh, &h->dFitT,
                       &h->dFitVc, &h->dFitLogdet, &h->dFitJeff, &h->dLogw, &h->dW, &h->dCum, &h->dScal,
                       &h->dInds, &h->dIds, &h->dOutDraws, &h->dTmpLogr, &h->dTmpPool, &h->dGenX, &h->dGenY, &h->dIota, &h->dTopSeeds,
-                      &h->dLbX0, &h->dLbX, &h->dLbG, &h->dLbFX, &h->dLbWs, &h->dLbNp, &h->dLbSt, &h->dLbNev, &h->dLbSrc};
+                      &h->dLbX0, &h->dLbX, &h->dLbG, &h->dLbFX, &h->dLbWs, &h->dLbNp, &h->dLbSt, &h->dLbNev, &h->dLbSrc, &h->dSortWork, &h->dSortTmp};
     for (auto* b : bufs) b->release();
     if (h->cublas) cublasDestroy(h->cublas);
+    for (int i = 0; i < 2; ++i) {
+        if (h->hX[i]) cudaFreeHost(h->hX[i]);
+        if (h->hc_k[i]) cudaEventDestroy(h->hc_k[i]);
+        if (h->hc_c[i]) cudaEventDestroy(h->hc_c[i]);
+    }
+    if (h->hLp) cudaFreeHost(h->hLp);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto& ev : h->ev) cudaEventDestroy(ev);
     for (auto& ev : h->lb_ev) cudaEventDestroy(ev);
     cudaStreamDestroy(h->stream);
@@ -462,7 +483,72 @@ extern "C" int pfb_lbfgs_ms(pfb_handle h, double* ms) {
 }
 
 static bool model_is_external(const pfb_engine* h) {
-    return h->model == PFB_MODEL_DENSENORMAL || h->model == PFB_MODEL_HLOGISTIC;
+    return h->model == PFB_MODEL_DENSENORMAL || h->model == PFB_MODEL_HLOGISTIC ||
+           h->model == PFB_MODEL_HOSTCALLBACK;
+}
+
+static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list, double* logp, double* logq,
+                             double* draws, int K_over = 0, const uint64_t* seeds_over = nullptr);
+
+extern "C" int pfb_register_host_model(pfb_handle h, int n, pfb_logp_callback cb, void* user) {
+    if (!h) return PFB_ERR_ARG;
+    if (n < 1 || !cb) PFB_FAIL(h, PFB_ERR_ARG, "host model needs n >= 1 and a callback");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (!h->copy_stream) {
+        PFB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            PFB_CUDA(h, cudaEventCreateWithFlags(&h->hc_k[i], cudaEventDisableTiming));
+            PFB_CUDA(h, cudaEventCreateWithFlags(&h->hc_c[i], cudaEventDisableTiming));
+        }
+    }
+    h->host_cb = cb;
+    h->host_user = user;
+    h->model = PFB_MODEL_HOSTCALLBACK;
+    h->model_n = n;
+    return PFB_OK;
+}
+
+static int host_staging(pfb_engine* h, size_t x_bytes, size_t lp_bytes) {
+    if (x_bytes > h->hX_cap) {
+        for (int i = 0; i < 2; ++i) {
+            if (h->hX[i]) cudaFreeHost(h->hX[i]);
+            h->hX[i] = nullptr;
+        }
+        h->hX_cap = 0;
+        for (int i = 0; i < 2; ++i) PFB_CUDA(h, cudaMallocHost((void**)&h->hX[i], x_bytes));
+        h->hX_cap = x_bytes;
+    }
+    if (lp_bytes > h->hLp_cap) {
+        if (h->hLp) cudaFreeHost(h->hLp);
+        h->hLp = nullptr;
+        h->hLp_cap = 0;
+        PFB_CUDA(h, cudaMallocHost((void**)&h->hLp, lp_bytes));
+        h->hLp_cap = lp_bytes;
+    }
+    return PFB_OK;
+}
+
+// dst[slot][k] = src[unit_of_slot][k] (NaN for unit < 0): log p of the best-iteration draws is the
+// ELBO stage's own (K5 regenerates the same draws), so the host callback is not asked twice
+__global__ void pfb_gather_unit_rows(int K, const int32_t* __restrict__ unit_of_slot, const double* __restrict__ src,
+                                     double* __restrict__ dst) {
+    const int u = unit_of_slot[blockIdx.x];
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        dst[(int64_t)blockIdx.x * K + k] = u >= 0 ? src[(int64_t)u * K + k] : NAN;
+}
+
+// log p of M = cnt * K materialised device draws through the host callback (synchronous).
+static int host_logp_sync(pfb_engine* h, const double* dX, int64_t M, double* d_logp) {
+    const size_t n = (size_t)h->n;
+    int rc = host_staging(h, (size_t)M * n * 8, (size_t)M * 8);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    PFB_CUDA(h, cudaMemcpyAsync(h->hX[0], dX, (size_t)M * n * 8, cudaMemcpyDeviceToHost, st));
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    h->host_cb(h->host_user, h->hX[0], (int64_t)n, M, h->hLp);
+    PFB_CUDA(h, cudaMemcpyAsync(d_logp, h->hLp, (size_t)M * 8, cudaMemcpyHostToDevice, st));
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    return PFB_OK;
 }
 
 // K8: log p of M = nslots * K materialised draws X [n x M] for the GEMM-shaped families.
@@ -494,7 +580,7 @@ static int generic_logp(pfb_engine* h, const double* X, int64_t M, const int32_t
 
 // K_over > 0 / seeds_over != NULL: fresh draws from the fitted normals (top-up draws, resample()).
 static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list, double* logp, double* logq,
-                             double* draws, int K_over = 0, const uint64_t* seeds_over = nullptr) {
+                             double* draws, int K_over, const uint64_t* seeds_over) {
     const double* mp0 = model_is_external(h) ? nullptr : h->dModel.as<double>();
     const double* mp1 = mp0 ? mp0 + h->model_n : nullptr;
     const double* un = (h->have_normals && !seeds_over) ? h->dNormals.as<double>() : nullptr;
@@ -502,6 +588,64 @@ static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list
     return fn(h->stream, h->model, h->n, K_over > 0 ? K_over : h->K, nslots, unit_list, h->dFR2.as<double>(),
               h->dHDR.as<double>(), seeds_over ? seeds_over : h->dSeeds.as<uint64_t>(), un, mp0, mp1, h->model_c0,
               logp, logq, draws, h->cfg.elbo_mode == 1);
+}
+
+// ELBO stage for a host-callback target (row f2): K3 materialises chunk c + 2 and the copy stream
+// brings chunk c + 1 to pinned memory while the host evaluates chunk c.
+static int run_host_callback_stage(pfb_engine* h) {
+    const int n = h->n, K = h->K, U = (int)h->U;
+    const size_t per_unit = (size_t)n * (size_t)K * 8;
+    int chunk = (int)std::max<size_t>(1, ((size_t)64 << 20) / per_unit);
+    chunk = std::min(chunk, U);
+    const bool mat = h->cfg.materialize_all != 0;
+    cudaStream_t st = h->stream, cs = h->copy_stream;
+    if (!mat) PFB_CUDA(h, h->dGenX.ensure(2 * per_unit * (size_t)chunk));
+    PFB_CUDA(h, h->dIota.ensure((size_t)U * 4));
+    {
+        std::vector<int32_t> iota((size_t)U);
+        for (int u = 0; u < U; ++u) iota[(size_t)u] = u;
+        PFB_CUDA(h, cudaMemcpyAsync(h->dIota.p, iota.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
+        PFB_CUDA(h, cudaStreamSynchronize(st));
+    }
+    int rc = host_staging(h, per_unit * (size_t)chunk, (size_t)U * K * 8);
+    if (rc) return rc;
+    const int nchunks = (U + chunk - 1) / chunk;
+    h->host_cb_s = 0.0;
+    auto sample_and_copy = [&](int c) -> int {
+        const int u0 = c * chunk, cnt = std::min(chunk, U - u0), b = c & 1;
+        double* xbuf = mat ? h->dAllDraws.as<double>() + (size_t)u0 * n * K
+                           : h->dGenX.as<double>() + (size_t)b * chunk * n * K;
+        if (c >= 2) PFB_CUDA(h, cudaStreamWaitEvent(st, h->hc_c[b], 0));  // device buffer b drained
+        PFB_CUDA(h, launch_k3(h, cnt, h->dIota.as<int32_t>() + u0, h->dLogp.as<double>() + (size_t)u0 * K,
+                              h->dLogq.as<double>() + (size_t)u0 * K, xbuf, 0, nullptr));
+        h->launches += 1;
+        PFB_CUDA(h, cudaEventRecord(h->hc_k[b], st));
+        PFB_CUDA(h, cudaStreamWaitEvent(cs, h->hc_k[b], 0));
+        PFB_CUDA(h, cudaMemcpyAsync(h->hX[b], xbuf, per_unit * (size_t)cnt, cudaMemcpyDeviceToHost, cs));
+        PFB_CUDA(h, cudaEventRecord(h->hc_c[b], cs));
+        return PFB_OK;
+    };
+    for (int c = 0; c < std::min(2, nchunks); ++c) {
+        rc = sample_and_copy(c);
+        if (rc) return rc;
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        const int u0 = c * chunk, cnt = std::min(chunk, U - u0), b = c & 1;
+        PFB_CUDA(h, cudaEventSynchronize(h->hc_c[b]));
+        double* lp = h->hLp + (size_t)u0 * K;
+        cudaEvent_t dummy = nullptr;
+        (void)dummy;
+        const auto t0 = std::chrono::steady_clock::now();
+        h->host_cb(h->host_user, h->hX[b], (int64_t)n, (int64_t)cnt * K, lp);
+        h->host_cb_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        PFB_CUDA(h, cudaMemcpyAsync(h->dLogp.as<double>() + (size_t)u0 * K, lp, (size_t)cnt * K * 8,
+                                    cudaMemcpyHostToDevice, st));
+        if (c + 2 < nchunks) {
+            rc = sample_and_copy(c + 2);
+            if (rc) return rc;
+        }
+    }
+    return PFB_OK;
 }
 
 extern "C" int pfb_batch_run(pfb_handle h) {
@@ -530,6 +674,11 @@ extern "C" int pfb_batch_run(pfb_handle h) {
         PFB_CUDA(h, launch_k3(h, U, nullptr, h->dLogp.as<double>(), h->dLogq.as<double>(),
                               h->cfg.materialize_all ? h->dAllDraws.as<double>() : nullptr));
         h->launches += (U > 0);
+    } else if (h->model == PFB_MODEL_HOSTCALLBACK) {
+        if (U > 0) {
+            int rc = run_host_callback_stage(h);
+            if (rc) return rc;
+        }
     } else if (U > 0) {
         // GEMM-shaped log p: materialise the draws of a chunk of units (K3), then K8 (cuBLAS + epilogue)
         const size_t per_unit = (size_t)n * (size_t)K * 8;
@@ -566,7 +715,12 @@ extern "C" int pfb_batch_run(pfb_handle h) {
     PFB_CUDA(h, launch_k3(h, P, h->dBestUnit.as<int32_t>(), h->dPoolLogp.as<double>(), h->dPoolLogq.as<double>(),
                           h->dPool.as<double>()));
     h->launches += (P > 0);
-    if (model_is_external(h) && P > 0) {
+    if (h->model == PFB_MODEL_HOSTCALLBACK && P > 0) {
+        pfb_gather_unit_rows<<<P, 256, 0, st>>>(K, h->dBestUnit.as<int32_t>(), h->dLogp.as<double>(),
+                                                h->dPoolLogp.as<double>());
+        PFB_CUDA(h, cudaGetLastError());
+        h->launches += 1;
+    } else if (model_is_external(h) && P > 0) {
         int rc = generic_logp(h, h->dPool.as<double>(), (int64_t)P * K, h->dBestUnit.as<int32_t>(),
                               h->dPoolLogp.as<double>());
         if (rc) return rc;
@@ -646,7 +800,10 @@ extern "C" int pfb_draw_from_fits(pfb_handle h, int K_new, const uint64_t* seeds
     PFB_CUDA(h, Lq->ensure((size_t)K_new * P * 8 + 8));
     PFB_CUDA(h, launch_k3(h, (int)P, h->dBestUnit.as<int32_t>(), Lp->as<double>(), Lq->as<double>(), X->as<double>(),
                           K_new, h->dTopSeeds.as<uint64_t>()));
-    if (model_is_external(h)) {
+    if (h->model == PFB_MODEL_HOSTCALLBACK) {
+        int rc = host_logp_sync(h, X->as<double>(), (int64_t)P * K_new, Lp->as<double>());
+        if (rc) return rc;
+    } else if (model_is_external(h)) {
         int rc = generic_logp(h, X->as<double>(), (int64_t)P * K_new, h->dBestUnit.as<int32_t>(), Lp->as<double>(),
                               K_new);
         if (rc) return rc;
@@ -778,9 +935,10 @@ extern "C" int pfb_batch_device_view(pfb_handle h, pfb_device_view* v) {
 
 static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const double* d_logp,
                               const double* d_logq, const double* d_logr, const double* d_pool, uint64_t seed,
-                              int ndraws, int importance, pfb_resample_out* o) {
+                              int ndraws, int importance, int replace, pfb_resample_out* o) {
     if (N < 1 || N > 2147483647LL) PFB_FAIL(h, PFB_ERR_SHAPE, "pool size out of range");
     if (K_run < 1 || ndraws < 0) PFB_FAIL(h, PFB_ERR_ARG, "bad K_run / ndraws");
+    if (!replace && ndraws > N) PFB_FAIL(h, PFB_ERR_ARG, "Cannot draw more samples without replacement.");
     cudaStream_t st = h->stream;
     PFB_CUDA(h, h->dScal.ensure(pfb_psis_scalars_size()));
     PFB_CUDA(h, h->dInds.ensure((size_t)ndraws * 8 + 8));
@@ -798,9 +956,25 @@ static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const 
         PFB_CUDA(h, pfb_launch_k6(st, (int)N, M, m_grid, d_logp, d_logq, d_logr, h->dLogw.as<double>(),
                                   h->dW.as<double>(), h->dCum.as<uint64_t>(), h->dScal.p));
     }
-    PFB_CUDA(h, pfb_launch_k7(st, n, (int)N, K_run, seed, ndraws, importance ? h->dCum.as<uint64_t>() : nullptr,
-                              h->dScal.p, want_draws ? d_pool : nullptr, h->dInds.as<int64_t>(),
-                              h->dIds.as<int64_t>(), want_draws ? h->dOutDraws.as<double>() : nullptr));
+    if (replace) {
+        PFB_CUDA(h, pfb_launch_k7(st, n, (int)N, K_run, seed, ndraws, importance ? h->dCum.as<uint64_t>() : nullptr,
+                                  h->dScal.p, want_draws ? d_pool : nullptr, h->dInds.as<int64_t>(),
+                                  h->dIds.as<int64_t>(), want_draws ? h->dOutDraws.as<double>() : nullptr));
+    } else {
+        // K7b: exponential-key order statistics (weighted sampling without replacement)
+        size_t tmp_bytes = 0;
+        PFB_CUDA(h, pfb_k7b_temp_bytes((int)N, &tmp_bytes));
+        PFB_CUDA(h, h->dSortWork.ensure((size_t)N * 24 + 64));
+        PFB_CUDA(h, h->dSortTmp.ensure(tmp_bytes + 16));
+        uint64_t* k_in = h->dSortWork.as<uint64_t>();
+        uint64_t* k_out = k_in + N;
+        int32_t* i_in = reinterpret_cast<int32_t*>(k_out + N);
+        int32_t* i_out = i_in + N;
+        PFB_CUDA(h, pfb_launch_k7b(st, n, (int)N, K_run, seed, ndraws, importance ? h->dLogw.as<double>() : nullptr,
+                                   want_draws ? d_pool : nullptr, k_in, k_out, i_in, i_out, h->dSortTmp.p, tmp_bytes,
+                                   h->dInds.as<int64_t>(), h->dIds.as<int64_t>(),
+                                   want_draws ? h->dOutDraws.as<double>() : nullptr));
+    }
     psis_scalars_host sc;
     memset(&sc, 0, sizeof(sc));
     if (importance) {
@@ -817,27 +991,28 @@ static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const 
     return PFB_OK;
 }
 
-extern "C" int pfb_psis_resample(pfb_handle h, uint64_t seed, int ndraws, int importance, pfb_resample_out* o) {
+extern "C" int pfb_psis_resample(pfb_handle h, uint64_t seed, int ndraws, int importance, int replace,
+                                 pfb_resample_out* o) {
     if (!h || !o) return PFB_ERR_ARG;
     if (!h->ran || h->poolK <= 0) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
     return psis_resample_impl(h, h->n, (int64_t)h->P * h->poolK, h->poolK, h->dPoolLogp.as<double>(),
                               h->dPoolLogq.as<double>(), nullptr, h->dPool.as<double>(), seed, ndraws,
-                              importance, o);
+                              importance, replace, o);
 }
 
 extern "C" int pfb_psis_resample_device(pfb_handle h, int n, int64_t N, int K_run, const void* d_logp,
                                         const void* d_logq, const void* d_pool, uint64_t seed, int ndraws,
-                                        int importance, pfb_resample_out* o) {
+                                        int importance, int replace, pfb_resample_out* o) {
     if (!h || !o) return PFB_ERR_ARG;
     if (importance && (!d_logp || !d_logq)) PFB_FAIL(h, PFB_ERR_ARG, "d_logp / d_logq are NULL");
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
     return psis_resample_impl(h, n, N, K_run, (const double*)d_logp, (const double*)d_logq, nullptr,
-                              (const double*)d_pool, seed, ndraws, importance, o);
+                              (const double*)d_pool, seed, ndraws, importance, replace, o);
 }
 
 extern "C" int pfb_psis_resample_host(pfb_handle h, int n, int64_t N, int K_run, const double* log_ratios,
-                                      const double* pool, uint64_t seed, int ndraws, int importance,
+                                      const double* pool, uint64_t seed, int ndraws, int importance, int replace,
                                       pfb_resample_out* o) {
     if (!h || !o) return PFB_ERR_ARG;
     if (N < 1) PFB_FAIL(h, PFB_ERR_SHAPE, "empty pool");
@@ -856,7 +1031,7 @@ extern "C" int pfb_psis_resample_host(pfb_handle h, int n, int64_t N, int K_run,
         PFB_CUDA(h, cudaMemcpyAsync(h->dTmpPool.p, pool, (size_t)n * N * 8, cudaMemcpyHostToDevice, st));
         d_pool = h->dTmpPool.as<double>();
     }
-    return psis_resample_impl(h, n, N, K_run, nullptr, nullptr, d_logr, d_pool, seed, ndraws, importance, o);
+    return psis_resample_impl(h, n, N, K_run, nullptr, nullptr, d_logr, d_pool, seed, ndraws, importance, replace, o);
 }
 
 extern "C" int pfb_get_timings(pfb_handle h, double* ms6) {

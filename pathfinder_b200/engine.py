@@ -44,7 +44,7 @@ class ElboBatchResult:
 
 class Engine:
     def __init__(self, n, model_family, model_blob=None, history_length=6, ndraws_elbo=5,
-                 device=0, materialize_all=False, eps=1e-12, two_pass=False):
+                 device=0, materialize_all=False, eps=1e-12, two_pass=False, host_logp=None):
         self.lib = _lib.load()
         self.n = int(n)
         self.K = int(ndraws_elbo)
@@ -57,13 +57,49 @@ class Engine:
         self.h = h
         self.KP = self.lib.pfb_kp(self.h)
         self.materialize_all = bool(materialize_all)
-        blob = None if model_blob is None else np.ascontiguousarray(model_blob, dtype=np.float64)
-        _lib.check(self.h, self.lib.pfb_register_model(
-            self.h, int(model_family), self.n, _ptr(blob), 0 if blob is None else blob.size))
+        self._cb = None
+        self._cb_error = None
+        if int(model_family) == _lib.PFB_MODEL_HOSTCALLBACK:
+            if host_logp is None:
+                raise ValueError("a host-callback model needs host_logp(X[n, m]) -> logp[m]")
+            self._register_host(host_logp)
+        else:
+            blob = None if model_blob is None else np.ascontiguousarray(model_blob, dtype=np.float64)
+            _lib.check(self.h, self.lib.pfb_register_model(
+                self.h, int(model_family), self.n, _ptr(blob), 0 if blob is None else blob.size))
         self._P = 0
         self._U = 0
         self._offsets = None
         self._poolK = self.K
+
+    @classmethod
+    def for_model(cls, model, history_length=6, ndraws_elbo=5, device=0, **kw):
+        """Engine for a model object of models.py (registered family, or HostModel)."""
+        return cls(model.n, model.family, getattr(model, "blob", None), history_length, ndraws_elbo, device,
+                   host_logp=getattr(model, "logp_batch", None), **kw)
+
+    def _register_host(self, host_logp):
+        """Row f2: the target density is a host function (the reference's `logp` closure,
+        src/elbo.jl:15).  The C callback wraps the pinned staging buffer as an n x m F-order array
+        without copying; an exception inside the callback is re-raised by run()."""
+        n = self.n
+
+        def cb(_user, xptr, n_, m, out):
+            try:
+                X = np.ctypeslib.as_array(xptr, shape=(int(m), int(n_))).T
+                res = np.ctypeslib.as_array(out, shape=(int(m),))
+                res[:] = np.asarray(host_logp(X), dtype=np.float64).reshape(int(m))
+            except BaseException as e:  # noqa: BLE001 — must not unwind through C
+                self._cb_error = e
+                np.ctypeslib.as_array(out, shape=(int(m),))[:] = np.nan
+
+        self._cb = _lib.pfb_logp_callback(cb)  # keep the trampoline alive as long as the engine
+        _lib.check(self.h, self.lib.pfb_register_host_model(self.h, n, self._cb, None))
+
+    def _raise_cb_error(self):
+        if self._cb_error is not None:
+            e, self._cb_error = self._cb_error, None
+            raise e
 
     def close(self):
         if getattr(self, "h", None):
@@ -162,6 +198,7 @@ class Engine:
 
     def run(self):
         _lib.check(self.h, self.lib.pfb_batch_run(self.h))
+        self._raise_cb_error()
         self._poolK = self.K
 
     def sync(self):
@@ -223,6 +260,7 @@ class Engine:
         lq = np.empty((int(K_new), P), order="F")
         _lib.check(self.h, self.lib.pfb_draw_from_fits(self.h, int(K_new), _ptr(sd), _ptr(draws), _ptr(lp), _ptr(lq),
                                                        int(bool(keep_as_pool))))
+        self._raise_cb_error()
         if keep_as_pool:
             self._poolK = int(K_new)
         return draws, lp, lq
@@ -259,15 +297,15 @@ class Engine:
         r["tail_len"] = int(r["tail_len"][0])
         return r
 
-    def psis_resample(self, seed, ndraws, importance=True):
+    def psis_resample(self, seed, ndraws, importance=True, replace=True):
         """On the pool of the last batch / the last draw_from_fits(keep_as_pool=True) (device resident)."""
         N = self._P * self._poolK
         out, r = self._resample_out(N, ndraws, importance, True)
         _lib.check(self.h, self.lib.pfb_psis_resample(self.h, C.c_uint64(int(seed)), int(ndraws),
-                                                      int(bool(importance)), C.byref(out)))
+                                                      int(bool(importance)), int(bool(replace)), C.byref(out)))
         return self._finish(r)
 
-    def psis_resample_host(self, log_ratios, K_run, seed, ndraws, importance=True, pool=None, N=None):
+    def psis_resample_host(self, log_ratios, K_run, seed, ndraws, importance=True, pool=None, N=None, replace=True):
         lr = None if log_ratios is None else np.ascontiguousarray(log_ratios, dtype=np.float64)
         if pool is not None:
             pool = np.asfortranarray(pool, dtype=np.float64)
@@ -279,14 +317,14 @@ class Engine:
         out, r = self._resample_out(N, ndraws, importance, pool is not None)
         _lib.check(self.h, self.lib.pfb_psis_resample_host(
             self.h, self.n, N, int(K_run), _ptr(lr), _ptr(pool), C.c_uint64(int(seed)), int(ndraws),
-            int(bool(importance)), C.byref(out)))
+            int(bool(importance)), int(bool(replace)), C.byref(out)))
         return self._finish(r)
 
-    def psis_resample_device(self, N, K_run, d_logp, d_logq, d_pool, seed, ndraws, importance=True):
+    def psis_resample_device(self, N, K_run, d_logp, d_logq, d_pool, seed, ndraws, importance=True, replace=True):
         """d_* are raw device pointers (ints), e.g. torch tensors' data_ptr()."""
         out, r = self._resample_out(N, ndraws, importance, d_pool is not None)
         _lib.check(self.h, self.lib.pfb_psis_resample_device(
             self.h, self.n, int(N), int(K_run), C.c_void_p(d_logp), C.c_void_p(d_logq),
             C.c_void_p(d_pool) if d_pool else None, C.c_uint64(int(seed)), int(ndraws),
-            int(bool(importance)), C.byref(out)))
+            int(bool(importance)), int(bool(replace)), C.byref(out)))
         return self._finish(r)

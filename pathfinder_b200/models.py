@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 
 from ._lib import (PFB_MODEL_DENSENORMAL, PFB_MODEL_DIAGNORMAL, PFB_MODEL_FUNNEL, PFB_MODEL_HLOGISTIC,
-                   PFB_MODEL_ISONORMAL)
+                   PFB_MODEL_HOSTCALLBACK, PFB_MODEL_ISONORMAL)
 
 
 class IsoNormal:
@@ -130,3 +130,30 @@ class HierLogistic:
         g[1] = -b0 / 6.25 + float(np.sum(r))
         g[2:] = -b * e2 + self.X.T @ r
         return g
+
+
+class HostModel:
+    """Arbitrary target density evaluated on the HOST: what the reference accepts
+    everywhere — a closure / LogDensityProblems object (src/singlepath.jl:142-152, :186).
+
+    ``logp_batch(X)`` maps an ``n x m`` array of draws (columns) to ``m`` log densities — the batched
+    form of ``logp.(eachcol(x))`` (src/elbo.jl:15); ``grad(x)`` is the gradient of the log density
+    for the host L-BFGS.  The device streams draw tiles to pinned memory and overlaps the callback
+    with sampling the next tile."""
+
+    family = PFB_MODEL_HOSTCALLBACK
+    blob = None
+
+    def __init__(self, n, logp_batch, grad, logp=None):
+        self.n = int(n)
+        self.logp_batch = logp_batch
+        self._grad = grad
+        self._logp = logp
+
+    def logp(self, x):
+        if self._logp is not None:
+            return float(self._logp(x))
+        return float(np.asarray(self.logp_batch(np.asarray(x, dtype=np.float64)[:, None])).reshape(-1)[0])
+
+    def grad(self, x):
+        return np.asarray(self._grad(x), dtype=np.float64)

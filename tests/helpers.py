@@ -33,7 +33,10 @@ def synthetic_trajectory(n, L, seed, scale=1.0):
 
 
 def oracle_logp_fn(model):
-    from pathfinder_b200 import DenseNormal, DiagNormal, Funnel, HierLogistic, IsoNormal
+    from pathfinder_b200 import DenseNormal, DiagNormal, Funnel, HierLogistic, HostModel, IsoNormal
+
+    if isinstance(model, HostModel):
+        return model.logp_batch
 
     if isinstance(model, DenseNormal):
         return O.make_logp_dense_gaussian(model.mean, model.prec)

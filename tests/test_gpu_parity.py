@@ -573,3 +573,123 @@ def test_device_optimizer_pipeline_equals_host_fed_pipeline():
     assert np.array_equal(r.sample_inds, rr["inds"]) and np.array_equal(r.draws, rr["draws"])
     assert np.array_equal(r.psis_result.weights, rr["weights"])
     eng.close()
+
+
+def test_resample_without_replacement_bit_exact():
+    """K7b (replace=false, src/resample.jl:61-66) against the oracle: identical indices, ids and
+    gathered draws, weighted and uniform; uniqueness (test/resample.jl:31-34); ndraws > N errors."""
+    import pathfinder_b200 as pf
+    from oracle import psis as OP
+
+    rng = np.random.default_rng(21)
+    n, K_run, P = 7, 50, 9
+    N = K_run * P
+    pool = np.asfortranarray(rng.normal(size=(n, N)))
+    logr = rng.normal(size=N) * 3.0
+    logr[5] = -np.inf
+    eng = _engine(pf.IsoNormal(n), K_run)
+    for nd in (1, 40, N):
+        r = eng.psis_resample_host(logr, K_run, 77, nd, True, pool=pool, replace=False)
+        ps = OP.psis(logr)
+        assert np.array_equal(r["log_weights"], ps["log_weights"], equal_nan=True)
+        ref = OP.resample_indices_norep(77, ps["log_weights"], N, nd)
+        assert np.array_equal(r["inds"], ref)
+        assert len(set(r["inds"])) == nd
+        assert np.array_equal(r["ids"], -(-ref // K_run))
+        assert np.array_equal(r["draws"], pool[:, ref - 1])
+        ru = eng.psis_resample_host(None, K_run, 78, nd, False, pool=pool, replace=False)
+        assert np.array_equal(ru["inds"], OP.resample_indices_norep(78, None, N, nd))
+    assert r["inds"][-1] == 6  # the zero-weight entry is taken last
+    with pytest.raises(pf.PfbError) as ei:
+        eng.psis_resample_host(logr, K_run, 1, N + 1, True, pool=pool, replace=False)
+    assert ei.value.code == -1
+    eng.close()
+
+
+# ---- row f2: host-callback target density ----------------------------------------------------------
+def test_host_callback_model_matches_device_family_and_oracle():
+    """The same funnel, once as the registered device family and once as a HOST closure evaluated
+    through the pinned-memory pipeline (several chunks in flight): ELBO tables, best iterations,
+    pool log ratios agree; and the host-callback path agrees with the oracle."""
+    import pathfinder_b200 as pf
+    from oracle import pf_oracle as O
+    from tests.helpers import make_trajectories, oracle_batch
+
+    n, K, J = 40, 256, 6
+    dev_model = pf.Funnel(n)
+    calls = []
+
+    def logp_batch(X):
+        calls.append(X.shape)
+        return O.logp_funnel(X)
+
+    host_model = pf.HostModel(n, logp_batch, dev_model.grad)
+    trajs = make_trajectories(dev_model, 4, seed=5, init_scale=3.0, maxiters=25, min_len=4)
+    seeds = _seeds(trajs, 9)
+    offsets, X, G = pf.Engine.pack(trajs)
+    e1 = _engine(dev_model, K, J, two_pass=True)
+    r1 = e1.elbo_batch(offsets, X, G, np.concatenate(seeds), draws=True, per_draw=True)
+    e2 = pf.Engine.for_model(host_model, J, K, 0)
+    r2 = e2.elbo_batch(offsets, X, G, np.concatenate(seeds), draws=True, per_draw=True)
+    assert sum(s[1] for s in calls) == K * r1.elbo.size and all(s[0] == n for s in calls)
+    assert np.array_equal(r1.logq, r2.logq, equal_nan=True)          # same sampling kernel
+    assert np.array_equal(r1.draws, r2.draws, equal_nan=True)
+    ok = np.isfinite(r1.elbo)
+    assert np.array_equal(ok, np.isfinite(r2.elbo))
+    assert _rel(r2.elbo[ok], r1.elbo[ok]) < 1e-9                     # exp() of libm vs libdevice
+    assert np.array_equal(r1.best_iter, r2.best_iter)
+    assert _rel(r2.draws_logp, r1.draws_logp) < 1e-9
+    # against the oracle (same tolerance policy as the device families)
+    orc = oracle_batch(host_model, trajs, seeds, K, J)
+    sens = _sensitivity(host_model, trajs, seeds, K, J, orc)
+    u = 0
+    for p, o in enumerate(orc):
+        for l, est in enumerate(o["ests"]):
+            if np.isfinite(est["value"]):
+                tol = max(RTOL, 50 * sens[p][l]) * max(1.0, abs(est["value"]))
+                assert abs(r2.elbo[u] - est["value"]) <= tol, (p, l)
+            u += 1
+    # PSIS + resampling on the pool, and fresh draws through the callback
+    rr = e2.psis_resample(3, 50, True)
+    assert rr["draws"].shape == (n, 50)
+    xd, lp, lq = e2.draw_from_fits(32, np.arange(4, dtype=np.uint64) + 5)
+    fin = np.isfinite(lp)
+    np.testing.assert_allclose(lp[fin], O.logp_funnel(xd.reshape(n, -1, order="F")).reshape(32, 4, order="F")[fin],
+                               rtol=1e-12)
+    e1.close(); e2.close()
+
+
+def test_host_callback_exception_is_raised_not_swallowed():
+    import pathfinder_b200 as pf
+    from tests.helpers import synthetic_trajectory
+
+    def bad(X):
+        raise RuntimeError("boom")
+
+    n = 6
+    model = pf.HostModel(n, bad, lambda x: -x)
+    X, G = synthetic_trajectory(n, 5, 1)
+    offsets, Xp, Gp = pf.Engine.pack([(X, G)])
+    eng = pf.Engine.for_model(model, 6, 16, 0)
+    with pytest.raises(RuntimeError, match="boom"):
+        eng.elbo_batch(offsets, Xp, Gp, np.arange(5, dtype=np.uint64))
+    eng.close()
+
+
+def test_pathfinder_api_with_a_host_model():
+    """pathfinder() on a correlated Gaussian given only as host closures (the reference's generic
+    entry point, src/singlepath.jl:142-152): recovers mean and covariance like test/multipath.jl:12-61."""
+    import pathfinder_b200 as pf
+
+    rng = np.random.default_rng(3)
+    n = 10
+    A = rng.normal(size=(n, n))
+    Sigma = A @ A.T / n + np.eye(n) * 0.5
+    Pm = np.linalg.inv(Sigma)
+    mu = rng.normal(size=n)
+    model = pf.HostModel(n, lambda X: -0.5 * np.einsum("ij,ij->j", X - mu[:, None], Pm @ (X - mu[:, None])),
+                         lambda x: -(Pm @ (x - mu)))
+    r = pf.multipathfinder(model, 4000, nruns=8, ndraws_elbo=200, rng=np.random.default_rng(0))
+    assert r.draws.shape == (n, 4000)
+    assert np.max(np.abs(r.draws.mean(axis=1) - mu)) < 0.15
+    assert np.max(np.abs(np.cov(r.draws) - Sigma)) < 0.35

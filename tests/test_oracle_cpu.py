@@ -418,3 +418,28 @@ def test_lbfgs_nonfinite_start_is_recorded_and_stops():
     x0[1:] = 1.0
     X, FX, G, st, nev = OL.lbfgs_path(OL.FAMILY_FUNNEL, x0)
     assert X.shape[1] == 1 and OL.STATUS[st] == "nonfinite" and nev == 1
+
+
+# ---- resampling without replacement (test/resample.jl:31-34) --------------------------------------
+def test_resample_without_replacement_unique_and_weighted():
+    rng = np.random.default_rng(0)
+    n, K_run, P = 3, 10, 4
+    dpc = rng.normal(size=(n, K_run, P))
+    draws, ids, inds = OP.resample(5, dpc, None, 5, replace=False)       # test/resample.jl:32-33
+    assert len({tuple(c) for c in draws.T}) == 5 and len(set(inds)) == 5
+    draws, ids, inds = OP.resample(5, dpc, None, K_run * P, replace=False)   # a permutation of the pool
+    assert sorted(inds) == list(range(1, K_run * P + 1))
+    assert np.array_equal(ids, -(-inds // K_run))
+    with pytest.raises(ValueError):
+        OP.resample(5, dpc, None, K_run * P + 1, replace=False)
+    # weight only the first component (test/resample.jl:36-49): every draw comes from it
+    lw = np.full((K_run, P), -1000.0)
+    lw[:, 0] = 0.0
+    ps = OP.psis(lw.reshape(-1, order="F"))
+    _, ids, inds = OP.resample(9, dpc, ps, K_run, replace=False)
+    assert np.all(ids == 1) and len(set(inds)) == K_run
+    # inclusion frequencies follow the weights: P(first pick = i) = w_i
+    w = np.array([0.5, 0.25, 0.125, 0.125])
+    first = np.array([OP.resample_indices_norep(s, np.log(w), 4, 2)[0] for s in range(4000)])
+    freq = np.bincount(first, minlength=5)[1:] / 4000.0
+    assert np.max(np.abs(freq - w)) < 0.03
