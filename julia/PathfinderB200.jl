@@ -192,6 +192,66 @@ function psis_resample(e::Engine, P::Integer, seed::UInt64, ndraws::Integer; imp
             draw_component_ids=ids, draws)
 end
 
+# mirrors `pfb_lbfgs_opts`
+struct PfbLbfgsOpts
+    maxiters::Int32
+    max_points::Int32
+    gtol::Float64
+    ftol::Float64
+end
+
+"""
+    register_host_model!(engine, logp)
+
+Row f2: make an arbitrary Julia closure `logp(x::AbstractVector)` the target density
+(src/singlepath.jl:186; `logp.(eachcol(ϕ))`, src/elbo.jl:15).  The engine calls it on pinned tiles
+of draws while the next tile is being sampled.  Keep `logp` alive as long as the engine.
+"""
+function _logp_tile(user::Ptr{Cvoid}, x::Ptr{Float64}, n::Int64, m::Int64, out::Ptr{Float64})::Cvoid
+    logp = unsafe_pointer_to_objref(user).x
+    X = unsafe_wrap(Array, x, (n, m)); o = unsafe_wrap(Array, out, m)
+    @inbounds for k in 1:m
+        o[k] = try logp(view(X, :, k)) catch; NaN end
+    end
+    return nothing
+end
+function register_host_model!(e::Engine, logp)
+    box = Ref{Any}(logp)
+    cb = @cfunction(_logp_tile, Cvoid, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}))
+    rc = ccall((:pfb_register_host_model, LIB[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+               e.handle, e.n, cb, pointer_from_objref(box))
+    check(e, rc)
+    return box  # the caller GC.@preserve's this around every engine call
+end
+
+"""
+    lbfgs_batch(engine, inits; maxiters=1000, gtol=1e-8, ftol=1e-14) -> (npoints, status)
+
+Row f1: the L-BFGS trajectories of all paths in one kernel launch (closed-form families); the
+traces stay on the device — follow with `batch_from_lbfgs(engine, seeds)` and the usual run /
+download calls, and `lbfgs_download` for the `OptimizationTrace` fields (src/optimize.jl:110-114).
+"""
+function lbfgs_batch(e::Engine, inits::Matrix{Float64}; maxiters::Integer=1000, gtol=1e-8, ftol=1e-14)
+    P = size(inits, 2)
+    npts = Vector{Int64}(undef, P); status = Vector{Int32}(undef, P)
+    opts = Ref(PfbLbfgsOpts(maxiters, maxiters + 1, gtol, ftol))
+    rc = ccall((:pfb_lbfgs_batch, LIB[]), Cint,
+               (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ref{PfbLbfgsOpts}, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}),
+               e.handle, e.n, P, inits, opts, npts, status, C_NULL)
+    check(e, rc)
+    return npts, status
+end
+function batch_from_lbfgs(e::Engine, seeds::Vector{UInt64})
+    check(e, ccall((:pfb_batch_from_lbfgs, LIB[]), Cint, (Ptr{Cvoid}, Ptr{UInt64}), e.handle, seeds))
+end
+function lbfgs_download(e::Engine, npts::Vector{Int64})
+    T = sum(npts)
+    X = Matrix{Float64}(undef, e.n, T); G = similar(X); fx = Vector{Float64}(undef, T)
+    check(e, ccall((:pfb_lbfgs_download, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   e.handle, X, G, fx))
+    return X, G, fx
+end
+
 """
     multipathfinder_b200(optimize_one, model_family, dim, ndraws; nruns, ndraws_elbo, rng, ...)
 
