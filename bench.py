@@ -454,7 +454,7 @@ def main():
                                           * CONFIGS[name][5], J, 1000) for p in range(min(P, 8))]
         host_lbfgs_s = (time.perf_counter() - t0) * P / max(1, min(P, 8))
         mpf = {"ours_s": float(min(walls[1:])), "ours_first_call_s": float(walls[0]), "optimizer": f"device K0, "
-               f"maxiters {MAXIT}", "units": int(units_w), "k0_ms": float(k0_ms),
+               f"maxiters {MAXIT}; caller-owned engine: per-path draws stay device-resident until accessed", "units": int(units_w), "k0_ms": float(k0_ms),
                "host_scipy_lbfgs_s_for_the_same_paths": float(host_lbfgs_s), "paths": P, "K": K, "ndraws": ndraws}
         line["multipathfinder_wall"] = mpf
 

@@ -176,6 +176,12 @@ int pfb_batch_fit_only(pfb_handle h, const int64_t* best_iter);
 int pfb_draw_from_fits(pfb_handle h, int K_new, const uint64_t* seeds, double* draws, double* logp,
                        double* logq, int keep_as_pool);
 
+/* Paths [p0, p1) of the device pool (best-iteration draws [n x K x (p1-p0)], their logp / logq
+ * [K x (p1-p0)]; K = ndraws_elbo, or K_new after pfb_draw_from_fits(keep_as_pool)): the lazy form of
+ * pfb_elbo_out.draws — PathfinderResult.draws (src/singlepath.jl:231-232) fetched on first use.
+ * Any pointer may be NULL. */
+int pfb_pool_download(pfb_handle h, int p0, int p1, double* draws, double* logp, double* logq);
+
 /* Replaces _compute_psis_result + _resample (src/multipath.jl:220-225, src/resample.jl:58-95)
  * on the pool produced by the last batch (N = P * K draws; log ratios reuse the ELBO stage's
  * logp - logq, which src/resample.jl:81-95 recomputes).  importance = 0: uniform resampling

@@ -51,20 +51,50 @@ class FitDistribution:
     history_length_effective: int
 
 
-@dataclass
 class PathfinderResult:
-    input: object
-    rng: object
-    fit_distribution: FitDistribution | None
-    draws: np.ndarray                  # [n, ndraws]
-    fit_iteration: int                 # 1-based; 0 = failed before any iteration
-    num_tries: int
-    optim_trace: OptimizationTrace
-    elbo_estimates: list
-    num_bfgs_updates_rejected: int
-    success: bool = True
-    draws_logp: np.ndarray | None = None
-    draws_logq: np.ndarray | None = None
+    """src/singlepath.jl:53-70.  `draws` (and their log densities) may still be on the device when
+    the result is built (`multipathfinder(..., engine=...)` on a caller-owned engine): they are
+    fetched on first access, or when the engine's pool is about to be overwritten."""
+
+    def __init__(self, input, rng, fit_distribution, draws, fit_iteration, num_tries, optim_trace, elbo_estimates,
+                 num_bfgs_updates_rejected, success=True, draws_logp=None, draws_logq=None, lazy=None):
+        self.input = input
+        self.rng = rng
+        self.fit_distribution = fit_distribution
+        self._draws = draws                  # [n, ndraws]
+        self.fit_iteration = fit_iteration   # 1-based; 0 = failed before any iteration
+        self.num_tries = num_tries
+        self.optim_trace = optim_trace
+        self.elbo_estimates = elbo_estimates
+        self.num_bfgs_updates_rejected = num_bfgs_updates_rejected
+        self.success = success
+        self._draws_logp = draws_logp
+        self._draws_logq = draws_logq
+        self._lazy = lazy                    # (ElboBatchResult, path index, ndraws)
+
+    def _fetch(self):
+        if self._lazy is not None:
+            res, j, nd = self._lazy
+            self._lazy = None
+            res.fetch_draws()
+            self._draws = res.draws[:, :nd, j]
+            self._draws_logp = res.draws_logp[:nd, j]
+            self._draws_logq = res.draws_logq[:nd, j]
+
+    @property
+    def draws(self):
+        self._fetch()
+        return self._draws
+
+    @property
+    def draws_logp(self):
+        self._fetch()
+        return self._draws_logp
+
+    @property
+    def draws_logq(self):
+        self._fetch()
+        return self._draws_logq
 
 
 @dataclass
@@ -108,9 +138,10 @@ def _use_device_optimizer(model, optimizer):
 
 
 def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntries, init_scale, ndraws_run=None,
-               optimizer="host", gtol=1e-8, ftol=1e-14):
+               optimizer="host", gtol=1e-8, ftol=1e-14, lazy_draws=False):
     """Optimise every path (host L-BFGS, or kernel K0 for the closed-form families), run the ELBO
-    stage as one batch, retry failures."""
+    stage as one batch, retry failures.  lazy_draws: leave the best-iteration draws on the device."""
+    want_draws = "lazy" if (lazy_draws and not (ndraws_run is not None and ndraws_run > engine.K)) else True
     device_opt = _use_device_optimizer(model, optimizer)
     P = len(inits)
     final = [None] * P
@@ -129,7 +160,7 @@ def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntr
             seeds = [_draw_seeds(path_rngs[p], int(npts[j]) - 1) for j, p in enumerate(todo)]  # src/elbo.jl:2
             engine.batch_from_lbfgs(np.concatenate(seeds) if seeds else np.zeros(0, np.uint64))
             engine.run()
-            res = engine.download(draws=True, fit=True)
+            res = engine.download(draws=want_draws, fit=True)
             off, Xd, FXd, Gd = engine.lbfgs_download()
             traces = [OptimizationTrace(Xd[:, off[j]:off[j + 1]], FXd[off[j]:off[j + 1]], Gd[:, off[j]:off[j + 1]])
                       for j in range(len(todo))]
@@ -144,7 +175,7 @@ def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntr
                 seeds.append(_draw_seeds(path_rngs[p], len(tr) - 1))  # src/elbo.jl:2
             offsets, X, G = Engine.pack([(t.points, t.gradients) for t in traces])
             res = engine.elbo_batch(offsets, X, G, np.concatenate(seeds) if seeds else np.zeros(0, np.uint64),
-                                    draws=True, fit=True)
+                                    draws=want_draws, fit=True)
         if ndraws_run is not None and ndraws_run > engine.K:
             # top-up draws from the fitted normal with the path's rng (src/singlepath.jl:228-230)
             top_seeds = np.array([int(_draw_seeds(path_rngs[p], 1)[0]) for p in todo], dtype=np.uint64)
@@ -187,6 +218,9 @@ def _assemble_path(model, rng, entry, ndraws, K):
         f = res.fit
         fit = FitDistribution(f["mu"][:, j].copy(), f["alpha"][:, j].copy(), f["vh"][:, :, j].copy(),
                               f["T"][j].copy(), f["Vc"][j].copy(), float(f["logdet"][j]), int(f["jeff"][j]))
+    if res.draws is None:  # still on the device (lazy): fetched on first access
+        return PathfinderResult(model, rng, fit, None, int(res.best_iter[j]), ntry, trace, ests, rej, ok,
+                                lazy=(res, j, ndraws))
     # views into the batch's download buffers (F-order, so each path's slab is contiguous): no copies
     draws = res.draws[:, :ndraws, j]
     return PathfinderResult(model, rng, fit, draws, int(res.best_iter[j]), ntry, trace, ests, rej, ok,
@@ -250,9 +284,12 @@ def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT
     own = engine is None
     if own:
         engine = Engine.for_model(model, history_length, ndraws_elbo, device)
+    # on a caller-owned engine the per-path draws stay device-resident until looked at (the engine
+    # hands them over before its pool is overwritten or freed); an engine owned by this call is
+    # closed on return, so its draws come back eagerly
     final, last = _run_paths(engine, model, inits[lo:hi], path_rngs[lo:hi], history_length=history_length,
                              maxiters=maxiters, ntries=ntries, init_scale=init_scale, ndraws_run=ndraws_per_run,
-                             optimizer=optimizer)
+                             optimizer=optimizer, lazy_draws=(not own and not dist_on))
     results = [_assemble_path(model, path_rngs[lo + j], final[j], ndraws_per_run, ndraws_elbo)
                for j in range(hi - lo)]
     # PSIS pool: draw-fastest, component-slowest (test/resample.jl:81-88)

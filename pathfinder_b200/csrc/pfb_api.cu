@@ -911,6 +911,29 @@ extern "C" int pfb_batch_download(pfb_handle h, pfb_elbo_out* o) {
     return PFB_OK;
 }
 
+// Paths [p0, p1) of the device pool (the best-iteration draws left by pfb_batch_run, or the fresh
+// draws of pfb_draw_from_fits(keep_as_pool)): lets a caller leave per-path draws on the device and
+// fetch them only when they are looked at.
+extern "C" int pfb_pool_download(pfb_handle h, int p0, int p1, double* draws, double* logp, double* logq) {
+    if (!h) return PFB_ERR_ARG;
+    if (!h->ran || h->poolK <= 0) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
+    if (p0 < 0 || p1 < p0 || p1 > h->P) PFB_FAIL(h, PFB_ERR_ARG, "path range out of bounds");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const size_t n = h->n, K = (size_t)h->poolK, cnt = (size_t)(p1 - p0);
+    if (draws && cnt)
+        PFB_CUDA(h, cudaMemcpyAsync(draws, h->dPool.as<double>() + (size_t)p0 * n * K, cnt * n * K * 8,
+                                    cudaMemcpyDeviceToHost, st));
+    if (logp && cnt)
+        PFB_CUDA(h, cudaMemcpyAsync(logp, h->dPoolLogp.as<double>() + (size_t)p0 * K, cnt * K * 8,
+                                    cudaMemcpyDeviceToHost, st));
+    if (logq && cnt)
+        PFB_CUDA(h, cudaMemcpyAsync(logq, h->dPoolLogq.as<double>() + (size_t)p0 * K, cnt * K * 8,
+                                    cudaMemcpyDeviceToHost, st));
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    return PFB_OK;
+}
+
 extern "C" int pfb_elbo_batch(pfb_handle h, int n, int P, const int64_t* offsets, const double* positions,
                               const double* gradients, const uint64_t* seeds, const double* normals,
                               pfb_elbo_out* out) {

@@ -7,6 +7,7 @@ resident in HBM.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -41,6 +42,19 @@ class ElboBatchResult:
         o = self.offsets
         return slice(int(o[p] - p), int(o[p + 1] - p - 1))
 
+    # lazy pool (download(draws="lazy")): the best-iteration draws stay on the device until looked at
+    _lazy_engine = None
+
+    def fetch_draws(self):
+        """Bring the (device-resident) best-iteration draws of this batch to the host, once."""
+        if self.draws is None and self._lazy_engine is not None:
+            eng = self._lazy_engine()
+            self._lazy_engine = None
+            if eng is None or eng.h is None:
+                raise RuntimeError("the engine holding these draws is gone")
+            self.draws, self.draws_logp, self.draws_logq = eng._pool_download()
+        return self.draws
+
 
 class Engine:
     def __init__(self, n, model_family, model_blob=None, history_length=6, ndraws_elbo=5,
@@ -71,6 +85,7 @@ class Engine:
         self._U = 0
         self._offsets = None
         self._poolK = self.K
+        self._pending = []  # weakrefs of results whose draws are still on the device
 
     @classmethod
     def for_model(cls, model, history_length=6, ndraws_elbo=5, device=0, **kw):
@@ -101,7 +116,29 @@ class Engine:
             e, self._cb_error = self._cb_error, None
             raise e
 
+    def _pool_download(self):
+        P, K = self._P, self._poolK
+        draws = np.empty((self.n, K, P), order="F")
+        lp = np.empty((K, P), order="F")
+        lq = np.empty((K, P), order="F")
+        _lib.check(self.h, self.lib.pfb_pool_download(self.h, 0, P, _ptr(draws), _ptr(lp), _ptr(lq)))
+        return draws, lp, lq
+
+    def _flush_pending(self):
+        """The device pool is about to be overwritten / freed: results that still point at it get
+        their draws now."""
+        pend, self._pending = self._pending, []
+        for ref in pend:
+            res = ref()
+            if res is not None and res.draws is None and res._lazy_engine is not None:
+                res.fetch_draws()
+
     def close(self):
+        if getattr(self, "h", None) and getattr(self, "_pending", None):
+            try:
+                self._flush_pending()
+            except Exception:
+                pass
         if getattr(self, "h", None):
             self.lib.pfb_destroy(self.h)
             self.h = None
@@ -143,6 +180,7 @@ class Engine:
             normals = np.asfortranarray(normals, dtype=np.float64)
             if normals.shape != (self.n, self.K, U):
                 raise ValueError("normals must be n x K x U")
+        self._flush_pending()
         _lib.check(self.h, self.lib.pfb_batch_upload(self.h, self.n, P, _ptr(offsets), _ptr(X), _ptr(G),
                                                      _ptr(seeds), _ptr(normals)))
         self._P, self._U, self._offsets = P, U, offsets.copy()
@@ -176,6 +214,7 @@ class Engine:
         seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
         if seeds.size != U:
             raise ValueError("need one seed per (path, iteration)")
+        self._flush_pending()
         _lib.check(self.h, self.lib.pfb_batch_from_lbfgs(self.h, _ptr(seeds)))
         self._P, self._U, self._offsets = P, U, offsets
 
@@ -213,7 +252,10 @@ class Engine:
         out.elbo, out.elbo_se = _ptr(elbo), _ptr(se)
         out.best_iter, out.success, out.n_rejected = _ptr(best), _ptr(succ), _ptr(rej)
         res = ElboBatchResult(self._offsets, elbo, se, best, None, rej)
-        if draws:
+        if draws == "lazy":
+            res._lazy_engine = weakref.ref(self)
+            self._pending.append(weakref.ref(res))
+        elif draws:
             res.draws = np.empty((n, K, P), order="F")
             res.draws_logp = np.empty((K, P), order="F")
             res.draws_logq = np.empty((K, P), order="F")
@@ -255,6 +297,8 @@ class Engine:
         if sd.size != self._P:
             raise ValueError("need one seed per path")
         P = self._P
+        if keep_as_pool:
+            self._flush_pending()
         draws = np.empty((self.n, int(K_new), P), order="F") if want_draws else None
         lp = np.empty((int(K_new), P), order="F")
         lq = np.empty((int(K_new), P), order="F")

@@ -693,3 +693,29 @@ def test_pathfinder_api_with_a_host_model():
     assert r.draws.shape == (n, 4000)
     assert np.max(np.abs(r.draws.mean(axis=1) - mu)) < 0.15
     assert np.max(np.abs(np.cov(r.draws) - Sigma)) < 0.35
+
+
+def test_lazy_per_path_draws_on_a_caller_owned_engine():
+    """With a caller-owned engine multipathfinder leaves PathfinderResult.draws on the device; they
+    are fetched on first access, or automatically before the engine's pool is overwritten — and
+    equal the eagerly downloaded ones bit for bit."""
+    import pathfinder_b200 as pf
+
+    n, P, K = 24, 6, 48
+    model = pf.Funnel(n)
+    kw = dict(nruns=P, ndraws_elbo=K, init_scale=3.0, maxiters=20, optimizer="device", ntries=1)
+    eager = pf.multipathfinder(model, 30, rng=np.random.default_rng(4), **kw)          # engine owned by the call
+    eng = pf.Engine.for_model(model, 6, K, 0)
+    lazy1 = pf.multipathfinder(model, 30, rng=np.random.default_rng(4), engine=eng, **kw)
+    assert all(pr._lazy is not None for pr in lazy1.pathfinder_results)
+    assert np.array_equal(lazy1.draws, eager.draws) and np.array_equal(lazy1.sample_inds, eager.sample_inds)
+    # access path 2 only -> one fetch serves the whole batch
+    assert np.array_equal(lazy1.pathfinder_results[2].draws, eager.pathfinder_results[2].draws)
+    lazy2 = pf.multipathfinder(model, 30, rng=np.random.default_rng(4), engine=eng, **kw)
+    # a third run overwrites the pool: lazy2's draws are handed over first
+    lazy3 = pf.multipathfinder(model, 30, rng=np.random.default_rng(5), engine=eng, **kw)
+    for a, b in zip(lazy2.pathfinder_results, eager.pathfinder_results):
+        assert np.array_equal(a.draws, b.draws, equal_nan=True)
+        assert np.array_equal(a.draws_logp, b.draws_logp, equal_nan=True)
+    eng.close()   # closing hands over lazy3's draws
+    assert lazy3.pathfinder_results[0].draws.shape == (n, K)
