@@ -206,12 +206,18 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
     const int unit = unit_list ? unit_list[slot] : slot;
     const int DPS = NW * DS * 8;                 // draws per sweep
     const int S = (K + DPS - 1) / DPS;           // sweeps of this unit
-    if (unit < 0) {  // path without a usable iteration (K5 only)
-        for (int sw = split; sw < S; sw += splits)
-            for (int k = sw * DPS + tid; k < min(K, (sw + 1) * DPS); k += blockDim.x) {
+    if (unit < 0) {  // path without a usable iteration (K5 only): no fitted normal, NaN draws
+        for (int sw = split; sw < S; sw += splits) {
+            const int ka = sw * DPS, kb = min(K, (sw + 1) * DPS);
+            for (int k = ka + tid; k < kb; k += blockDim.x) {
                 logp_out[(int64_t)slot * K + k] = NAN;
                 logq_out[(int64_t)slot * K + k] = NAN;
             }
+            if (MATERIALIZE && draws_out != nullptr && kb > ka) {
+                double* d0 = draws_out + ((int64_t)slot * K + ka) * n;
+                for (int64_t e = tid; e < (int64_t)(kb - ka) * n; e += blockDim.x) d0[e] = NAN;
+            }
+        }
         return;
     }
     const int npad = pfb_npad8(n);

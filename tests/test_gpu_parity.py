@@ -719,3 +719,27 @@ def test_lazy_per_path_draws_on_a_caller_owned_engine():
         assert np.array_equal(a.draws_logp, b.draws_logp, equal_nan=True)
     eng.close()   # closing hands over lazy3's draws
     assert lazy3.pathfinder_results[0].draws.shape == (n, K)
+
+
+def test_edge_cases_single_draw_and_empty_batch():
+    """K = 1: mean = the single log ratio, std_err = NaN (var with K - 1 = 0, src/elbo.jl:18);
+    P = 0 and all-paths-L=0 batches run and return empty / failed results instead of erroring."""
+    import pathfinder_b200 as pf
+    from tests.helpers import synthetic_trajectory
+
+    model = pf.IsoNormal(6)
+    X, G = synthetic_trajectory(6, 3, 8)
+    eng = _engine(model, 1)
+    offsets, Xp, Gp = pf.Engine.pack([(X, G)])
+    res = eng.elbo_batch(offsets, Xp, Gp, np.arange(3, dtype=np.uint64), per_draw=True)
+    assert np.allclose(res.elbo, (res.logp - res.logq)[0]) and np.all(np.isnan(res.elbo_se))
+    assert res.best_iter[0] >= 1 and res.success[0]
+    # every path has only its initial point: no units, nothing succeeds (src/singlepath.jl:309-314)
+    res0 = eng.elbo_batch(np.array([0, 1, 2]), Xp[:, :2], Gp[:, :2], np.zeros(0, np.uint64))
+    assert res0.elbo.size == 0 and list(res0.best_iter) == [0, 0] and not res0.success.any()
+    assert np.all(np.isnan(res0.draws))
+    # no paths at all
+    resE = eng.elbo_batch(np.array([0]), np.zeros((6, 0), order="F"), np.zeros((6, 0), order="F"),
+                          np.zeros(0, np.uint64))
+    assert resE.elbo.size == 0 and resE.best_iter.size == 0
+    eng.close()
