@@ -252,6 +252,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists for the product path)")
     torch.cuda.set_device(local_rank)
+    # NCCL prints its version banner on stdout (NCCL_DEBUG=VERSION): keep stdout = the one JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -300,8 +304,10 @@ def main():
             dist.all_gather_into_tensor(g_logp, pool_logp)
             dist.all_gather_into_tensor(g_logq, pool_logq)
         ext.synchronize()
+        # device-resident timing: the N-sized weight vectors stay on the device (the e2e leg below
+        # brings them to the host)
         r = eng.psis_resample_device(world * K * P, K, g_logp.data_ptr(), g_logq.data_ptr(), None,
-                                     resample_seed, ndraws, True)
+                                     resample_seed, ndraws, True, want_weights=False)
         inds = torch.from_numpy(r["inds"] - 1).to(f"cuda:{local_rank}")
         with torch.cuda.stream(ext):
             mine = (inds >= rank * K * P) & (inds < (rank + 1) * K * P)
@@ -424,7 +430,9 @@ def main():
                    "re-materialised by K5)", "l2": "per-step working set (factor records %.0f MB) exceeds the "
                    "126 MB L2" % (U * n * (KP + 2) * 8 / 1e6), "parallelism": f"paths sharded over {world} GPU(s)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": int((stage_ms[-1]["launches"] + 2) * args.steps),
+        # K1..K5 as counted by the engine + the PSIS stage's own kernels (K6a..K6g, K7; CUB's sort
+        # launches inside K6 are library kernels and not counted)
+        "gpu_launches": int((stage_ms[-1]["launches"] + 8) * args.steps),
         "clocks": clocks,
         "roofline": roofline,
         "stage_ms": {k: float(np.mean([s[k] for s in stage_ms])) for k in ("k1", "k2", "k3", "k4", "k5", "total")},
@@ -509,7 +517,10 @@ def main():
             cpu_s = cpu_lbfgs_s + mpf["units"] * K / (done / secs)
             mpf["cpu_port_single_thread_est_s"] = float(cpu_s)
             mpf["speedup_vs_cpu_port_est"] = float(cpu_s / mpf["ours_s"])
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

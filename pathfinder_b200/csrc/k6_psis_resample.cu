@@ -42,109 +42,47 @@ struct pfb_psis_scalars {
     uint64_t Z;
     int64_t tail_len;
     int64_t smoothed;  // 1 if the tail was replaced
+    uint64_t maxkey;   // ordered key of max(log weights) (device-internal)
 };
 
+// ---- K6 in stages.  Everything O(N) and elementwise runs grid-wide; everything whose floating-
+// point ORDER is part of the contract with oracle/psis.py (the sums) keeps its single-CTA shape:
+// 1024 lane-strided sequential partials, xor butterflies.  One CTA doing all of it was bound by a
+// single SM's instruction rate (0.5 ms at N = 64 k, 3.3 ms at the 8-GPU pool N = 512 k).
+#include <cub/device/device_radix_sort.cuh>
+
+// K6a: log ratios, their order-preserving integer keys and indices (grid-wide)
+__global__ void pfb_k6a_keys(int N, const double* __restrict__ logp, const double* __restrict__ logq,
+                             const double* __restrict__ logr_in, double* __restrict__ logw,
+                             uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double v = logr_in ? logr_in[i] : (logp[i] - logq[i]);
+    logw[i] = v;
+    keys[i] = pfb_ordered_key(v);
+    idx[i] = (uint32_t)i;
+}
+
+// K6b: one CTA.  The last M + 1 entries of the ascending (key, index) sort are the cutoff element
+// and the tail (ascending) — a stable radix sort orders ties by index, which is the composite order
+// of the contract.  GPD fit (Zhang & Stephens) and tail replacement; writes the scalars.
 __global__ void __launch_bounds__(PFB_K6_THREADS)
-pfb_k6_psis(int N, int M, int m_grid, const double* __restrict__ logp, const double* __restrict__ logq,
-            const double* __restrict__ logr_in, double* __restrict__ logw, double* __restrict__ weights,
-            uint64_t* __restrict__ cum, pfb_psis_scalars* __restrict__ out) {
+pfb_k6b_fit(int N, int M, int m_grid, const uint32_t* __restrict__ sorted_idx, double* __restrict__ logw,
+            pfb_psis_scalars* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* cKey = reinterpret_cast<uint64_t*>(smem_raw);       // MAXCAND
-    double* sX = reinterpret_cast<double*>(cKey + PFB_K6_MAXCAND);  // MAXCAND   tail sample x
+    double* sX = reinterpret_cast<double*>(smem_raw);                   // MAXCAND   tail sample x
     uint32_t* cIdx = reinterpret_cast<uint32_t*>(sX + PFB_K6_MAXCAND);  // MAXCAND
-    __shared__ uint32_t hist[256];
     __shared__ double sB[128], sKj[128], sLL[128], sWj[128];
-    __shared__ double scratch[32];
-    __shared__ uint64_t sScanU[PFB_K6_THREADS / 32];
-    __shared__ uint64_t sKthKey;
-    __shared__ uint32_t sKthIdx, sWant, sCnt;
     __shared__ int sAllFinite;
     __shared__ double sScal[8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NT = PFB_K6_THREADS;
-
-    // ---- 0. log ratios ---------------------------------------------------------------------------
-    for (int i = tid; i < N; i += NT) logw[i] = logr_in ? logr_in[i] : (logp[i] - logq[i]);
-    __syncthreads();
-
     double pareto_k = NAN, sigma = NAN, logu = NAN;
     int smoothed = 0;
     if (M >= 5) {
-        // ---- 1. radix select of the (M+1)-th largest composite (key, idx) -------------------------
-        if (tid == 0) { sKthKey = 0; sKthIdx = 0; sWant = (uint32_t)(M + 1); }
-        __syncthreads();
-        for (int d = 0; d < 12; ++d) {
-            for (int b = tid; b < 256; b += NT) hist[b] = 0;
-            __syncthreads();
-            const uint64_t pk = sKthKey;
-            const uint32_t pi = sKthIdx;
-            for (int i = tid; i < N; i += NT) {
-                const uint64_t key = pfb_ordered_key(logw[i]);
-                bool match;
-                uint32_t digit;
-                if (d < 8) {
-                    const int sh = 64 - 8 * d;  // bits above the current digit
-                    match = (d == 0) || ((key >> sh) == (pk >> sh));
-                    digit = (uint32_t)(key >> (sh - 8)) & 255u;
-                } else {
-                    const int sh = 32 - 8 * (d - 8);
-                    match = (key == pk) && ((d == 8) || (((uint32_t)i >> sh) == (pi >> sh)));
-                    digit = ((uint32_t)i >> (sh - 8)) & 255u;
-                }
-                if (match) atomicAdd(&hist[digit], 1u);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                uint32_t want = sWant, acc = 0;
-                int b = 255;
-                for (; b > 0; --b) {
-                    if (acc + hist[b] >= want) break;
-                    acc += hist[b];
-                }
-                sWant = want - acc;
-                if (d < 8) sKthKey |= (uint64_t)b << (56 - 8 * d);
-                else sKthIdx |= (uint32_t)b << (24 - 8 * (d - 8));
-            }
-            __syncthreads();
-        }
-        // ---- 2. compact the M+1 selected elements, bitonic sort ascending by (key, idx) ------------
-        int P2 = 1;
-        while (P2 < M + 1) P2 <<= 1;
-        for (int t = tid; t < P2; t += NT) { cKey[t] = 0xFFFFFFFFFFFFFFFFull; cIdx[t] = 0xFFFFFFFFu; }
-        if (tid == 0) sCnt = 0;
-        __syncthreads();
-        {
-            const uint64_t kk = sKthKey;
-            const uint32_t ki = sKthIdx;
-            for (int i = tid; i < N; i += NT) {
-                const uint64_t key = pfb_ordered_key(logw[i]);
-                if (key > kk || (key == kk && (uint32_t)i >= ki)) {
-                    uint32_t pos = atomicAdd(&sCnt, 1u);
-                    cKey[pos] = key;
-                    cIdx[pos] = (uint32_t)i;
-                }
-            }
-        }
-        __syncthreads();
-        for (int size = 2; size <= P2; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int t = tid; t < P2 / 2; t += NT) {
-                    const int lo = 2 * t - (t & (stride - 1));  // index with bit `stride` clear
-                    const int hi = lo + stride;
-                    const bool up = ((lo & size) == 0);
-                    const uint64_t ka = cKey[lo], kb = cKey[hi];
-                    const uint32_t ia = cIdx[lo], ib = cIdx[hi];
-                    const bool a_gt_b = (ka > kb) || (ka == kb && ia > ib);
-                    if (a_gt_b == up) {
-                        cKey[lo] = kb; cKey[hi] = ka;
-                        cIdx[lo] = ib; cIdx[hi] = ia;
-                    }
-                }
-                __syncthreads();
-            }
-        }
         // cIdx[0] = cutoff element, cIdx[1..M] = tail ascending
+        for (int t = tid; t < M + 1; t += NT) cIdx[t] = sorted_idx[N - (M + 1) + t];
         if (tid == 0) sAllFinite = 1;
         __syncthreads();
         for (int t = tid; t < M; t += NT) {
@@ -158,7 +96,7 @@ pfb_k6_psis(int N, int M, int m_grid, const double* __restrict__ logp, const dou
             const double mu_s = pf_exp(logu - lw_max);
             for (int t = tid; t < M; t += NT) sX[t] = pf_exp(logw[cIdx[1 + t]] - lw_max) - mu_s;
             __syncthreads();
-            // ---- 3. Zhang & Stephens empirical-Bayes fit ------------------------------------------
+            // ---- Zhang & Stephens empirical-Bayes fit ---------------------------------------------
             const double dM = (double)M;
             const double xmax = sX[M - 1];
             const double xq = sX[(int)floor(dM / 4.0 + 0.5) - 1];
@@ -206,7 +144,7 @@ pfb_k6_psis(int N, int M, int m_grid, const double* __restrict__ logp, const dou
             __syncthreads();
             sigma = sScal[1];
             pareto_k = sScal[2];
-            // ---- 4. replace the tail by GPD quantiles ---------------------------------------------
+            // ---- replace the tail by GPD quantiles ------------------------------------------------
             if (fabs(pareto_k) <= 1.7976931348623157e308) {
                 smoothed = 1;
                 for (int t = tid; t < M; t += NT) {
@@ -222,39 +160,77 @@ pfb_k6_psis(int N, int M, int m_grid, const double* __restrict__ logp, const dou
                 }
             }
         }
-        __syncthreads();
     }
-    // ---- 5. normalise: logw -= logsumexp(logw); weights = exp(logw) --------------------------------
+    if (tid == 0) {
+        out->pareto_k = pareto_k;
+        out->sigma = sigma;
+        out->logu = logu;
+        out->tail_len = M;
+        out->smoothed = smoothed;
+        out->maxkey = pfb_ordered_key(-INFINITY);  // running maximum of K6c (NaN ignored)
+    }
+}
+
+// K6c: maximum of the (smoothed) log weights, NaN ignored (grid-wide, exact in any order)
+__global__ void pfb_k6c_max(int N, const double* __restrict__ logw, pfb_psis_scalars* __restrict__ out) {
     double mx = -INFINITY;
-    for (int i = tid; i < N; i += NT) mx = fmax(mx, logw[i]);  // fmax ignores NaN
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+        mx = fmax(mx, logw[i]);  // fmax ignores NaN
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    if (lane == 0) scratch[warp] = mx;
-    __syncthreads();
-    mx = scratch[lane];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    __syncthreads();
+    if ((threadIdx.x & 31) == 0)
+        atomicMax(reinterpret_cast<unsigned long long*>(&out->maxkey), (unsigned long long)pfb_ordered_key(mx));
+}
+
+__device__ __forceinline__ double pfb_key_to_double(uint64_t k) {
+    const uint64_t u = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
+// K6d: e_i = exp(logw_i - max) (grid-wide, elementwise)
+__global__ void pfb_k6d_exp(int N, const double* __restrict__ logw, const pfb_psis_scalars* __restrict__ sc,
+                            double* __restrict__ e) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    e[i] = pf_exp(logw[i] - pfb_key_to_double(sc->maxkey));
+}
+
+// K6e: one CTA — the canonical sum (1024 lane-strided sequential partials, butterflies) and lse
+__global__ void __launch_bounds__(PFB_K6_THREADS)
+pfb_k6e_sum(int N, const double* __restrict__ e, pfb_psis_scalars* __restrict__ out) {
+    __shared__ double scratch[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double acc = 0.0;
-    for (int i = tid; i < N; i += NT) acc = acc + pf_exp(logw[i] - mx);
+    for (int i = tid; i < N; i += PFB_K6_THREADS) acc = acc + e[i];
     acc = pfb_butterfly32(acc);
     if (lane == 0) scratch[warp] = acc;
     __syncthreads();
     const double ssum = pfb_butterfly32(scratch[lane]);
-    const double lse = mx + pf_log(ssum);
-    // ---- 6. fixed-point weights and their inclusive prefix sums ------------------------------------
+    if (tid == 0) out->lse = pfb_key_to_double(out->maxkey) + pf_log(ssum);
+}
+
+// K6f: normalised log weights, weights, fixed-point (2^52) weights (grid-wide, elementwise)
+__global__ void pfb_k6f_weights(int N, double* __restrict__ logw, double* __restrict__ weights,
+                                uint64_t* __restrict__ cum, const pfb_psis_scalars* __restrict__ sc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double lw = logw[i] - sc->lse;
+    const double wv = pf_exp(lw);
+    logw[i] = lw;
+    weights[i] = wv;
+    cum[i] = (wv > 0.0) ? (uint64_t)(wv * 4503599627370496.0) : 0ull;
+}
+
+// K6g: one CTA — inclusive prefix sums of the integer weights (exact in any order), Z = total
+__global__ void __launch_bounds__(PFB_K6_THREADS)
+pfb_k6g_scan(int N, uint64_t* __restrict__ cum, pfb_psis_scalars* __restrict__ out) {
+    __shared__ uint64_t sScanU[PFB_K6_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = PFB_K6_THREADS;
     const int per = (N + NT - 1) / NT;
     const int i0 = min(N, tid * per), i1 = min(N, i0 + per);
     uint64_t local = 0;
-    for (int i = i0; i < i1; ++i) {
-        const double lw = logw[i] - lse;
-        const double wv = pf_exp(lw);
-        logw[i] = lw;
-        weights[i] = wv;
-        const uint64_t qv = (wv > 0.0) ? (uint64_t)(wv * 4503599627370496.0) : 0ull;
-        local += qv;
-        cum[i] = qv;  // converted to the running sum below
-    }
+    for (int i = i0; i < i1; ++i) local += cum[i];
     uint64_t incl = local;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -278,15 +254,7 @@ pfb_k6_psis(int N, int M, int m_grid, const double* __restrict__ logp, const dou
         run += cum[i];
         cum[i] = run;
     }
-    if (tid == 0) {
-        out->pareto_k = pareto_k;
-        out->lse = lse;
-        out->sigma = sigma;
-        out->logu = logu;
-        out->Z = sScanU[31];
-        out->tail_len = M;
-        out->smoothed = smoothed;
-    }
+    if (tid == 0) out->Z = sScanU[31];
 }
 
 // K7: one CTA per output draw.  cum == nullptr => uniform sampling (importance = false).
@@ -326,16 +294,49 @@ pfb_k7_resample_gather(int n, int N, int K_run, uint64_t seed, const uint64_t* _
 
 extern "C" size_t pfb_psis_scalars_size() { return sizeof(pfb_psis_scalars); }
 
+// Workspace of K6: keys in/out (2 N u64), indices in/out (2 N u32), e (N doubles), CUB scratch.
+static size_t k6_cub_bytes(int N) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, N);
+    return bytes;
+}
+extern "C" size_t pfb_k6_workspace_bytes(int N) {
+    return (size_t)N * (16 + 8 + 8) + 256 + k6_cub_bytes(N);
+}
+
 extern "C" cudaError_t pfb_launch_k6(cudaStream_t st, int N, int M, int m_grid, const double* logp,
                                      const double* logq, const double* logr, double* logw, double* weights,
-                                     uint64_t* cum, void* scalars) {
+                                     uint64_t* cum, void* scalars, void* work, size_t work_bytes) {
     if (N <= 0) return cudaErrorInvalidValue;
     if (M + 1 > PFB_K6_MAXCAND || m_grid > 128) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)PFB_K6_MAXCAND * (8 + 8 + 4);
-    cudaError_t e = cudaFuncSetAttribute(pfb_k6_psis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    pfb_k6_psis<<<1, PFB_K6_THREADS, smem, st>>>(N, M, m_grid, logp, logq, logr, logw, weights, cum,
-                                                 (pfb_psis_scalars*)scalars);
+    if (work_bytes < pfb_k6_workspace_bytes(N)) return cudaErrorInvalidValue;
+    pfb_psis_scalars* sc = (pfb_psis_scalars*)scalars;
+    uint64_t* k_in = (uint64_t*)work;
+    uint64_t* k_out = k_in + N;
+    double* e = (double*)(k_out + N);
+    uint32_t* i_in = (uint32_t*)(e + N);
+    uint32_t* i_out = i_in + N;
+    void* tmp = (void*)(((uintptr_t)(i_out + N) + 255) & ~(uintptr_t)255);
+    size_t tmp_bytes = k6_cub_bytes(N);
+    const int TB = 256, GB = (N + TB - 1) / TB;
+    pfb_k6a_keys<<<GB, TB, 0, st>>>(N, logp, logq, logr, logw, k_in, i_in);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    if (M >= 5) {
+        err = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, i_in, i_out, N, 0, 64, st);
+        if (err != cudaSuccess) return err;
+    }
+    const size_t smem = (size_t)PFB_K6_MAXCAND * (8 + 4);
+    err = cudaFuncSetAttribute(pfb_k6b_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    pfb_k6b_fit<<<1, PFB_K6_THREADS, smem, st>>>(N, M, m_grid, i_out, logw, sc);
+    const int GR = GB < 1184 ? GB : 1184;  // 148 SMs x 8
+    pfb_k6c_max<<<GR, TB, 0, st>>>(N, logw, sc);
+    pfb_k6d_exp<<<GB, TB, 0, st>>>(N, logw, sc, e);
+    pfb_k6e_sum<<<1, PFB_K6_THREADS, 0, st>>>(N, e, sc);
+    pfb_k6f_weights<<<GB, TB, 0, st>>>(N, logw, weights, cum, sc);
+    pfb_k6g_scan<<<1, PFB_K6_THREADS, 0, st>>>(N, cum, sc);
     return cudaGetLastError();
 }
 
@@ -358,7 +359,6 @@ extern "C" cudaError_t pfb_launch_k7(cudaStream_t st, int n, int N, int K_run, u
 // index.  importance = false: log w = 0 (a uniform random subset in random order).  Zero / NaN
 // weights get key = +Inf and are taken only when nothing else is left.  pf_log makes the keys
 // bit-identical to the oracle's (oracle/psis.py::resample_indices_norep).
-#include <cub/device/device_radix_sort.cuh>
 
 __global__ void pfb_k7b_keys(int N, uint64_t seed, const double* __restrict__ logw, uint64_t* __restrict__ keys,
                              int32_t* __restrict__ idx) {

@@ -42,8 +42,9 @@ size_t pfb_psis_scalars_size();
 cudaError_t pfb_k7b_temp_bytes(int, size_t*);
 cudaError_t pfb_launch_k7b(cudaStream_t, int, int, int, uint64_t, int, const double*, const double*, uint64_t*,
                            uint64_t*, int32_t*, int32_t*, void*, size_t, int64_t*, int64_t*, double*);
+size_t pfb_k6_workspace_bytes(int);
 cudaError_t pfb_launch_k6(cudaStream_t, int, int, int, const double*, const double*, const double*, double*,
-                          double*, uint64_t*, void*);
+                          double*, uint64_t*, void*, void*, size_t);
 cudaError_t pfb_launch_k7(cudaStream_t, int, int, int, uint64_t, int, const uint64_t*, const void*,
                           const double*, int64_t*, int64_t*, double*);
 }
@@ -76,6 +77,7 @@ struct psis_scalars_host {
     double pareto_k, lse, sigma, logu;
     uint64_t Z;
     int64_t tail_len, smoothed;
+    uint64_t maxkey;
 };
 
 }  // namespace
@@ -976,8 +978,10 @@ static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const 
         PFB_CUDA(h, h->dLogw.ensure((size_t)N * 8));
         PFB_CUDA(h, h->dW.ensure((size_t)N * 8));
         PFB_CUDA(h, h->dCum.ensure((size_t)N * 8));
+        const size_t wb = pfb_k6_workspace_bytes((int)N);
+        PFB_CUDA(h, h->dSortWork.ensure(wb));
         PFB_CUDA(h, pfb_launch_k6(st, (int)N, M, m_grid, d_logp, d_logq, d_logr, h->dLogw.as<double>(),
-                                  h->dW.as<double>(), h->dCum.as<uint64_t>(), h->dScal.p));
+                                  h->dW.as<double>(), h->dCum.as<uint64_t>(), h->dScal.p, h->dSortWork.p, wb));
     }
     if (replace) {
         PFB_CUDA(h, pfb_launch_k7(st, n, (int)N, K_run, seed, ndraws, importance ? h->dCum.as<uint64_t>() : nullptr,

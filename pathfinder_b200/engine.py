@@ -320,13 +320,13 @@ class Engine:
         return v
 
     # ---- PSIS + resample stage -------------------------------------------------------------
-    def _resample_out(self, N, ndraws, importance, want_draws):
+    def _resample_out(self, N, ndraws, importance, want_draws, want_weights=True):
         out = pfb_resample_out()
         r = dict(inds=np.empty(ndraws, dtype=np.int64), ids=np.empty(ndraws, dtype=np.int64),
                  pareto_k=np.full(1, np.nan), tail_len=np.zeros(1, dtype=np.int64))
         out.inds, out.ids = _ptr(r["inds"]), _ptr(r["ids"])
         out.pareto_k, out.tail_len = _ptr(r["pareto_k"]), _ptr(r["tail_len"])
-        if importance:
+        if importance and want_weights:
             r["log_weights"] = np.empty(N)
             r["weights"] = np.empty(N)
             out.log_weights, out.weights = _ptr(r["log_weights"]), _ptr(r["weights"])
@@ -364,9 +364,11 @@ class Engine:
             int(bool(importance)), int(bool(replace)), C.byref(out)))
         return self._finish(r)
 
-    def psis_resample_device(self, N, K_run, d_logp, d_logq, d_pool, seed, ndraws, importance=True, replace=True):
-        """d_* are raw device pointers (ints), e.g. torch tensors' data_ptr()."""
-        out, r = self._resample_out(N, ndraws, importance, d_pool is not None)
+    def psis_resample_device(self, N, K_run, d_logp, d_logq, d_pool, seed, ndraws, importance=True, replace=True,
+                             want_weights=True):
+        """d_* are raw device pointers (ints), e.g. torch tensors' data_ptr().  want_weights=False
+        leaves the N-sized weight vectors on the device (only indices, ids, k-hat come back)."""
+        out, r = self._resample_out(N, ndraws, importance, d_pool is not None, want_weights)
         _lib.check(self.h, self.lib.pfb_psis_resample_device(
             self.h, self.n, int(N), int(K_run), C.c_void_p(d_logp), C.c_void_p(d_logq),
             C.c_void_p(d_pool) if d_pool else None, C.c_uint64(int(seed)), int(ndraws),
