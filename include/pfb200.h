@@ -214,6 +214,11 @@ int pfb_psis_resample_device(pfb_handle h, int n, int64_t N, int K_run, const vo
                              const void* d_logq, const void* d_pool, uint64_t seed, int ndraws,
                              int importance, int replace, pfb_resample_out* out);
 
+/* Page-lock (cudaHostRegister) / unlock a caller-owned host buffer.  Optional: output buffers a
+ * caller reuses across batches then receive their copies at full PCIe rate. */
+int pfb_host_register(void* p, size_t bytes);
+int pfb_host_unregister(void* p);
+
 /* Timings of the last batch in milliseconds (CUDA events on the engine stream):
  * ms[0..5] = K1, K2, K3, K4, K5, total; returns the number of kernels launched. */
 int pfb_get_timings(pfb_handle h, double* ms6);

@@ -94,6 +94,8 @@ SYMBOLS = {
     "pfb_batch_device_view": (C.c_int, [C.c_void_p, C.POINTER(pfb_device_view)]),
     "pfb_psis_resample_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, _dp, _dp, _dp,
                                            C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(pfb_resample_out)]),
+    "pfb_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "pfb_host_unregister": (C.c_int, [C.c_void_p]),
     "pfb_get_timings": (C.c_int, [C.c_void_p, _dp]),
     "pfb_measure_fp64_fma_tflops": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "pfb_measure_fp64_dmma_tflops": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),

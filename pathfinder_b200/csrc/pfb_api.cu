@@ -1061,6 +1061,27 @@ extern "C" int pfb_psis_resample_host(pfb_handle h, int n, int64_t N, int K_run,
     return psis_resample_impl(h, n, N, K_run, nullptr, nullptr, d_logr, d_pool, seed, ndraws, importance, replace, o);
 }
 
+// Page-lock / unlock a caller-owned host buffer (cudaHostRegister): output buffers that a caller
+// reuses across batches then receive their device-to-host copies at full PCIe rate.
+extern "C" int pfb_host_register(void* p, size_t bytes) {
+    if (!p || bytes == 0) return PFB_ERR_ARG;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return PFB_OK;
+    }
+    return e == cudaSuccess ? PFB_OK : (int)e;
+}
+extern "C" int pfb_host_unregister(void* p) {
+    if (!p) return PFB_ERR_ARG;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e == cudaErrorHostMemoryNotRegistered) {
+        cudaGetLastError();
+        return PFB_OK;
+    }
+    return e == cudaSuccess ? PFB_OK : (int)e;
+}
+
 extern "C" int pfb_get_timings(pfb_handle h, double* ms6) {
     if (!h || !ms6) return PFB_ERR_ARG;
     if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "no batch has run");

@@ -243,31 +243,62 @@ class Engine:
     def sync(self):
         _lib.check(self.h, self.lib.pfb_batch_sync(self.h))
 
-    def download(self, draws=True, per_draw=False, fit=False, all_draws=False) -> ElboBatchResult:
+    def pin(self, *arrays):
+        """Page-lock caller-owned output arrays in place (cudaHostRegister) so that reusing them
+        through download(into=...) / psis_resample(into=...) gets full-rate D2H copies."""
+        for a in arrays:
+            if a is not None and a.nbytes > 0:
+                rc = self.lib.pfb_host_register(_ptr(a), a.nbytes)
+                if rc != 0:
+                    raise _lib.PfbError(rc, "cudaHostRegister failed")
+        return arrays
+
+    def unpin(self, *arrays):
+        for a in arrays:
+            if a is not None and a.nbytes > 0:
+                self.lib.pfb_host_unregister(_ptr(a))
+
+    def download(self, draws=True, per_draw=False, fit=False, all_draws=False, into=None) -> ElboBatchResult:
+        """into: a result of an earlier download of the SAME batch shape whose arrays are reused
+        (the caller-owned output buffers of the C ABI; pin() them for full-rate copies)."""
         n, K, P, U, KP = self.n, self.K, self._P, self._U, self.KP
         out = pfb_elbo_out()
-        elbo = np.empty(U); se = np.empty(U)
-        best = np.empty(P, dtype=np.int64); succ = np.empty(P, dtype=np.int32)
-        rej = np.empty(P, dtype=np.int64)
+
+        def buf(name, shape, dtype=np.float64, order="C", src=None):
+            prev = None if into is None else (src if src is not None else getattr(into, name, None))
+            if prev is not None and prev.shape == tuple(np.atleast_1d(shape)) and prev.dtype == dtype and \
+                    (prev.flags.f_contiguous if order == "F" else prev.flags.c_contiguous):
+                return prev
+            return np.empty(shape, dtype=dtype, order=order)
+
+        elbo = buf("elbo", U); se = buf("elbo_se", U)
+        best = buf("best_iter", P, np.int64)
+        succ = buf("_succ32", P, np.int32)
+        rej = buf("n_rejected", P, np.int64)
         out.elbo, out.elbo_se = _ptr(elbo), _ptr(se)
         out.best_iter, out.success, out.n_rejected = _ptr(best), _ptr(succ), _ptr(rej)
         res = ElboBatchResult(self._offsets, elbo, se, best, None, rej)
+        res._succ32 = succ
         if draws == "lazy":
             res._lazy_engine = weakref.ref(self)
             self._pending.append(weakref.ref(res))
         elif draws:
-            res.draws = np.empty((n, K, P), order="F")
-            res.draws_logp = np.empty((K, P), order="F")
-            res.draws_logq = np.empty((K, P), order="F")
+            res.draws = buf("draws", (n, K, P), order="F")
+            res.draws_logp = buf("draws_logp", (K, P), order="F")
+            res.draws_logq = buf("draws_logq", (K, P), order="F")
             out.draws, out.draws_logp, out.draws_logq = _ptr(res.draws), _ptr(res.draws_logp), _ptr(res.draws_logq)
         if per_draw:
-            res.logp = np.empty((K, U), order="F")
-            res.logq = np.empty((K, U), order="F")
+            res.logp = buf("logp", (K, U), order="F")
+            res.logq = buf("logq", (K, U), order="F")
             out.logp, out.logq = _ptr(res.logp), _ptr(res.logq)
         if fit:
-            f = dict(mu=np.empty((n, P), order="F"), alpha=np.empty((n, P), order="F"),
-                     vh=np.empty((n, KP, P), order="F"), T=np.empty((P, KP, KP)),
-                     Vc=np.empty((P, KP, KP)), logdet=np.empty(P), jeff=np.empty(P, dtype=np.int32))
+            pf_ = into.fit if (into is not None and into.fit is not None) else {}
+            f = dict(mu=buf("mu", (n, P), order="F", src=pf_.get("mu")),
+                     alpha=buf("alpha", (n, P), order="F", src=pf_.get("alpha")),
+                     vh=buf("vh", (n, KP, P), order="F", src=pf_.get("vh")),
+                     T=buf("T", (P, KP, KP), src=pf_.get("T")), Vc=buf("Vc", (P, KP, KP), src=pf_.get("Vc")),
+                     logdet=buf("logdet", P, src=pf_.get("logdet")),
+                     jeff=buf("jeff", P, np.int32, src=pf_.get("jeff")))
             out.fit_mu, out.fit_alpha, out.fit_vh = _ptr(f["mu"]), _ptr(f["alpha"]), _ptr(f["vh"])
             out.fit_T, out.fit_Vc = _ptr(f["T"]), _ptr(f["Vc"])
             out.fit_logdet, out.fit_jeff = _ptr(f["logdet"]), _ptr(f["jeff"])
@@ -278,6 +309,15 @@ class Engine:
         _lib.check(self.h, self.lib.pfb_batch_download(self.h, C.byref(out)))
         res.success = succ.astype(bool)
         return res
+
+    @staticmethod
+    def result_arrays(res):
+        """Every host array of a download() result (for pin / unpin)."""
+        out = [res.elbo, res.elbo_se, res.best_iter, res.n_rejected, getattr(res, "_succ32", None), res.draws,
+               res.draws_logp, res.draws_logq, res.logp, res.logq, res.all_draws]
+        if res.fit:
+            out += list(res.fit.values())
+        return [a for a in out if a is not None]
 
     def elbo_batch(self, offsets, X, G, seeds, normals=None, **kw) -> ElboBatchResult:
         self.upload(offsets, X, G, seeds, normals)
@@ -320,8 +360,20 @@ class Engine:
         return v
 
     # ---- PSIS + resample stage -------------------------------------------------------------
-    def _resample_out(self, N, ndraws, importance, want_draws, want_weights=True):
+    def _resample_out(self, N, ndraws, importance, want_draws, want_weights=True, into=None):
         out = pfb_resample_out()
+        if into is not None and into["inds"].shape == (ndraws,) and \
+                (not (importance and want_weights) or into.get("weights", np.empty(0)).shape == (N,)) and \
+                (not want_draws or into.get("draws", np.empty((0, 0))).shape == (self.n, ndraws)):
+            r = dict(into)  # reuse the caller's (possibly pinned) output arrays
+            r["pareto_k"] = np.full(1, np.nan); r["tail_len"] = np.zeros(1, dtype=np.int64)
+            out.inds, out.ids = _ptr(r["inds"]), _ptr(r["ids"])
+            out.pareto_k, out.tail_len = _ptr(r["pareto_k"]), _ptr(r["tail_len"])
+            if importance and want_weights:
+                out.log_weights, out.weights = _ptr(r["log_weights"]), _ptr(r["weights"])
+            if want_draws:
+                out.draws = _ptr(r["draws"])
+            return out, r
         r = dict(inds=np.empty(ndraws, dtype=np.int64), ids=np.empty(ndraws, dtype=np.int64),
                  pareto_k=np.full(1, np.nan), tail_len=np.zeros(1, dtype=np.int64))
         out.inds, out.ids = _ptr(r["inds"]), _ptr(r["ids"])
@@ -341,10 +393,11 @@ class Engine:
         r["tail_len"] = int(r["tail_len"][0])
         return r
 
-    def psis_resample(self, seed, ndraws, importance=True, replace=True):
-        """On the pool of the last batch / the last draw_from_fits(keep_as_pool=True) (device resident)."""
+    def psis_resample(self, seed, ndraws, importance=True, replace=True, into=None):
+        """On the pool of the last batch / the last draw_from_fits(keep_as_pool=True) (device resident).
+        into: the dict of an earlier call with the same shapes, whose arrays are reused."""
         N = self._P * self._poolK
-        out, r = self._resample_out(N, ndraws, importance, True)
+        out, r = self._resample_out(N, ndraws, importance, True, into=into)
         _lib.check(self.h, self.lib.pfb_psis_resample(self.h, C.c_uint64(int(seed)), int(ndraws),
                                                       int(bool(importance)), int(bool(replace)), C.byref(out)))
         return self._finish(r)

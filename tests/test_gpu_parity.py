@@ -743,3 +743,36 @@ def test_edge_cases_single_draw_and_empty_batch():
                           np.zeros(0, np.uint64))
     assert resE.elbo.size == 0 and resE.best_iter.size == 0
     eng.close()
+
+
+def test_reused_pinned_output_buffers_give_identical_results():
+    """download(into=...) / psis_resample(into=...) write into the caller's page-locked arrays of an
+    earlier call (pfb_host_register); the numbers are the same as with fresh arrays."""
+    import pathfinder_b200 as pf
+    from tests.helpers import synthetic_trajectory
+
+    n, K = 20, 64
+    model = pf.IsoNormal(n)
+    trajs = [synthetic_trajectory(n, L, 40 + L) for L in (3, 7)]
+    seeds = np.concatenate(_seeds(trajs, 2))
+    offsets, X, G = pf.Engine.pack(trajs)
+    eng = _engine(model, K)
+    fresh = eng.elbo_batch(offsets, X, G, seeds, draws=True, fit=True)
+    r_fresh = eng.psis_resample(11, 25, True)
+    eng.pin(*pf.Engine.result_arrays(fresh))
+    eng.pin(r_fresh["weights"], r_fresh["log_weights"], r_fresh["draws"])
+    keep = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in r_fresh.items()}
+    elbo0, vh0, draws0 = fresh.elbo.copy(), fresh.fit["vh"].copy(), fresh.draws.copy()
+    fresh.elbo[:] = 0; fresh.fit["vh"][:] = 0; fresh.draws[:] = 0
+    again = eng.elbo_batch(offsets, X, G, seeds, draws=True, fit=True, into=fresh)
+    assert again.elbo is fresh.elbo and again.fit["vh"] is fresh.fit["vh"] and again.draws is fresh.draws
+    assert np.array_equal(again.elbo, elbo0) and np.array_equal(again.fit["vh"], vh0, equal_nan=True)
+    assert np.array_equal(again.draws, draws0)
+    r2 = eng.psis_resample(11, 25, True, into=r_fresh)
+    assert r2["weights"] is r_fresh["weights"]
+    for k in ("weights", "log_weights", "inds", "ids", "draws"):
+        assert np.array_equal(r2[k], keep[k], equal_nan=True)
+    assert r2["pareto_k"] == keep["pareto_k"] or (np.isnan(r2["pareto_k"]) and np.isnan(keep["pareto_k"]))
+    eng.unpin(*pf.Engine.result_arrays(fresh))
+    eng.unpin(r_fresh["weights"], r_fresh["log_weights"], r_fresh["draws"])
+    eng.close()
