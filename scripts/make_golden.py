@@ -57,7 +57,21 @@ def main():
     uinds = OP.resample_indices(4242, None, lr.size, 64)
     np.savez(os.path.join(OUT, "psis_resample.npz"), log_ratios=lr, log_weights=res["log_weights"],
              weights=res["weights"], pareto_k=res["pareto_k"], tail_length=res["tail_length"], seed=4242,
-             inds=inds, uniform_inds=uinds)
+             inds=inds, uniform_inds=uinds,
+             norep_inds=OP.resample_indices_norep(4242, res["log_weights"], lr.size, 64),
+             norep_uniform_inds=OP.resample_indices_norep(4242, None, lr.size, 64))
+
+    # 4. the L-BFGS trajectory contract (pf_lbfgs.h): funnel and independent normals, small n
+    from oracle import lbfgs as OL
+
+    rng = np.random.default_rng(5)
+    x0f = rng.uniform(-4, 4, size=12)
+    Xf, FXf, Gf, stf, nevf = OL.lbfgs_path(OL.FAMILY_FUNNEL, x0f, 6, 25)
+    mean, sd = rng.normal(size=9), rng.uniform(0.2, 5.0, size=9)
+    x0d = rng.uniform(-2, 2, size=9)
+    Xd, FXd, Gd, std, nevd = OL.lbfgs_path(OL.FAMILY_DIAGNORMAL, x0d, 6, 1000, mean=mean, sd=sd)
+    np.savez(os.path.join(OUT, "lbfgs_traces.npz"), x0f=x0f, Xf=Xf, FXf=FXf, Gf=Gf, stf=stf, nevf=nevf,
+             mean=mean, sd=sd, x0d=x0d, Xd=Xd, FXd=FXd, Gd=Gd, std=std, nevd=nevd)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 

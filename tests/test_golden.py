@@ -43,6 +43,45 @@ def test_oracle_reproduces_psis_resample():
     assert res["pareto_k"] == float(g["pareto_k"]) and res["tail_length"] == int(g["tail_length"])
     assert np.array_equal(OP.resample_indices(int(g["seed"]), res["weights"], g["log_ratios"].size, 64), g["inds"])
     assert np.array_equal(OP.resample_indices(int(g["seed"]), None, g["log_ratios"].size, 64), g["uniform_inds"])
+    N = g["log_ratios"].size
+    assert np.array_equal(OP.resample_indices_norep(int(g["seed"]), res["log_weights"], N, 64), g["norep_inds"])
+    assert np.array_equal(OP.resample_indices_norep(int(g["seed"]), None, N, 64), g["norep_uniform_inds"])
+
+
+def test_oracle_reproduces_lbfgs_traces():
+    from oracle import lbfgs as OL
+
+    g = _load("lbfgs_traces.npz")
+    X, FX, G, st, nev = OL.lbfgs_path(OL.FAMILY_FUNNEL, g["x0f"], 6, 25)
+    assert np.array_equal(X, g["Xf"]) and np.array_equal(G, g["Gf"]) and np.array_equal(FX, g["FXf"])
+    assert (st, nev) == (int(g["stf"]), int(g["nevf"]))
+    X, FX, G, st, nev = OL.lbfgs_path(OL.FAMILY_DIAGNORMAL, g["x0d"], 6, 1000, mean=g["mean"], sd=g["sd"])
+    assert np.array_equal(X, g["Xd"]) and np.array_equal(G, g["Gd"]) and np.array_equal(FX, g["FXd"])
+    assert (st, nev) == (int(g["std"]), int(g["nevd"]))
+
+
+@pytest.mark.gpu
+def test_gpu_matches_golden_lbfgs_and_norep():
+    import pathfinder_b200 as pf
+
+    g = _load("lbfgs_traces.npz")
+    eng = pf.Engine(12, pf.PFB_MODEL_FUNNEL, None, 6, 8, 0)
+    npts, st, nev = eng.lbfgs_batch(g["x0f"][:, None], 25)
+    off, X, FX, G = eng.lbfgs_download()
+    assert np.array_equal(X, g["Xf"]) and np.array_equal(G, g["Gf"]) and np.array_equal(FX, g["FXf"])
+    assert (int(st[0]), int(nev[0])) == (int(g["stf"]), int(g["nevf"]))
+    eng.close()
+    m = pf.DiagNormal(g["mean"], g["sd"])
+    eng = pf.Engine.for_model(m, 6, 8, 0)
+    eng.lbfgs_batch(g["x0d"][:, None], 1000)
+    off, X, FX, G = eng.lbfgs_download()
+    assert np.array_equal(X, g["Xd"]) and np.array_equal(G, g["Gd"]) and np.array_equal(FX, g["FXd"])
+    p = _load("psis_resample.npz")
+    r = eng.psis_resample_host(p["log_ratios"], 100, int(p["seed"]), 64, True, replace=False)
+    assert np.array_equal(r["inds"], p["norep_inds"])
+    ru = eng.psis_resample_host(None, 100, int(p["seed"]), 64, False, N=p["log_ratios"].size, replace=False)
+    assert np.array_equal(ru["inds"], p["norep_uniform_inds"])
+    eng.close()
 
 
 @pytest.mark.gpu
