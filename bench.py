@@ -213,7 +213,9 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * per_step_budget, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "n": n, "paths": P, "K": K, "history": J},
+        "config": {"workload": name, "n": n, "paths_per_gpu": P, "K": K, "history": J, "ndraws": ndraws,
+                   "mode": "reference CPU algorithm (every iteration's draws materialised, as src/elbo.jl:19)",
+                   "parallelism": f"one path per host process, {cores} processes"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"ELBO stage (fit_mvnormals + maximize_elbo) of the oracle port, one path per "
                                    f"core for {per_step_budget:.0f} s per step; Julia is not installed so the "
