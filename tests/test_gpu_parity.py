@@ -776,3 +776,71 @@ def test_reused_pinned_output_buffers_give_identical_results():
     eng.unpin(*pf.Engine.result_arrays(fresh))
     eng.unpin(r_fresh["weights"], r_fresh["log_weights"], r_fresh["draws"])
     eng.close()
+
+
+def test_full_size_config3_properties():
+    """BASELINE config 3 at its full per-unit size (1024-dim funnel, K = 1000, history 6, real L-BFGS
+    trajectories; 6 paths instead of 64 so the test stays in seconds) through size-independent
+    properties, plus the oracle on a bounded sample of units."""
+    import pathfinder_b200 as pf
+    from oracle import pf_oracle as O
+    from tests.helpers import make_trajectories
+
+    n, K, J, P = 1024, 1000, 6, 6
+    model = pf.Funnel(n)
+    trajs = make_trajectories(model, P, seed=20261017, init_scale=10.0, maxiters=25, min_len=8)
+    seeds = _seeds(trajs, 4)
+    offsets, X, G = pf.Engine.pack(trajs)
+    sd = np.concatenate(seeds)
+    lean = _engine(model, K, J)
+    a = lean.elbo_batch(offsets, X, G, sd, draws=True, per_draw=True, fit=True)
+    mm = _engine(model, K, J, materialize_all=True, two_pass=True)
+    b = mm.elbo_batch(offsets, X, G, sd, draws=True, per_draw=True, all_draws=True)
+    U = a.elbo.size
+    # (1) the single-pass statistics formulation == the generic two-pass kernel (algebraic identity)
+    fin = np.isfinite(b.elbo)
+    assert np.array_equal(fin, np.isfinite(a.elbo))
+    scale = np.maximum(1.0, np.nanmax(np.abs(b.logp), axis=0))
+    with np.errstate(invalid="ignore"):
+        dev = np.nanmax(np.abs(a.logp - b.logp), axis=0) / scale
+    assert np.nanmax(dev[fin]) < 1e-7, np.nanmax(dev[fin])   # cancellation in ill-conditioned units, still << 1e-6
+    np.testing.assert_allclose(a.logq, b.logq, rtol=1e-12, atol=1e-9)
+    # (2) ELBO = mean(logp - logq), SE = sd / sqrt(K)  (src/elbo.jl:16-18)
+    logr = b.logp - b.logq
+    np.testing.assert_allclose(b.elbo[fin], logr.mean(axis=0)[fin], rtol=1e-10)
+    np.testing.assert_allclose(b.elbo_se[fin], (logr.std(axis=0, ddof=1) / np.sqrt(K))[fin], rtol=1e-8)
+    # (3) logp of the materialised draws is the model's (host evaluation of the same x)
+    for u in (0, U // 2, U - 1):
+        ref = O.logp_funnel(b.all_draws[:, :, u])
+        ok = np.isfinite(ref)
+        np.testing.assert_allclose(b.logp[ok, u], ref[ok], rtol=1e-10, atol=1e-8)
+    # (4) K5 regenerates the best iteration's draws bit for bit; argmax follows _findmax_skipnan
+    for p in range(P):
+        sl = b.unit_slice(p)
+        ev = b.elbo[sl]
+        assert b.best_iter[p] == O.findmax_skipnan(list(ev))[1]
+        ub = sl.start + int(b.best_iter[p]) - 1
+        assert np.array_equal(b.draws[:, :, p], b.all_draws[:, :, ub])
+        assert np.array_equal(a.draws[:, :, p], b.draws[:, :, p]) or a.best_iter[p] != b.best_iter[p]
+    # (5) the oracle on a bounded sample: the first two units of path 0 at full size (they depend on
+    # the first three trajectory points only); tolerance policy of _compare_batch: 1e-6, or 50x the
+    # oracle's own response to a 1-ulp input perturbation where the history is near-collinear
+    from tests.helpers import oracle_batch
+
+    trunc = [(trajs[0][0][:, :3], trajs[0][1][:, :3])]
+    sd2 = [seeds[0][:2]]
+    orc = oracle_batch(model, trunc, sd2, K, J)
+    sens = _sensitivity(model, trunc, sd2, K, J, orc)[0]
+    for l in (1, 2):
+        est = orc[0]["ests"][l - 1]
+        tol = max(RTOL, 50.0 * float(sens[l - 1]))
+        assert abs(b.elbo[l - 1] - est["value"]) <= tol * max(1.0, abs(est["value"])), (l, tol)
+        assert _rel(b.all_draws[:, :, l - 1], est["draws"]) < tol, (l, tol)
+    # (6) pool of P * K draws: weights sum to 1 (test/resample.jl:103-108), resampled columns are
+    # pool columns, ids consistent (test/resample.jl:51-59)
+    r = lean.psis_resample(9, 500, True)
+    assert abs(np.nansum(r["weights"]) - 1.0) < 1e-12 and r["tail_len"] == min(-(-P * K // 5), int(np.ceil(3 * np.sqrt(P * K))))
+    pool = a.draws.reshape(n, K * P, order="F")
+    assert np.array_equal(r["draws"], pool[:, r["inds"] - 1])
+    assert np.array_equal(r["ids"], -(-r["inds"] // K))
+    lean.close(); mm.close()
