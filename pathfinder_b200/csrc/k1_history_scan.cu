@@ -13,11 +13,11 @@
 // writing alpha: 8n*3 bytes per unit.
 #include "pfb_common.cuh"
 
-#define PFB_K1_THREADS 256
-#define PFB_K1_RPT 16  // rows per thread held in registers => n <= 4096 in registers
+#define PFB_K1_RPT_WIDE 8   // up to 512 threads x 8 rows (n <= 4096): short links of the sequential chain
+#define PFB_K1_RPT_TALL 16  // 256 threads x 16 rows otherwise; beyond that alpha lives in global memory
 
-template <bool IN_REGS>
-__global__ void __launch_bounds__(PFB_K1_THREADS)
+template <bool IN_REGS, int PFB_K1_RPT>
+__global__ void __launch_bounds__(PFB_K1_RPT == PFB_K1_RPT_WIDE ? 512 : 256)
 pfb_k1_history_scan(int n, int J, double eps, const double* __restrict__ X,
                     const double* __restrict__ G, const int64_t* __restrict__ point_off,
                     double* __restrict__ alpha_out,   // [n x U]
@@ -125,11 +125,18 @@ extern "C" cudaError_t pfb_launch_k1(cudaStream_t st, int n, int P, int J, doubl
                                      const double* G, const int64_t* point_off, double* alpha,
                                      int32_t* hist, int32_t* hist_cnt, int64_t* n_rejected) {
     if (P <= 0) return cudaSuccess;
-    if (n <= PFB_K1_THREADS * PFB_K1_RPT)
-        pfb_k1_history_scan<true><<<P, PFB_K1_THREADS, 0, st>>>(n, J, eps, X, G, point_off, alpha, hist,
-                                                                hist_cnt, n_rejected);
-    else
-        pfb_k1_history_scan<false><<<P, PFB_K1_THREADS, 0, st>>>(n, J, eps, X, G, point_off, alpha,
-                                                                 hist, hist_cnt, n_rejected);
+    // only P CTAs exist and each is a sequential chain over the trajectory: more threads per CTA
+    // shorten every link (2 rows per thread at n = 1024)
+    if (n <= 512 * PFB_K1_RPT_WIDE) {
+        const int threads = n >= 512 ? 512 : 256;
+        pfb_k1_history_scan<true, PFB_K1_RPT_WIDE><<<P, threads, 0, st>>>(n, J, eps, X, G, point_off, alpha, hist,
+                                                                          hist_cnt, n_rejected);
+    } else if (n <= 256 * PFB_K1_RPT_TALL) {
+        pfb_k1_history_scan<true, PFB_K1_RPT_TALL><<<P, 256, 0, st>>>(n, J, eps, X, G, point_off, alpha, hist,
+                                                                      hist_cnt, n_rejected);
+    } else {
+        pfb_k1_history_scan<false, PFB_K1_RPT_TALL><<<P, 256, 0, st>>>(n, J, eps, X, G, point_off, alpha, hist,
+                                                                       hist_cnt, n_rejected);
+    }
     return cudaGetLastError();
 }

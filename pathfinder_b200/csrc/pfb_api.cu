@@ -27,7 +27,7 @@ cudaError_t pfb_launch_k2(cudaStream_t, int, int, int, int, const double*, const
 PFB_DECL_K3(pfb_launch_k3_kp12)
 PFB_DECL_K3(pfb_launch_k3_kp20)
 PFB_DECL_K3(pfb_launch_k3_kp24)
-cudaError_t pfb_launch_k4(cudaStream_t, int, int, const int64_t*, const double*, const double*, double*,
+cudaError_t pfb_launch_k4(cudaStream_t, int, int, int64_t, const int64_t*, const double*, const double*, double*,
                           double*, int64_t*, int32_t*, int32_t*);
 int pfb_k2_uses_smem_panel(int KP, int n);
 cudaError_t pfb_launch_k8_dense(cudaStream_t, int, int64_t, int, const int32_t*, const double*, const double*,
@@ -707,10 +707,10 @@ extern "C" int pfb_batch_run(pfb_handle h) {
         }
     }
     PFB_CUDA(h, cudaEventRecord(h->ev[3], st));
-    PFB_CUDA(h, pfb_launch_k4(st, P, K, h->dOff.as<int64_t>(), h->dLogp.as<double>(), h->dLogq.as<double>(),
+    PFB_CUDA(h, pfb_launch_k4(st, P, K, (int64_t)U, h->dOff.as<int64_t>(), h->dLogp.as<double>(), h->dLogq.as<double>(),
                               h->dElbo.as<double>(), h->dSe.as<double>(), h->dBestIter.as<int64_t>(),
                               h->dBestUnit.as<int32_t>(), h->dSucc.as<int32_t>()));
-    h->launches += (P > 0);
+    h->launches += (P > 0) + (U > 0);
     PFB_CUDA(h, cudaEventRecord(h->ev[4], st));
     // K5: materialise the best iteration of every path into the pool (regenerated, identical
     // to the ELBO draws because the RNG is counter based)
