@@ -19,7 +19,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _lib = None
 
-FAMILY_ISONORMAL, FAMILY_FUNNEL, FAMILY_DIAGNORMAL = 0, 1, 2
+FAMILY_ISONORMAL, FAMILY_FUNNEL, FAMILY_DIAGNORMAL, FAMILY_DENSENORMAL = 0, 1, 2, 3
 STATUS = {0: "gtol", 1: "ftol", 2: "maxiters", 3: "linesearch", 4: "nonfinite"}
 
 
@@ -40,7 +40,7 @@ def clib():
 
 
 def lbfgs_path(family, x0, history_length=6, maxiters=1000, max_points=None, gtol=1e-8, ftol=1e-14,
-               mean=None, sd=None):
+               mean=None, sd=None, prec=None):
     """One trajectory: returns (points [n, L+1], log_densities [L+1], gradients [n, L+1], status, nevals)."""
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
     n = x0.size
@@ -59,6 +59,9 @@ def lbfgs_path(family, x0, history_length=6, maxiters=1000, max_points=None, gto
         c0 = -0.5 * n * 1.8378770664093453
         for v in sd:
             c0 -= np.log(v)
+    if family == FAMILY_DENSENORMAL:
+        mp0 = np.ascontiguousarray(mean, dtype=np.float64)
+        mp1 = np.asfortranarray(prec, dtype=np.float64)
     np_ = clib().pfo_lbfgs_path(int(family), n, None if mp0 is None else mp0.ctypes.data,
                                 None if mp1 is None else mp1.ctypes.data, float(c0), int(history_length),
                                 int(maxiters), int(max_points), float(gtol), float(ftol), x0.ctypes.data,

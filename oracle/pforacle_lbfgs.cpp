@@ -76,13 +76,13 @@ struct HostCtx {
 }  // namespace
 
 // One path.  X, G: n x max_points column-major, FX[max_points].  mp0 / mp1: DIAGNORMAL mean and
-// 1 / sd.  Returns the number of recorded points.
+// 1 / sd; DENSENORMAL mean and precision (n x n column-major).  Returns the number of recorded points.
 extern "C" int pfo_lbfgs_path(int family, int n, const double* mp0, const double* mp1, double mc0, int J,
                               int maxiters, int max_points, double gtol, double ftol, const double* x0, double* X,
                               double* G, double* FX, int* status, int* nevals) {
-    pf_lbfgs_model m{family, n, mp0, mp1, mc0};
+    std::vector<double> ws((size_t)(2 * J + 2) * n);
+    pf_lbfgs_model m{family, n, mp0, mp1, mc0, ws.data() + (size_t)(2 * J + 1) * n};
     pf_lbfgs_opts o{J, maxiters, max_points, gtol, ftol};
-    std::vector<double> ws((size_t)(2 * J + 1) * n);
     HostCtx c{n};
     return pf_lbfgs_run(c, m, o, x0, X, G, FX, ws.data(), status, nevals);
 }

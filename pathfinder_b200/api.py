@@ -126,14 +126,14 @@ def _draw_seeds(rng, m):
     return rng.integers(0, 2**64, size=m, dtype=np.uint64)
 
 
-DEVICE_LBFGS_FAMILIES = (0, 1, 2)  # iso-normal, funnel, independent normals (include/pfb200.h)
+DEVICE_LBFGS_FAMILIES = (0, 1, 2, 3)  # iso-normal, funnel, independent normals, dense normal (include/pfb200.h)
 
 
 def _use_device_optimizer(model, optimizer):
     if optimizer not in ("auto", "device", "host"):
         raise ValueError("optimizer must be 'auto', 'device' or 'host'")
     if optimizer == "device" and model.family not in DEVICE_LBFGS_FAMILIES:
-        raise ValueError("the device L-BFGS covers the closed-form families only; use optimizer='host'")
+        raise ValueError("the device L-BFGS does not cover this family; use optimizer='host'")
     return optimizer == "device" or (optimizer == "auto" and model.family in DEVICE_LBFGS_FAMILIES)
 
 

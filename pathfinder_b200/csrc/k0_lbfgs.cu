@@ -63,8 +63,10 @@ pfb_k0_lbfgs(pf_lbfgs_model m, pf_lbfgs_opts o, const double* __restrict__ x0, d
     const size_t slab = (size_t)m.n * (size_t)o.max_points;
     pfb_lbfgs_dev_ctx c{m.n, scratch};
     int st = 0, nev = 0;
+    double* wsp = ws + (size_t)p * (2 * o.J + 2) * m.n;
+    m.zbuf = wsp + (size_t)(2 * o.J + 1) * m.n;
     const int np = pf_lbfgs_run(c, m, o, x0 + (size_t)p * m.n, X + (size_t)p * slab, G + (size_t)p * slab,
-                                FX + (size_t)p * o.max_points, ws + (size_t)p * (2 * o.J + 1) * m.n, &st, &nev);
+                                FX + (size_t)p * o.max_points, wsp, &st, &nev);
     if (threadIdx.x == 0) {
         npoints[p] = np;
         status[p] = st;
@@ -88,7 +90,7 @@ extern "C" cudaError_t pfb_launch_k0(cudaStream_t st, int family, int n, int P, 
                                      const double* x0, double* X, double* G, double* FX, double* ws,
                                      int64_t* npoints, int32_t* status, int32_t* nevals) {
     if (P <= 0) return cudaSuccess;
-    pf_lbfgs_model m{family, n, mp0, mp1, mc0};
+    pf_lbfgs_model m{family, n, mp0, mp1, mc0, nullptr};
     pf_lbfgs_opts o{J, maxiters, max_points, gtol, ftol};
     pfb_k0_lbfgs<<<P, PF_LBFGS_T, 0, st>>>(m, o, x0, X, G, FX, ws, npoints, status, nevals);
     return cudaGetLastError();

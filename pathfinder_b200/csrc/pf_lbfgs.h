@@ -37,6 +37,7 @@
 #define PF_LBFGS_ISONORMAL 0
 #define PF_LBFGS_FUNNEL 1
 #define PF_LBFGS_DIAGNORMAL 2
+#define PF_LBFGS_DENSENORMAL 3
 
 #define PF_LBFGS_CONVERGED_G 0   // max |grad| <= gtol
 #define PF_LBFGS_CONVERGED_F 1   // relative decrease <= ftol
@@ -47,9 +48,10 @@
 struct pf_lbfgs_model {
     int family;
     int n;
-    const double* p0;  // DIAGNORMAL: mean[n]
-    const double* p1;  // DIAGNORMAL: 1 / sd[n]
+    const double* p0;  // DIAGNORMAL / DENSENORMAL: mean[n]
+    const double* p1;  // DIAGNORMAL: 1 / sd[n];  DENSENORMAL: precision P[n x n], column-major (symmetric)
     double c0;         // DIAGNORMAL: -sum(log sd) - n/2 log(2 pi)
+    double* zbuf;      // DENSENORMAL: n doubles of per-path scratch (x - mean)
 };
 
 struct pf_lbfgs_opts {
@@ -75,6 +77,21 @@ PF_HD void pf_lbfgs_eval(Ctx& c, const pf_lbfgs_model& m, const double* x, doubl
         logp = (fma(t3, t3, (double)(n - 1) * x0) + e * ss) / -2.0;
         const double g0 = (((2.0 * x0) / 9.0 + (double)(n - 1)) - e * ss) / -2.0;
         c.each([&](int i) { glog[i] = (i == 0) ? g0 : -(e * x[i]); });
+    } else if (m.family == PF_LBFGS_DENSENORMAL) {
+        // docs/src/examples/quickstart.md:17-24: log p = -(x - m)' P (x - m) / 2, gradient -P (x - m).
+        // Row i of the product is one sequential fma chain over the columns (the order the oracle
+        // repeats); consecutive rows sit in consecutive threads, so every column step is coalesced.
+        double* z = m.zbuf;
+        c.each([&](int i) { z[i] = x[i] - m.p0[i]; });
+        c.sync();
+        c.each([&](int i) {
+            double acc = 0.0;
+            const double* Pi = m.p1 + i;
+            for (int j = 0; j < n; ++j) acc = fma(Pi[(size_t)j * n], z[j], acc);
+            glog[i] = -acc;
+        });
+        const double q = c.sum([&](int i, double a) { return fma(z[i], -glog[i], a); });
+        logp = q / -2.0;
     } else if (m.family == PF_LBFGS_DIAGNORMAL) {
         const double ss = c.sum([&](int i, double a) {
             const double z = (x[i] - m.p0[i]) * m.p1[i];
@@ -94,7 +111,7 @@ PF_HD void pf_lbfgs_eval(Ctx& c, const pf_lbfgs_model& m, const double* x, doubl
 }
 
 // Runs one path.  X, G: n x max_points column-major slabs (points, gradients of the LOG density),
-// FX[max_points] log densities; ws: (2 J + 1) n doubles.  Returns the number of points recorded
+// FX[max_points] log densities; ws: (2 J + 1) n doubles (m.zbuf: n more for the dense normal).  Returns the number of points recorded
 // (L + 1 >= 1); *status = PF_LBFGS_*, *nevals = density evaluations.
 template <class Ctx>
 PF_HD int pf_lbfgs_run(Ctx& c, const pf_lbfgs_model& m, const pf_lbfgs_opts& o, const double* x0, double* X,
