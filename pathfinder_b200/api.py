@@ -168,10 +168,7 @@ def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntr
             for p in todo:
                 tries[p] += 1
                 tr = optimize_with_trace(model, cur_init[p], history_length, maxiters)
-                if len(tr) == 0:  # non-finite at the initial point: an empty trace, L = 0
-                    x0 = np.asarray(cur_init[p], dtype=np.float64)[:, None]
-                    tr = OptimizationTrace(x0, np.array([np.nan]), np.zeros_like(x0))
-                traces.append(tr)
+                traces.append(tr)  # a non-finite start leaves a 1-point trace (L = 0): the path fails
                 seeds.append(_draw_seeds(path_rngs[p], len(tr) - 1))  # src/elbo.jl:2
             offsets, X, G = Engine.pack([(t.points, t.gradients) for t in traces])
             res = engine.elbo_batch(offsets, X, G, np.concatenate(seeds) if seeds else np.zeros(0, np.uint64),

@@ -34,17 +34,17 @@ def optimize_with_trace(model, x0, history_length=6, maxiters=1000, fail_on_nonf
     pts, lps, grads = [], [], []
 
     def record(x):
-        lp = model.logp(x)
-        g = model.grad(x)
-        # src/optimize.jl:103-105: NaN / +Inf objective or non-finite gradient ends the run
-        bad = np.isnan(lp) or lp == np.inf or not np.all(np.isfinite(g))
-        if bad and fail_on_nonfinite:
-            return False
+        with np.errstate(all="ignore"):
+            lp = model.logp(x)
+            g = model.grad(x)
+        # src/optimize.jl:94-105: the callback pushes the point FIRST, then a NaN / +Inf log density
+        # or a non-finite gradient ends the run — the offending point stays in the trace
         pts.append(np.array(x, copy=True)); lps.append(lp); grads.append(g)
-        return True
+        bad = np.isnan(lp) or lp == np.inf or not np.all(np.isfinite(g))
+        return not (bad and fail_on_nonfinite)
 
     if not record(x0):
-        return OptimizationTrace(np.zeros((x0.size, 0)), np.zeros(0), np.zeros((x0.size, 0)))
+        return OptimizationTrace(np.stack(pts, axis=1), np.array(lps), np.stack(grads, axis=1))
 
     def fun(x):
         with np.errstate(all="ignore"):

@@ -94,7 +94,9 @@ def test_optimize_with_trace_records_points_and_gradients():
         def logp(self, x):
             return float("nan")
 
-    assert len(pf.optimize_with_trace(Bad(3), np.ones(3))) == 0  # non-finite at the initial point
+    # non-finite at the initial point: the callback pushes the point, then stops (src/optimize.jl:94-105)
+    bad = pf.optimize_with_trace(Bad(3), np.ones(3))
+    assert len(bad) == 1 and np.isnan(bad.log_densities[0]) and np.array_equal(bad.points[:, 0], np.ones(3))
 
 
 def test_model_gradients_match_finite_differences():
