@@ -176,6 +176,12 @@ int pfb_batch_fit_only(pfb_handle h, const int64_t* best_iter);
 int pfb_draw_from_fits(pfb_handle h, int K_new, const uint64_t* seeds, double* draws, double* logp,
                        double* logq, int keep_as_pool);
 
+/* The ELBOEstimate payload of src/elbo.jl:22-29 on demand: draws[n x K x nunits], logp / logq
+ * [K x nunits] of arbitrary units (0-based unit indices, path-major / iteration-minor) of the
+ * current batch, regenerated from their seeds — bit-identical to what the ELBO stage evaluated.
+ * Any output pointer may be NULL. */
+int pfb_unit_draws(pfb_handle h, int nunits, const int32_t* units, double* draws, double* logp, double* logq);
+
 /* Paths [p0, p1) of the device pool (best-iteration draws [n x K x (p1-p0)], their logp / logq
  * [K x (p1-p0)]; K = ndraws_elbo, or K_new after pfb_draw_from_fits(keep_as_pool)): the lazy form of
  * pfb_elbo_out.draws — PathfinderResult.draws (src/singlepath.jl:231-232) fetched on first use.

@@ -31,8 +31,9 @@ DEFAULT_NDRAWS_ELBO = 5     # src/Pathfinder.jl:27
 
 @dataclass
 class ELBOEstimate:
-    """src/elbo.jl:22-29 (draws / per-draw densities are kept for the best iteration only;
-    the engine regenerates any other iteration's on demand from its seed)."""
+    """src/elbo.jl:22-29 (draws / per-draw densities are kept for the best iteration only; while the
+    batch is current, `Engine.unit_draws` regenerates any other iteration's bit for bit from its
+    seed — pfb_unit_draws)."""
 
     value: float
     std_err: float

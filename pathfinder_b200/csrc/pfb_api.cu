@@ -822,6 +822,45 @@ extern "C" int pfb_draw_from_fits(pfb_handle h, int K_new, const uint64_t* seeds
     return PFB_OK;
 }
 
+// Draws, log p and log q of arbitrary (path, iteration) units of the CURRENT batch, regenerated
+// from their seeds (counter-based RNG => identical to what the ELBO stage saw): the
+// ELBOEstimate.draws / .log_densities_* payload of src/elbo.jl:22-29 on demand, instead of keeping
+// n x K doubles for every iteration like the reference does.
+extern "C" int pfb_unit_draws(pfb_handle h, int nunits, const int32_t* units, double* draws, double* logp,
+                              double* logq) {
+    if (!h || (nunits > 0 && !units)) return PFB_ERR_ARG;
+    if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "no fitted batch (pfb_batch_run)");
+    if (nunits <= 0) return PFB_OK;
+    for (int i = 0; i < nunits; ++i)
+        if (units[i] < 0 || units[i] >= h->U) PFB_FAIL(h, PFB_ERR_ARG, "unit index out of range");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const size_t n = h->n, K = h->K, M = (size_t)nunits * K;
+    PFB_CUDA(h, h->dIota.ensure((size_t)std::max<int64_t>(h->U, nunits) * 4 + (size_t)nunits * 4));
+    // the unit list lives behind the iota area so that a running external-model batch is not disturbed
+    int32_t* d_units = h->dIota.as<int32_t>() + std::max<int64_t>(h->U, nunits);
+    PFB_CUDA(h, cudaMemcpyAsync(d_units, units, (size_t)nunits * 4, cudaMemcpyHostToDevice, st));
+    PFB_CUDA(h, h->dGenX.ensure(M * n * 8 + 8));
+    PFB_CUDA(h, h->dTmpLogr.ensure(M * 8 + 8));
+    PFB_CUDA(h, h->dTmpPool.ensure(M * 8 + 8));
+    double* X = h->dGenX.as<double>();
+    double* Lp = h->dTmpLogr.as<double>();
+    double* Lq = h->dTmpPool.as<double>();
+    PFB_CUDA(h, launch_k3(h, nunits, d_units, Lp, Lq, X));
+    if (h->model == PFB_MODEL_HOSTCALLBACK) {
+        int rc = host_logp_sync(h, X, (int64_t)M, Lp);
+        if (rc) return rc;
+    } else if (model_is_external(h)) {
+        int rc = generic_logp(h, X, (int64_t)M, d_units, Lp);
+        if (rc) return rc;
+    }
+    if (draws) PFB_CUDA(h, cudaMemcpyAsync(draws, X, M * n * 8, cudaMemcpyDeviceToHost, st));
+    if (logp) PFB_CUDA(h, cudaMemcpyAsync(logp, Lp, M * 8, cudaMemcpyDeviceToHost, st));
+    if (logq) PFB_CUDA(h, cudaMemcpyAsync(logq, Lq, M * 8, cudaMemcpyDeviceToHost, st));
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    return PFB_OK;
+}
+
 extern "C" int pfb_batch_sync(pfb_handle h) {
     if (!h) return PFB_ERR_ARG;
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));

@@ -349,6 +349,19 @@ class Engine:
             self._poolK = int(K_new)
         return draws, lp, lq
 
+    def unit_draws(self, units):
+        """(draws [n, K, m], logp [K, m], logq [K, m]) of the given 0-based units of the current batch,
+        regenerated on the device from their seeds: ELBOEstimate.draws etc. (src/elbo.jl:22-29) on
+        demand.  `ElboBatchResult.unit_slice(p).start + l - 1` is the unit of iteration l of path p."""
+        u = np.ascontiguousarray(units, dtype=np.int32)
+        m = u.size
+        draws = np.empty((self.n, self.K, m), order="F")
+        lp = np.empty((self.K, m), order="F")
+        lq = np.empty((self.K, m), order="F")
+        _lib.check(self.h, self.lib.pfb_unit_draws(self.h, m, _ptr(u), _ptr(draws), _ptr(lp), _ptr(lq)))
+        self._raise_cb_error()
+        return draws, lp, lq
+
     def timings(self):
         ms = np.zeros(6)
         nl = self.lib.pfb_get_timings(self.h, _ptr(ms))

@@ -851,3 +851,30 @@ def test_full_size_config3_properties():
     assert np.array_equal(r["draws"], pool[:, r["inds"] - 1])
     assert np.array_equal(r["ids"], -(-r["inds"] // K))
     lean.close(); mm.close()
+
+
+def test_unit_draws_on_demand_equal_the_elbo_stage_payload():
+    """pfb_unit_draws regenerates ELBOEstimate.draws / logp / logq (src/elbo.jl:22-29) of any
+    iteration: bit-identical to the materialise-all run, for a device family and a GEMM-shaped one."""
+    import pathfinder_b200 as pf
+    from tests.helpers import synthetic_trajectory
+
+    n, K = 18, 40
+    trajs = [synthetic_trajectory(n, L, 50 + L, scale=0.3) for L in (4, 6)]
+    seeds = np.concatenate(_seeds(trajs, 6))
+    offsets, X, G = pf.Engine.pack(trajs)
+    rng = np.random.default_rng(1)
+    Pm = np.linalg.inv(_rand_pd(rng, n))
+    for model in (pf.Funnel(n), pf.DenseNormal(rng.normal(size=n), 0.5 * (Pm + Pm.T))):
+        full = _engine(model, K, materialize_all=True, two_pass=True)
+        a = full.elbo_batch(offsets, X, G, seeds, per_draw=True, all_draws=True)
+        lean = _engine(model, K, two_pass=True)
+        b = lean.elbo_batch(offsets, X, G, seeds, per_draw=True)
+        units = [0, 3, 9, 5]
+        d, lp, lq = lean.unit_draws(units)
+        assert np.array_equal(d, a.all_draws[:, :, units])
+        assert np.array_equal(lq, a.logq[:, units]) and np.array_equal(lp, a.logp[:, units], equal_nan=True)
+        assert np.array_equal(lp, b.logp[:, units], equal_nan=True)
+        with pytest.raises(pf.PfbError):
+            lean.unit_draws([10])
+        full.close(); lean.close()
