@@ -878,3 +878,35 @@ def test_unit_draws_on_demand_equal_the_elbo_stage_payload():
         with pytest.raises(pf.PfbError):
             lean.unit_draws([10])
         full.close(); lean.close()
+
+
+def test_readme_usage_runs():
+    """The README's usage snippet at small sizes: device optimiser, resample with / without
+    replacement and from fresh draws, a host-closure model, engine-level reuse of pinned outputs."""
+    import pathfinder_b200 as pf
+
+    model = pf.Funnel(16)
+    res = pf.multipathfinder(model, 100, nruns=6, ndraws_elbo=50, init_scale=3.0, rng=np.random.default_rng(0),
+                             optimizer="device", maxiters=30)
+    assert res.draws.shape == (16, 100) and len(res.pathfinder_results) == 6
+    pr = res.pathfinder_results[0]
+    assert pr.draws.shape == (16, 50) and len(pr.elbo_estimates) == len(pr.optim_trace) - 1
+    again = pf.resample(res, 60, replace=False)
+    assert len(set(again.sample_inds)) == 60
+    fresh = pf.resample(res, 60, ndraws_per_run=200)
+    assert fresh.pathfinder_results[0].draws.shape == (16, 200)
+    host = pf.HostModel(10, logp_batch=lambda X: -0.5 * (X * X).sum(axis=0), grad=lambda x: -x)
+    r1 = pf.pathfinder(host, ndraws_elbo=100, ndraws=100, rng=np.random.default_rng(1))
+    assert r1.success and np.allclose(r1.fit_distribution.mu, 0.0, atol=1e-6)   # test/singlepath.jl:13-41
+    eng = pf.Engine.for_model(model, history_length=6, ndraws_elbo=50)
+    offsets, X, G = pf.Engine.pack([(p.optim_trace.points, p.optim_trace.gradients) for p in res.pathfinder_results])
+    seeds = np.arange(int(offsets[-1]) - 6, dtype=np.uint64)
+    out = eng.elbo_batch(offsets, X, G, seeds, draws=False, fit=True)
+    eng.pin(*pf.Engine.result_arrays(out))
+    e0 = out.elbo.copy()
+    out = eng.elbo_batch(offsets, X, G, seeds, draws=False, fit=True, into=out)
+    assert np.array_equal(out.elbo, e0, equal_nan=True)
+    d, lp, lq = eng.unit_draws([0, 5])
+    assert d.shape == (16, 50, 2)
+    eng.unpin(*pf.Engine.result_arrays(out))
+    eng.close()
