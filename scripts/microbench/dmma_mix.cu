@@ -36,6 +36,26 @@ __global__ void __launch_bounds__(1024) k_mix(double* out, int iters, double a, 
                 } else if (KIND == 2) {
                     if (j & 1) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(f0) : "d"(a), "d"(b));
                     else asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(f1) : "d"(a), "d"(b));
+                } else if (KIND == 4) {
+                    // philox round with separate mul.hi / mul.lo instead of mul.wide
+                    unsigned ph, pl, qh, ql;
+                    asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(ph) : "r"(x0), "r"(0xD2511F53u));
+                    asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(pl) : "r"(x0), "r"(0xD2511F53u));
+                    asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(qh) : "r"(x2), "r"(0xCD9E8D57u));
+                    asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(ql) : "r"(x2), "r"(0xCD9E8D57u));
+                    unsigned n0, n2;
+                    asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(n0) : "r"(qh), "r"(x1), "r"(k));
+                    asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(n2) : "r"(ph), "r"(x3), "r"(k));
+                    x0 = n0; x1 = ql; x2 = n2; x3 = pl;
+                } else if (KIND == 5) {
+                    // 16-bit split multiplies on the full-rate 32-bit IMAD path (x * M = (xh * M) << 16 + xl * M needs carries: cost model only)
+                    unsigned a0 = x0 & 0xFFFFu, a1 = x0 >> 16, b0 = x2 & 0xFFFFu, b1 = x2 >> 16;
+                    unsigned p0, p1, q0, q1;
+                    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(p0) : "r"(a0), "r"(0x1F53u), "r"(x1));
+                    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(p1) : "r"(a1), "r"(0xD251u), "r"(p0));
+                    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(q0) : "r"(b0), "r"(0x8D57u), "r"(x3));
+                    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(q1) : "r"(b1), "r"(0xCD9Eu), "r"(q0));
+                    x0 = q1 ^ k; x1 = p0; x2 = p1 ^ k; x3 = q0;
                 } else {
                     unsigned long long p, q;
                     asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(x0), "r"(0xD2511F53u));
@@ -96,6 +116,12 @@ int main() {
     run<8, 2, 3>("DMMA + 2 philox rounds each", d, sms);
     run<8, 4, 3>("DMMA + 4 philox rounds each", d, sms);
     run<8, 5, 3>("DMMA + 5 philox rounds each", d, sms);
+    run<8, 2, 4>("DMMA + 2 philox(hi/lo) rounds each", d, sms);
+    run<8, 5, 4>("DMMA + 5 philox(hi/lo) rounds each", d, sms);
+    run<1, 20, 4>("1 DMMA + 20 philox(hi/lo) rounds", d, sms);
+    run<8, 2, 5>("DMMA + 2x4 mad.lo.u32 each", d, sms);
+    run<8, 5, 5>("DMMA + 5x4 mad.lo.u32 each", d, sms);
+    run<1, 20, 5>("1 DMMA + 20x4 mad.lo.u32", d, sms);
     run<1, 20, 3>("1 DMMA + 20 philox rounds", d, sms);
     run<1, 40, 0>("1 DMMA + 40 LOP3", d, sms);
     run<1, 40, 1>("1 DMMA + 40 IMAD.WIDE", d, sms);
