@@ -65,18 +65,34 @@ def make_model(kind, n):
 
 
 def build_workload(name, rank, world):
+    """Trajectories of this rank's paths.  N > 1: every rank optimises all world x P paths (seeded,
+    identical everywhere, untimed set-up) and takes its share of an LPT assignment on the iteration
+    counts (work is proportional to L_p), P paths per rank."""
     import pathfinder_b200 as pf
 
     kind, n, P, K, J, scale, ndraws = CONFIGS[name]
     model, model_flops = make_model(kind, n)
-    trajs, seeds = [], []
-    for p in range(P):
-        gp = rank * P + p
+
+    def one(gp):
         rng = np.random.default_rng(MASTER_SEED + gp)
         x0 = (rng.random(n) * 2.0 - 1.0) * scale
         tr = pf.optimize_with_trace(model, x0, J, 1000)
-        trajs.append((tr.points, tr.gradients))
-        seeds.append(rng.integers(0, 2**64, size=len(tr) - 1, dtype=np.uint64))
+        return (tr.points, tr.gradients), rng.integers(0, 2**64, size=len(tr) - 1, dtype=np.uint64)
+
+    if world == 1:
+        mine = list(range(P))
+        paths = {gp: one(gp) for gp in mine}
+    else:
+        paths = {gp: one(gp) for gp in range(world * P)}
+        L = np.array([paths[gp][0][0].shape[1] - 1 for gp in range(world * P)])
+        loads, owned = np.zeros(world), [[] for _ in range(world)]
+        for gp in np.argsort(-L, kind="stable"):
+            r = min((q for q in range(world) if len(owned[q]) < P), key=lambda q: (loads[q], q))
+            loads[r] += L[gp]
+            owned[r].append(int(gp))
+        mine = sorted(owned[rank])
+    trajs = [paths[gp][0] for gp in mine]
+    seeds = [paths[gp][1] for gp in mine]
     return model, trajs, seeds, (n, P, K, J, ndraws, model_flops)
 
 
@@ -441,7 +457,7 @@ def main():
         "config": {"workload": name, "n": n, "paths_per_gpu": P, "K": K, "history": J, "ndraws": ndraws,
                    "units_per_gpu_rank0": U, "mode": "F (lean: per-draw logp/logq only; best-iteration draws "
                    "re-materialised by K5)", "l2": "per-step working set (factor records %.0f MB) exceeds the "
-                   "126 MB L2" % (U * n * (KP + 2) * 8 / 1e6), "parallelism": f"paths sharded over {world} GPU(s)"},
+                   "126 MB L2" % (U * n * (KP + 2) * 8 / 1e6), "parallelism": f"paths sharded over {world} GPU(s)" + (", LPT-balanced on iteration counts" if world > 1 else "")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         # K1..K5 as counted by the engine + the PSIS stage's own kernels (K6a..K6g, K7; CUB's sort
         # launches inside K6 are library kernels and not counted)
