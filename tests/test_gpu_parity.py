@@ -910,3 +910,17 @@ def test_readme_usage_runs():
     assert d.shape == (16, 50, 2)
     eng.unpin(*pf.Engine.result_arrays(out))
     eng.close()
+
+
+def test_large_n_global_panel_and_ring_mode():
+    """n = 2304 (and the odd 2051): K2's panel no longer fits shared memory (global-memory FR rows,
+    256-thread CTAs), K1 runs its tall variant, K3 streams the record through the TMA ring — all three
+    against the oracle, in both the materialise-all two-pass mode and the lean single-pass mode."""
+    import pathfinder_b200 as pf
+    from tests.helpers import synthetic_trajectory
+
+    for n in (2304, 2051):
+        model = pf.IsoNormal(n)
+        trajs = [synthetic_trajectory(n, L, 5 + L, scale=0.2) for L in (2, 7)]
+        _compare_batch(model, trajs, K=40, J=6)
+        _lean_vs_oracle(model, trajs, K=40, J=6)
