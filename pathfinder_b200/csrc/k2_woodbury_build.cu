@@ -394,7 +394,7 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
             constexpr int RS2 = (KP == 12) ? 16 : 32;
             double* r2 = FR2 + ((int64_t)u * pfb_npad8(n) + i) * RS2;
             const int sw = pfb_swz(i);
-            const double pi_ = d * alpha[i], ri_ = d * sa * e;
+            const double pi_ = d * alpha[i], ri_ = 2.0 * (d * sa * e);  // slot KP + 3 holds 2 r (K3 single pass)
 #pragma unroll
             for (int c = 0; c < RS2; ++c) {
                 double v = (c < KP) ? PNL(i, c)

@@ -308,11 +308,11 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
         pfb_model_acc<MODEL> macc[DS];
         double wacc[DS][NT0][2];  // pass 0 accumulators: column cc = 8h + 2t + {0,1} of draw g
         double ncf[DS][NS1];      // pass 1 A fragments: -c[draw g][j = 4s + t]
-        double qsum[DS], s1sum[DS], u0[DS];  // QUAD: sum p u~^2, sum r u~, u~_0 (lane t = 0)
+        double qsum[DS], u0[DS];  // QUAD: sum u~ (p u~ + 2 r) = sum p u~^2 + 2 sum r u~;  u~_0 (lane t = 0)
 #pragma unroll
         for (int d = 0; d < DS; ++d) {
             unormsq[d] = 0.0;
-            qsum[d] = s1sum[d] = u0[d] = 0.0;
+            qsum[d] = u0[d] = 0.0;
             macc[d].init();
 #pragma unroll
             for (int h = 0; h < NT0; ++h) wacc[d][h][0] = wacc[d][h][1] = 0.0;
@@ -474,10 +474,9 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 if (QUAD) {
-                                    const double zz = z[d][e] * z[d][e];
-                                    if (!headrow) unormsq[d] += zz;
-                                    qsum[d] = fma(pr[e].x, zz, qsum[d]);
-                                    s1sum[d] = fma(pr[e].y, z[d][e], s1sum[d]);
+                                    // record slot KP + 3 holds 2 r: one fused chain per statistic
+                                    if (!headrow) unormsq[d] = fma(z[d][e], z[d][e], unormsq[d]);
+                                    qsum[d] = fma(fma(pr[e].x, z[d][e], pr[e].y), z[d][e], qsum[d]);
                                 } else if (!headrow) {
                                     unormsq[d] = fma(z[d][e], z[d][e], unormsq[d]);
                                 }
@@ -648,8 +647,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                                                 if (d == dsi) {
                                                     unormsq[d] = fma(zz, zz, unormsq[d]);
                                                     if (QUAD) {
-                                                        qsum[d] = fma(pz, zz, qsum[d]);
-                                                        s1sum[d] = fma(rr[(KP + 3) ^ swz], zz, s1sum[d]);
+                                                        qsum[d] = fma(pz + rr[(KP + 3) ^ swz], zz, qsum[d]);
                                                     }
                                                 }
                                         }
@@ -750,7 +748,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                         part = fma(cf[d][s1], mc - 2.0 * (cv[KP + a] + sRv[a]), part);
                         v0c = fma(fr[a], cf[d][s1], v0c);  // Vh[0][a] c_a (row 0: swizzle 0)
                     }
-                    part += qsum[d] + 2.0 * s1sum[d];
+                    part += qsum[d];
                     part += __shfl_xor_sync(0xffffffffu, part, 1);
                     part += __shfl_xor_sync(0xffffffffu, part, 2);
                     v0c += __shfl_xor_sync(0xffffffffu, v0c, 1);

@@ -26,7 +26,7 @@ __host__ __device__ inline int pfb_kp_of(int J) { return J <= 6 ? 12 : (J <= 10 
 __host__ __device__ inline int pfb_rs_of(int KP) { return KP + 2; }
 __host__ __device__ inline int pfb_hs_of(int KP) { return 3 * KP * KP + KP + 8; }
 // K3's tensor-core record layout (FR2): per unit pfb_npad8(n) rows of RS2 doubles
-//   { Vh[i][0..KP), sqrt(alpha_i), mu_i, p_i, r_i, 0... } (p, r: see PFB_HDR_M), rows >= n all zero, and inside a row the
+//   { Vh[i][0..KP), sqrt(alpha_i), mu_i, p_i, 2 r_i, 0... } (p, r: see PFB_HDR_M), rows >= n all zero, and inside a row the
 //   4-double groups XOR-swizzled: logical column c lives at c ^ pfb_swz(i).  pfb_swz takes 4
 //   distinct values both over rows {4q..4q+3} and over rows {r, r+2, r+4, r+6}, which makes the
 //   two DMMA fragment access patterns of K3 shared-memory bank-conflict free.
@@ -41,7 +41,7 @@ __host__ __device__ inline int pfb_swz(int row) {
 // statistics of the diagonal-quadratic target family for K3's single-pass mode (written by K2):
 //   logp(x) = g(S, x_0),  S = sum_i d_i (x_i - m_i)^2  (iso-normal: d = 1, m = 0; funnel: d_0 = 0,
 //   d_i = 1, m = 0; independent normals: d_i = 1 / sd_i^2, m_i = mean_i).  With x = a (u~ - Vh c) + mu,
-//   p_i = d_i alpha_i and r_i = d_i a_i (mu_i - m_i) (record slots KP+2, KP+3):
+//   p_i = d_i alpha_i and r_i = d_i a_i (mu_i - m_i) (record slots KP+2 and KP+3, the latter as 2 r_i):
 //   S = sum p u~^2 - 2 c'(Vh' (p u~)) + c' M c + 2 sum r u~ - 2 c' rv + e0,
 //   M = Vh' diag(p) Vh,  rv = Vh' r,  e0 = sum d (mu - m)^2.
 #define PFB_HDR_E0(KP) (2 * (KP) * (KP) + 3)
