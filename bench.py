@@ -473,7 +473,7 @@ def main():
     # goes up and only the result struct comes back.  maxiters = 64 keeps the unit count close to the
     # host-trajectory workload above (SURVEY §8d "fixed-L stress input").
     mpf = None
-    if rank == 0 and world == 1 and model.family in (0, 1, 2):
+    if rank == 0 and world == 1 and model.family in (0, 1, 2, 3, 4):
         MAXIT = 64
         engw = pf.Engine(n, model.family, model.blob, J, K, local_rank)
         walls, units_w = [], 0
@@ -541,7 +541,8 @@ def main():
             t0 = time.perf_counter()
             for p in range(min(P, 8)):
                 x0 = (np.random.default_rng(MASTER_SEED + 1000 + p).random(n) * 2 - 1) * CONFIGS[name][5]
-                kw = dict(mean=model.mean, sd=model.sd) if model.family == 2 else {}
+                kw = {2: lambda: dict(mean=model.mean, sd=model.sd), 3: lambda: dict(mean=model.mean, prec=model.prec),
+                      4: lambda: dict(Xobs=model.X, yobs=model.y)}.get(model.family, dict)()
                 OL.lbfgs_path(model.family, x0, J, 64, **kw)
             cpu_lbfgs_s = (time.perf_counter() - t0) * P / max(1, min(P, 8))
             cpu_s = cpu_lbfgs_s + mpf["units"] * K / (done / secs)

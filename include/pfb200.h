@@ -135,8 +135,7 @@ int pfb_batch_run(pfb_handle h);  /* K1..K5, asynchronous on the engine stream *
 int pfb_batch_sync(pfb_handle h);
 int pfb_batch_download(pfb_handle h, pfb_elbo_out* out);
 
-/* Row f1 — batched device L-BFGS for the iso-normal, funnel, independent-normal and dense-normal
- * families.  Replaces the per-path trajectory producer
+/* Row f1 — batched device L-BFGS for every registered device-side family.  Replaces the per-path trajectory producer
  *   optimize_with_trace(prob, optimizer; maxiters)                src/optimize.jl:35-59
  *   (default_optimizer = Optim.LBFGS(m = history_length, ...),    src/Pathfinder.jl:29-35)
  * mapped over the runs by _chunk_tmap (src/multipath.jl:190-208): one CTA per path runs the whole
@@ -145,7 +144,7 @@ int pfb_batch_download(pfb_handle h, pfb_elbo_out* out);
  * device.  x0[n x P]: initial points.  npoints[P] = L_p + 1 trace points; status[P] = PF_LBFGS_*
  * (0 gradient tolerance, 1 objective tolerance, 2 maxiters, 3 line search failed, 4 non-finite:
  * the point is recorded and the run stops, src/optimize.jl:103-105); nevals[P] density evaluations
- * (may be NULL).  PFB_ERR_UNSUPPORTED for the other families (hierarchical logistic, host callback: optimise on the host). */
+ * (may be NULL).  PFB_ERR_UNSUPPORTED for a host-callback target (optimise it on the host). */
 typedef struct {
     int32_t maxiters;   /* 1000, src/optimize.jl:40                                       */
     int32_t max_points; /* capacity of the per-path trace on the device (<= maxiters + 1) */

@@ -19,7 +19,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _lib = None
 
-FAMILY_ISONORMAL, FAMILY_FUNNEL, FAMILY_DIAGNORMAL, FAMILY_DENSENORMAL = 0, 1, 2, 3
+FAMILY_ISONORMAL, FAMILY_FUNNEL, FAMILY_DIAGNORMAL, FAMILY_DENSENORMAL, FAMILY_HLOGISTIC = 0, 1, 2, 3, 4
 STATUS = {0: "gtol", 1: "ftol", 2: "maxiters", 3: "linesearch", 4: "nonfinite"}
 
 
@@ -31,7 +31,8 @@ def clib():
             subprocess.check_call(["make", "-C", _HERE, "-s"])
         lib = ctypes.CDLL(path)
         lib.pfo_lbfgs_path.restype = ctypes.c_int
-        lib.pfo_lbfgs_path.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
+        lib.pfo_lbfgs_path.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_double,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p]
@@ -39,8 +40,14 @@ def clib():
     return _lib
 
 
+def hlogistic_c0(n):
+    """Constant of the hierarchical-logistic prior: -(n / 2) log(2 pi) - log(2.5), as pfb_register_model
+    forms it."""
+    return -0.5 * n * 1.8378770664093453 - float(np.log(2.5))
+
+
 def lbfgs_path(family, x0, history_length=6, maxiters=1000, max_points=None, gtol=1e-8, ftol=1e-14,
-               mean=None, sd=None, prec=None):
+               mean=None, sd=None, prec=None, Xobs=None, yobs=None):
     """One trajectory: returns (points [n, L+1], log_densities [L+1], gradients [n, L+1], status, nevals)."""
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
     n = x0.size
@@ -62,7 +69,13 @@ def lbfgs_path(family, x0, history_length=6, maxiters=1000, max_points=None, gto
     if family == FAMILY_DENSENORMAL:
         mp0 = np.ascontiguousarray(mean, dtype=np.float64)
         mp1 = np.asfortranarray(prec, dtype=np.float64)
-    np_ = clib().pfo_lbfgs_path(int(family), n, None if mp0 is None else mp0.ctypes.data,
+    nobs = 0
+    if family == FAMILY_HLOGISTIC:
+        mp0 = np.asfortranarray(Xobs, dtype=np.float64)
+        mp1 = np.ascontiguousarray(yobs, dtype=np.float64)
+        nobs = mp0.shape[0]
+        c0 = hlogistic_c0(n)
+    np_ = clib().pfo_lbfgs_path(int(family), n, int(nobs), None if mp0 is None else mp0.ctypes.data,
                                 None if mp1 is None else mp1.ctypes.data, float(c0), int(history_length),
                                 int(maxiters), int(max_points), float(gtol), float(ftol), x0.ctypes.data,
                                 X.ctypes.data, G.ctypes.data, FX.ctypes.data, ctypes.byref(st), ctypes.byref(nev))

@@ -43,11 +43,19 @@ struct HostCtx {
         for (int i = 0; i < n; ++i) f(i);
     }
     template <class F>
+    void each_n(int count, F f) {
+        for (int i = 0; i < count; ++i) f(i);
+    }
+    template <class F>
     double sum(F f) {
+        return sum_n(n, f);
+    }
+    template <class F>
+    double sum_n(int count, F f) {
         double part[PF_LBFGS_T];
         for (int t = 0; t < PF_LBFGS_T; ++t) {
             double acc = 0.0;
-            for (int i = t; i < n; i += PF_LBFGS_T) acc = f(i, acc);
+            for (int i = t; i < count; i += PF_LBFGS_T) acc = f(i, acc);
             part[t] = acc;
         }
         return block_tree(part);
@@ -76,12 +84,12 @@ struct HostCtx {
 }  // namespace
 
 // One path.  X, G: n x max_points column-major, FX[max_points].  mp0 / mp1: DIAGNORMAL mean and
-// 1 / sd; DENSENORMAL mean and precision (n x n column-major).  Returns the number of recorded points.
-extern "C" int pfo_lbfgs_path(int family, int n, const double* mp0, const double* mp1, double mc0, int J,
+// 1 / sd; DENSENORMAL mean and precision (n x n column-major); HLOGISTIC X (nobs x (n-2)) and y.  Returns the number of recorded points.
+extern "C" int pfo_lbfgs_path(int family, int n, int nobs, const double* mp0, const double* mp1, double mc0, int J,
                               int maxiters, int max_points, double gtol, double ftol, const double* x0, double* X,
                               double* G, double* FX, int* status, int* nevals) {
-    std::vector<double> ws((size_t)(2 * J + 2) * n);
-    pf_lbfgs_model m{family, n, mp0, mp1, mc0, ws.data() + (size_t)(2 * J + 1) * n};
+    std::vector<double> ws((size_t)(2 * J + 1) * n + (size_t)(nobs > n ? nobs : n));
+    pf_lbfgs_model m{family, n, mp0, mp1, mc0, ws.data() + (size_t)(2 * J + 1) * n, nobs};
     pf_lbfgs_opts o{J, maxiters, max_points, gtol, ftol};
     HostCtx c{n};
     return pf_lbfgs_run(c, m, o, x0, X, G, FX, ws.data(), status, nevals);

@@ -127,7 +127,7 @@ def _draw_seeds(rng, m):
     return rng.integers(0, 2**64, size=m, dtype=np.uint64)
 
 
-DEVICE_LBFGS_FAMILIES = (0, 1, 2, 3)  # iso-normal, funnel, independent normals, dense normal (include/pfb200.h)
+DEVICE_LBFGS_FAMILIES = (0, 1, 2, 3, 4)  # every registered device-side family (include/pfb200.h)
 
 
 def _use_device_optimizer(model, optimizer):

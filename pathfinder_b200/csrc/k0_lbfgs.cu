@@ -22,9 +22,17 @@ struct pfb_lbfgs_dev_ctx {
         for (int i = threadIdx.x; i < n; i += PF_LBFGS_T) f(i);
     }
     template <class F>
+    __device__ __forceinline__ void each_n(int count, F f) {
+        for (int i = threadIdx.x; i < count; i += PF_LBFGS_T) f(i);
+    }
+    template <class F>
     __device__ __forceinline__ double sum(F f) {
+        return sum_n(n, f);
+    }
+    template <class F>
+    __device__ __forceinline__ double sum_n(int count, F f) {
         double acc = 0.0;
-        for (int i = threadIdx.x; i < n; i += PF_LBFGS_T) acc = f(i, acc);
+        for (int i = threadIdx.x; i < count; i += PF_LBFGS_T) acc = f(i, acc);
         double v[1] = {acc};
         pfb_block_sum<1>(v, scratch);
         return v[0];
@@ -63,7 +71,8 @@ pfb_k0_lbfgs(pf_lbfgs_model m, pf_lbfgs_opts o, const double* __restrict__ x0, d
     const size_t slab = (size_t)m.n * (size_t)o.max_points;
     pfb_lbfgs_dev_ctx c{m.n, scratch};
     int st = 0, nev = 0;
-    double* wsp = ws + (size_t)p * (2 * o.J + 2) * m.n;
+    const size_t zlen = (size_t)(m.nobs > m.n ? m.nobs : m.n);
+    double* wsp = ws + (size_t)p * ((size_t)(2 * o.J + 1) * m.n + zlen);
     m.zbuf = wsp + (size_t)(2 * o.J + 1) * m.n;
     const int np = pf_lbfgs_run(c, m, o, x0 + (size_t)p * m.n, X + (size_t)p * slab, G + (size_t)p * slab,
                                 FX + (size_t)p * o.max_points, wsp, &st, &nev);
@@ -85,12 +94,12 @@ __global__ void pfb_k0_pack(int n, const int64_t* __restrict__ src, const double
     }
 }
 
-extern "C" cudaError_t pfb_launch_k0(cudaStream_t st, int family, int n, int P, const double* mp0, const double* mp1,
-                                     double mc0, int J, int maxiters, int max_points, double gtol, double ftol,
+extern "C" cudaError_t pfb_launch_k0(cudaStream_t st, int family, int n, int nobs, int P, const double* mp0,
+                                     const double* mp1, double mc0, int J, int maxiters, int max_points, double gtol, double ftol,
                                      const double* x0, double* X, double* G, double* FX, double* ws,
                                      int64_t* npoints, int32_t* status, int32_t* nevals) {
     if (P <= 0) return cudaSuccess;
-    pf_lbfgs_model m{family, n, mp0, mp1, mc0, nullptr};
+    pf_lbfgs_model m{family, n, mp0, mp1, mc0, nullptr, nobs};
     pf_lbfgs_opts o{J, maxiters, max_points, gtol, ftol};
     pfb_k0_lbfgs<<<P, PF_LBFGS_T, 0, st>>>(m, o, x0, X, G, FX, ws, npoints, status, nevals);
     return cudaGetLastError();

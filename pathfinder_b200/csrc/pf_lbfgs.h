@@ -23,6 +23,7 @@
 //   template <class F> double sum(F f)      acc = f(i, acc), acc starts at 0; block-wide total
 //   template <class F> void   sum2(F f, double& a, double& b)   f(i, a, b) updates both partials
 //   template <class F> double maxv(F f)     max of f(i) >= 0 (0 when empty)
+//   each_n(count, f) / sum_n(count, f)      the same over an index range other than the dimension
 //   void sync()                             make element writes visible to every caller
 // Build contract: -fmad=false / -ffp-contract=off (pf_math.h).
 #pragma once
@@ -38,6 +39,7 @@
 #define PF_LBFGS_FUNNEL 1
 #define PF_LBFGS_DIAGNORMAL 2
 #define PF_LBFGS_DENSENORMAL 3
+#define PF_LBFGS_HLOGISTIC 4
 
 #define PF_LBFGS_CONVERGED_G 0   // max |grad| <= gtol
 #define PF_LBFGS_CONVERGED_F 1   // relative decrease <= ftol
@@ -50,8 +52,9 @@ struct pf_lbfgs_model {
     int n;
     const double* p0;  // DIAGNORMAL / DENSENORMAL: mean[n]
     const double* p1;  // DIAGNORMAL: 1 / sd[n];  DENSENORMAL: precision P[n x n], column-major (symmetric)
-    double c0;         // DIAGNORMAL: -sum(log sd) - n/2 log(2 pi)
-    double* zbuf;      // DENSENORMAL: n doubles of per-path scratch (x - mean)
+    double c0;         // DIAGNORMAL: -sum(log sd) - n/2 log(2 pi);  HLOGISTIC: the prior's constant
+    double* zbuf;      // DENSENORMAL: n doubles of per-path scratch (x - mean);  HLOGISTIC: nobs doubles
+    int nobs;          // HLOGISTIC: observations; p0 = X[nobs x (n-2)] column-major, p1 = y[nobs]
 };
 
 struct pf_lbfgs_opts {
@@ -92,6 +95,54 @@ PF_HD void pf_lbfgs_eval(Ctx& c, const pf_lbfgs_model& m, const double* x, doubl
         });
         const double q = c.sum([&](int i, double a) { return fma(z[i], -glog[i], a); });
         logp = q / -2.0;
+    } else if (m.family == PF_LBFGS_HLOGISTIC) {
+        // theta = (log tau, b0, b_1..b_p); log tau ~ N(0,1), b0 ~ N(0, 2.5^2),
+        // b_j ~ N(0, tau^2), y_i ~ Bernoulli(sigmoid(b0 + x_i'b)).  eta: one sequential fma chain per
+        // observation (coalesced column sweep); X'r: one sequential chain per coefficient.
+        const int p = n - 2, nobs = m.nobs;
+        const double lt = x[0], b0 = x[1];
+        const double* Xm = m.p0;
+        const double* yv = m.p1;
+        double* r = m.zbuf;
+        c.each_n(nobs, [&](int i) {
+            double eta = b0;
+            for (int j = 0; j < p; ++j) eta = fma(Xm[(size_t)j * nobs + i], x[2 + j], eta);
+            r[i] = eta;
+        });
+        // log-likelihood sum_i y eta - log(1 + exp(eta)), evaluated without overflow
+        const double ll = c.sum_n(nobs, [&](int i, double a) {
+            const double eta = r[i];
+            const double l1pe = (eta > 0.0) ? eta + pf_log1p(pf_exp(-eta)) : pf_log1p(pf_exp(eta));
+            return a + (yv[i] * eta - l1pe);
+        });
+        c.sync();
+        c.each_n(nobs, [&](int i) {
+            const double eta = r[i];
+            double sg;
+            if (eta >= 0.0) {
+                sg = 1.0 / (1.0 + pf_exp(-eta));
+            } else {
+                const double e = pf_exp(eta);
+                sg = e / (1.0 + e);
+            }
+            r[i] = yv[i] - sg;
+        });
+        const double rsum = c.sum_n(nobs, [&](int i, double a) { return a + r[i]; });
+        const double bb = c.sum([&](int i, double a) { return i >= 2 ? fma(x[i], x[i], a) : a; });
+        const double e2 = pf_exp(-2.0 * lt);
+        logp = ((((-0.5 * lt) * lt - 0.5 * ((b0 / 2.5) * (b0 / 2.5))) - (0.5 * bb) * e2) - (double)p * lt) + m.c0 + ll;
+        c.each([&](int i) {
+            if (i == 0) {
+                glog[i] = (bb * e2 - lt) - (double)p;
+            } else if (i == 1) {
+                glog[i] = rsum - b0 / 6.25;
+            } else {
+                const double* col = Xm + (size_t)(i - 2) * nobs;
+                double acc = 0.0;
+                for (int k = 0; k < nobs; ++k) acc = fma(col[k], r[k], acc);
+                glog[i] = acc - x[i] * e2;
+            }
+        });
     } else if (m.family == PF_LBFGS_DIAGNORMAL) {
         const double ss = c.sum([&](int i, double a) {
             const double z = (x[i] - m.p0[i]) * m.p1[i];

@@ -34,7 +34,7 @@ cudaError_t pfb_launch_k8_dense(cudaStream_t, int, int64_t, int, const int32_t*,
                                 const double*, double, double*);
 cudaError_t pfb_launch_k8_logistic(cudaStream_t, int, int, int64_t, int, const int32_t*, const double*,
                                    const double*, const double*, double*);
-cudaError_t pfb_launch_k0(cudaStream_t, int, int, int, const double*, const double*, double, int, int, int, double,
+cudaError_t pfb_launch_k0(cudaStream_t, int, int, int, int, const double*, const double*, double, int, int, int, double,
                           double, const double*, double*, double*, double*, double*, int64_t*, int32_t*, int32_t*);
 cudaError_t pfb_launch_k0_pack(cudaStream_t, int, int64_t, const int64_t*, const double*, const double*, double*,
                                double*);
@@ -375,7 +375,7 @@ extern "C" int pfb_batch_upload(pfb_handle h, int n, int P, const int64_t* offse
 // ---- K0: batched device L-BFGS ---------------------------------------------
 static bool model_has_device_lbfgs(const pfb_engine* h) {
     return h->model == PFB_MODEL_ISONORMAL || h->model == PFB_MODEL_FUNNEL || h->model == PFB_MODEL_DIAGNORMAL ||
-           h->model == PFB_MODEL_DENSENORMAL;
+           h->model == PFB_MODEL_DENSENORMAL || h->model == PFB_MODEL_HLOGISTIC;
 }
 
 extern "C" int pfb_lbfgs_batch(pfb_handle h, int n, int P, const double* x0, const pfb_lbfgs_opts* o,
@@ -385,8 +385,8 @@ extern "C" int pfb_lbfgs_batch(pfb_handle h, int n, int P, const double* x0, con
     if (h->model < 0) PFB_FAIL(h, PFB_ERR_STATE, "no model registered");
     if (h->model_n != n) PFB_FAIL(h, PFB_ERR_SHAPE, "dimension differs from the registered model's");
     if (!model_has_device_lbfgs(h))
-        PFB_FAIL(h, PFB_ERR_UNSUPPORTED, "device L-BFGS covers the iso-normal, funnel, independent-normal and dense-"
-                                         "normal families; optimise this family on the host");
+        PFB_FAIL(h, PFB_ERR_UNSUPPORTED, "device L-BFGS covers the registered device-side families; a host-callback "
+                                         "target is optimised on the host");
     if (o->maxiters < 0 || o->max_points < 1) PFB_FAIL(h, PFB_ERR_ARG, "maxiters >= 0 and max_points >= 1 required");
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = h->stream;
@@ -398,7 +398,8 @@ extern "C" int pfb_lbfgs_batch(pfb_handle h, int n, int P, const double* x0, con
     PFB_CUDA(h, h->dLbX.ensure(slab * 8 + 8));
     PFB_CUDA(h, h->dLbG.ensure(slab * 8 + 8));
     PFB_CUDA(h, h->dLbFX.ensure((size_t)maxpts * P * 8 + 8));
-    PFB_CUDA(h, h->dLbWs.ensure((size_t)(2 * J + 2) * n * P * 8 + 8));
+    const size_t zlen = (size_t)std::max(n, h->model == PFB_MODEL_HLOGISTIC ? h->model_nobs : 0);
+    PFB_CUDA(h, h->dLbWs.ensure(((size_t)(2 * J + 1) * n + zlen) * P * 8 + 8));
     PFB_CUDA(h, h->dLbNp.ensure((size_t)P * 8 + 8));
     PFB_CUDA(h, h->dLbSt.ensure((size_t)P * 4 + 8));
     PFB_CUDA(h, h->dLbNev.ensure((size_t)P * 4 + 8));
@@ -410,11 +411,16 @@ extern "C" int pfb_lbfgs_batch(pfb_handle h, int n, int P, const double* x0, con
     }
     PFB_CUDA(h, cudaMemcpyAsync(h->dLbX0.p, x0, (size_t)n * P * 8, cudaMemcpyHostToDevice, st));
     // DIAGNORMAL blob on the device: { mean[n], 1/sd[n] };  DENSENORMAL: { m[n], P m[n], P[n x n] }
-    const double* mp0 = (h->model == PFB_MODEL_DIAGNORMAL || h->model == PFB_MODEL_DENSENORMAL)
-                            ? h->dModel.as<double>() : nullptr;
-    const double* mp1 = !mp0 ? nullptr : (h->model == PFB_MODEL_DENSENORMAL ? mp0 + 2 * (size_t)n : mp0 + n);
+    //   HLOGISTIC: { X[nobs x (n-2)], y[nobs] }
+    const double* mp0 = (h->model == PFB_MODEL_DIAGNORMAL || h->model == PFB_MODEL_DENSENORMAL ||
+                         h->model == PFB_MODEL_HLOGISTIC) ? h->dModel.as<double>() : nullptr;
+    const double* mp1 = !mp0 ? nullptr
+                        : (h->model == PFB_MODEL_DENSENORMAL ? mp0 + 2 * (size_t)n
+                           : (h->model == PFB_MODEL_HLOGISTIC ? mp0 + (size_t)h->model_nobs * (n - 2) : mp0 + n));
+    const int nobs = h->model == PFB_MODEL_HLOGISTIC ? h->model_nobs : 0;
+    const double mc0 = h->model == PFB_MODEL_HLOGISTIC ? (-0.5 * n * PFB_LOG2PI - log(2.5)) : h->model_c0;
     PFB_CUDA(h, cudaEventRecord(h->lb_ev[0], st));
-    PFB_CUDA(h, pfb_launch_k0(st, h->model, n, P, mp0, mp1, h->model_c0, J, o->maxiters, maxpts,
+    PFB_CUDA(h, pfb_launch_k0(st, h->model, n, nobs, P, mp0, mp1, mc0, J, o->maxiters, maxpts,
                               o->gtol, o->ftol, h->dLbX0.as<double>(), h->dLbX.as<double>(), h->dLbG.as<double>(),
                               h->dLbFX.as<double>(), h->dLbWs.as<double>(), h->dLbNp.as<int64_t>(),
                               h->dLbSt.as<int32_t>(), h->dLbNev.as<int32_t>()));

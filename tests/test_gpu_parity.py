@@ -480,6 +480,8 @@ def _oracle_traces(model, x0s, J, maxiters, max_points=None, gtol=1e-8, ftol=1e-
         kw = dict(mean=model.mean, sd=model.sd)
     if model.family == OL.FAMILY_DENSENORMAL:
         kw = dict(mean=model.mean, prec=model.prec)
+    if model.family == OL.FAMILY_HLOGISTIC:
+        kw = dict(Xobs=model.X, yobs=model.y)
     return [OL.lbfgs_path(model.family, x0s[:, p], J, maxiters, max_points, gtol, ftol, **kw)
             for p in range(x0s.shape[1])]
 
@@ -487,7 +489,7 @@ def _oracle_traces(model, x0s, J, maxiters, max_points=None, gtol=1e-8, ftol=1e-
 @pytest.mark.parametrize("kind,n,J,scale,maxiters", [
     ("iso", 10, 6, 2.0, 1000), ("funnel", 5, 6, 3.0, 60), ("funnel", 100, 6, 10.0, 80),
     ("funnel", 1024, 6, 10.0, 40), ("funnel", 257, 10, 10.0, 50), ("diag", 333, 6, 2.0, 1000),
-    ("dense", 150, 6, 2.0, 1000),
+    ("dense", 150, 6, 2.0, 1000), ("hlogistic", 40, 6, 2.0, 300),
 ])
 def test_device_lbfgs_trajectories_bit_exact(kind, n, J, scale, maxiters):
     """Kernel K0 against the CPU restatement of the same contract (pf_lbfgs.h): points, gradients,
@@ -499,6 +501,11 @@ def test_device_lbfgs_trajectories_bit_exact(kind, n, J, scale, maxiters):
         model = pf.IsoNormal(n)
     elif kind == "funnel":
         model = pf.Funnel(n)
+    elif kind == "hlogistic":
+        nobs, p = 700, n - 2
+        Xo = rng.normal(size=(nobs, p))
+        yo = (rng.random(nobs) < 1.0 / (1.0 + np.exp(-(Xo @ (rng.normal(size=p) * 0.5))))).astype(np.float64)
+        model = pf.HierLogistic(Xo, yo)
     elif kind == "dense":
         Sg = _rand_pd(rng, n)
         Pm = np.linalg.inv(Sg)
@@ -540,8 +547,8 @@ def test_device_lbfgs_capacity_nonfinite_and_unsupported_family():
     res = eng.download()
     assert list(res.success) == [True, False, True] and res.best_iter[1] == 0
     eng.close()
-    hl = pf.HierLogistic(np.random.default_rng(0).normal(size=(8, 2)), np.ones(8))
-    eng = _engine(hl, 8)
+    hm = pf.HostModel(4, lambda X: -0.5 * (X * X).sum(axis=0), lambda x: -x)   # host closures: no device L-BFGS
+    eng = pf.Engine.for_model(hm, 6, 8, 0)
     with pytest.raises(pf.PfbError) as ei:
         eng.lbfgs_batch(np.zeros((4, 2)), 10)
     assert ei.value.code == -3

@@ -443,3 +443,41 @@ def test_resample_without_replacement_unique_and_weighted():
     first = np.array([OP.resample_indices_norep(s, np.log(w), 4, 2)[0] for s in range(4000)])
     freq = np.bincount(first, minlength=5)[1:] / 4000.0
     assert np.max(np.abs(freq - w)) < 0.03
+
+
+def test_lbfgs_dense_normal_and_hier_logistic_reach_the_scipy_optimum():
+    """The GEMM-shaped families of the L-BFGS contract: gradients / log densities equal the host
+    models', and the optimum equals SciPy's."""
+    from scipy.optimize import minimize
+
+    import pathfinder_b200 as pf
+    from oracle import lbfgs as OL
+
+    rng = np.random.default_rng(7)
+    n = 30
+    Q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    prec = (Q / (rng.random(n) * 0.95 + 0.05)) @ Q.T
+    prec = 0.5 * (prec + prec.T)
+    mean = rng.normal(size=n)
+    dm = pf.DenseNormal(mean, prec)
+    X, FX, G, st, _ = OL.lbfgs_path(OL.FAMILY_DENSENORMAL, rng.uniform(-2, 2, n), 6, 1000, mean=mean, prec=prec)
+    assert OL.STATUS[st] in ("gtol", "ftol")
+    np.testing.assert_allclose(X[:, -1], mean, atol=1e-6)
+    for l in (0, X.shape[1] // 2, X.shape[1] - 1):
+        np.testing.assert_allclose(G[:, l], dm.grad(X[:, l]), rtol=1e-10, atol=1e-12)
+        assert np.isclose(FX[l], dm.logp(X[:, l]), rtol=1e-10, atol=1e-12)
+
+    nobs, p = 400, 10
+    Xo = rng.normal(size=(nobs, p))
+    yo = (rng.random(nobs) < 1.0 / (1.0 + np.exp(-(Xo @ (rng.normal(size=p) * 0.5))))).astype(np.float64)
+    hm = pf.HierLogistic(Xo, yo)
+    x0 = rng.uniform(-2, 2, p + 2)
+    X, FX, G, st, _ = OL.lbfgs_path(OL.FAMILY_HLOGISTIC, x0, 6, 1000, Xobs=Xo, yobs=yo)
+    assert OL.STATUS[st] in ("gtol", "ftol")
+    for l in (0, 2, X.shape[1] - 1):
+        np.testing.assert_allclose(G[:, l], hm.grad(X[:, l]), rtol=1e-9, atol=1e-9)
+        assert np.isclose(FX[l], hm.logp(X[:, l]), rtol=1e-11)
+    ref = minimize(lambda t: (-hm.logp(t), -hm.grad(t)), x0, jac=True, method="L-BFGS-B",
+                   options=dict(maxcor=6, gtol=1e-10, ftol=1e-15, maxiter=2000))
+    assert abs(FX[-1] + ref.fun) < 1e-6 * max(1.0, abs(ref.fun))
+    assert np.max(np.abs(G[:, -1])) < 1e-4
