@@ -32,7 +32,7 @@ def clib():
         lib = ctypes.CDLL(path)
         lib.pfo_lbfgs_path.restype = ctypes.c_int
         lib.pfo_lbfgs_path.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
-                                       ctypes.c_double,
+                                       ctypes.c_void_p, ctypes.c_double,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p]
@@ -70,13 +70,16 @@ def lbfgs_path(family, x0, history_length=6, maxiters=1000, max_points=None, gto
         mp0 = np.ascontiguousarray(mean, dtype=np.float64)
         mp1 = np.asfortranarray(prec, dtype=np.float64)
     nobs = 0
+    mp2 = None
     if family == FAMILY_HLOGISTIC:
         mp0 = np.asfortranarray(Xobs, dtype=np.float64)
         mp1 = np.ascontiguousarray(yobs, dtype=np.float64)
+        mp2 = np.ascontiguousarray(Xobs, dtype=np.float64)  # row-major X == column-major X'
         nobs = mp0.shape[0]
         c0 = hlogistic_c0(n)
     np_ = clib().pfo_lbfgs_path(int(family), n, int(nobs), None if mp0 is None else mp0.ctypes.data,
-                                None if mp1 is None else mp1.ctypes.data, float(c0), int(history_length),
+                                None if mp1 is None else mp1.ctypes.data, None if mp2 is None else mp2.ctypes.data,
+                                float(c0), int(history_length),
                                 int(maxiters), int(max_points), float(gtol), float(ftol), x0.ctypes.data,
                                 X.ctypes.data, G.ctypes.data, FX.ctypes.data, ctypes.byref(st), ctypes.byref(nev))
     return (np.asfortranarray(X[:, :np_]), FX[:np_].copy(), np.asfortranarray(G[:, :np_]), st.value, nev.value)

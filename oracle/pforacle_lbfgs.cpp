@@ -46,6 +46,15 @@ struct HostCtx {
     void each_n(int count, F f) {
         for (int i = 0; i < count; ++i) f(i);
     }
+    // one sequential fma chain over the columns per row; column-outer so the matrix streams once
+    void matvec_cols(int nr, int nc, const double* A, const double* v, double init, double* out) {
+        for (int i = 0; i < nr; ++i) out[i] = init;
+        for (int j = 0; j < nc; ++j) {
+            const double* col = A + (size_t)j * nr;
+            const double vj = v[j];
+            for (int i = 0; i < nr; ++i) out[i] = fma(col[i], vj, out[i]);
+        }
+    }
     template <class F>
     double sum(F f) {
         return sum_n(n, f);
@@ -84,12 +93,13 @@ struct HostCtx {
 }  // namespace
 
 // One path.  X, G: n x max_points column-major, FX[max_points].  mp0 / mp1: DIAGNORMAL mean and
-// 1 / sd; DENSENORMAL mean and precision (n x n column-major); HLOGISTIC X (nobs x (n-2)) and y.  Returns the number of recorded points.
-extern "C" int pfo_lbfgs_path(int family, int n, int nobs, const double* mp0, const double* mp1, double mc0, int J,
+// 1 / sd; DENSENORMAL mean and precision (n x n column-major); HLOGISTIC X (nobs x (n-2)) and y, mp2 = X' ((n-2) x nobs).  Returns the number of recorded points.
+extern "C" int pfo_lbfgs_path(int family, int n, int nobs, const double* mp0, const double* mp1, const double* mp2,
+                              double mc0, int J,
                               int maxiters, int max_points, double gtol, double ftol, const double* x0, double* X,
                               double* G, double* FX, int* status, int* nevals) {
     std::vector<double> ws((size_t)(2 * J + 1) * n + (size_t)(nobs > n ? nobs : n));
-    pf_lbfgs_model m{family, n, mp0, mp1, mc0, ws.data() + (size_t)(2 * J + 1) * n, nobs};
+    pf_lbfgs_model m{family, n, mp0, mp1, mc0, ws.data() + (size_t)(2 * J + 1) * n, nobs, mp2};
     pf_lbfgs_opts o{J, maxiters, max_points, gtol, ftol};
     HostCtx c{n};
     return pf_lbfgs_run(c, m, o, x0, X, G, FX, ws.data(), status, nevals);

@@ -14,16 +14,44 @@
 #include "pfb_common.cuh"
 #include "pf_lbfgs.h"
 
+// NT physical threads per path.  Elementwise work is spread over all of them; the reductions keep
+// the contract's shape — PF_LBFGS_T strided partials held by the first PF_LBFGS_T threads, the rest
+// contribute exact zeros — so the result does not depend on NT.
+template <int NT>
 struct pfb_lbfgs_dev_ctx {
     int n;
     double* scratch;  // 64 doubles of shared memory
     template <class F>
     __device__ __forceinline__ void each(F f) {
-        for (int i = threadIdx.x; i < n; i += PF_LBFGS_T) f(i);
+        for (int i = threadIdx.x; i < n; i += NT) f(i);
     }
     template <class F>
     __device__ __forceinline__ void each_n(int count, F f) {
-        for (int i = threadIdx.x; i < count; i += PF_LBFGS_T) f(i);
+        for (int i = threadIdx.x; i < count; i += NT) f(i);
+    }
+    // out[i] = init + sum_j A[i + j nr] v[j]: a thread interleaves up to 4 rows (independent chains,
+    // so several loads are in flight) and sweeps the columns once; consecutive rows sit in consecutive
+    // threads => every column step is a coalesced read
+    __device__ __forceinline__ void matvec_cols(int nr, int nc, const double* __restrict__ A,
+                                                const double* __restrict__ v, double init, double* out) {
+        for (int i0 = threadIdx.x; i0 < nr; i0 += 4 * NT) {
+            double acc[4] = {init, init, init, init};
+            const int i1 = i0 + NT, i2 = i0 + 2 * NT, i3 = i0 + 3 * NT;
+            const bool h1 = i1 < nr, h2 = i2 < nr, h3 = i3 < nr;
+#pragma unroll 4
+            for (int j = 0; j < nc; ++j) {
+                const double* col = A + (size_t)j * nr;
+                const double vj = v[j];
+                acc[0] = fma(col[i0], vj, acc[0]);
+                if (h1) acc[1] = fma(col[i1], vj, acc[1]);
+                if (h2) acc[2] = fma(col[i2], vj, acc[2]);
+                if (h3) acc[3] = fma(col[i3], vj, acc[3]);
+            }
+            out[i0] = acc[0];
+            if (h1) out[i1] = acc[1];
+            if (h2) out[i2] = acc[2];
+            if (h3) out[i3] = acc[3];
+        }
     }
     template <class F>
     __device__ __forceinline__ double sum(F f) {
@@ -32,7 +60,8 @@ struct pfb_lbfgs_dev_ctx {
     template <class F>
     __device__ __forceinline__ double sum_n(int count, F f) {
         double acc = 0.0;
-        for (int i = threadIdx.x; i < count; i += PF_LBFGS_T) acc = f(i, acc);
+        if (threadIdx.x < PF_LBFGS_T)
+            for (int i = threadIdx.x; i < count; i += PF_LBFGS_T) acc = f(i, acc);
         double v[1] = {acc};
         pfb_block_sum<1>(v, scratch);
         return v[0];
@@ -40,7 +69,8 @@ struct pfb_lbfgs_dev_ctx {
     template <class F>
     __device__ __forceinline__ void sum2(F f, double& a, double& b) {
         double v[2] = {0.0, 0.0};
-        for (int i = threadIdx.x; i < n; i += PF_LBFGS_T) f(i, v[0], v[1]);
+        if (threadIdx.x < PF_LBFGS_T)
+            for (int i = threadIdx.x; i < n; i += PF_LBFGS_T) f(i, v[0], v[1]);
         pfb_block_sum<2>(v, scratch);
         a = v[0];
         b = v[1];
@@ -48,14 +78,14 @@ struct pfb_lbfgs_dev_ctx {
     template <class F>
     __device__ __forceinline__ double maxv(F f) {
         double acc = 0.0;
-        for (int i = threadIdx.x; i < n; i += PF_LBFGS_T) acc = fmax(acc, f(i));
+        for (int i = threadIdx.x; i < n; i += NT) acc = fmax(acc, f(i));
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) acc = fmax(acc, __shfl_xor_sync(0xffffffffu, acc, off));
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         __syncthreads();
         if (lane == 0) scratch[warp] = acc;
         __syncthreads();
-        double t = (lane < PF_LBFGS_T / 32) ? scratch[lane] : 0.0;
+        double t = (lane < NT / 32) ? scratch[lane] : 0.0;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, off));
         return t;
@@ -63,13 +93,14 @@ struct pfb_lbfgs_dev_ctx {
     __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 
-__global__ void __launch_bounds__(PF_LBFGS_T)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 pfb_k0_lbfgs(pf_lbfgs_model m, pf_lbfgs_opts o, const double* __restrict__ x0, double* X, double* G, double* FX,
              double* ws, int64_t* npoints, int32_t* status, int32_t* nevals) {
     __shared__ double scratch[64];
     const int p = blockIdx.x;
     const size_t slab = (size_t)m.n * (size_t)o.max_points;
-    pfb_lbfgs_dev_ctx c{m.n, scratch};
+    pfb_lbfgs_dev_ctx<NT> c{m.n, scratch};
     int st = 0, nev = 0;
     const size_t zlen = (size_t)(m.nobs > m.n ? m.nobs : m.n);
     double* wsp = ws + (size_t)p * ((size_t)(2 * o.J + 1) * m.n + zlen);
@@ -95,13 +126,17 @@ __global__ void pfb_k0_pack(int n, const int64_t* __restrict__ src, const double
 }
 
 extern "C" cudaError_t pfb_launch_k0(cudaStream_t st, int family, int n, int nobs, int P, const double* mp0,
-                                     const double* mp1, double mc0, int J, int maxiters, int max_points, double gtol, double ftol,
+                                     const double* mp1, const double* mp2, double mc0, int J, int maxiters, int max_points, double gtol, double ftol,
                                      const double* x0, double* X, double* G, double* FX, double* ws,
                                      int64_t* npoints, int32_t* status, int32_t* nevals) {
     if (P <= 0) return cudaSuccess;
-    pf_lbfgs_model m{family, n, mp0, mp1, mc0, nullptr, nobs};
+    pf_lbfgs_model m{family, n, mp0, mp1, mc0, nullptr, nobs, mp2};
     pf_lbfgs_opts o{J, maxiters, max_points, gtol, ftol};
-    pfb_k0_lbfgs<<<P, PF_LBFGS_T, 0, st>>>(m, o, x0, X, G, FX, ws, npoints, status, nevals);
+    // the GEMM-shaped families stream a matrix per evaluation: more threads = more loads in flight
+    if (family == PF_LBFGS_DENSENORMAL || family == PF_LBFGS_HLOGISTIC)
+        pfb_k0_lbfgs<512><<<P, 512, 0, st>>>(m, o, x0, X, G, FX, ws, npoints, status, nevals);
+    else
+        pfb_k0_lbfgs<PF_LBFGS_T><<<P, PF_LBFGS_T, 0, st>>>(m, o, x0, X, G, FX, ws, npoints, status, nevals);
     return cudaGetLastError();
 }
 

@@ -24,6 +24,9 @@
 //   template <class F> void   sum2(F f, double& a, double& b)   f(i, a, b) updates both partials
 //   template <class F> double maxv(F f)     max of f(i) >= 0 (0 when empty)
 //   each_n(count, f) / sum_n(count, f)      the same over an index range other than the dimension
+//   matvec_cols(nr, nc, A, v, init, out)    out[i] = init + sum_j A[i + j nr] v[j], ONE sequential fma
+//                                           chain over j per row (column-major A): which thread owns a
+//                                           row, and how many rows it interleaves, does not change a bit
 //   void sync()                             make element writes visible to every caller
 // Build contract: -fmad=false / -ffp-contract=off (pf_math.h).
 #pragma once
@@ -55,6 +58,7 @@ struct pf_lbfgs_model {
     double c0;         // DIAGNORMAL: -sum(log sd) - n/2 log(2 pi);  HLOGISTIC: the prior's constant
     double* zbuf;      // DENSENORMAL: n doubles of per-path scratch (x - mean);  HLOGISTIC: nobs doubles
     int nobs;          // HLOGISTIC: observations; p0 = X[nobs x (n-2)] column-major, p1 = y[nobs]
+    const double* p2;  // HLOGISTIC: X' [(n-2) x nobs] column-major (the same numbers, transposed)
 };
 
 struct pf_lbfgs_opts {
@@ -87,14 +91,11 @@ PF_HD void pf_lbfgs_eval(Ctx& c, const pf_lbfgs_model& m, const double* x, doubl
         double* z = m.zbuf;
         c.each([&](int i) { z[i] = x[i] - m.p0[i]; });
         c.sync();
-        c.each([&](int i) {
-            double acc = 0.0;
-            const double* Pi = m.p1 + i;
-            for (int j = 0; j < n; ++j) acc = fma(Pi[(size_t)j * n], z[j], acc);
-            glog[i] = -acc;
-        });
-        const double q = c.sum([&](int i, double a) { return fma(z[i], -glog[i], a); });
+        c.matvec_cols(n, n, m.p1, z, 0.0, glog);  // glog = P z for now
+        c.sync();
+        const double q = c.sum([&](int i, double a) { return fma(z[i], glog[i], a); });
         logp = q / -2.0;
+        c.each([&](int i) { glog[i] = -glog[i]; });
     } else if (m.family == PF_LBFGS_HLOGISTIC) {
         // theta = (log tau, b0, b_1..b_p); log tau ~ N(0,1), b0 ~ N(0, 2.5^2),
         // b_j ~ N(0, tau^2), y_i ~ Bernoulli(sigmoid(b0 + x_i'b)).  eta: one sequential fma chain per
@@ -104,11 +105,8 @@ PF_HD void pf_lbfgs_eval(Ctx& c, const pf_lbfgs_model& m, const double* x, doubl
         const double* Xm = m.p0;
         const double* yv = m.p1;
         double* r = m.zbuf;
-        c.each_n(nobs, [&](int i) {
-            double eta = b0;
-            for (int j = 0; j < p; ++j) eta = fma(Xm[(size_t)j * nobs + i], x[2 + j], eta);
-            r[i] = eta;
-        });
+        c.matvec_cols(nobs, p, Xm, x + 2, b0, r);  // eta = b0 + X b
+        c.sync();
         // log-likelihood sum_i y eta - log(1 + exp(eta)), evaluated without overflow
         const double ll = c.sum_n(nobs, [&](int i, double a) {
             const double eta = r[i];
@@ -131,16 +129,16 @@ PF_HD void pf_lbfgs_eval(Ctx& c, const pf_lbfgs_model& m, const double* x, doubl
         const double bb = c.sum([&](int i, double a) { return i >= 2 ? fma(x[i], x[i], a) : a; });
         const double e2 = pf_exp(-2.0 * lt);
         logp = ((((-0.5 * lt) * lt - 0.5 * ((b0 / 2.5) * (b0 / 2.5))) - (0.5 * bb) * e2) - (double)p * lt) + m.c0 + ll;
+        c.sync();
+        c.matvec_cols(p, nobs, m.p2, r, 0.0, glog + 2);  // X'r: one chain over the observations per coefficient
+        c.sync();
         c.each([&](int i) {
             if (i == 0) {
                 glog[i] = (bb * e2 - lt) - (double)p;
             } else if (i == 1) {
                 glog[i] = rsum - b0 / 6.25;
             } else {
-                const double* col = Xm + (size_t)(i - 2) * nobs;
-                double acc = 0.0;
-                for (int k = 0; k < nobs; ++k) acc = fma(col[k], r[k], acc);
-                glog[i] = acc - x[i] * e2;
+                glog[i] = glog[i] - x[i] * e2;
             }
         });
     } else if (m.family == PF_LBFGS_DIAGNORMAL) {

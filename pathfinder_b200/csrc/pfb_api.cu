@@ -34,7 +34,8 @@ cudaError_t pfb_launch_k8_dense(cudaStream_t, int, int64_t, int, const int32_t*,
                                 const double*, double, double*);
 cudaError_t pfb_launch_k8_logistic(cudaStream_t, int, int, int64_t, int, const int32_t*, const double*,
                                    const double*, const double*, double*);
-cudaError_t pfb_launch_k0(cudaStream_t, int, int, int, int, const double*, const double*, double, int, int, int, double,
+cudaError_t pfb_launch_k0(cudaStream_t, int, int, int, int, const double*, const double*, const double*, double, int, int,
+                          int, double,
                           double, const double*, double*, double*, double*, double*, int64_t*, int32_t*, int32_t*);
 cudaError_t pfb_launch_k0_pack(cudaStream_t, int, int64_t, const int64_t*, const double*, const double*, double*,
                                double*);
@@ -270,9 +271,16 @@ extern "C" int pfb_register_model(pfb_handle h, int family, int n, const double*
             const size_t nb = (size_t)n - 2;
             if (nobs < 1 || ndoubles != 1 + (size_t)nobs * nb + (size_t)nobs)
                 PFB_FAIL(h, PFB_ERR_SHAPE, "HLOGISTIC blob = {nobs, X[nobs x (n-2)], y[nobs]}");
-            // device: { X[nobs x (n-2)], y[nobs] }
-            PFB_CUDA(h, h->dModel.ensure((ndoubles - 1) * 8));
+            // device: { X[nobs x (n-2)], y[nobs], X'[(n-2) x nobs] } (the transposed copy gives K0's
+            // X'r sweep coalesced reads)
+            const size_t nx = (size_t)nobs * nb;
+            std::vector<double> xt(nx);
+            for (size_t j = 0; j < nb; ++j)
+                for (size_t k = 0; k < (size_t)nobs; ++k) xt[j + k * nb] = blob[1 + k + j * (size_t)nobs];
+            PFB_CUDA(h, h->dModel.ensure((ndoubles - 1 + nx) * 8));
             PFB_CUDA(h, cudaMemcpyAsync(h->dModel.p, blob + 1, (ndoubles - 1) * 8, cudaMemcpyHostToDevice, h->stream));
+            PFB_CUDA(h, cudaMemcpyAsync(h->dModel.as<double>() + (ndoubles - 1), xt.data(), nx * 8,
+                                        cudaMemcpyHostToDevice, h->stream));
             PFB_CUDA(h, cudaStreamSynchronize(h->stream));
             h->model_nobs = (int)nobs;
             break;
@@ -418,9 +426,10 @@ extern "C" int pfb_lbfgs_batch(pfb_handle h, int n, int P, const double* x0, con
                         : (h->model == PFB_MODEL_DENSENORMAL ? mp0 + 2 * (size_t)n
                            : (h->model == PFB_MODEL_HLOGISTIC ? mp0 + (size_t)h->model_nobs * (n - 2) : mp0 + n));
     const int nobs = h->model == PFB_MODEL_HLOGISTIC ? h->model_nobs : 0;
+    const double* mp2 = h->model == PFB_MODEL_HLOGISTIC ? mp1 + nobs : nullptr;  // X' follows y
     const double mc0 = h->model == PFB_MODEL_HLOGISTIC ? (-0.5 * n * PFB_LOG2PI - log(2.5)) : h->model_c0;
     PFB_CUDA(h, cudaEventRecord(h->lb_ev[0], st));
-    PFB_CUDA(h, pfb_launch_k0(st, h->model, n, nobs, P, mp0, mp1, mc0, J, o->maxiters, maxpts,
+    PFB_CUDA(h, pfb_launch_k0(st, h->model, n, nobs, P, mp0, mp1, mp2, mc0, J, o->maxiters, maxpts,
                               o->gtol, o->ftol, h->dLbX0.as<double>(), h->dLbX.as<double>(), h->dLbG.as<double>(),
                               h->dLbFX.as<double>(), h->dLbWs.as<double>(), h->dLbNp.as<int64_t>(),
                               h->dLbSt.as<int32_t>(), h->dLbNev.as<int32_t>()));
