@@ -481,3 +481,46 @@ def test_lbfgs_dense_normal_and_hier_logistic_reach_the_scipy_optimum():
                    options=dict(maxcor=6, gtol=1e-10, ftol=1e-15, maxiter=2000))
     assert abs(FX[-1] + ref.fun) < 1e-6 * max(1.0, abs(ref.fun))
     assert np.max(np.abs(G[:, -1])) < 1e-4
+
+
+def _psis_independent(log_ratios):
+    """A second, independently written restatement of published PSIS (Vehtari et al., Algorithm 1;
+    `gpdfit` of Zhang & Stephens 2009 as in the loo / ArviZ packages) in plain NumPy/libm — no
+    shared code with oracle/psis.py — to cross-check the oracle's smoothed weights and k-hat."""
+    x = np.array(log_ratios, dtype=np.float64)
+    S = x.size
+    M = int(min(math.ceil(S / 5), math.ceil(3 * math.sqrt(S))))
+    mx = x.max()
+    x = x - mx
+    order = np.argsort(x, kind="stable")
+    cutoff = x[order[S - M - 1]]
+    tail = order[S - M:]                                # ascending
+    xt = np.exp(x[tail]) - np.exp(cutoff)
+    n = M
+    m_est = 30 + int(math.sqrt(n))
+    b = 1.0 - np.sqrt(m_est / (np.arange(1, m_est + 1) - 0.5))
+    b = b / (3.0 * xt[int(n / 4 + 0.5) - 1]) + 1.0 / xt[-1]
+    kk = np.log1p(-b[:, None] * xt[None, :]).mean(axis=1)
+    L = n * (np.log(-(b / kk)) - kk - 1.0)
+    with np.errstate(over="ignore"):
+        w = 1.0 / np.exp(L[None, :] - L[:, None]).sum(axis=1)
+    w = w / w.sum()
+    b_post = float(np.sum(b * w))
+    k_post = float(np.log1p(-b_post * xt).mean())
+    sigma = -k_post / b_post
+    k_hat = (n * k_post + 10 * 0.5) / (n + 10)
+    p = (np.arange(n) + 0.5) / n
+    q = sigma * np.expm1(-k_hat * np.log1p(-p)) / k_hat
+    x[tail] = np.minimum(np.log(q + np.exp(cutoff)), 0.0)
+    x = x - (np.log(np.sum(np.exp(x - x.max()))) + x.max())
+    return x, k_hat, M
+
+
+def test_psis_oracle_agrees_with_an_independent_restatement():
+    rng = np.random.default_rng(12)
+    for lr in (rng.normal(size=3000) * 2.0, rng.standard_t(3, size=8000) * 1.5, rng.gumbel(size=1200) - 50.0):
+        got = OP.psis(lr)
+        lw, k_hat, M = _psis_independent(lr)
+        assert got["tail_length"] == M
+        assert abs(got["pareto_k"] - k_hat) < 1e-10 * max(1.0, abs(k_hat))
+        np.testing.assert_allclose(got["log_weights"], lw, rtol=1e-10, atol=1e-10)
