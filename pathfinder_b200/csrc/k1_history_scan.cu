@@ -23,11 +23,12 @@ pfb_k1_history_scan(int n, int J, double eps, const double* __restrict__ X,
                     double* __restrict__ alpha_out,   // [n x U]
                     int32_t* __restrict__ hist,       // [U x J] point columns (global), oldest first
                     int32_t* __restrict__ hist_cnt,   // [U]
-                    int64_t* __restrict__ n_rejected  // [P]
+                    int64_t* __restrict__ n_rejected, // [P]
+                    int p_base                        // first path of this launch (pipelined uploads)
 ) {
     __shared__ double scratch[4 * 32];
     __shared__ int32_t ring[64];  // J <= 20
-    const int p = blockIdx.x;
+    const int p = blockIdx.x + p_base;
     const int64_t c0 = point_off[p];
     const int L = (int)(point_off[p + 1] - c0) - 1;
     const int64_t u0 = c0 - p;  // first unit of this path
@@ -121,22 +122,31 @@ pfb_k1_history_scan(int n, int J, double eps, const double* __restrict__ X,
     if (tid == 0) n_rejected[p] = rejected;
 }
 
+// paths [p_base, p_base + P)
+extern "C" cudaError_t pfb_launch_k1_range(cudaStream_t st, int n, int p_base, int P, int J, double eps, const double* X,
+                                           const double* G, const int64_t* point_off, double* alpha,
+                                           int32_t* hist, int32_t* hist_cnt, int64_t* n_rejected);
 extern "C" cudaError_t pfb_launch_k1(cudaStream_t st, int n, int P, int J, double eps, const double* X,
                                      const double* G, const int64_t* point_off, double* alpha,
                                      int32_t* hist, int32_t* hist_cnt, int64_t* n_rejected) {
+    return pfb_launch_k1_range(st, n, 0, P, J, eps, X, G, point_off, alpha, hist, hist_cnt, n_rejected);
+}
+extern "C" cudaError_t pfb_launch_k1_range(cudaStream_t st, int n, int p_base, int P, int J, double eps, const double* X,
+                                           const double* G, const int64_t* point_off, double* alpha,
+                                           int32_t* hist, int32_t* hist_cnt, int64_t* n_rejected) {
     if (P <= 0) return cudaSuccess;
     // only P CTAs exist and each is a sequential chain over the trajectory: more threads per CTA
     // shorten every link (2 rows per thread at n = 1024)
     if (n <= 512 * PFB_K1_RPT_WIDE) {
         const int threads = n >= 512 ? 512 : 256;
         pfb_k1_history_scan<true, PFB_K1_RPT_WIDE><<<P, threads, 0, st>>>(n, J, eps, X, G, point_off, alpha, hist,
-                                                                          hist_cnt, n_rejected);
+                                                                          hist_cnt, n_rejected, p_base);
     } else if (n <= 256 * PFB_K1_RPT_TALL) {
         pfb_k1_history_scan<true, PFB_K1_RPT_TALL><<<P, 256, 0, st>>>(n, J, eps, X, G, point_off, alpha, hist,
-                                                                      hist_cnt, n_rejected);
+                                                                      hist_cnt, n_rejected, p_base);
     } else {
         pfb_k1_history_scan<false, PFB_K1_RPT_TALL><<<P, 256, 0, st>>>(n, J, eps, X, G, point_off, alpha, hist,
-                                                                       hist_cnt, n_rejected);
+                                                                       hist_cnt, n_rejected, p_base);
     }
     return cudaGetLastError();
 }

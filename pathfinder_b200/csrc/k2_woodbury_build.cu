@@ -27,7 +27,7 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
                       const int32_t* __restrict__ unit_col, const double* __restrict__ alpha_all,
                       const int32_t* __restrict__ hist, const int32_t* __restrict__ hist_cnt,
                       double* __restrict__ FR, double* __restrict__ HDR, double* __restrict__ FR2,
-                      int model, const double* __restrict__ mp0, const double* __restrict__ mp1) {
+                      int model, const double* __restrict__ mp0, const double* __restrict__ mp1, int u_base) {
     constexpr int RS = KP + 2;
     constexpr int JM = KP / 2;
     __shared__ double sStY[JM][JM], sYaY[JM][JM], sNRinv[JM][JM], sM[JM][JM];
@@ -37,7 +37,7 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
     __shared__ double sBcast[2];
     __shared__ int sFlag;
 
-    const int u = blockIdx.x;
+    const int u = blockIdx.x + u_base;  // u_base: first unit of this launch (pipelined uploads)
     const int tid = threadIdx.x, nt = blockDim.x;
     const int jeff = hist_cnt[u];
     const int kc = 2 * jeff;
@@ -454,7 +454,7 @@ extern "C" int pfb_k2_uses_smem_panel(int KP, int n) {
 }
 
 template <int KP>
-static cudaError_t launch_k2(cudaStream_t st, int n, int U, int J, const double* X, const double* G,
+static cudaError_t launch_k2(cudaStream_t st, int n, int u_base, int U, int J, const double* X, const double* G,
                              const int32_t* unit_col, const double* alpha, const int32_t* hist,
                              const int32_t* hist_cnt, double* FR, double* HDR, double* FR2, int model,
                              const double* mp0, const double* mp1) {
@@ -465,7 +465,8 @@ static cudaError_t launch_k2(cudaStream_t st, int n, int U, int J, const double*
         const size_t smem = k2_panel_bytes(KP, n) + k2_scratch_bytes(KP);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<U, threads, smem, st>>>(n, J, X, G, unit_col, alpha, hist, hist_cnt, nullptr, HDR, FR2, model, mp0, mp1);
+        kern<<<U, threads, smem, st>>>(n, J, X, G, unit_col, alpha, hist, hist_cnt, nullptr, HDR, FR2, model, mp0, mp1,
+                                       u_base);
         return cudaGetLastError();
     }
     if (FR == nullptr) return cudaErrorInvalidValue;
@@ -473,19 +474,34 @@ static cudaError_t launch_k2(cudaStream_t st, int n, int U, int J, const double*
     if (threads < 64) threads = 64;
     pfb_k2_woodbury_build<KP, false><<<U, threads, k2_scratch_bytes(KP), st>>>(n, J, X, G, unit_col, alpha, hist,
                                                                               hist_cnt, FR, HDR, FR2, model, mp0,
-                                                                              mp1);
+                                                                              mp1, u_base);
     return cudaGetLastError();
 }
 
+// units [u_base, u_base + U)
+extern "C" cudaError_t pfb_launch_k2_range(cudaStream_t st, int KP, int n, int u_base, int U, int J, const double* X,
+                                           const double* G, const int32_t* unit_col, const double* alpha,
+                                           const int32_t* hist, const int32_t* hist_cnt, double* FR,
+                                           double* HDR, double* FR2, int model, const double* mp0,
+                                           const double* mp1);
 extern "C" cudaError_t pfb_launch_k2(cudaStream_t st, int KP, int n, int U, int J, const double* X,
                                      const double* G, const int32_t* unit_col, const double* alpha,
                                      const int32_t* hist, const int32_t* hist_cnt, double* FR,
                                      double* HDR, double* FR2, int model, const double* mp0,
                                      const double* mp1) {
+    return pfb_launch_k2_range(st, KP, n, 0, U, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR, FR2, model, mp0,
+                               mp1);
+}
+extern "C" cudaError_t pfb_launch_k2_range(cudaStream_t st, int KP, int n, int u_base, int U, int J, const double* X,
+                                           const double* G, const int32_t* unit_col, const double* alpha,
+                                           const int32_t* hist, const int32_t* hist_cnt, double* FR,
+                                           double* HDR, double* FR2, int model, const double* mp0,
+                                           const double* mp1) {
     if (U <= 0) return cudaSuccess;
     switch (KP) {
 #define PFB_K2_CASE(k) \
-    case k: return launch_k2<k>(st, n, U, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR, FR2, model, mp0, mp1);
+    case k:            \
+        return launch_k2<k>(st, n, u_base, U, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR, FR2, model, mp0, mp1);
         PFB_K2_CASE(12)
         PFB_K2_CASE(20)
         PFB_K2_CASE(24)

@@ -29,6 +29,11 @@ PFB_DECL_K3(pfb_launch_k3_kp20)
 PFB_DECL_K3(pfb_launch_k3_kp24)
 cudaError_t pfb_launch_k4(cudaStream_t, int, int, int64_t, const int64_t*, const double*, const double*, double*,
                           double*, int64_t*, int32_t*, int32_t*);
+cudaError_t pfb_launch_k1_range(cudaStream_t, int, int, int, int, double, const double*, const double*, const int64_t*,
+                                double*, int32_t*, int32_t*, int64_t*);
+cudaError_t pfb_launch_k2_range(cudaStream_t, int, int, int, int, int, const double*, const double*, const int32_t*,
+                                const double*, const int32_t*, const int32_t*, double*, double*, double*, int,
+                                const double*, const double*);
 int pfb_k2_uses_smem_panel(int KP, int n);
 cudaError_t pfb_launch_k8_dense(cudaStream_t, int, int64_t, int, const int32_t*, const double*, const double*,
                                 const double*, double, double*);
@@ -117,6 +122,13 @@ struct pfb_engine {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t hc_k[2] = {}, hc_c[2] = {};
     double host_cb_s = 0.0;  // seconds spent inside the callback during the last run
+    // pipelined upload of pfb_elbo_batch: path groups, one event per group
+    static constexpr int kUpGroups = 4;
+    cudaEvent_t up_ev[kUpGroups] = {};
+    cudaEvent_t k1_ev[kUpGroups] = {};
+    cudaStream_t k1_stream = nullptr;  // K1 is a per-path latency chain: its groups run beside K2 / the copies
+    int up_ngroups = 0;               // 0: the trajectories are already resident
+    int up_p[kUpGroups + 1] = {};     // path boundaries of the groups
     // device L-BFGS (K0): trajectory slabs [n x max_points] per path
     DevBuf dLbX0, dLbX, dLbG, dLbFX, dLbWs, dLbNp, dLbSt, dLbNev, dLbSrc;
     std::vector<int64_t> lb_np;
@@ -207,6 +219,11 @@ extern "C" int pfb_destroy(pfb_handle h) {
         if (h->hc_c[i]) cudaEventDestroy(h->hc_c[i]);
     }
     if (h->hLp) cudaFreeHost(h->hLp);
+    for (auto& ev : h->up_ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->k1_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (h->k1_stream) cudaStreamDestroy(h->k1_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto& ev : h->ev) cudaEventDestroy(ev);
     for (auto& ev : h->lb_ev) cudaEventDestroy(ev);
@@ -678,18 +695,43 @@ extern "C" int pfb_batch_run(pfb_handle h) {
     const int U = (int)h->U;
     h->launches = 0;
     PFB_CUDA(h, cudaEventRecord(h->ev[0], st));
-    PFB_CUDA(h, pfb_launch_k1(st, n, P, J, h->cfg.eps, h->dX.as<double>(), h->dG.as<double>(),
-                              h->dOff.as<int64_t>(), h->dAlpha.as<double>(), h->dHist.as<int32_t>(),
-                              h->dHistCnt.as<int32_t>(), h->dRej.as<int64_t>()));
-    h->launches += (P > 0);
-    PFB_CUDA(h, cudaEventRecord(h->ev[1], st));
-    PFB_CUDA(h, pfb_launch_k2(st, KP, n, U, J, h->dX.as<double>(), h->dG.as<double>(), h->dUnitCol.as<int32_t>(),
-                              h->dAlpha.as<double>(), h->dHist.as<int32_t>(), h->dHistCnt.as<int32_t>(),
-                              h->dFR.as<double>(), h->dHDR.as<double>(), h->dFR2.as<double>(),
-                              model_is_external(h) ? PFB_MODEL_ISONORMAL : h->model,
-                              model_is_external(h) ? nullptr : h->dModel.as<double>(),
-                              (h->dModel.p && !model_is_external(h)) ? h->dModel.as<double>() + h->model_n : nullptr));
-    h->launches += (U > 0);
+    const int k2_model = model_is_external(h) ? PFB_MODEL_ISONORMAL : h->model;
+    const double* k2_mp0 = model_is_external(h) ? nullptr : h->dModel.as<double>();
+    const double* k2_mp1 = (h->dModel.p && !model_is_external(h)) ? h->dModel.as<double>() + h->model_n : nullptr;
+    if (h->up_ngroups > 0) {
+        // pfb_elbo_batch: the trajectories are still arriving group by group on the copy stream; K1 and
+        // K2 of a group start as soon as its points are resident (timers: k1 = first group, k2 = the rest)
+        for (int g = 0; g < h->up_ngroups; ++g) {
+            const int p0 = h->up_p[g], p1 = h->up_p[g + 1];
+            const int u0 = (int)(h->h_off[(size_t)p0] - p0), u1 = (int)(h->h_off[(size_t)p1] - p1);
+            // K1 takes the same time for 16 paths as for 64 (a sequential chain per path), so its
+            // groups run on their own stream, beside the copies and beside K2 of the previous group
+            PFB_CUDA(h, cudaStreamWaitEvent(h->k1_stream, h->up_ev[g], 0));
+            PFB_CUDA(h, pfb_launch_k1_range(h->k1_stream, n, p0, p1 - p0, J, h->cfg.eps, h->dX.as<double>(),
+                                            h->dG.as<double>(), h->dOff.as<int64_t>(), h->dAlpha.as<double>(),
+                                            h->dHist.as<int32_t>(), h->dHistCnt.as<int32_t>(), h->dRej.as<int64_t>()));
+            PFB_CUDA(h, cudaEventRecord(h->k1_ev[g], h->k1_stream));
+            PFB_CUDA(h, cudaStreamWaitEvent(st, h->k1_ev[g], 0));
+            if (g == 0) PFB_CUDA(h, cudaEventRecord(h->ev[1], st));
+            PFB_CUDA(h, pfb_launch_k2_range(st, KP, n, u0, u1 - u0, J, h->dX.as<double>(), h->dG.as<double>(),
+                                            h->dUnitCol.as<int32_t>(), h->dAlpha.as<double>(), h->dHist.as<int32_t>(),
+                                            h->dHistCnt.as<int32_t>(), h->dFR.as<double>(), h->dHDR.as<double>(),
+                                            h->dFR2.as<double>(), k2_model, k2_mp0, k2_mp1));
+            h->launches += (p1 > p0) + (u1 > u0);
+        }
+        h->up_ngroups = 0;
+    } else {
+        PFB_CUDA(h, pfb_launch_k1(st, n, P, J, h->cfg.eps, h->dX.as<double>(), h->dG.as<double>(),
+                                  h->dOff.as<int64_t>(), h->dAlpha.as<double>(), h->dHist.as<int32_t>(),
+                                  h->dHistCnt.as<int32_t>(), h->dRej.as<int64_t>()));
+        h->launches += (P > 0);
+        PFB_CUDA(h, cudaEventRecord(h->ev[1], st));
+        PFB_CUDA(h, pfb_launch_k2(st, KP, n, U, J, h->dX.as<double>(), h->dG.as<double>(), h->dUnitCol.as<int32_t>(),
+                                  h->dAlpha.as<double>(), h->dHist.as<int32_t>(), h->dHistCnt.as<int32_t>(),
+                                  h->dFR.as<double>(), h->dHDR.as<double>(), h->dFR2.as<double>(), k2_model, k2_mp0,
+                                  k2_mp1));
+        h->launches += (U > 0);
+    }
     PFB_CUDA(h, cudaEventRecord(h->ev[2], st));
     if (!model_is_external(h)) {
         PFB_CUDA(h, launch_k3(h, U, nullptr, h->dLogp.as<double>(), h->dLogq.as<double>(),
@@ -997,10 +1039,66 @@ extern "C" int pfb_pool_download(pfb_handle h, int p0, int p1, double* draws, do
 extern "C" int pfb_elbo_batch(pfb_handle h, int n, int P, const int64_t* offsets, const double* positions,
                               const double* gradients, const uint64_t* seeds, const double* normals,
                               pfb_elbo_out* out) {
-    int rc = pfb_batch_upload(h, n, P, offsets, positions, gradients, seeds, normals);
+    // One call owns upload, compute and download, so the upload can be pipelined: the trajectories go
+    // up in path groups on a copy stream and K1 / K2 of a group start when its points are resident
+    // (the host buffers are not touched after the final synchronisation in pfb_batch_download).
+    if (!h) return PFB_ERR_ARG;
+    if (normals || P < 8 || !offsets || n < 1) {  // parity mode / tiny batches: the plain sequence
+        int rc0 = pfb_batch_upload(h, n, P, offsets, positions, gradients, seeds, normals);
+        if (rc0) return rc0;
+        rc0 = pfb_batch_run(h);
+        if (rc0) return rc0;
+        return pfb_batch_download(h, out);
+    }
+    {
+        const int64_t T = offsets[P], U = T - P;
+        if (T > 0 && (!positions || !gradients)) PFB_FAIL(h, PFB_ERR_ARG, "positions / gradients are NULL");
+        if (U > 0 && !seeds) PFB_FAIL(h, PFB_ERR_ARG, "seeds is NULL");
+    }
+    int rc = batch_prepare(h, n, P, offsets);
     if (rc) return rc;
+    cudaStream_t st = h->stream;
+    if (!h->copy_stream) PFB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->k1_stream) PFB_CUDA(h, cudaStreamCreateWithFlags(&h->k1_stream, cudaStreamNonBlocking));
+    for (auto& ev : h->up_ev)
+        if (!ev) PFB_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : h->k1_ev)
+        if (!ev) PFB_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (h->U > 0) PFB_CUDA(h, cudaMemcpyAsync(h->dSeeds.p, seeds, (size_t)h->U * 8, cudaMemcpyHostToDevice, st));
+    h->have_normals = false;
+    // groups of paths with about the same number of points
+    const int NG = pfb_engine::kUpGroups;
+    h->up_p[0] = 0;
+    for (int g = 1; g < NG; ++g) {
+        const int64_t want = offsets[P] * g / NG;
+        int p = h->up_p[g - 1];
+        while (p < P && offsets[p] < want) ++p;
+        h->up_p[g] = p;
+    }
+    h->up_p[NG] = P;
+    // the copy stream must not overwrite X / G while an earlier batch's kernels still read them
+    PFB_CUDA(h, cudaEventRecord(h->up_ev[0], st));
+    PFB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->up_ev[0], 0));
+    PFB_CUDA(h, cudaStreamWaitEvent(h->k1_stream, h->up_ev[0], 0));
+    for (int g = 0; g < NG; ++g) {
+        const int64_t c0 = offsets[h->up_p[g]], c1 = offsets[h->up_p[g + 1]];
+        const size_t bytes = (size_t)(c1 - c0) * (size_t)n * 8;
+        if (bytes) {
+            PFB_CUDA(h, cudaMemcpyAsync(h->dX.as<double>() + (size_t)c0 * n, positions + (size_t)c0 * n, bytes,
+                                        cudaMemcpyHostToDevice, h->copy_stream));
+            PFB_CUDA(h, cudaMemcpyAsync(h->dG.as<double>() + (size_t)c0 * n, gradients + (size_t)c0 * n, bytes,
+                                        cudaMemcpyHostToDevice, h->copy_stream));
+        }
+        PFB_CUDA(h, cudaEventRecord(h->up_ev[g], h->copy_stream));
+    }
+    h->up_ngroups = NG;
+    h->have_batch = true;
     rc = pfb_batch_run(h);
-    if (rc) return rc;
+    if (rc) {
+        h->up_ngroups = 0;
+        cudaStreamSynchronize(h->copy_stream);
+        return rc;
+    }
     return pfb_batch_download(h, out);
 }
 

@@ -261,6 +261,12 @@ class Engine:
     def download(self, draws=True, per_draw=False, fit=False, all_draws=False, into=None) -> ElboBatchResult:
         """into: a result of an earlier download of the SAME batch shape whose arrays are reused
         (the caller-owned output buffers of the C ABI; pin() them for full-rate copies)."""
+        out, res, succ = self._out_struct(draws, per_draw, fit, all_draws, into)
+        _lib.check(self.h, self.lib.pfb_batch_download(self.h, C.byref(out)))
+        res.success = succ.astype(bool)
+        return res
+
+    def _out_struct(self, draws, per_draw, fit, all_draws, into):
         n, K, P, U, KP = self.n, self.K, self._P, self._U, self.KP
         out = pfb_elbo_out()
 
@@ -306,9 +312,7 @@ class Engine:
         if all_draws:
             res.all_draws = np.empty((n, K, U), order="F")
             out.all_draws = _ptr(res.all_draws)
-        _lib.check(self.h, self.lib.pfb_batch_download(self.h, C.byref(out)))
-        res.success = succ.astype(bool)
-        return res
+        return out, res, succ
 
     @staticmethod
     def result_arrays(res):
@@ -319,10 +323,33 @@ class Engine:
             out += list(res.fit.values())
         return [a for a in out if a is not None]
 
-    def elbo_batch(self, offsets, X, G, seeds, normals=None, **kw) -> ElboBatchResult:
-        self.upload(offsets, X, G, seeds, normals)
-        self.run()
-        return self.download(**kw)
+    def elbo_batch(self, offsets, X, G, seeds, normals=None, draws=True, per_draw=False, fit=False,
+                   all_draws=False, into=None) -> ElboBatchResult:
+        """Upload, ELBO stage and download as ONE library call (pfb_elbo_batch): the trajectories go up
+        in path groups on a copy stream while K1 / K2 already work on the groups that have arrived."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        P = offsets.size - 1
+        U = int(offsets[-1]) - P
+        X = np.asfortranarray(X, dtype=np.float64)
+        G = np.asfortranarray(G, dtype=np.float64)
+        if X.shape != (self.n, int(offsets[-1])) or G.shape != X.shape:
+            raise ValueError("positions / gradients must be n x offsets[-1]")
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        if seeds.size != U:
+            raise ValueError("need one seed per (path, iteration)")
+        if normals is not None:
+            normals = np.asfortranarray(normals, dtype=np.float64)
+            if normals.shape != (self.n, self.K, U):
+                raise ValueError("normals must be n x K x U")
+        self._flush_pending()
+        self._P, self._U, self._offsets = P, U, offsets.copy()
+        out, res, succ = self._out_struct(draws, per_draw, fit, all_draws, into)
+        _lib.check(self.h, self.lib.pfb_elbo_batch(self.h, self.n, P, _ptr(offsets), _ptr(X), _ptr(G), _ptr(seeds),
+                                                   _ptr(normals), C.byref(out)))
+        self._raise_cb_error()
+        self._poolK = self.K
+        res.success = succ.astype(bool)
+        return res
 
     def fit_only(self, best_iter):
         """K1 + K2 with caller-given best iterations (resample() re-entry)."""
