@@ -57,8 +57,15 @@ struct pfb_lbfgs_dev_ctx {
     __device__ __forceinline__ double sum(F f) {
         return sum_n(n, f);
     }
+    // With NT > PF_LBFGS_T the reductions read elements that `each` (stride NT) wrote from OTHER
+    // threads, so every reduction starts with a barrier; with NT == PF_LBFGS_T a thread reduces
+    // exactly the elements it wrote itself.
+    __device__ __forceinline__ void pre_reduce() {
+        if (NT != PF_LBFGS_T) __syncthreads();
+    }
     template <class F>
     __device__ __forceinline__ double sum_n(int count, F f) {
+        pre_reduce();
         double acc = 0.0;
         if (threadIdx.x < PF_LBFGS_T)
             for (int i = threadIdx.x; i < count; i += PF_LBFGS_T) acc = f(i, acc);
@@ -68,6 +75,7 @@ struct pfb_lbfgs_dev_ctx {
     }
     template <class F>
     __device__ __forceinline__ void sum2(F f, double& a, double& b) {
+        pre_reduce();
         double v[2] = {0.0, 0.0};
         if (threadIdx.x < PF_LBFGS_T)
             for (int i = threadIdx.x; i < n; i += PF_LBFGS_T) f(i, v[0], v[1]);

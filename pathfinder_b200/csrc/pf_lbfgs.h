@@ -27,7 +27,9 @@
 //   matvec_cols(nr, nc, A, v, init, out)    out[i] = init + sum_j A[i + j nr] v[j], ONE sequential fma
 //                                           chain over j per row (column-major A): which thread owns a
 //                                           row, and how many rows it interleaves, does not change a bit
-//   void sync()                             make element writes visible to every caller
+//   void sync()                             make element writes visible to every caller (a context whose
+//                                           reductions and element loops have different owners also
+//                                           synchronises at the start of every reduction)
 // Build contract: -fmad=false / -ffp-contract=off (pf_math.h).
 #pragma once
 #include <float.h>
@@ -125,6 +127,7 @@ PF_HD void pf_lbfgs_eval(Ctx& c, const pf_lbfgs_model& m, const double* x, doubl
             }
             r[i] = yv[i] - sg;
         });
+        c.sync();
         const double rsum = c.sum_n(nobs, [&](int i, double a) { return a + r[i]; });
         const double bb = c.sum([&](int i, double a) { return i >= 2 ? fma(x[i], x[i], a) : a; });
         const double e2 = pf_exp(-2.0 * lt);
