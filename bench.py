@@ -326,11 +326,14 @@ def main():
         # brings them to the host)
         r = eng.psis_resample_device(world * K * P, K, g_logp.data_ptr(), g_logq.data_ptr(), None,
                                      resample_seed, ndraws, True, want_weights=False)
-        inds = torch.from_numpy(r["inds"] - 1).to(f"cuda:{local_rank}")
+        # the pool's draws are never materialised: each rank regenerates the selected columns it owns
+        # (K3 over the per-path lists of the resampled indices) and the ranks sum-reduce the result
+        inds = torch.from_numpy(r["inds"]).to(f"cuda:{local_rank}")  # 1-based global pool indices
         with torch.cuda.stream(ext):
-            mine = (inds >= rank * K * P) & (inds < (rank + 1) * K * P)
             out_draws.zero_()
-            out_draws[mine] = pool_draws[(inds[mine] - rank * K * P)]
+        ext.synchronize()
+        eng.pool_columns_device(ndraws, inds.data_ptr(), rank * K * P, out_draws.data_ptr())
+        with torch.cuda.stream(ext):
             dist.all_reduce(out_draws)
         ext.synchronize()
         r["draws"] = out_draws

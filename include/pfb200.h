@@ -213,6 +213,15 @@ typedef struct {
 } pfb_device_view;
 int pfb_batch_device_view(pfb_handle h, pfb_device_view* view);
 
+/* The pool's log densities are always resident after pfb_batch_run; its DRAWS are materialised on
+ * demand (a draws download, pfb_pool_download, or this call) — pfb_psis_resample regenerates only the
+ * columns it selects.  Call before reading pfb_device_view.pool_draws. */
+int pfb_pool_materialize(pfb_handle h);
+/* Multi-GPU resampling without materialising the pool: d_inds[m] = 1-based indices into the GLOBAL
+ * pool (device, int64), this engine's runs cover [base, base + P K); its columns are regenerated into
+ * d_out [n x m] (device), the others left untouched (zero d_out first, then sum-reduce over the ranks). */
+int pfb_pool_columns_device(pfb_handle h, int m, const void* d_inds, int64_t base, void* d_out);
+
 /* PSIS + resampling on DEVICE buffers (an all-gathered pool): d_logp/d_logq [N], d_pool [n x N];
  * outputs in `out` are HOST pointers. */
 int pfb_psis_resample_device(pfb_handle h, int n, int64_t N, int K_run, const void* d_logp,

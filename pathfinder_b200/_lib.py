@@ -87,6 +87,8 @@ SYMBOLS = {
     "pfb_batch_fit_only": (C.c_int, [C.c_void_p, _dp]),
     "pfb_draw_from_fits": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, C.c_int]),
     "pfb_unit_draws": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]),
+    "pfb_pool_materialize": (C.c_int, [C.c_void_p]),
+    "pfb_pool_columns_device": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int64, _dp]),
     "pfb_pool_download": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]),
     "pfb_psis_resample": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(pfb_resample_out)]),

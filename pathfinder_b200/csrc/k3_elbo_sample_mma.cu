@@ -67,6 +67,15 @@ __device__ __forceinline__ void pfb_sqacc_unless(double& acc, double x, uint32_t
     asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p fma.rn.f64 %0, %1, %1, %0;\n\t}" : "+d"(acc) : "d"(x), "r"(flag));
 }
 
+// Column selection (MODE 1 only): instead of all K draws of a slot's unit, produce the draws
+// list[slot * cap + j].x (j < cnt[slot]) and write each to column list[..].y of draws_out — the
+// resampled draws regenerated on demand, so that the whole pool need not be materialised.
+struct pfb_k3_sel {
+    const int32_t* cnt;  // [nslots] or nullptr = all K draws
+    const int2* list;    // [nslots x cap] (draw index, output column)
+    int cap;
+};
+
 struct pfb_model_params {
     const double* p0;  // DIAGNORMAL: mean[n]
     const double* p1;  // DIAGNORMAL: 1/sd[n]
@@ -168,13 +177,13 @@ struct pfb_ic {
 //         normals are generated ONCE; S = sum d (x - m)^2 and x_0 follow from linear functionals of
 //         u~ (w = Vh' u~, Vh' (p u~), r' u~ — all DMMA columns) and sum p u~^2, so the second
 //         Philox/ziggurat sweep (the kernel's bottleneck) disappears.
-template <int KP, int MODEL, int MODE>
+template <int KP, int MODEL, int MODE, bool SELM = false>
 __global__ void __launch_bounds__(PFB_K3_MAXWARPS * 32, 1)
 pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__ unit_list,
                    const double* __restrict__ FR2, const double* __restrict__ HDR,
                    const uint64_t* __restrict__ seeds, const double* __restrict__ u_host,
                    pfb_model_params mp, double* __restrict__ logp_out, double* __restrict__ logq_out,
-                   double* __restrict__ draws_out) {
+                   double* __restrict__ draws_out, pfb_k3_sel sel) {
     constexpr bool MATERIALIZE = (MODE == 1);
     constexpr bool QUAD = (MODE == 2);
     constexpr int RS2 = (KP == 12) ? 16 : 32;
@@ -205,17 +214,28 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
     const int split = blockIdx.x - slot * splits;
     const int unit = unit_list ? unit_list[slot] : slot;
     const int DPS = NW * DS * 8;                 // draws per sweep
-    const int S = (K + DPS - 1) / DPS;           // sweeps of this unit
+    constexpr bool SEL = SELM;  // column selection is its own instantiation: the other kernels are untouched
+    const int2* sel_list = SEL ? sel.list + (int64_t)slot * sel.cap : nullptr;
+    const int Kslot = SEL ? sel.cnt[slot] : K;   // draws this slot produces
+    const int S = (Kslot + DPS - 1) / DPS;       // sweeps of this unit
+    if (SEL && split >= S) return;               // (column selection: most CTAs of a slot have nothing to do)
     if (unit < 0) {  // path without a usable iteration (K5 only): no fitted normal, NaN draws
         for (int sw = split; sw < S; sw += splits) {
-            const int ka = sw * DPS, kb = min(K, (sw + 1) * DPS);
-            for (int k = ka + tid; k < kb; k += blockDim.x) {
-                logp_out[(int64_t)slot * K + k] = NAN;
-                logq_out[(int64_t)slot * K + k] = NAN;
-            }
-            if (MATERIALIZE && draws_out != nullptr && kb > ka) {
-                double* d0 = draws_out + ((int64_t)slot * K + ka) * n;
-                for (int64_t e = tid; e < (int64_t)(kb - ka) * n; e += blockDim.x) d0[e] = NAN;
+            const int ka = sw * DPS, kb = min(Kslot, (sw + 1) * DPS);
+            if (!SEL) {
+                for (int k = ka + tid; k < kb; k += blockDim.x) {
+                    if (logp_out) logp_out[(int64_t)slot * K + k] = NAN;
+                    if (logq_out) logq_out[(int64_t)slot * K + k] = NAN;
+                }
+                if (MATERIALIZE && draws_out != nullptr && kb > ka) {
+                    double* d0 = draws_out + ((int64_t)slot * K + ka) * n;
+                    for (int64_t e = tid; e < (int64_t)(kb - ka) * n; e += blockDim.x) d0[e] = NAN;
+                }
+            } else {
+                for (int j = ka; j < kb; ++j) {
+                    double* d0 = draws_out + (int64_t)sel_list[j].y * n;
+                    for (int e = tid; e < n; e += blockDim.x) d0[e] = NAN;
+                }
             }
         }
         return;
@@ -297,12 +317,15 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 #pragma unroll 1
     for (int sw = split; sw < S; sw += splits) {
         uint32_t kd[DS];      // draw index (clamped)
+        int64_t ocol[DS];     // MODE 1: output column of the draw (the lean modes recompute it at the end)
         uint32_t actmask = 0u;  // pending-nibble mask of the active draw sets (bit d*2+e)
 #pragma unroll
         for (int d = 0; d < DS; ++d) {
             const int kraw = sw * DPS + (warp * DS + d) * 8 + g;
-            if (kraw < K) actmask |= 3u << (2 * d);
-            kd[d] = (uint32_t)(kraw < K ? kraw : K - 1);
+            if (kraw < Kslot) actmask |= 3u << (2 * d);
+            const int pos = kraw < Kslot ? kraw : Kslot - 1;
+            kd[d] = SEL ? (uint32_t)sel_list[pos].x : (uint32_t)pos;
+            if (MATERIALIZE) ocol[d] = SEL ? (int64_t)sel_list[pos].y : (int64_t)slot * K + kd[d];
         }
         double unormsq[DS];
         pfb_model_acc<MODEL> macc[DS];
@@ -512,7 +535,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                             const double x0 = fma(am[0].x, d0, am[0].y);
                             const double x1 = fma(am[1].x, d1, am[1].y);
                             const bool act = (actmask >> (2 * d)) & 1u;
-                            double* xo = MATERIALIZE ? draws_out + ((int64_t)slot * K + kd[d]) * n : nullptr;
+                            double* xo = MATERIALIZE ? draws_out + ocol[d] * n : nullptr;
                             if (!SPECIAL) {
                                 macc[d].add_nz_unless(R, x0, mp, nib & (1u << (2 * d)));
                                 macc[d].add_nz_unless(R + 1, x1, mp, nib & (2u << (2 * d)));
@@ -614,8 +637,8 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                         for (int it = lane; it < nitems; it += 32) {
                             const uint32_t row = (uint32_t)(r0 + wl.row[it]);
                             const int kraw = sw * DPS + (warp * DS + wl.ds[it]) * 8 + (wl.src[it] >> 2);
-                            wl.z[it] = pf_normal_finish_slow(row, (uint32_t)kraw, k0, k1, PF_ZIG_KW_DEV,
-                                                             PF_ZIG_F_DEV);
+                            const uint32_t kdraw = SEL ? (uint32_t)sel_list[kraw].x : (uint32_t)kraw;
+                            wl.z[it] = pf_normal_finish_slow(row, kdraw, k0, k1, PF_ZIG_KW_DEV, PF_ZIG_F_DEV);
                         }
                         __syncwarp();
                         if (PASS == 0) {
@@ -677,7 +700,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                                         if (d == dsi) {
                                             macc[d].add(r0 + row, x, mp);
                                             if (MATERIALIZE)
-                                                draws_out[((int64_t)slot * K + kd[d]) * n + r0 + row] = x;
+                                                draws_out[ocol[d] * n + r0 + row] = x;
                                         }
                                 }
                                 ++flat;
@@ -771,8 +794,14 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
             if (t == 0 && ((actmask >> (2 * d)) & 1u)) {
                 double logq = (fma((double)n, PFB_LOG2PI, logdet) + us) / -2.0;
                 if (!pd_ok) logq = NAN;
-                logp_out[(int64_t)slot * K + kd[d]] = macc[d].finish(n, mp);
-                logq_out[(int64_t)slot * K + kd[d]] = logq;
+                const int64_t oc = MATERIALIZE ? ocol[d] : (int64_t)slot * K + kd[d];
+                if (MATERIALIZE) {
+                    if (logp_out) logp_out[oc] = macc[d].finish(n, mp);
+                    if (logq_out) logq_out[oc] = logq;
+                } else {
+                    logp_out[oc] = macc[d].finish(n, mp);
+                    logq_out[oc] = logq;
+                }
             }
         }
         __syncwarp();
@@ -791,8 +820,9 @@ template <int KP, int MODEL>
 static cudaError_t launch_k3_m(cudaStream_t st, int n, int K, int nslots, const int32_t* unit_list,
                                const double* FR2, const double* HDR, const uint64_t* seeds,
                                const double* u_host, pfb_model_params mp, double* logp, double* logq,
-                               double* draws, int two_pass) {
+                               double* draws, int two_pass, pfb_k3_sel sel) {
     if (nslots <= 0) return cudaSuccess;
+    if (sel.cnt != nullptr && draws == nullptr) return cudaErrorInvalidValue;
     // every registered family is diagonal-quadratic, so the lean path runs single pass unless
     // the caller asks for the generic two-pass kernel (or wants x written out)
     const bool quad = (draws == nullptr) && !two_pass;
@@ -803,6 +833,7 @@ static cudaError_t launch_k3_m(cudaStream_t st, int n, int K, int nslots, const 
     // warps: enough for K draws, at most 16 (256 draws per sweep)
     int NW = (K + PFB_K3_DS * 8 - 1) / (PFB_K3_DS * 8);
     NW = NW < 1 ? 1 : (NW > PFB_K3_MAXWARPS ? PFB_K3_MAXWARPS : NW);
+    if (sel.cnt != nullptr && NW > 4) NW = 4;  // selections are short lists: 64 draws per sweep
     const int DPS = NW * PFB_K3_DS * 8;
     const int S = (K + DPS - 1) / DPS;
     const int C = (pfb_npad8(n) + PFB_K3_RC - 1) / PFB_K3_RC;
@@ -813,11 +844,20 @@ static cudaError_t launch_k3_m(cudaStream_t st, int n, int K, int nslots, const 
     // split a unit's sweeps over several CTAs only when there are too few units to fill the GPU
     int splits = (4 * nsm + nslots - 1) / nslots;
     splits = splits < 1 ? 1 : (splits > S ? S : splits);
+    // column selection: the number of sweeps is per slot and only known on the device; resampling
+    // with concentrated weights puts most columns into a few slots, so give every slot enough CTAs for
+    // the worst case (sel.cap columns) — the ones without a sweep return at once
+    if (sel.cnt != nullptr) {
+        splits = (sel.cap + DPS - 1) / DPS;
+        splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
+    }
     const int64_t grid = (int64_t)nslots * splits;
     if (grid > 2147483647LL) return cudaErrorInvalidValue;
     void (*kern)(int, int, int, int, const int32_t*, const double*, const double*, const uint64_t*, const double*,
-                 pfb_model_params, double*, double*, double*);
-    if constexpr (MODEL == PFB_MODEL_EXTERNAL) {
+                 pfb_model_params, double*, double*, double*, pfb_k3_sel);
+    if (sel.cnt != nullptr) {
+        kern = pfb_k3_elbo_sample<KP, MODEL, 1, true>;
+    } else if constexpr (MODEL == PFB_MODEL_EXTERNAL) {
         kern = pfb_k3_elbo_sample<KP, MODEL, 1>;
     } else {
         kern = draws ? pfb_k3_elbo_sample<KP, MODEL, 1>
@@ -826,7 +866,7 @@ static cudaError_t launch_k3_m(cudaStream_t st, int n, int K, int nslots, const 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(unsigned)grid, NW * 32, smem, st>>>(n, K, splits, NS, unit_list, FR2, HDR, seeds, u_host, mp, logp,
-                                                logq, draws);
+                                                logq, draws, sel);
     return cudaGetLastError();
 }
 
@@ -834,23 +874,23 @@ template <int KP>
 static cudaError_t launch_k3_k(cudaStream_t st, int model, int n, int K, int nslots,
                                const int32_t* unit_list, const double* FR2, const double* HDR,
                                const uint64_t* seeds, const double* u_host, pfb_model_params mp,
-                               double* logp, double* logq, double* draws, int two_pass) {
+                               double* logp, double* logq, double* draws, int two_pass, pfb_k3_sel sel) {
     switch (model) {
         case PFB_MODEL_ISONORMAL:
             return launch_k3_m<KP, PFB_MODEL_ISONORMAL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host,
-                                                        mp, logp, logq, draws, two_pass);
+                                                        mp, logp, logq, draws, two_pass, sel);
         case PFB_MODEL_FUNNEL:
             return launch_k3_m<KP, PFB_MODEL_FUNNEL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host, mp,
-                                                     logp, logq, draws, two_pass);
+                                                     logp, logq, draws, two_pass, sel);
         case PFB_MODEL_DIAGNORMAL:
             return launch_k3_m<KP, PFB_MODEL_DIAGNORMAL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host,
-                                                         mp, logp, logq, draws, two_pass);
+                                                         mp, logp, logq, draws, two_pass, sel);
         case PFB_MODEL_DENSENORMAL:
         case PFB_MODEL_HLOGISTIC:
         case PFB_MODEL_HOSTCALLBACK:
             if (draws == nullptr) return cudaErrorInvalidValue;  // these families need x written out (K8)
             return launch_k3_m<KP, PFB_MODEL_EXTERNAL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host, mp,
-                                                       logp, logq, draws, 1);
+                                                       logp, logq, draws, 1, sel);
     }
     return cudaErrorInvalidValue;
 }
@@ -861,8 +901,10 @@ extern "C" cudaError_t PFB_K3_ENTRY(cudaStream_t st, int model, int n, int K, in
                                     const int32_t* unit_list, const double* FR2, const double* HDR,
                                     const uint64_t* seeds, const double* u_host, const double* mp0,
                                     const double* mp1, double mc0, double* logp, double* logq,
-                                    double* draws, int two_pass) {
+                                    double* draws, int two_pass, const int32_t* sel_cnt, const void* sel_list,
+                                    int sel_cap) {
     pfb_model_params mp{mp0, mp1, mc0};
+    pfb_k3_sel sel{sel_cnt, reinterpret_cast<const int2*>(sel_list), sel_cap};
     return launch_k3_k<PFB_K3_KP>(st, model, n, K, nslots, unit_list, FR2, HDR, seeds, u_host, mp, logp, logq,
-                                  draws, two_pass);
+                                  draws, two_pass, sel);
 }

@@ -410,3 +410,30 @@ extern "C" cudaError_t pfb_launch_k7b(cudaStream_t st, int n, int N, int K_run, 
     pfb_k7b_gather<<<ndraws, 128, 0, st>>>(n, K_run, idx_out, pool, inds, ids, draws_out);
     return cudaGetLastError();
 }
+
+// ---- K7r: bin the resampled pool indices by path, so that K3 can regenerate exactly those draws ----
+// inds[t] (1-based pool index; the pool of this engine covers [base, base + P * K)) -> per path p the
+// list of (draw k, output column t) in increasing t (one warp per path: ballot + prefix count, so the
+// lists are deterministic).  Entries of other ranks' paths are skipped.
+__global__ void pfb_k7r_bin(int P, int K, int m, int64_t base, const int64_t* __restrict__ inds,
+                            int32_t* __restrict__ cnt, int2* __restrict__ list) {
+    const int p = blockIdx.x, lane = threadIdx.x;
+    int c = 0;
+    for (int t0 = 0; t0 < m; t0 += 32) {
+        const int t = t0 + lane;
+        int64_t loc = -1;
+        if (t < m) loc = inds[t] - 1 - base;
+        const bool mine = (loc >= 0) && (loc / K == p) && (loc < (int64_t)P * K);
+        const unsigned bal = __ballot_sync(0xffffffffu, mine);
+        if (mine) list[(int64_t)p * m + c + __popc(bal & ((1u << lane) - 1u))] = make_int2((int)(loc % K), t);
+        c += __popc(bal);
+    }
+    if (lane == 0) cnt[p] = c;
+}
+
+extern "C" cudaError_t pfb_launch_k7r_bin(cudaStream_t st, int P, int K, int m, int64_t base, const int64_t* inds,
+                                          int32_t* cnt, void* list) {
+    if (P <= 0 || m <= 0) return cudaSuccess;
+    pfb_k7r_bin<<<P, 32, 0, st>>>(P, K, m, base, inds, cnt, reinterpret_cast<int2*>(list));
+    return cudaGetLastError();
+}

@@ -23,7 +23,7 @@ cudaError_t pfb_launch_k2(cudaStream_t, int, int, int, int, const double*, const
 #define PFB_DECL_K3(name)                                                                                  \
     cudaError_t name(cudaStream_t, int, int, int, int, const int32_t*, const double*, const double*,        \
                      const uint64_t*, const double*, const double*, const double*, double, double*, double*, \
-                     double*, int);
+                     double*, int, const int32_t*, const void*, int);
 PFB_DECL_K3(pfb_launch_k3_kp12)
 PFB_DECL_K3(pfb_launch_k3_kp20)
 PFB_DECL_K3(pfb_launch_k3_kp24)
@@ -45,6 +45,7 @@ cudaError_t pfb_launch_k0(cudaStream_t, int, int, int, int, const double*, const
 cudaError_t pfb_launch_k0_pack(cudaStream_t, int, int64_t, const int64_t*, const double*, const double*, double*,
                                double*);
 size_t pfb_psis_scalars_size();
+cudaError_t pfb_launch_k7r_bin(cudaStream_t, int, int, int, int64_t, const int64_t*, int32_t*, void*);
 cudaError_t pfb_k7b_temp_bytes(int, size_t*);
 cudaError_t pfb_launch_k7b(cudaStream_t, int, int, int, uint64_t, int, const double*, const double*, uint64_t*,
                            uint64_t*, int32_t*, int32_t*, void*, size_t, int64_t*, int64_t*, double*);
@@ -106,6 +107,8 @@ struct pfb_engine {
     int64_t T = 0, U = 0;
     bool have_batch = false, ran = false, have_normals = false;
     int poolK = 0;  // draws per path in the device pool (K, or the count of the last pfb_draw_from_fits)
+    bool pool_ready = false;  // the pool's DRAWS are materialised (its logp / logq always are after a run)
+    DevBuf dSelCnt, dSelList;
     int launches = 0;
     std::vector<int64_t> h_off;
     DevBuf dX, dG, dOff, dSeeds, dUnitCol, dNormals;
@@ -210,7 +213,7 @@ extern "C" int pfb_destroy(pfb_handle h) {
                       &h->dPoolLogq, &h->dAllDraws, &h->dFitMu, &h->dFitAlpha, &h->dFitVh, &h->dFitT,
                       &h->dFitVc, &h->dFitLogdet, &h->dFitJeff, &h->dLogw, &h->dW, &h->dCum, &h->dScal,
                       &h->dInds, &h->dIds, &h->dOutDraws, &h->dTmpLogr, &h->dTmpPool, &h->dGenX, &h->dGenY, &h->dIota, &h->dTopSeeds,
-                      &h->dLbX0, &h->dLbX, &h->dLbG, &h->dLbFX, &h->dLbWs, &h->dLbNp, &h->dLbSt, &h->dLbNev, &h->dLbSrc, &h->dSortWork, &h->dSortTmp};
+                      &h->dLbX0, &h->dLbX, &h->dLbG, &h->dLbFX, &h->dLbWs, &h->dLbNp, &h->dLbSt, &h->dLbNev, &h->dLbSrc, &h->dSortWork, &h->dSortTmp, &h->dSelCnt, &h->dSelList};
     for (auto* b : bufs) b->release();
     if (h->cublas) cublasDestroy(h->cublas);
     for (int i = 0; i < 2; ++i) {
@@ -526,7 +529,8 @@ static bool model_is_external(const pfb_engine* h) {
 }
 
 static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list, double* logp, double* logq,
-                             double* draws, int K_over = 0, const uint64_t* seeds_over = nullptr);
+                             double* draws, int K_over = 0, const uint64_t* seeds_over = nullptr,
+                             const int32_t* sel_cnt = nullptr, const void* sel_list = nullptr, int sel_cap = 0);
 
 extern "C" int pfb_register_host_model(pfb_handle h, int n, pfb_logp_callback cb, void* user) {
     if (!h) return PFB_ERR_ARG;
@@ -618,14 +622,42 @@ static int generic_logp(pfb_engine* h, const double* X, int64_t M, const int32_t
 
 // K_over > 0 / seeds_over != NULL: fresh draws from the fitted normals (top-up draws, resample()).
 static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list, double* logp, double* logq,
-                             double* draws, int K_over, const uint64_t* seeds_over) {
+                             double* draws, int K_over, const uint64_t* seeds_over, const int32_t* sel_cnt,
+                             const void* sel_list, int sel_cap) {
     const double* mp0 = model_is_external(h) ? nullptr : h->dModel.as<double>();
     const double* mp1 = mp0 ? mp0 + h->model_n : nullptr;
     const double* un = (h->have_normals && !seeds_over) ? h->dNormals.as<double>() : nullptr;
     auto fn = h->KP == 12 ? pfb_launch_k3_kp12 : (h->KP == 20 ? pfb_launch_k3_kp20 : pfb_launch_k3_kp24);
     return fn(h->stream, h->model, h->n, K_over > 0 ? K_over : h->K, nslots, unit_list, h->dFR2.as<double>(),
               h->dHDR.as<double>(), seeds_over ? seeds_over : h->dSeeds.as<uint64_t>(), un, mp0, mp1, h->model_c0,
-              logp, logq, draws, h->cfg.elbo_mode == 1);
+              logp, logq, draws, h->cfg.elbo_mode == 1, sel_cnt, sel_list, sel_cap);
+}
+
+// K5, on demand: materialise the best-iteration draws of every path into the pool (regenerated, hence
+// identical to the ELBO-stage draws because the RNG is counter based).  The pool's logp / logq are
+// gathered from the ELBO stage by pfb_batch_run; the draws are only produced when somebody looks at
+// them (PathfinderResult.draws, pool exchange) — the resample stage regenerates just its columns.
+static int ensure_pool(pfb_engine* h) {
+    if (h->pool_ready || h->P <= 0) return PFB_OK;
+    if (!h->ran || h->poolK != h->K) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
+    PFB_CUDA(h, launch_k3(h, h->P, h->dBestUnit.as<int32_t>(), nullptr, nullptr, h->dPool.as<double>()));
+    h->launches += 1;
+    h->pool_ready = true;
+    return PFB_OK;
+}
+
+// Columns inds[t] (1-based pool indices; this engine's pool covers [base, base + P K)) regenerated
+// straight into d_out [n x m]; columns owned elsewhere are left untouched.
+static int regen_columns(pfb_engine* h, int m, const int64_t* d_inds, int64_t base, double* d_out) {
+    if (m <= 0 || h->P <= 0) return PFB_OK;
+    cudaStream_t st = h->stream;
+    PFB_CUDA(h, h->dSelCnt.ensure((size_t)h->P * 4 + 8));
+    PFB_CUDA(h, h->dSelList.ensure((size_t)h->P * (size_t)m * 8 + 8));
+    PFB_CUDA(h, pfb_launch_k7r_bin(st, h->P, h->K, m, base, d_inds, h->dSelCnt.as<int32_t>(), h->dSelList.p));
+    PFB_CUDA(h, launch_k3(h, h->P, h->dBestUnit.as<int32_t>(), nullptr, nullptr, d_out, 0, nullptr,
+                          h->dSelCnt.as<int32_t>(), h->dSelList.p, m));
+    h->launches += 2;
+    return PFB_OK;
 }
 
 // ELBO stage for a host-callback target (row f2): K3 materialises chunk c + 2 and the copy stream
@@ -773,22 +805,17 @@ extern "C" int pfb_batch_run(pfb_handle h) {
                               h->dBestUnit.as<int32_t>(), h->dSucc.as<int32_t>()));
     h->launches += (P > 0) + (U > 0);
     PFB_CUDA(h, cudaEventRecord(h->ev[4], st));
-    // K5: materialise the best iteration of every path into the pool (regenerated, identical
-    // to the ELBO draws because the RNG is counter based)
-    PFB_CUDA(h, launch_k3(h, P, h->dBestUnit.as<int32_t>(), h->dPoolLogp.as<double>(), h->dPoolLogq.as<double>(),
-                          h->dPool.as<double>()));
-    h->launches += (P > 0);
-    if (h->model == PFB_MODEL_HOSTCALLBACK && P > 0) {
+    // the pool's log densities are the ELBO stage's own (same draws); its draws are materialised on
+    // demand (ensure_pool) or column by column (regen_columns)
+    if (P > 0) {
         pfb_gather_unit_rows<<<P, 256, 0, st>>>(K, h->dBestUnit.as<int32_t>(), h->dLogp.as<double>(),
                                                 h->dPoolLogp.as<double>());
+        pfb_gather_unit_rows<<<P, 256, 0, st>>>(K, h->dBestUnit.as<int32_t>(), h->dLogq.as<double>(),
+                                                h->dPoolLogq.as<double>());
         PFB_CUDA(h, cudaGetLastError());
-        h->launches += 1;
-    } else if (model_is_external(h) && P > 0) {
-        int rc = generic_logp(h, h->dPool.as<double>(), (int64_t)P * K, h->dBestUnit.as<int32_t>(),
-                              h->dPoolLogp.as<double>());
-        if (rc) return rc;
         h->launches += 2;
     }
+    h->pool_ready = false;
     PFB_CUDA(h, cudaEventRecord(h->ev[5], st));
     h->ran = true;
     h->poolK = K;
@@ -829,6 +856,7 @@ extern "C" int pfb_batch_fit_only(pfb_handle h, const int64_t* best_iter) {
     h->launches = 2;
     h->ran = true;
     h->poolK = 0;
+    h->pool_ready = false;
     return PFB_OK;
 }
 
@@ -875,7 +903,10 @@ extern "C" int pfb_draw_from_fits(pfb_handle h, int K_new, const uint64_t* seeds
     if (logp) PFB_CUDA(h, cudaMemcpyAsync(logp, Lp->p, (size_t)K_new * P * 8, cudaMemcpyDeviceToHost, st));
     if (logq) PFB_CUDA(h, cudaMemcpyAsync(logq, Lq->p, (size_t)K_new * P * 8, cudaMemcpyDeviceToHost, st));
     PFB_CUDA(h, cudaStreamSynchronize(st));
-    if (keep_as_pool) h->poolK = K_new;
+    if (keep_as_pool) {
+        h->poolK = K_new;
+        h->pool_ready = true;
+    }
     return PFB_OK;
 }
 
@@ -976,6 +1007,10 @@ extern "C" int pfb_batch_download(pfb_handle h, pfb_elbo_out* o) {
     PFB_D2H(o->best_iter, h->dBestIter.p, P * 8);
     PFB_D2H(o->success, h->dSucc.p, P * 4);
     PFB_D2H(o->n_rejected, h->dRej.p, P * 8);
+    if (o->draws) {
+        int rcp = ensure_pool(h);
+        if (rcp) return rcp;
+    }
     PFB_D2H(o->draws, h->dPool.p, n * K * P * 8);
     PFB_D2H(o->draws_logp, h->dPoolLogp.p, K * P * 8);
     PFB_D2H(o->draws_logq, h->dPoolLogq.p, K * P * 8);
@@ -1023,6 +1058,10 @@ extern "C" int pfb_pool_download(pfb_handle h, int p0, int p1, double* draws, do
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = h->stream;
     const size_t n = h->n, K = (size_t)h->poolK, cnt = (size_t)(p1 - p0);
+    if (draws && cnt) {
+        int rcp = ensure_pool(h);
+        if (rcp) return rcp;
+    }
     if (draws && cnt)
         PFB_CUDA(h, cudaMemcpyAsync(draws, h->dPool.as<double>() + (size_t)p0 * n * K, cnt * n * K * 8,
                                     cudaMemcpyDeviceToHost, st));
@@ -1102,9 +1141,27 @@ extern "C" int pfb_elbo_batch(pfb_handle h, int n, int P, const int64_t* offsets
     return pfb_batch_download(h, out);
 }
 
+extern "C" int pfb_pool_materialize(pfb_handle h) {
+    if (!h) return PFB_ERR_ARG;
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    return ensure_pool(h);
+}
+
+// Multi-GPU resample: inds are 1-based indices into the GLOBAL pool (all ranks, run order); this
+// engine owns [base, base + P K).  Its columns are written to d_out [n x m] (device); the others are
+// left as they are (zero them first and sum-reduce across ranks).
+extern "C" int pfb_pool_columns_device(pfb_handle h, int m, const void* d_inds, int64_t base, void* d_out) {
+    if (!h || !d_inds || !d_out) return PFB_ERR_ARG;
+    if (!h->ran || h->poolK <= 0) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
+    if (h->poolK != h->K) PFB_FAIL(h, PFB_ERR_STATE, "column regeneration needs the pool of pfb_batch_run");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    return regen_columns(h, m, (const int64_t*)d_inds, base, (double*)d_out);
+}
+
 extern "C" int pfb_batch_device_view(pfb_handle h, pfb_device_view* v) {
     if (!h || !v) return PFB_ERR_ARG;
     if (!h->have_batch) PFB_FAIL(h, PFB_ERR_STATE, "no batch");
+    // pool_draws is valid after pfb_pool_materialize (or a draws download); the log densities always are
     v->pool_draws = h->dPool.p;
     v->pool_logp = h->dPoolLogp.p;
     v->pool_logq = h->dPoolLogq.p;
@@ -1116,7 +1173,9 @@ extern "C" int pfb_batch_device_view(pfb_handle h, pfb_device_view* v) {
 
 static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const double* d_logp,
                               const double* d_logq, const double* d_logr, const double* d_pool, uint64_t seed,
-                              int ndraws, int importance, int replace, pfb_resample_out* o) {
+                              int ndraws, int importance, int replace, pfb_resample_out* o, bool regen = false) {
+    // regen: the engine's own pool, whose draws are not materialised: the selected columns are
+    // regenerated by K3 (bit-identical to the pool's) instead of gathered
     if (N < 1 || N > 2147483647LL) PFB_FAIL(h, PFB_ERR_SHAPE, "pool size out of range");
     if (K_run < 1 || ndraws < 0) PFB_FAIL(h, PFB_ERR_ARG, "bad K_run / ndraws");
     if (!replace && ndraws > N) PFB_FAIL(h, PFB_ERR_ARG, "Cannot draw more samples without replacement.");
@@ -1124,8 +1183,9 @@ static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const 
     PFB_CUDA(h, h->dScal.ensure(pfb_psis_scalars_size()));
     PFB_CUDA(h, h->dInds.ensure((size_t)ndraws * 8 + 8));
     PFB_CUDA(h, h->dIds.ensure((size_t)ndraws * 8 + 8));
-    const bool want_draws = (o->draws != nullptr) && (d_pool != nullptr);
-    if (want_draws) PFB_CUDA(h, h->dOutDraws.ensure((size_t)n * ndraws * 8 + 8));
+    const bool want_regen = regen && (o->draws != nullptr) && ndraws > 0;
+    const bool want_draws = (o->draws != nullptr) && (d_pool != nullptr) && !want_regen;
+    if (want_draws || want_regen) PFB_CUDA(h, h->dOutDraws.ensure((size_t)n * ndraws * 8 + 8));
     if (importance) {
         // tail_length(r_eff = 1, S) = min(cld(S, 5), ceil(3 sqrt(S)));  grid m = 30 + floor(sqrt(M))
         const int M = (int)std::min<int64_t>((N + 4) / 5, (int64_t)ceil(3.0 * sqrt((double)N)));
@@ -1158,6 +1218,10 @@ static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const 
                                    h->dInds.as<int64_t>(), h->dIds.as<int64_t>(),
                                    want_draws ? h->dOutDraws.as<double>() : nullptr));
     }
+    if (want_regen) {
+        int rcr = regen_columns(h, ndraws, h->dInds.as<int64_t>(), 0, h->dOutDraws.as<double>());
+        if (rcr) return rcr;
+    }
     psis_scalars_host sc;
     memset(&sc, 0, sizeof(sc));
     if (importance) {
@@ -1167,7 +1231,7 @@ static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const 
     }
     PFB_D2H(o->inds, h->dInds.p, (size_t)ndraws * 8);
     PFB_D2H(o->ids, h->dIds.p, (size_t)ndraws * 8);
-    if (want_draws) PFB_D2H(o->draws, h->dOutDraws.p, (size_t)n * ndraws * 8);
+    if (want_draws || want_regen) PFB_D2H(o->draws, h->dOutDraws.p, (size_t)n * ndraws * 8);
     PFB_CUDA(h, cudaStreamSynchronize(st));
     if (o->pareto_k) *o->pareto_k = importance ? sc.pareto_k : NAN;
     if (o->tail_len) *o->tail_len = importance ? sc.tail_len : 0;
@@ -1181,7 +1245,7 @@ extern "C" int pfb_psis_resample(pfb_handle h, uint64_t seed, int ndraws, int im
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
     return psis_resample_impl(h, h->n, (int64_t)h->P * h->poolK, h->poolK, h->dPoolLogp.as<double>(),
                               h->dPoolLogq.as<double>(), nullptr, h->dPool.as<double>(), seed, ndraws,
-                              importance, replace, o);
+                              importance, replace, o, /*regen=*/!h->pool_ready);
 }
 
 extern "C" int pfb_psis_resample_device(pfb_handle h, int n, int64_t N, int K_run, const void* d_logp,

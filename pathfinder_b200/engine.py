@@ -394,6 +394,16 @@ class Engine:
         nl = self.lib.pfb_get_timings(self.h, _ptr(ms))
         return dict(k1=ms[0], k2=ms[1], k3=ms[2], k4=ms[3], k5=ms[4], total=ms[5], launches=nl)
 
+    def pool_materialize(self):
+        """Materialise the pool's draws on the device (needed before device_view().pool_draws is read)."""
+        _lib.check(self.h, self.lib.pfb_pool_materialize(self.h))
+
+    def pool_columns_device(self, m, d_inds, base, d_out):
+        """Regenerate this engine's share of the globally indexed (1-based) pool columns d_inds[m]
+        (device int64 pointer) into d_out [n x m] (device pointer); see pfb_pool_columns_device."""
+        _lib.check(self.h, self.lib.pfb_pool_columns_device(self.h, int(m), C.c_void_p(int(d_inds)), int(base),
+                                                            C.c_void_p(int(d_out))))
+
     def device_view(self) -> pfb_device_view:
         v = pfb_device_view()
         _lib.check(self.h, self.lib.pfb_batch_device_view(self.h, C.byref(v)))
