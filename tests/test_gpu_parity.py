@@ -967,3 +967,37 @@ def test_resampled_columns_regenerated_without_materialising_the_pool(kind):
     d, lp, lq = lean._pool_download()
     assert np.array_equal(d, a.draws, equal_nan=True) and np.array_equal(lp, a.draws_logp, equal_nan=True)
     ref.close(); lean.close()
+
+
+def test_pool_columns_device_regenerates_only_the_owned_columns():
+    """The multi-GPU resample step (pfb_pool_columns_device): global 1-based indices, this engine owns
+    [base, base + P K); its columns are regenerated bit-identically, the others are left untouched."""
+    import torch
+
+    import pathfinder_b200 as pf
+    from tests.helpers import synthetic_trajectory
+
+    n, K = 20, 96
+    model = pf.Funnel(n)
+    trajs = [synthetic_trajectory(n, L, 90 + L, scale=0.3) for L in (4, 6, 3)]
+    seeds = np.concatenate(_seeds(trajs, 13))
+    offsets, X, G = pf.Engine.pack(trajs)
+    eng = _engine(model, K)
+    eng.elbo_batch(offsets, X, G, seeds, draws=False)
+    Nloc = 3 * K
+    base = 2 * Nloc                                   # "rank 2 of 4"
+    rng = np.random.default_rng(0)
+    inds = rng.integers(1, 4 * Nloc + 1, size=400).astype(np.int64)
+    inds[:5] = [base + 1, base + Nloc, base, base + Nloc + 1, base + 7]   # the edges of the owned range
+    d_inds = torch.from_numpy(inds).cuda()
+    out = torch.full((400, n), -7.0, dtype=torch.float64, device="cuda")
+    eng.pool_columns_device(400, d_inds.data_ptr(), base, out.data_ptr())
+    eng.sync()
+    got = out.cpu().numpy()
+    pool, _, _ = eng._pool_download()                # materialise for comparison
+    pool = pool.reshape(n, -1, order="F")
+    mine = (inds > base) & (inds <= base + Nloc)
+    assert mine[0] and mine[1] and not mine[2] and not mine[3]
+    assert np.array_equal(got[mine], pool[:, inds[mine] - 1 - base].T, equal_nan=True)
+    assert np.all(got[~mine] == -7.0)
+    eng.close()
