@@ -253,6 +253,34 @@ function lbfgs_download(e::Engine, npts::Vector{Int64})
 end
 
 """
+    unit_draws(engine, units) -> (draws, logp, logq)
+
+`ELBOEstimate.draws / .log_densities_target / .log_densities_fit` (src/elbo.jl:22-29) of arbitrary
+iterations of the current batch, regenerated on the device from their seeds (0-based unit indices:
+`offsets[p] - (p - 1) + l - 1` for iteration `l` of path `p`, with 1-based `p`, 0-based `offsets`).
+"""
+function unit_draws(e::Engine, units::Vector{Int32})
+    m = length(units)
+    draws = Array{Float64}(undef, e.n, e.K, m); lp = Matrix{Float64}(undef, e.K, m); lq = similar(lp)
+    check(e, ccall((:pfb_unit_draws, LIB[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   e.handle, m, units, draws, lp, lq))
+    return draws, lp, lq
+end
+
+"""
+    pool_draws(engine, P) -> (draws, logp, logq)
+
+`PathfinderResult.draws` of every run (src/singlepath.jl:231-232), fetched when needed: the engine
+materialises the pool's draws only on request — `psis_resample` regenerates just the resampled columns.
+"""
+function pool_draws(e::Engine, P::Integer)
+    draws = Array{Float64}(undef, e.n, e.K, P); lp = Matrix{Float64}(undef, e.K, P); lq = similar(lp)
+    check(e, ccall((:pfb_pool_download, LIB[]), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   e.handle, 0, P, draws, lp, lq))
+    return draws, lp, lq
+end
+
+"""
     multipathfinder_b200(optimize_one, model_family, dim, ndraws; nruns, ndraws_elbo, rng, ...)
 
 Drop-in for the ELBO-and-resample part of `multipathfinder` (src/multipath.jl:118-245).
