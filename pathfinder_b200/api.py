@@ -118,8 +118,13 @@ class MultiPathfinderResult:
     engine: Engine = field(default=None, repr=False)
 
 
-def _uniform_init(rng, n, scale):
-    """UniformSampler (src/singlepath.jl:332-344): iid U[-scale, scale]."""
+def _uniform_init(rng, n, scale, init_sampler=None):
+    """UniformSampler (src/singlepath.jl:332-344): iid U[-scale, scale]; or the caller's
+    `init_sampler(rng, x)` filling `x` in place like the reference's keyword (src/singlepath.jl:108-110)."""
+    if init_sampler is not None:
+        x = np.empty(n, dtype=np.float64)
+        out = init_sampler(rng, x)
+        return np.asarray(x if out is None else out, dtype=np.float64)
     return (rng.random(n) * 2.0 - 1.0) * scale
 
 
@@ -139,7 +144,7 @@ def _use_device_optimizer(model, optimizer):
 
 
 def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntries, init_scale, ndraws_run=None,
-               optimizer="host", gtol=1e-8, ftol=1e-14, lazy_draws=False):
+               optimizer="host", gtol=1e-8, ftol=1e-14, lazy_draws=False, init_sampler=None):
     """Optimise every path (host L-BFGS, or kernel K0 for the closed-form families), run the ELBO
     stage as one batch, retry failures.  lazy_draws: leave the best-iteration draws on the device."""
     want_draws = "lazy" if (lazy_draws and not (ndraws_run is not None and ndraws_run > engine.K)) else True
@@ -189,7 +194,7 @@ def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntr
             if ok or tries[p] >= ntries:
                 final[p] = (j, res, traces[j], tries[p])
             else:
-                cur_init[p] = _uniform_init(path_rngs[p], model.n, init_scale)  # src/singlepath.jl:278
+                cur_init[p] = _uniform_init(path_rngs[p], model.n, init_scale, init_sampler)  # src/singlepath.jl:278
                 retry.append(p)
         if retry and len(retry) < len(todo):
             # keep the successful paths' device-resident results: assemble them now
@@ -225,14 +230,16 @@ def _assemble_path(model, rng, entry, ndraws, K):
                             res.draws_logp[:ndraws, j], res.draws_logq[:ndraws, j])
 
 
-def pathfinder(model, *, init=None, init_scale=2.0, ndraws_elbo=DEFAULT_NDRAWS_ELBO, ndraws=None, rng=None,
-               history_length=DEFAULT_HISTORY_LENGTH, ntries=1000, maxiters=1000, device=0, engine=None,
-               optimizer="host"):
+def pathfinder(model, *, init=None, init_scale=2.0, init_sampler=None, ndraws_elbo=DEFAULT_NDRAWS_ELBO, ndraws=None,
+               rng=None, history_length=DEFAULT_HISTORY_LENGTH, ntries=1000, maxiters=1000, device=0, engine=None,
+               optimizer="host", ntasks=None):
     """Single-path Pathfinder (src/singlepath.jl:101-139).  optimizer: 'host' (SciPy L-BFGS on the
-    CPU, like src/optimize.jl), 'device' (kernel K0, closed-form families) or 'auto'."""
+    CPU, like src/optimize.jl), 'device' (kernel K0, registered families) or 'auto'.  `ntasks` is
+    accepted for signature compatibility: results never depend on it (src/singlepath.jl:114-117), the
+    device batches over iterations instead of tasks."""
     rng = np.random.default_rng() if rng is None else rng
     ndraws = ndraws_elbo if ndraws is None else ndraws
-    x0 = _uniform_init(rng, model.n, init_scale) if init is None else np.asarray(init, dtype=np.float64)
+    x0 = _uniform_init(rng, model.n, init_scale, init_sampler) if init is None else np.asarray(init, dtype=np.float64)
     if x0.shape != (model.n,):
         raise ValueError("init has the wrong dimension")
     own = engine is None
@@ -240,7 +247,8 @@ def pathfinder(model, *, init=None, init_scale=2.0, ndraws_elbo=DEFAULT_NDRAWS_E
         engine = Engine.for_model(model, history_length, ndraws_elbo, device)
     try:
         final, _ = _run_paths(engine, model, [x0], [rng], history_length=history_length, maxiters=maxiters,
-                              ntries=ntries, init_scale=init_scale, ndraws_run=ndraws, optimizer=optimizer)
+                              ntries=ntries, init_scale=init_scale, ndraws_run=ndraws, optimizer=optimizer,
+                              init_sampler=init_sampler)
         return _assemble_path(model, rng, final[0], ndraws, ndraws_elbo)
     finally:
         if own:
@@ -249,9 +257,10 @@ def pathfinder(model, *, init=None, init_scale=2.0, ndraws_elbo=DEFAULT_NDRAWS_E
 
 def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT_NDRAWS_ELBO,
                     ndraws_per_run=None, importance=True, rng=None, history_length=DEFAULT_HISTORY_LENGTH,
-                    init_scale=2.0, ntries=1000, maxiters=1000, device=0, engine=None, group=None,
-                    optimizer="host"):
-    """Multi-path Pathfinder (src/multipath.jl:94-245).
+                    init_scale=2.0, init_sampler=None, ntries=1000, maxiters=1000, device=0, engine=None, group=None,
+                    optimizer="host", ntasks=None, ntasks_per_run=None):
+    """Multi-path Pathfinder (src/multipath.jl:94-245).  `ntasks` / `ntasks_per_run` are accepted for
+    signature compatibility (results never depend on them, src/multipath.jl:104-108).
 
     Under an initialised ``torch.distributed`` process group (one process per GPU) the runs shard
     across the ranks (distributed.py): every rank must call with the same arguments and an
@@ -271,7 +280,8 @@ def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT
         warnings.warn("More draws requested than total number of draws across replicas. Draws will not be unique.")
     run_seeds = _draw_seeds(rng, nruns)  # src/multipath.jl:162
     path_rngs = [np.random.Generator(np.random.Philox(key=int(s))) for s in run_seeds]
-    inits = [(_uniform_init(path_rngs[p], model.n, init_scale) if x is None else x) for p, x in enumerate(inits)]
+    inits = [(_uniform_init(path_rngs[p], model.n, init_scale, init_sampler) if x is None else x)
+             for p, x in enumerate(inits)]
     seed = int(_draw_seeds(rng, 1)[0])
     dist_on = D.is_distributed(group)
     lo, hi = 0, nruns
@@ -287,7 +297,7 @@ def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT
     # closed on return, so its draws come back eagerly
     final, last = _run_paths(engine, model, inits[lo:hi], path_rngs[lo:hi], history_length=history_length,
                              maxiters=maxiters, ntries=ntries, init_scale=init_scale, ndraws_run=ndraws_per_run,
-                             optimizer=optimizer, lazy_draws=(not own and not dist_on))
+                             optimizer=optimizer, lazy_draws=(not own and not dist_on), init_sampler=init_sampler)
     results = [_assemble_path(model, path_rngs[lo + j], final[j], ndraws_per_run, ndraws_elbo)
                for j in range(hi - lo)]
     # PSIS pool: draw-fastest, component-slowest (test/resample.jl:81-88)

@@ -1001,3 +1001,26 @@ def test_pool_columns_device_regenerates_only_the_owned_columns():
     assert np.array_equal(got[mine], pool[:, inds[mine] - 1 - base].T, equal_nan=True)
     assert np.all(got[~mine] == -7.0)
     eng.close()
+
+
+def test_init_sampler_and_ntasks_keywords():
+    """`init_sampler(rng, x)` (src/singlepath.jl:108-110, :332-344) replaces the uniform initialiser,
+    also for retries; `ntasks` / `ntasks_per_run` are accepted and change nothing."""
+    import pathfinder_b200 as pf
+
+    calls = []
+
+    def sampler(rng, x):
+        x[:] = rng.normal(size=x.size) * 0.5
+        calls.append(x.copy())
+
+    model = pf.IsoNormal(7)
+    a = pf.multipathfinder(model, 40, nruns=3, ndraws_elbo=20, rng=np.random.default_rng(2), init_sampler=sampler,
+                           ntasks=4, ntasks_per_run=2)
+    assert len(calls) == 3
+    for pr, x0 in zip(a.pathfinder_results, calls):
+        assert np.array_equal(pr.optim_trace.points[:, 0], x0)
+    b = pf.multipathfinder(model, 40, nruns=3, ndraws_elbo=20, rng=np.random.default_rng(2), init_sampler=sampler)
+    assert np.array_equal(a.draws, b.draws)
+    r = pf.pathfinder(model, ndraws_elbo=10, rng=np.random.default_rng(3), init_sampler=sampler, ntasks=2)
+    assert np.array_equal(r.optim_trace.points[:, 0], calls[-1])
