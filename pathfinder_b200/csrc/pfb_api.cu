@@ -703,8 +703,6 @@ static int run_host_callback_stage(pfb_engine* h) {
         const int u0 = c * chunk, cnt = std::min(chunk, U - u0), b = c & 1;
         PFB_CUDA(h, cudaEventSynchronize(h->hc_c[b]));
         double* lp = h->hLp + (size_t)u0 * K;
-        cudaEvent_t dummy = nullptr;
-        (void)dummy;
         const auto t0 = std::chrono::steady_clock::now();
         h->host_cb(h->host_user, h->hX[b], (int64_t)n, (int64_t)cnt * K, lp);
         h->host_cb_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

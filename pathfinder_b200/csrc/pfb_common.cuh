@@ -117,30 +117,6 @@ __device__ __forceinline__ void pfb_block_sum_fast(double (&v)[NV], double* scra
         if ((mask >> a) & 1u) v[a] = totals[a];
 }
 
-// Runtime-count variant: values live in shared memory vals[t * stride + a]? No — each thread
-// passes a pointer to its private array of `nv` values (nv <= NVMAX, loops fully unrolled).
-template <int NVMAX>
-__device__ __forceinline__ void pfb_block_sum_n(double (&v)[NVMAX], int nv, double* scratch) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int a = 0; a < NVMAX; ++a)
-        if (a < nv) v[a] = pfb_warp_sum(v[a]);
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-        for (int a = 0; a < NVMAX; ++a)
-            if (a < nv) scratch[a * 32 + warp] = v[a];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int a = 0; a < NVMAX; ++a) {
-        if (a < nv) {
-            double t = (lane < nwarp) ? scratch[a * 32 + lane] : 0.0;
-            v[a] = pfb_warp_sum(t);
-        }
-    }
-}
-
 // ---- mbarrier + 1-D bulk TMA (cp.async.bulk, SASS: UBLKCP) ------------------------------------
 __device__ __forceinline__ uint32_t pfb_smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
