@@ -194,3 +194,21 @@ def test_pool_exchange_world_size_2_gloo(nruns, importance):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+def test_bench_lpt_assignment_is_a_balanced_partition():
+    """bench.py (N > 1): every rank computes the same LPT assignment of the world x P paths on their
+    iteration counts; the shares are disjoint, equally sized and balanced."""
+    import bench
+
+    name, world = "cfg2_funnel100_p8_k1000_j6", 4
+    shares, units = [], []
+    for rank in range(world):
+        _, trajs, seeds, (n, P, K, J, nd, _) = bench.build_workload(name, rank, world)
+        assert len(trajs) == P and all(s.size == X.shape[1] - 1 for (X, _), s in zip(trajs, seeds))
+        shares.append({X[:, 0].tobytes() for X, _ in trajs})        # a path is identified by its initial point
+        units.append(sum(X.shape[1] - 1 for X, _ in trajs))
+    assert len(set().union(*shares)) == world * P                    # disjoint, complete
+    assert max(units) <= 1.1 * (sum(units) / world)
+    _, t1, _, _ = bench.build_workload(name, 0, 1)
+    assert len(t1) == 8
