@@ -212,3 +212,23 @@ def test_bench_lpt_assignment_is_a_balanced_partition():
     assert max(units) <= 1.1 * (sum(units) / world)
     _, t1, _, _ = bench.build_workload(name, 0, 1)
     assert len(t1) == 8
+
+
+def test_product_code_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under pathfinder_b200/ (Python or CUDA) may import,
+    link or include it, and libpfb200.so must not depend on the oracle's shared objects."""
+    import subprocess
+
+    pkg = os.path.join(ROOT, "pathfinder_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "_build" in dirpath or "__pycache__" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), (dirpath, f)
+                assert "pforacle" not in txt and '"oracle/' not in txt and "../oracle" not in txt, (dirpath, f)
+    so = os.path.join(pkg, "libpfb200.so")
+    if os.path.exists(so):
+        deps = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+        assert "pforacle" not in deps
