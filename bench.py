@@ -311,10 +311,16 @@ def main():
 
     resample_seed = MASTER_SEED
 
+    step_bufs = {"r": None}  # caller-owned, page-locked result buffers reused across steps
+
     def step():
         eng.run()
         if world == 1:
-            return eng.psis_resample(resample_seed, ndraws, True)
+            r = eng.psis_resample(resample_seed, ndraws, True, into=step_bufs["r"])
+            if step_bufs["r"] is None:
+                eng.pin(r["log_weights"], r["weights"], r["draws"], r["inds"], r["ids"])
+                step_bufs["r"] = r
+            return r
         # C1 (lean variant): all-gather the per-draw log densities (16 B per pool draw); PSIS and
         # the index draw run replicated and deterministic on every rank; each rank contributes
         # the selected columns it owns, summed into the n x ndraws result.
