@@ -455,8 +455,9 @@ def main():
                 "peak_source": "measured live: pfb_measure_fp64_dmma_tflops (mma.sync m8n8k4 f64 chains); "
                                "MEASURED_PEAKS.json has bf16 and HBM figures only",
                 "dfma_peak_tflops": peak2.value,
-                "note": "the kernel is limited by the half-rate integer path (Philox4x32-10 + ziggurat), not by "
-                        "FP64 math or HBM: see DESIGN.md section 4 and profiles/",
+                "note": "co-bound by the FP64 pipe (12 DMMA + 20 scalar FP64 per 8-row x 16-draw block) and the "
+                        "Philox4x32-10 integer multiplies, which serialise on this part instead of overlapping "
+                        "(profiles/r1_microbench_fp64.md); HBM is idle: see DESIGN.md section 4",
                 "k3_share_of_step": k3_avg_ms * args.steps / max_ms}
 
     line = {
