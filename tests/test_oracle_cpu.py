@@ -524,3 +524,29 @@ def test_psis_oracle_agrees_with_an_independent_restatement():
         assert got["tail_length"] == M
         assert abs(got["pareto_k"] - k_hat) < 1e-10 * max(1.0, abs(k_hat))
         np.testing.assert_allclose(got["log_weights"], lw, rtol=1e-10, atol=1e-10)
+
+
+def test_psis_and_resample_contract_properties():
+    """Size-independent properties of the PSIS / resample contract: shift invariance and permutation
+    equivariance of the smoothed weights, prefix consistency of both index streams (counter-based
+    RNG: asking for more draws never changes the earlier ones)."""
+    rng = np.random.default_rng(21)
+    lr = rng.standard_t(4, size=2500) * 1.3
+    base = OP.psis(lr)
+    shifted = OP.psis(lr + 123.456)
+    np.testing.assert_allclose(shifted["weights"], base["weights"], rtol=1e-9, atol=1e-300)
+    assert abs(shifted["pareto_k"] - base["pareto_k"]) < 1e-9
+    perm = rng.permutation(lr.size)
+    permuted = OP.psis(lr[perm])
+    np.testing.assert_allclose(permuted["weights"], base["weights"][perm], rtol=1e-9, atol=1e-300)
+    w = base["weights"]
+    long_ = OP.resample_indices(17, w, lr.size, 500)
+    assert np.array_equal(OP.resample_indices(17, w, lr.size, 120), long_[:120])
+    nr_all = OP.resample_indices_norep(17, base["log_weights"], lr.size, lr.size)
+    assert np.array_equal(OP.resample_indices_norep(17, base["log_weights"], lr.size, 300), nr_all[:300])
+    assert sorted(nr_all) == list(range(1, lr.size + 1))
+    # heavier weights are picked earlier on average
+    rank_of = np.empty(lr.size, dtype=np.int64)
+    rank_of[nr_all - 1] = np.arange(lr.size)
+    top = np.argsort(-w)[:50]
+    assert rank_of[top].mean() < 0.25 * lr.size
