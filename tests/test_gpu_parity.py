@@ -1024,3 +1024,20 @@ def test_init_sampler_and_ntasks_keywords():
     assert np.array_equal(a.draws, b.draws)
     r = pf.pathfinder(model, ndraws_elbo=10, rng=np.random.default_rng(3), init_sampler=sampler, ntasks=2)
     assert np.array_equal(r.optim_trace.points[:, 0], calls[-1])
+
+
+def test_gpu_index_streams_are_prefix_consistent():
+    """Counter-based RNG on the device: asking for more resampled draws never changes the earlier
+    ones (with and without replacement), and the stream depends on the seed."""
+    import pathfinder_b200 as pf
+
+    rng = np.random.default_rng(30)
+    N, K_run = 4000, 100
+    lr = rng.standard_t(4, size=N) * 1.2
+    eng = _engine(pf.IsoNormal(4), K_run)
+    for replace in (True, False):
+        a = eng.psis_resample_host(lr, K_run, 5, 900, True, replace=replace)["inds"]
+        b = eng.psis_resample_host(lr, K_run, 5, 150, True, replace=replace)["inds"]
+        c = eng.psis_resample_host(lr, K_run, 6, 150, True, replace=replace)["inds"]
+        assert np.array_equal(a[:150], b) and not np.array_equal(b, c)
+    eng.close()
