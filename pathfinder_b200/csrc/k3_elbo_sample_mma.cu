@@ -11,8 +11,9 @@
 //   logp = log pi(x) for the registered model  (src/elbo.jl:15)
 //
 // Mapping.  A warp owns 8 * DS draws; lane (g = lane / 4, t = lane % 4) owns, for draw g of each
-// draw set, the rows {8 b + 2 t, 8 b + 2 t + 1} of every 8-row block b — exactly one Philox call
-// (row pair 4 b + t) per block and draw.  With that ownership both halves of the Q-apply are
+// draw set, the rows {8 b + 2 t, 8 b + 2 t + 1} of every 8-row block b — exactly ONE Philox4x32-7
+// call (row pair 4 b + t, draw pair {k, k + 8}: pf_rng.h) per block for the lane's four variates of
+// its two draw sets.  With that ownership both halves of the Q-apply are
 // DMMA m8n8k4 products whose A / C fragments are the lane's own normals:
 //   pass 0   w[draw][j]  += sum_rows  u~[draw][row] * Vh[row][j]      A = u~ (8 draws x 4 rows),
 //                                                                     B = Vh  (4 rows x 8 j)
@@ -26,8 +27,9 @@
 // brought into shared memory by 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx) in chunks of
 // PFB_K3_RC rows: all chunks stay resident when they fit (n <= ~1150 at history 6), otherwise they
 // stream through a ring, twice per sweep.  A CTA loops over the sweeps (256 draws) of its unit so
-// the record is loaded once per unit.  The 1024-layer ziggurat table sits in shared memory twice
-// (even / odd lanes) to halve the bank conflicts of the random layer lookups.  Elements that leave
+// the record is loaded once per unit.  The 1024-layer ziggurat table (8-byte packed entries, one
+// LDS.64 per variate) sits in shared memory four times, interleaved entry by entry (copy = lane % 4),
+// which spreads the random layer lookups of a half-warp over all 16 bank pairs.  Elements that leave
 // the ziggurat fast path (0.43 %) are deferred and finished warp-cooperatively per chunk.
 // Lean mode writes 16 B per draw (logp, logq); with a draws pointer x is written as well.
 #include "pfb_common.cuh"
@@ -48,8 +50,8 @@
 #define PFB_K3_DS 2      // draw sets (8 draws each) per warp
 #define PFB_K3_RC 128    // record rows per TMA chunk (16 blocks of 8 rows)
 #define PFB_K3_DCAP 32   // deferred-list capacity per warp and round
-#define PFB_K3_ZREP 2    // copies of the 1024-layer ziggurat table in shared memory (32 KB)
-static_assert(PF_ZIG_LAYERS == 1024 && PFB_K3_ZREP == 2, "pfb_zig_fast_rep address arithmetic");
+#define PFB_K3_ZREP 4    // interleaved copies of the 1024-layer ziggurat table (8-byte entries) in shared memory (32 KB)
+static_assert(PF_ZIG_LAYERS == 1024 && PFB_K3_ZREP == 4, "pfb_zig_fast_rep address arithmetic");
 
 __device__ __forceinline__ double pfb_lds64(uint32_t addr) {
     double v;
@@ -128,18 +130,9 @@ struct pfb_model_acc {
     }
 };
 
-// replicated ziggurat table entry (16 B): layer edge x_i, high word of the fast-accept threshold
-struct __align__(16) pfb_zig_e {
-    double xe;
-    uint32_t kqh;
-    uint32_t pad;
-};
-
 struct pfb_k3_warp_list {
     double z[PFB_K3_DCAP];
-    uint16_t row[PFB_K3_DCAP];  // row offset inside the chunk
-    uint8_t src[PFB_K3_DCAP];   // owner lane
-    uint8_t ds[PFB_K3_DCAP];    // draw set
+    uint32_t meta[PFB_K3_DCAP];  // row offset inside the chunk | owner lane << 16 | draw set << 24
 };
 
 __device__ __forceinline__ void pfb_dmma(double& d0, double& d1, double a, double b) {
@@ -149,18 +142,19 @@ __device__ __forceinline__ void pfb_dmma(double& d0, double& d1, double a, doubl
 }
 
 // Fast ziggurat step on the replicated table (zig_base = shared-memory byte address of this
-// lane's table copy; word layout: pf_rng.h).  Returns 0 and the variate in z when accepted,
-// 1 and z = 0 when the element has to take the slow path.
-__device__ __forceinline__ uint32_t pfb_zig_fast_rep(uint32_t lo, uint32_t hi, uint32_t zig_base, double& z) {
-    uint32_t elo, ehi, kqh, pad;
-    const uint32_t addr = ((hi >> 16) & 0x7FE0u) + zig_base;  // layer (bits 21-30 of hi) * 32
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(elo), "=r"(ehi), "=r"(kqh), "=r"(pad) : "r"(addr));
-    uint32_t mh;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(mh) : "r"(hi), "r"(0xFFFFFu), "r"(0x3FF00000u));  // (a&b)|c
-    const double m = __hiloint2double((int)mh, (int)lo);    // 1 + j 2^-52
+// lane's table copy; 32-bit word layout and the packed 8-byte entry: pf_rng.h).  Returns 0 and the
+// variate in z when accepted, 1 and z = 0 when the element has to take the slow path.
+__device__ __forceinline__ uint32_t pfb_zig_fast_rep(uint32_t w, uint32_t zig_base, double& z) {
+    uint32_t elo, ehi;
+    const uint32_t addr = ((w >> 16) & 0x7FE0u) + zig_base;  // layer (bits 21-30) * 32 = 4 copies * 8 B
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(elo), "=r"(ehi) : "r"(addr));
+    uint32_t mh, kqh;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(mh) : "r"(w), "r"(0xFFFFFu), "r"(0x3FF00000u));    // (a&b)|c
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(kqh) : "r"(elo), "r"(0xFFFFFu), "r"(0x3FF00000u));
+    const double m = __hiloint2double((int)mh, 0);          // 1 + j 2^-20
     const double xe = __hiloint2double((int)ehi, (int)elo);
-    const double x = fma(m, xe, -xe);                       // j * w, rounded once
-    z = __hiloint2double(__double2hiint(x) ^ (int)(hi & 0x80000000u), __double2loint(x));
+    const double x = fma(m, xe, -xe);                       // j 2^-20 x_i, rounded once
+    z = __hiloint2double(__double2hiint(x) ^ (int)(w & 0x80000000u), __double2loint(x));
     uint32_t bad;
     asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %2, %3;\n\tselp.u32 %1, 1, 0, p;\n\t@p mov.f64 %0, 0d0000000000000000;\n\t}"
         : "+d"(z), "=r"(bad) : "r"(mh), "r"(kqh));
@@ -202,7 +196,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sStage = reinterpret_cast<double*>(smem_raw);                      // NS * RC * RS2
-    pfb_zig_e* sZig = reinterpret_cast<pfb_zig_e*>(sStage + (size_t)NS * RC * RS2);  // 1024 * 2
+    uint64_t* sZig = reinterpret_cast<uint64_t*>(sStage + (size_t)NS * RC * RS2);  // 1024 * 4, copy-interleaved
     double* sT = reinterpret_cast<double*>(sZig + PF_ZIG_LAYERS * PFB_K3_ZREP);  // KP*KP
     double* sVc = sT + KP * KP;                                                // KP*KP
     double* sM = sVc + KP * KP;                                                // KP*KP + KP (QUAD)
@@ -258,14 +252,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
     }
     if (QUAD)
         for (int e = tid; e < KP * KP + KP; e += blockDim.x) sM[e] = hdr[PFB_HDR_M(KP) + e];  // M, then rv
-    for (int e = tid; e < PF_ZIG_LAYERS * PFB_K3_ZREP; e += blockDim.x) {
-        const pf_zig_kw_t kw = PF_ZIG_KW_DEV[e / PFB_K3_ZREP];
-        pfb_zig_e ze;
-        ze.xe = pf_zig_edge(kw.w);
-        ze.kqh = pf_zig_kqh(kw.kq);
-        ze.pad = 0u;
-        sZig[e] = ze;
-    }
+    for (int e = tid; e < PF_ZIG_LAYERS * PFB_K3_ZREP; e += blockDim.x) sZig[e] = PF_ZIG_XK_DEV[e / PFB_K3_ZREP];
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) pfb_mbar_init(&sBar[s], 1);
         pfb_fence_mbar_init();
@@ -308,7 +295,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 #pragma unroll
     for (int e = 0; e < 2; ++e) offam[e] = 8u * (uint32_t)((2 * t + e) * RS2 + (KP ^ pfb_swz(2 * t + e)));
 
-    const uint32_t zig_base = pfb_smem_u32(sZig + (lane & (PFB_K3_ZREP - 1)));
+    const uint32_t zig_base = pfb_smem_u32(sZig + (lane & (PFB_K3_ZREP - 1)));  // copy = lane % 4: 8-byte stride
     pfb_k3_warp_list& wl = sList[warp];
     double* cw = sC + (size_t)warp * DS * 8 * CWW;  // this warp's [DS][8][CWW]: w (| Vh'(p u~)), then c = T w
 
@@ -319,6 +306,8 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
         uint32_t kd[DS];      // draw index (clamped)
         int64_t ocol[DS];     // MODE 1: output column of the draw (the lean modes recompute it at the end)
         uint32_t actmask = 0u;  // pending-nibble mask of the active draw sets (bit d*2+e)
+        // the Philox counter of the lane's two draws (k, k + 8) in an all-draws sweep (pf_rng.h)
+        const uint32_t dpair = pf_draw_pair((uint32_t)(sw * DPS + warp * DS * 8 + g));
 #pragma unroll
         for (int d = 0; d < DS; ++d) {
             const int kraw = sw * DPS + (warp * DS + d) * 8 + g;
@@ -364,7 +353,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                             z0 = uh[2 * jj];
                             if (2 * jj + 1 < H) z1 = uh[2 * jj + 1];
                         } else {
-                            pf_normal_pair((uint32_t)jj, kd[d], k0, k1, PF_ZIG_KW_DEV, PF_ZIG_F_DEV, &z0, &z1);
+                            pf_normal_pair((uint32_t)jj, kd[d], k0, k1, PF_ZIG_XK_DEV, PF_ZIG_F_DEV, &z0, &z1);
                             if (2 * jj + 1 >= H) z1 = 0.0;
                         }
                     }
@@ -427,12 +416,24 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                 auto gen = [&](int o, double (&z)[DS][2], uint32_t& nib) {
                     const int b = (r0 >> 3) + o;
                     nib = 0u;
+                    if (!SEL) {
+                        // ONE Philox4x32-7 call: the lane's 2 rows x 2 draw sets (draws k, k + 8)
+                        uint32_t w4[4];
+                        pf_bits4((uint32_t)(4 * b + t), 0u, dpair, k0, k1, 0u, w4);
 #pragma unroll
-                    for (int d = 0; d < DS; ++d) {
-                        uint64_t wa, wb;
-                        pf_bits((uint32_t)(4 * b + t), 0u, kd[d], k0, k1, 0u, &wa, &wb);
-                        nib |= pfb_zig_fast_rep((uint32_t)wa, (uint32_t)(wa >> 32), zig_base, z[d][0]) << (2 * d);
-                        nib |= pfb_zig_fast_rep((uint32_t)wb, (uint32_t)(wb >> 32), zig_base, z[d][1]) << (2 * d + 1);
+                        for (int d = 0; d < DS; ++d) {
+                            nib |= pfb_zig_fast_rep(w4[2 * d], zig_base, z[d][0]) << (2 * d);
+                            nib |= pfb_zig_fast_rep(w4[2 * d + 1], zig_base, z[d][1]) << (2 * d + 1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < DS; ++d) {  // arbitrary draws: one call per draw set
+                            uint32_t w4[4];
+                            pf_bits4((uint32_t)(4 * b + t), 0u, pf_draw_pair(kd[d]), k0, k1, 0u, w4);
+                            const bool hi = pf_draw_half(kd[d]) != 0u;
+                            nib |= pfb_zig_fast_rep(hi ? w4[2] : w4[0], zig_base, z[d][0]) << (2 * d);
+                            nib |= pfb_zig_fast_rep(hi ? w4[3] : w4[1], zig_base, z[d][1]) << (2 * d + 1);
+                        }
                     }
                 };
                 // SP = 0: consume the normals zin/nibin generated by gen();  SP = 1: special block
@@ -469,13 +470,12 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                                     z[d][0] = uh[R];
                                     if (R + 1 < n) z[d][1] = uh[R + 1];
                                 } else {
-                                    uint64_t wa, wb;
-                                    pf_bits((uint32_t)(4 * b + t), 0u, kd[d], k0, k1, 0u, &wa, &wb);
-                                    nib |= pfb_zig_fast_rep((uint32_t)wa, (uint32_t)(wa >> 32), zig_base, z[d][0])
-                                           << (2 * d);
+                                    uint32_t w4[4];
+                                    pf_bits4((uint32_t)(4 * b + t), 0u, pf_draw_pair(kd[d]), k0, k1, 0u, w4);
+                                    const bool hi = pf_draw_half(kd[d]) != 0u;
+                                    nib |= pfb_zig_fast_rep(hi ? w4[2] : w4[0], zig_base, z[d][0]) << (2 * d);
                                     if (R + 1 < n) {
-                                        nib |= pfb_zig_fast_rep((uint32_t)wb, (uint32_t)(wb >> 32), zig_base,
-                                                                z[d][1]) << (2 * d + 1);
+                                        nib |= pfb_zig_fast_rep(hi ? w4[3] : w4[1], zig_base, z[d][1]) << (2 * d + 1);
                                     } else {
                                         z[d][1] = 0.0;
                                     }
@@ -624,61 +624,69 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                             while (a0) {
                                 const int bit = __ffsll((long long)a0) - 1;
                                 a0 &= a0 - 1;
-                                if (flat >= 0 && flat < PFB_K3_DCAP) {
-                                    wl.row[flat] = (uint16_t)row_of(bit);
-                                    wl.src[flat] = (uint8_t)lane;
-                                    wl.ds[flat] = (uint8_t)((bit >> 1) & 1);
-                                }
+                                if (flat >= 0 && flat < PFB_K3_DCAP)
+                                    wl.meta[flat] = (uint32_t)row_of(bit) | ((uint32_t)lane << 16) |
+                                                    ((uint32_t)((bit >> 1) & 1) << 24);
                                 ++flat;
                             }
                         }
                         __syncwarp();
                         const int nitems = min(PFB_K3_DCAP, total - base);
                         for (int it = lane; it < nitems; it += 32) {
-                            const uint32_t row = (uint32_t)(r0 + wl.row[it]);
-                            const int kraw = sw * DPS + (warp * DS + wl.ds[it]) * 8 + (wl.src[it] >> 2);
+                            const uint32_t mt = wl.meta[it];
+                            const uint32_t row = (uint32_t)r0 + (mt & 0xFFFFu);
+                            const int kraw = sw * DPS + (warp * DS + (int)(mt >> 24)) * 8 + (int)((mt >> 18) & 7u);
                             const uint32_t kdraw = SEL ? (uint32_t)sel_list[kraw].x : (uint32_t)kraw;
-                            wl.z[it] = pf_normal_finish_slow(row, kdraw, k0, k1, PF_ZIG_KW_DEV, PF_ZIG_F_DEV);
+                            wl.z[it] = pf_normal_finish_slow(row, kdraw, k0, k1, PF_ZIG_XK_DEV, PF_ZIG_F_DEV);
                         }
                         __syncwarp();
                         if (PASS == 0) {
-                            // the owner folds z * Vh[row][:] into the warp's w corrections; the four
-                            // lanes of a draw group take turns (fixed order => deterministic)
+                            // w corrections, column-parallel: lane c owns column c of the warp's
+                            // [draw][CWW] correction table and walks the finished elements in list
+                            // order (fixed order => deterministic; every lane is busy, where an
+                            // owner-serial fold kept one lane of the warp busy for ~30 % of the kernel)
+                            if (lane < CWW) {
+                                const int col = lane < KP ? lane : lane - KP;
 #pragma unroll 1
-                            for (int ph = 0; ph < 4; ++ph) {
-                                if (t == ph) {
-                                    unsigned long long a0 = pend;
-                                    int flat = excl - base;
-                                    while (a0) {
-                                        const int bit = __ffsll((long long)a0) - 1;
-                                        a0 &= a0 - 1;
-                                        if (flat >= 0 && flat < PFB_K3_DCAP) {
-                                            const int row = row_of(bit), dsi = (bit >> 1) & 1;
-                                            const double zz = wl.z[flat];
-                                            const double* rr = st + row * RS2;
-                                            const int swz = pfb_swz(row);
-                                            double* cv = cw + (dsi * 8 + g) * CWW;
-                                            const double pz = QUAD ? rr[(KP + 2) ^ swz] * zz : 0.0;
-#pragma unroll
-                                            for (int j = 0; j < KP; ++j) {
-                                                const double v = rr[j ^ swz];
-                                                cv[j] = fma(v, zz, cv[j]);
-                                                if (QUAD) cv[KP + j] = fma(v, pz, cv[KP + j]);
-                                            }
-#pragma unroll
-                                            for (int d = 0; d < DS; ++d)
-                                                if (d == dsi) {
-                                                    unormsq[d] = fma(zz, zz, unormsq[d]);
-                                                    if (QUAD) {
-                                                        qsum[d] = fma(pz + rr[(KP + 3) ^ swz], zz, qsum[d]);
-                                                    }
-                                                }
-                                        }
-                                        ++flat;
+                                for (int it = 0; it < nitems; ++it) {
+                                    const uint32_t mt = wl.meta[it];
+                                    const int row = (int)(mt & 0xFFFFu);
+                                    const double zz = wl.z[it];
+                                    const double* rr = st + row * RS2;
+                                    const int swz = pfb_swz(row);
+                                    const double v = rr[col ^ swz];
+                                    double* cv = cw + (((mt >> 24) & 1u) * 8 + ((mt >> 18) & 7u)) * CWW + lane;
+                                    if (QUAD && lane >= KP) {
+                                        *cv = fma(v, rr[(KP + 2) ^ swz] * zz, *cv);
+                                    } else {
+                                        *cv = fma(v, zz, *cv);
                                     }
                                 }
-                                __syncwarp();
                             }
+                            // the owner adds its elements' share of |u|^2 (and of the quadratic statistics)
+                            {
+                                unsigned long long a0 = pend;
+                                int flat = excl - base;
+                                while (a0) {
+                                    const int bit = __ffsll((long long)a0) - 1;
+                                    a0 &= a0 - 1;
+                                    if (flat >= 0 && flat < PFB_K3_DCAP) {
+                                        const int row = row_of(bit), dsi = (bit >> 1) & 1;
+                                        const double zz = wl.z[flat];
+                                        const double* rr = st + row * RS2;
+                                        const int swz = pfb_swz(row);
+                                        const double pz = QUAD ? rr[(KP + 2) ^ swz] * zz : 0.0;
+#pragma unroll
+                                        for (int d = 0; d < DS; ++d)
+                                            if (d == dsi) {
+                                                unormsq[d] = fma(zz, zz, unormsq[d]);
+                                                if (QUAD) qsum[d] = fma(pz + rr[(KP + 3) ^ swz], zz, qsum[d]);
+                                            }
+                                    }
+                                    ++flat;
+                                }
+                            }
+                            __syncwarp();
                         } else {
                             unsigned long long a0 = pend;
                             int flat = excl - base;
@@ -810,7 +818,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 
 static size_t k3_smem_bytes(int KP, int NS, int NW, bool quad) {
     const int RS2 = pfb_rs2_of(KP);
-    return (size_t)NS * PFB_K3_RC * RS2 * 8 + (size_t)PF_ZIG_LAYERS * PFB_K3_ZREP * sizeof(pfb_zig_e) +
+    return (size_t)NS * PFB_K3_RC * RS2 * 8 + (size_t)PF_ZIG_LAYERS * PFB_K3_ZREP * sizeof(uint64_t) +
            (size_t)2 * KP * KP * 8 + (quad ? (size_t)(KP * KP + KP) * 8 : 0) +
            (size_t)NW * PFB_K3_DS * 8 * (quad ? 2 * KP : KP) * 8 + (size_t)NW * sizeof(pfb_k3_warp_list) +
            (size_t)(NS + 1) * 8;

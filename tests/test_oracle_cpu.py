@@ -78,6 +78,81 @@ def test_pf_math_against_libm():
     assert O.pf_exp(np.array([1000.0]))[0] == np.inf and O.pf_exp(np.array([-1000.0]))[0] == 0.0
 
 
+def test_philox4x32_7_known_answers():
+    """Random123 kat_vectors for philox4x32-7 (the round count of the normal stream, pf_rng.h), through
+    the contract's own round function applied seven times; ten rounds of the same function give the
+    philox4x32-10 vectors above."""
+    lib = O.clib()
+    out = np.zeros(4, dtype=np.uint32)
+
+    def call(rounds, c, k):
+        lib.pfo_philox_r(ctypes.c_int(rounds), *[ctypes.c_uint32(x) for x in c], *[ctypes.c_uint32(x) for x in k],
+                         ctypes.c_void_p(out.ctypes.data))
+        return [int(x) for x in out]
+
+    assert call(7, [0, 0, 0, 0], [0, 0]) == [0x5F6FB709, 0x0D893F64, 0x4F121F81, 0x4F730A48]
+    assert call(7, [0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x5207DDC2, 0x45165E59, 0x4D8EE751, 0x8C52F662]
+    assert call(7, [0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == \
+        [0x4DFCCABA, 0x190A87F0, 0xC47362BA, 0xB6B5242A]
+    assert call(10, [0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    # the contract call = philox4x32-7 with the fixed key and the documented counter layout
+    seed, rp, stream, dp, cl = 0x0123456789ABCDEF, 1234, 2, 77, 5
+    lib.pfo_bits4(ctypes.c_uint32(rp), ctypes.c_uint32(stream), ctypes.c_uint32(dp), ctypes.c_uint64(seed),
+                  ctypes.c_uint32(cl), ctypes.c_void_p(out.ctypes.data))
+    got = [int(x) for x in out]
+    assert got == call(7, [rp | stream << 28, dp, ((seed & 0xFFFFFFFF) + cl) & 0xFFFFFFFF, seed >> 32],
+                       [0xA4093822, 0x299F31D0])
+
+
+def test_contract_normal_elementwise_definition():
+    """pf_rng.h: element (row i, draw k) reads word 2 * ((k >> 3) & 1) + (i & 1) of the Philox call
+    (row_pair = i >> 1, draw_pair = (k >> 4) * 8 + (k & 7)): the bulk generator, K3's per-lane 2 x 2
+    patches and this element-wise definition are the same stream."""
+    lib = O.clib()
+    lib.pfo_normal_elem.restype = ctypes.c_double
+    for seed, n, K in ((77, 37, 45), (2**63 + 5, 8, 16), (3, 1, 9)):
+        U = np.asarray(O.contract_normals(seed, n, K))
+        for i in range(n):
+            for k in range(K):
+                assert U[i, k] == lib.pfo_normal_elem(ctypes.c_uint64(seed), ctypes.c_uint32(i), ctypes.c_uint32(k))
+    # a prefix in either direction is consistent (counter based): growing n or K never changes a variate
+    assert np.array_equal(np.asarray(O.contract_normals(9, 40, 50))[:17, :23], np.asarray(O.contract_normals(9, 17, 23)))
+
+
+def test_ziggurat_tables_are_consistent():
+    """The packed 8-byte entries (layer edge with the accept threshold in its low 20 mantissa bits):
+    thresholds are conservative, edges decrease, layers have equal areas to ~3e-7 (the packing
+    perturbs an edge by < 2^-32 relative), f is exp(-x^2/2) at the packed edges."""
+    lib = O.clib()
+    xk = np.zeros(1024, dtype=np.uint64)
+    f = np.zeros(1025)
+    lib.pfo_zig_tables(ctypes.c_void_p(xk.ctypes.data), ctypes.c_void_p(f.ctypes.data))
+    x = xk.view(np.float64)
+    kq = (xk & np.uint64(0xFFFFF)).astype(np.int64)
+    assert np.all(np.diff(x) < 0) and x[1] > 4.0 and x[0] > x[1]
+    xn = np.append(x[1:], 0.0)
+    assert np.all((kq - 1).clip(0) * 2.0**-20 * x < xn + 1e-300) and np.all((kq + 2) * 2.0**-20 * x > xn)
+    assert np.allclose(f[:1024], np.exp(-0.5 * x * x), rtol=1e-15) and f[1024] == 1.0
+    areas = x[1:] * (f[2:] - f[1:1024])
+    v = x[1] * f[1] + math.sqrt(math.pi / 2) * math.erfc(x[1] / math.sqrt(2))
+    assert np.abs(areas / v - 1).max() < 1e-6
+    assert abs(x[0] * f[1] / v - 1) < 1e-6      # base strip: x_0 f(r) = v
+    assert 0.995 < kq.sum() / 1024 / 2.0**20 < 0.9965   # fast-path share (99.57 %)
+
+
+def _normal_stats(seed0, nseeds, n, K, thr, nbins):
+    lib = O.clib()
+    thr = np.asarray(thr, dtype=np.float64)
+    edges = stats.norm.ppf(np.arange(1, nbins) / nbins)
+    out = np.zeros(5 + thr.size + 1)
+    hist = np.zeros(nbins, dtype=np.uint64)
+    lib.pfo_normal_stats(ctypes.c_uint64(seed0), ctypes.c_int(nseeds), ctypes.c_int(n), ctypes.c_int(K),
+                         ctypes.c_int(thr.size), ctypes.c_void_p(thr.ctypes.data), ctypes.c_int(nbins),
+                         ctypes.c_void_p(edges.ctypes.data), ctypes.c_void_p(out.ctypes.data),
+                         ctypes.c_void_p(hist.ctypes.data))
+    return out, hist.astype(np.float64)
+
+
 def test_contract_normals_are_standard_normal():
     """Moment / KS check of the engine's own normal stream (test/mvnormal.jl:71-107 checks the
     same of Julia's)."""
@@ -97,6 +172,36 @@ def test_contract_normals_are_standard_normal():
     v = np.asarray(O.contract_normals(2025, 1000, 100)).ravel()
     assert abs(np.corrcoef(u[:100000], v)[0, 1]) < 0.02
     assert np.array_equal(O.contract_normals(2024, 33, 7), O.contract_normals(2024, 33, 7))
+    # rows of one draw and draws of one row are uncorrelated (the four words of a Philox call feed a
+    # 2 x 2 patch: rows 2q, 2q+1 x draws k, k+8)
+    U = np.asarray(O.contract_normals(11, 512, 4096))
+    for a, b in ((U[0::2], U[1::2]), (U[:, :4088], U[:, 8:]), (U[:-1, :4088], U[1:, 8:])):
+        c = float(np.mean(a * b))
+        assert abs(c) < 5 / math.sqrt(a.size)
+
+
+def test_contract_normals_large_sample():
+    """1.3e8 variates (128 seeds x 1024 rows x 1000 draws — the shape of config 3's units) streamed
+    through the contract in C: moments to 5 sigma, tail masses beyond 1, 2, 3, 4, r (the ziggurat base
+    edge) and 5 to 5 sigma of their binomial spread, the slow-path share, and a 200-bin
+    equal-probability chi-square."""
+    thr = [1.0, 2.0, 3.0, 4.0, 4.038849846109505, 5.0]
+    nbins = 200
+    out, hist = _normal_stats(20261017, 128, 1024, 1000, thr, nbins)
+    N = out[0]
+    assert N == 128 * 1024 * 1000
+    m1, m2, m3, m4 = out[1] / N, out[2] / N, out[3] / N, out[4] / N
+    assert abs(m1) < 5 / math.sqrt(N)
+    assert abs(m2 - 1) < 5 * math.sqrt(2 / N)
+    assert abs(m3) < 5 * math.sqrt(15 / N)
+    assert abs(m4 - 3) < 5 * math.sqrt(96 / N)
+    for a, t in enumerate(thr):
+        p = 2 * stats.norm.sf(t)
+        assert abs(out[5 + a] - p * N) < 5 * math.sqrt(p * (1 - p) * N), (t, out[5 + a], p * N)
+    slow = out[5 + len(thr)] / N
+    assert 0.0040 < slow < 0.0046
+    chi2 = float(np.sum((hist - N / nbins) ** 2 / (N / nbins)))
+    assert stats.chi2.sf(chi2, nbins - 1) > 1e-4, chi2
 
 
 # ---- inverse Hessian / Woodbury ---------------------------------------------------------------
