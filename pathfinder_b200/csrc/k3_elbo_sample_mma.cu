@@ -29,8 +29,12 @@
 // stream through a ring, twice per sweep.  A CTA loops over the sweeps (256 draws) of its unit so
 // the record is loaded once per unit.  The 1024-layer ziggurat table (8-byte packed entries, one
 // LDS.64 per variate) sits in shared memory four times, interleaved entry by entry (copy = lane % 4),
-// which spreads the random layer lookups of a half-warp over all 16 bank pairs.  Elements that leave
-// the ziggurat fast path (0.43 %) are deferred and finished warp-cooperatively per chunk.
+// which spreads the random layer lookups of a half-warp over the bank pairs.  Elements that leave
+// the ziggurat fast path (0.43 %) keep their PROVISIONAL table value in the tensor-core sums and are
+// queued; the queue is finished 32 elements at a time (one element per lane: the real ziggurat
+// continuation) and only the differences (true - provisional; zero for the half that the wedge test
+// accepts) are folded in, column-parallel, through the warp's shared correction table.  With a
+// resident record the queue is flushed once per sweep.
 // Lean mode writes 16 B per draw (logp, logq); with a draws pointer x is written as well.
 #include "pfb_common.cuh"
 #include "pf_rng.h"
@@ -50,8 +54,9 @@
 #define PFB_K3_DS 2      // draw sets (8 draws each) per warp
 #define PFB_K3_RC 128    // record rows per TMA chunk (16 blocks of 8 rows)
 #define PFB_K3_DCAP 32   // deferred-list capacity per warp and round
-#define PFB_K3_ZREP 4    // interleaved copies of the 1024-layer ziggurat table (8-byte entries) in shared memory (32 KB)
-static_assert(PF_ZIG_LAYERS == 1024 && PFB_K3_ZREP == 4, "pfb_zig_fast_rep address arithmetic");
+#define PFB_K3_ZREP 2    // interleaved copies of the 1024-layer ziggurat table (8-byte entries) in shared memory (16 KB)
+#define PFB_K3_REQCAP 128  // queued slow-path elements per warp (a sweep of n = 1024 queues ~70)
+static_assert(PF_ZIG_LAYERS == 1024 && PFB_K3_ZREP == 2, "pfb_zig_fast_rep address arithmetic");
 
 __device__ __forceinline__ double pfb_lds64(uint32_t addr) {
     double v;
@@ -131,9 +136,21 @@ struct pfb_model_acc {
 };
 
 struct pfb_k3_warp_list {
-    double z[PFB_K3_DCAP];
-    uint32_t meta[PFB_K3_DCAP];  // row offset inside the chunk | owner lane << 16 | draw set << 24
+    // pass 0: the queue of elements that left the ziggurat fast path, and one batch of finished ones
+    uint32_t req[PFB_K3_REQCAP];  // row | owner lane << 20 | draw set << 25
+    double dz[33];                // true - provisional variate (33: the four arrays start in different banks)
+    double pdz[33];               // p_row * dz                     (single-pass statistics)
+    double dq[33];                // true^2 - provisional^2
+    double cq[33];                // p_row * dq + 2 r_row * dz      (single-pass statistics)
+    uint32_t bmeta[32];           // the batch's req words (0xFFFFFFFF: nothing to fold)
 };
+// pass 1 (two-pass modes): per-chunk list of finished variates; shares the batch arrays' memory
+struct pfb_k3_warp_list1 {
+    uint32_t req_unused[PFB_K3_REQCAP];
+    double z[PFB_K3_DCAP];
+    uint32_t meta[PFB_K3_DCAP];   // row offset inside the chunk | owner lane << 16 | draw set << 24
+};
+static_assert(sizeof(pfb_k3_warp_list1) <= sizeof(pfb_k3_warp_list), "pass-1 list aliases the pass-0 batch");
 
 __device__ __forceinline__ void pfb_dmma(double& d0, double& d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -143,10 +160,11 @@ __device__ __forceinline__ void pfb_dmma(double& d0, double& d1, double a, doubl
 
 // Fast ziggurat step on the replicated table (zig_base = shared-memory byte address of this
 // lane's table copy; 32-bit word layout and the packed 8-byte entry: pf_rng.h).  Returns 0 and the
-// variate in z when accepted, 1 and z = 0 when the element has to take the slow path.
+// variate in z when accepted, 1 and the PROVISIONAL table value in z when the element has to take the
+// slow path (the caller queues it; its outputs are corrected or overwritten later).
 __device__ __forceinline__ uint32_t pfb_zig_fast_rep(uint32_t w, uint32_t zig_base, double& z) {
     uint32_t elo, ehi;
-    const uint32_t addr = ((w >> 16) & 0x7FE0u) + zig_base;  // layer (bits 21-30) * 32 = 4 copies * 8 B
+    const uint32_t addr = ((w >> 17) & 0x3FF0u) + zig_base;  // layer (bits 21-30) * 16 = 2 copies * 8 B
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(elo), "=r"(ehi) : "r"(addr));
     uint32_t mh, kqh;
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(mh) : "r"(w), "r"(0xFFFFFu), "r"(0x3FF00000u));    // (a&b)|c
@@ -155,10 +173,7 @@ __device__ __forceinline__ uint32_t pfb_zig_fast_rep(uint32_t w, uint32_t zig_ba
     const double xe = __hiloint2double((int)ehi, (int)elo);
     const double x = fma(m, xe, -xe);                       // j 2^-20 x_i, rounded once
     z = __hiloint2double(__double2hiint(x) ^ (int)(w & 0x80000000u), __double2loint(x));
-    uint32_t bad;
-    asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %2, %3;\n\tselp.u32 %1, 1, 0, p;\n\t@p mov.f64 %0, 0d0000000000000000;\n\t}"
-        : "+d"(z), "=r"(bad) : "r"(mh), "r"(kqh));
-    return bad;
+    return mh >= kqh ? 1u : 0u;
 }
 
 template <int V>
@@ -188,6 +203,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
     constexpr int HB = (KP + 7) / 8;   // head blocks (rows < KP get the Vc' multiply)
     constexpr int NHP = (KP / 2 + 3) / 4;  // head row pairs generated per lane
     constexpr int CWW = QUAD ? 2 * KP : KP;  // per-draw shared accumulators: w (and Vh'(p u~))
+    constexpr int CWS = CWW + (QUAD ? 2 : 1);  // + the slow-path corrections of |u|^2 (and of the quadratic statistic)
     static_assert(DS == 2, "pending nibbles assume two draw sets");
     static_assert(RC / 8 * 4 <= 64, "pending mask is 64 bits per chunk");
 
@@ -196,12 +212,12 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sStage = reinterpret_cast<double*>(smem_raw);                      // NS * RC * RS2
-    uint64_t* sZig = reinterpret_cast<uint64_t*>(sStage + (size_t)NS * RC * RS2);  // 1024 * 4, copy-interleaved
+    uint64_t* sZig = reinterpret_cast<uint64_t*>(sStage + (size_t)NS * RC * RS2);  // 1024 * 2, copy-interleaved
     double* sT = reinterpret_cast<double*>(sZig + PF_ZIG_LAYERS * PFB_K3_ZREP);  // KP*KP
     double* sVc = sT + KP * KP;                                                // KP*KP
     double* sM = sVc + KP * KP;                                                // KP*KP + KP (QUAD)
     double* sC = sM + (QUAD ? KP * KP + KP : 0);                               // NW * DS * 8 * CWW
-    pfb_k3_warp_list* sList = reinterpret_cast<pfb_k3_warp_list*>(sC + (size_t)NW * DS * 8 * CWW);
+    pfb_k3_warp_list* sList = reinterpret_cast<pfb_k3_warp_list*>(sC + (size_t)NW * DS * 8 * CWS);
     uint64_t* sBar = reinterpret_cast<uint64_t*>(sList + NW);                  // NS
 
     const int slot = blockIdx.x / splits;
@@ -295,9 +311,10 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 #pragma unroll
     for (int e = 0; e < 2; ++e) offam[e] = 8u * (uint32_t)((2 * t + e) * RS2 + (KP ^ pfb_swz(2 * t + e)));
 
-    const uint32_t zig_base = pfb_smem_u32(sZig + (lane & (PFB_K3_ZREP - 1)));  // copy = lane % 4: 8-byte stride
+    const uint32_t zig_base = pfb_smem_u32(sZig + (lane & (PFB_K3_ZREP - 1)));  // copy = lane % 2: 8-byte stride
     pfb_k3_warp_list& wl = sList[warp];
-    double* cw = sC + (size_t)warp * DS * 8 * CWW;  // this warp's [DS][8][CWW]: w (| Vh'(p u~)), then c = T w
+    pfb_k3_warp_list1& wl1 = *reinterpret_cast<pfb_k3_warp_list1*>(&sList[warp]);
+    double* cw = sC + (size_t)warp * DS * 8 * CWS;  // this warp's [DS][8][CWS]: w (| Vh'(p u~)), then c = T w
 
     int q = 0;  // TMA load sequence number of the next chunk to consume (ring mode)
     bool first_pass = true;
@@ -331,8 +348,58 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 #pragma unroll
             for (int s1 = 0; s1 < NS1; ++s1) ncf[d][s1] = 0.0;
         }
-        for (int e = lane; e < DS * 8 * CWW; e += 32) cw[e] = 0.0;  // slow-path corrections of w
+        for (int e = lane; e < DS * 8 * CWS; e += 32) cw[e] = 0.0;  // slow-path corrections of w, |u|^2, ...
+        int nreq = 0;  // queued slow-path elements of this warp (pass 0)
         __syncwarp();
+
+        // Pass 0: finish the queued elements, 32 at a time (one per lane: the real ziggurat continuation),
+        // and fold the DIFFERENCES to their provisional values into the warp's correction table:
+        // lane c owns column c (w, Vh'(p u~), then the |u|^2 and quadratic-statistic corrections) and
+        // walks the batch in queue order (fixed order => deterministic).  rows: record rows in shared
+        // memory, row0: the record row of rows[0].
+        auto flush_queue = [&](const double* rows, int row0) {
+            __syncwarp();
+#pragma unroll 1
+            for (int b0 = 0; b0 < nreq; b0 += 32) {
+                const int it = b0 + lane;
+                if (it < nreq) {
+                    const uint32_t mt = wl.req[it];
+                    const uint32_t row = mt & 0xFFFFFu;
+                    const int kraw = sw * DPS + (warp * DS + (int)(mt >> 25)) * 8 + (int)((mt >> 22) & 7u);
+                    const uint32_t kdraw = SEL ? (uint32_t)sel_list[kraw].x : (uint32_t)kraw;
+                    const pf_slow_t fz = pf_normal_finish_slow(row, kdraw, k0, k1, PF_ZIG_XK_DEV, PF_ZIG_F_DEV);
+                    const double dz = fz.z - fz.zprov;
+                    const double dq = dz * (fz.z + fz.zprov);
+                    wl.dz[lane] = dz;
+                    wl.dq[lane] = dq;
+                    if (QUAD) {
+                        const double* rr = rows + ((int)row - row0) * RS2;
+                        const int swz = pfb_swz((int)row);
+                        const double pp = rr[(KP + 2) ^ swz];
+                        wl.pdz[lane] = pp * dz;
+                        wl.cq[lane] = fma(pp, dq, rr[(KP + 3) ^ swz] * dz);  // slot KP + 3 holds 2 r
+                    }
+                    wl.bmeta[lane] = dz != 0.0 ? mt : 0xFFFFFFFFu;  // the wedge test accepted it: nothing changes
+                }
+                __syncwarp();
+                const int nbt = min(32, nreq - b0);
+#pragma unroll
+                for (int cc = lane; cc < CWS; cc += 32) {  // CWS <= 50: at most two columns per lane
+                    const int col = cc < KP ? cc : cc - KP;
+                    const double* val = cc < KP ? wl.dz : (cc < CWW ? wl.pdz : (cc == CWW ? wl.dq : wl.cq));
+#pragma unroll 1
+                    for (int j = 0; j < nbt; ++j) {
+                        const uint32_t mt = wl.bmeta[j];
+                        if (mt == 0xFFFFFFFFu) continue;
+                        const int row = (int)(mt & 0xFFFFFu);
+                        const double v = cc < CWW ? rows[(row - row0) * RS2 + (col ^ pfb_swz(row))] : 1.0;
+                        double* cv = cw + ((mt >> 25) * 8 + ((mt >> 22) & 7u)) * CWS + cc;
+                        *cv = fma(v, val[j], *cv);
+                    }
+                }
+                __syncwarp();
+            }
+        };
 
         // One pass over all chunks.  PS::value = 0: accumulate w = Vh' u~ (QUAD: and the other
         // statistics);  1: x and the model sums.
@@ -483,7 +550,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                             }
                         }
                     }
-                    nib &= actmask;  // (z of a rejected element is already 0)
+                    nib &= actmask;  // (inactive draws are never queued; their sums are discarded)
                     pend = (pend << 4) | nib;
                     if (PASS == 0) {
                         const bool headrow = SPECIAL && R < H;  // |u|^2 of head rows: added with the raw normals
@@ -603,7 +670,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 #pragma unroll 1
                 for (; o < nb; ++o) block(pfb_ic<1>{}, o, zc, 0u);
 
-                // ---- deferred ziggurat slow path (warp-cooperative, deterministic order) -----------
+                // ---- elements that left the ziggurat fast path ------------------------------------------
                 if (!HOST_U) {
                     const int cnt = __popcll(pend);
                     int incl = cnt;
@@ -616,78 +683,59 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                     const int total = __shfl_sync(0xffffffffu, incl, 31);
                     // bit -> (block o, e, d): nibble index from the top, bit d*2+e inside
                     auto row_of = [&](int bit) { return (nb - 1 - (bit >> 2)) * 8 + 2 * t + (bit & 1); };
+                    if (PASS == 0) {
+                        // queue them (global row, owner lane, draw set); flushed when the queue is full,
+                        // when the chunk is about to leave shared memory (ring mode), and after the last
+                        // chunk of the pass (a resident record: the whole sweep's queue at once)
+                        const bool chunk_flush = !resident || c == C - 1;
 #pragma unroll 1
-                    for (int base = 0; base < total; base += PFB_K3_DCAP) {
-                        {
+                        for (int done = 0;;) {
+                            const int take = min(PFB_K3_REQCAP - nreq, total - done);
                             unsigned long long a0 = pend;
-                            int flat = excl - base;
+                            int flat = excl - done;
                             while (a0) {
                                 const int bit = __ffsll((long long)a0) - 1;
                                 a0 &= a0 - 1;
-                                if (flat >= 0 && flat < PFB_K3_DCAP)
-                                    wl.meta[flat] = (uint32_t)row_of(bit) | ((uint32_t)lane << 16) |
-                                                    ((uint32_t)((bit >> 1) & 1) << 24);
+                                if (flat >= 0 && flat < take)
+                                    wl.req[nreq + flat] = (uint32_t)(r0 + row_of(bit)) | ((uint32_t)lane << 20) |
+                                                          ((uint32_t)((bit >> 1) & 1) << 25);
                                 ++flat;
                             }
-                        }
-                        __syncwarp();
-                        const int nitems = min(PFB_K3_DCAP, total - base);
-                        for (int it = lane; it < nitems; it += 32) {
-                            const uint32_t mt = wl.meta[it];
-                            const uint32_t row = (uint32_t)r0 + (mt & 0xFFFFu);
-                            const int kraw = sw * DPS + (warp * DS + (int)(mt >> 24)) * 8 + (int)((mt >> 18) & 7u);
-                            const uint32_t kdraw = SEL ? (uint32_t)sel_list[kraw].x : (uint32_t)kraw;
-                            wl.z[it] = pf_normal_finish_slow(row, kdraw, k0, k1, PF_ZIG_XK_DEV, PF_ZIG_F_DEV);
-                        }
-                        __syncwarp();
-                        if (PASS == 0) {
-                            // w corrections, column-parallel: lane c owns column c of the warp's
-                            // [draw][CWW] correction table and walks the finished elements in list
-                            // order (fixed order => deterministic; every lane is busy, where an
-                            // owner-serial fold kept one lane of the warp busy for ~30 % of the kernel)
-                            if (lane < CWW) {
-                                const int col = lane < KP ? lane : lane - KP;
-#pragma unroll 1
-                                for (int it = 0; it < nitems; ++it) {
-                                    const uint32_t mt = wl.meta[it];
-                                    const int row = (int)(mt & 0xFFFFu);
-                                    const double zz = wl.z[it];
-                                    const double* rr = st + row * RS2;
-                                    const int swz = pfb_swz(row);
-                                    const double v = rr[col ^ swz];
-                                    double* cv = cw + (((mt >> 24) & 1u) * 8 + ((mt >> 18) & 7u)) * CWW + lane;
-                                    if (QUAD && lane >= KP) {
-                                        *cv = fma(v, rr[(KP + 2) ^ swz] * zz, *cv);
-                                    } else {
-                                        *cv = fma(v, zz, *cv);
-                                    }
-                                }
+                            nreq += take;
+                            done += take;
+                            const bool last = done >= total;
+                            if (nreq == PFB_K3_REQCAP || (last && chunk_flush && nreq > 0)) {
+                                flush_queue(resident ? sStage : st, resident ? 0 : r0);
+                                nreq = 0;
                             }
-                            // the owner adds its elements' share of |u|^2 (and of the quadratic statistics)
+                            if (last) break;
+                        }
+                    } else {
+                        // pass 1: the owner recomputes x of its queued elements from the finished variates
+#pragma unroll 1
+                        for (int base = 0; base < total; base += PFB_K3_DCAP) {
                             {
                                 unsigned long long a0 = pend;
                                 int flat = excl - base;
                                 while (a0) {
                                     const int bit = __ffsll((long long)a0) - 1;
                                     a0 &= a0 - 1;
-                                    if (flat >= 0 && flat < PFB_K3_DCAP) {
-                                        const int row = row_of(bit), dsi = (bit >> 1) & 1;
-                                        const double zz = wl.z[flat];
-                                        const double* rr = st + row * RS2;
-                                        const int swz = pfb_swz(row);
-                                        const double pz = QUAD ? rr[(KP + 2) ^ swz] * zz : 0.0;
-#pragma unroll
-                                        for (int d = 0; d < DS; ++d)
-                                            if (d == dsi) {
-                                                unormsq[d] = fma(zz, zz, unormsq[d]);
-                                                if (QUAD) qsum[d] = fma(pz + rr[(KP + 3) ^ swz], zz, qsum[d]);
-                                            }
-                                    }
+                                    if (flat >= 0 && flat < PFB_K3_DCAP)
+                                        wl1.meta[flat] = (uint32_t)row_of(bit) | ((uint32_t)lane << 16) |
+                                                        ((uint32_t)((bit >> 1) & 1) << 24);
                                     ++flat;
                                 }
                             }
                             __syncwarp();
-                        } else {
+                            const int nitems = min(PFB_K3_DCAP, total - base);
+                            for (int it = lane; it < nitems; it += 32) {
+                                const uint32_t mt = wl1.meta[it];
+                                const uint32_t row = (uint32_t)r0 + (mt & 0xFFFFu);
+                                const int kraw = sw * DPS + (warp * DS + (int)(mt >> 24)) * 8 + (int)((mt >> 18) & 7u);
+                                const uint32_t kdraw = SEL ? (uint32_t)sel_list[kraw].x : (uint32_t)kraw;
+                                wl1.z[it] = pf_normal_finish_slow(row, kdraw, k0, k1, PF_ZIG_XK_DEV, PF_ZIG_F_DEV).z;
+                            }
+                            __syncwarp();
                             unsigned long long a0 = pend;
                             int flat = excl - base;
                             while (a0) {
@@ -697,8 +745,8 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                                     const int row = row_of(bit), dsi = (bit >> 1) & 1;
                                     const double* rr = st + row * RS2;
                                     const int swz = pfb_swz(row);
-                                    const double* cv = cw + (dsi * 8 + g) * CWW;
-                                    double zz = wl.z[flat];
+                                    const double* cv = cw + (dsi * 8 + g) * CWS;
+                                    double zz = wl1.z[flat];
 #pragma unroll
                                     for (int j = 0; j < KP; ++j) zz = fma(-rr[j ^ swz], cv[j], zz);
                                     const double2 am = *reinterpret_cast<const double2*>(rr + (KP ^ swz));
@@ -727,10 +775,18 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 
         run_pass(pfb_ic<0>{});
         first_pass = false;
+
         {
             // c = T w (upper triangular): the w fragments join the slow-path corrections in shared
             // memory so that every lane can form its pass-1 A fragments -c[4s + t]
             __syncwarp();
+            if (t == 0) {
+#pragma unroll
+                for (int d = 0; d < DS; ++d) {
+                    unormsq[d] += cw[(d * 8 + g) * CWS + CWW];
+                    if (QUAD) qsum[d] += cw[(d * 8 + g) * CWS + CWW + 1];
+                }
+            }
 #pragma unroll
             for (int d = 0; d < DS; ++d)
 #pragma unroll
@@ -738,7 +794,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int cc = 8 * h + 2 * t + e;
-                        if (cc < CWW) cw[(d * 8 + g) * CWW + cc] += wacc[d][h][e];
+                        if (cc < CWW) cw[(d * 8 + g) * CWS + cc] += wacc[d][h][e];
                     }
             __syncwarp();
             double cf[DS][NS1];
@@ -750,7 +806,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                     double acc = 0.0;
 #pragma unroll
                     for (int bcol = 0; bcol < KP; ++bcol)
-                        if (bcol >= a) acc = fma(sT[a * KP + bcol], cw[(d * 8 + g) * CWW + bcol], acc);
+                        if (bcol >= a) acc = fma(sT[a * KP + bcol], cw[(d * 8 + g) * CWS + bcol], acc);
                     cf[d][s1] = acc;
                 }
             __syncwarp();
@@ -758,7 +814,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
             for (int d = 0; d < DS; ++d)
 #pragma unroll
                 for (int s1 = 0; s1 < NS1; ++s1) {
-                    cw[(d * 8 + g) * CWW + 4 * s1 + t] = cf[d][s1];
+                    cw[(d * 8 + g) * CWS + 4 * s1 + t] = cf[d][s1];
                     ncf[d][s1] = -cf[d][s1];
                 }
             __syncwarp();
@@ -768,7 +824,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                 const double* sRv = sM + KP * KP;
 #pragma unroll
                 for (int d = 0; d < DS; ++d) {
-                    const double* cv = cw + (d * 8 + g) * CWW;
+                    const double* cv = cw + (d * 8 + g) * CWS;
                     double part = 0.0, v0c = 0.0;
 #pragma unroll
                     for (int s1 = 0; s1 < NS1; ++s1) {
@@ -820,7 +876,7 @@ static size_t k3_smem_bytes(int KP, int NS, int NW, bool quad) {
     const int RS2 = pfb_rs2_of(KP);
     return (size_t)NS * PFB_K3_RC * RS2 * 8 + (size_t)PF_ZIG_LAYERS * PFB_K3_ZREP * sizeof(uint64_t) +
            (size_t)2 * KP * KP * 8 + (quad ? (size_t)(KP * KP + KP) * 8 : 0) +
-           (size_t)NW * PFB_K3_DS * 8 * (quad ? 2 * KP : KP) * 8 + (size_t)NW * sizeof(pfb_k3_warp_list) +
+           (size_t)NW * PFB_K3_DS * 8 * (quad ? 2 * KP + 2 : KP + 1) * 8 + (size_t)NW * sizeof(pfb_k3_warp_list) +
            (size_t)(NS + 1) * 8;
 }
 
@@ -831,6 +887,7 @@ static cudaError_t launch_k3_m(cudaStream_t st, int n, int K, int nslots, const 
                                double* draws, int two_pass, pfb_k3_sel sel) {
     if (nslots <= 0) return cudaSuccess;
     if (sel.cnt != nullptr && draws == nullptr) return cudaErrorInvalidValue;
+    if (n >= (1 << 20)) return cudaErrorInvalidValue;  // the slow-path queue packs the row into 20 bits
     // every registered family is diagonal-quadratic, so the lean path runs single pass unless
     // the caller asks for the generic two-pass kernel (or wants x written out)
     const bool quad = (draws == nullptr) && !two_pass;

@@ -190,13 +190,19 @@ PF_HD_NOINLINE void pf_normal_pair(uint32_t row_pair, uint32_t draw, uint32_t k0
 // Slow-path continuation of element (row, draw) from scratch: recomputes the element's first
 // word (so that any thread can finish any element; used by the warp-balanced deferred slow
 // path of K3).  Must only be called for elements whose first word failed pf_zig_fast32.
-PF_HD_NOINLINE double pf_normal_finish_slow(uint32_t row, uint32_t draw, uint32_t k0, uint32_t k1,
-                                            const uint64_t* xk, const double* ftab) {
+// Returns the variate and the provisional value the fast path computed from the first word — the
+// two are equal whenever the wedge test accepts the first candidate.
+typedef struct { double z, zprov; } pf_slow_t;
+PF_HD_NOINLINE pf_slow_t pf_normal_finish_slow(uint32_t row, uint32_t draw, uint32_t k0, uint32_t k1,
+                                               const uint64_t* xk, const double* ftab) {
     const uint32_t rp = row >> 1, dp = pf_draw_pair(draw), word = 2u * pf_draw_half(draw) + (row & 1u);
     uint32_t o[4];
     pf_bits4(rp, 0u, dp, k0, k1, 0u, o);
     const uint32_t w = word == 0 ? o[0] : (word == 1 ? o[1] : (word == 2 ? o[2] : o[3]));
-    return pf_zig_slow32(w, rp, dp, 1u + word, k0, k1, xk, ftab);
+    pf_slow_t r;
+    r.zprov = pf_zig_value32(w, xk[(w >> 21) & (PF_ZIG_LAYERS - 1)]);
+    r.z = pf_zig_slow32(w, rp, dp, 1u + word, k0, k1, xk, ftab);
+    return r;
 }
 
 // 64 random bits for resample draw t (two per Philox4x32-10 call), stream 3.
