@@ -30,6 +30,7 @@ extern "C" {
 #define PFB_ERR_SHAPE (-2)
 #define PFB_ERR_UNSUPPORTED (-3)
 #define PFB_ERR_STATE (-4)
+#define PFB_ERR_NUMERIC (-5) /* importance resampling with no usable weight at all */
 
 /* registered device-side target log densities */
 #define PFB_MODEL_ISONORMAL 0 /* logp(x) = -|x|^2/2          test/singlepath.jl:15          */
@@ -128,6 +129,16 @@ int pfb_elbo_batch(pfb_handle h, int n, int P, const int64_t* offsets, const dou
                    const double* gradients, const uint64_t* seeds, const double* normals_or_null,
                    pfb_elbo_out* out);
 
+/* Failed paths (success = 0: no iteration at all, or a NaN / -Inf best ELBO).  The reference then returns
+ *   rand(rng, fit_distributions[fit_iteration + 1], ndraws)            src/singlepath.jl:224-228
+ * — fresh draws from the fit of the "best" iteration (the identity fit N(theta_0 + grad_0, I) of iteration
+ * 0 when there is none) — and these enter the PSIS pool with their own log densities
+ * (src/multipath.jl:217, src/resample.jl:81-95).  The engine does the same with one UInt64 seed per path
+ * (drawn from the path's rng by the caller; consumed by the next pfb_batch_run / pfb_elbo_batch; when not
+ * set, a fixed per-path default is used): pfb_elbo_out.draws / draws_logp / draws_logq of a failed path
+ * are those fresh draws.  A NaN log ratio in the pool gets zero importance weight. */
+int pfb_set_fallback_seeds(pfb_handle h, int P, const uint64_t* seeds);
+
 /* The same, split so that callers can keep inputs resident / overlap / time the stages. */
 int pfb_batch_upload(pfb_handle h, int n, int P, const int64_t* offsets, const double* positions,
                      const double* gradients, const uint64_t* seeds, const double* normals_or_null);
@@ -181,6 +192,12 @@ int pfb_draw_from_fits(pfb_handle h, int K_new, const uint64_t* seeds, double* d
  * Any output pointer may be NULL. */
 int pfb_unit_draws(pfb_handle h, int nunits, const int32_t* units, double* draws, double* logp, double* logq);
 
+/* fit_distributions[l + 1] (src/singlepath.jl:64: the reference keeps every iteration's) of arbitrary
+ * units (0-based, path-major / iteration-minor) of the current batch, on demand, in the layout of the
+ * fit_* fields of pfb_elbo_out with P replaced by nunits.  Any output pointer may be NULL. */
+int pfb_unit_fits(pfb_handle h, int nunits, const int32_t* units, double* mu, double* alpha, double* vh,
+                  double* T, double* Vc, double* logdet, int32_t* jeff);
+
 /* Paths [p0, p1) of the device pool (best-iteration draws [n x K x (p1-p0)], their logp / logq
  * [K x (p1-p0)]; K = ndraws_elbo, or K_new after pfb_draw_from_fits(keep_as_pool)): the lazy form of
  * pfb_elbo_out.draws — PathfinderResult.draws (src/singlepath.jl:231-232) fetched on first use.
@@ -221,6 +238,35 @@ int pfb_pool_materialize(pfb_handle h);
  * pool (device, int64), this engine's runs cover [base, base + P K); its columns are regenerated into
  * d_out [n x m] (device), the others left untouched (zero d_out first, then sum-reduce over the ranks). */
 int pfb_pool_columns_device(pfb_handle h, int m, const void* d_inds, int64_t base, void* d_out);
+
+/* ---- multi-GPU: paths shard across GPUs, one exchange for the PSIS pool (src/multipath.jl:190-225) -------
+ * One handle per GPU.  The communicator is NCCL, loaded lazily with dlopen("libnccl.so.2") (inside a
+ * PyTorch process that is the NCCL torch already loaded), so a Julia / C caller gets multi-GPU without
+ * MPI bindings of its own:
+ *   - one process per GPU: rank 0 calls pfb_comm_unique_id, ships the 128 bytes to the other ranks by any
+ *     means (MPI, torch.distributed, a file), every rank calls pfb_comm_init(h, id, rank, world);
+ *   - one process, all GPUs: pfb_comm_init_all(handles, ndev) (handle i on device i is rank i), then the
+ *     *_all form of the exchange from the same thread.
+ * pfb_pool_exchange_resample replaces _compute_psis_result + _resample (src/multipath.jl:220-225) over
+ * the runs of ALL ranks: paths_per_rank[world] runs per rank in run order (the pool keeps the
+ * reference's component order, src/multipath.jl:217).  It all-gathers the per-draw log densities of
+ * the pools (16 B per pool draw), runs PSIS and the index draw replicated on every rank (deterministic
+ * kernels + counter RNG => identical results everywhere), lets every rank produce the selected columns
+ * it owns (regenerated from their seeds; the pools' draws never move) and sum-reduces the n x ndraws
+ * result.  No host synchronisation between the steps; every rank receives the same outputs. */
+#define PFB_COMM_ID_BYTES 128
+int pfb_comm_unique_id(void* id128);
+int pfb_comm_init(pfb_handle h, const void* id128, int rank, int world);
+int pfb_comm_init_all(pfb_handle* handles, int ndev);
+int pfb_comm_destroy(pfb_handle h);
+int pfb_pool_exchange_resample(pfb_handle h, const int32_t* paths_per_rank, uint64_t seed, int ndraws,
+                               int importance, int replace, pfb_resample_out* out);
+int pfb_pool_exchange_resample_all(pfb_handle* handles, int ndev, const int32_t* paths_per_rank, uint64_t seed,
+                                   int ndraws, int importance, int replace, pfb_resample_out* outs /*[ndev]*/);
+/* A device pool from HOST arrays (pools assembled on the host: top-up draws beyond ndraws_elbo, retried
+ * paths, a rank that owns no run: P = 0): draws[n x K_run x P], logp / logq[K_run x P]; it then takes
+ * part in pfb_psis_resample / pfb_pool_exchange_resample like the pool of a batch. */
+int pfb_pool_set(pfb_handle h, int P, int K_run, const double* draws, const double* logp, const double* logq);
 
 /* PSIS + resampling on DEVICE buffers (an all-gathered pool): d_logp/d_logq [N], d_pool [n x N];
  * outputs in `out` are HOST pointers. */

@@ -348,6 +348,15 @@ def maximize_elbo(seeds, logp_fn, mus, Hs, K, normals=None):
     return lopt, ests
 
 
+def failed_path_draws(fallback_seed, mu, W, K):
+    """reference: src/singlepath.jl:224-228.  A failed path returns rand(rng, fit_distributions[
+    fit_iteration + 1], ndraws): fresh draws from the fit of the "best" iteration (the identity fit of
+    iteration 0 when there is none) with the PATH's rng — here the engine's contract normals of the
+    path's fallback seed.  Returns (draws [n, K], logq [K])."""
+    u = contract_normals(int(fallback_seed), mu.shape[0], K)
+    return rand_and_logpdf(np.asarray(u), mu, W)
+
+
 def path_success(L, ests, lopt):
     """reference: src/singlepath.jl:297-314"""
     if L <= 0 or not ests:

@@ -104,6 +104,7 @@ def fit_gpd(x):
 def psis(log_ratios):
     """Returns dict(log_weights [normalised], weights, pareto_k, tail_length)."""
     logw = np.array(log_ratios, dtype=np.float64, copy=True).ravel()
+    logw[np.isnan(logw)] = -np.inf  # engine contract: an undefined log ratio carries no weight
     N = logw.size
     M = tail_length(N)
     pareto_k = float("nan")

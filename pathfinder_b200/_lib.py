@@ -87,6 +87,17 @@ SYMBOLS = {
     "pfb_batch_fit_only": (C.c_int, [C.c_void_p, _dp]),
     "pfb_draw_from_fits": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, C.c_int]),
     "pfb_unit_draws": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]),
+    "pfb_unit_fits": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "pfb_set_fallback_seeds": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "pfb_comm_unique_id": (C.c_int, [_dp]),
+    "pfb_comm_init": (C.c_int, [C.c_void_p, _dp, C.c_int, C.c_int]),
+    "pfb_comm_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "pfb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "pfb_pool_exchange_resample": (C.c_int, [C.c_void_p, _dp, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                             C.POINTER(pfb_resample_out)]),
+    "pfb_pool_exchange_resample_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, _dp, C.c_uint64, C.c_int, C.c_int,
+                                                 C.c_int, C.POINTER(pfb_resample_out)]),
+    "pfb_pool_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]),
     "pfb_pool_materialize": (C.c_int, [C.c_void_p]),
     "pfb_pool_columns_device": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int64, _dp]),
     "pfb_pool_download": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]),

@@ -150,6 +150,8 @@ def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntr
     want_draws = "lazy" if (lazy_draws and not (ndraws_run is not None and ndraws_run > engine.K)) else True
     device_opt = _use_device_optimizer(model, optimizer)
     P = len(inits)
+    if P == 0:  # a rank that owns no run (nruns < world size): nothing to optimise, an empty pool
+        return [], None
     final = [None] * P
     todo = list(range(P))
     tries = [0] * P
@@ -164,6 +166,8 @@ def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntr
             x0s = np.stack([np.asarray(cur_init[p], dtype=np.float64) for p in todo], axis=1)
             npts, _, _ = engine.lbfgs_batch(x0s, maxiters, None, gtol, ftol)
             seeds = [_draw_seeds(path_rngs[p], int(npts[j]) - 1) for j, p in enumerate(todo)]  # src/elbo.jl:2
+            # a failed path's draws are rand(rng, fit_distribution, ndraws) with the PATH's rng (src/singlepath.jl:226-228)
+            engine.set_fallback_seeds([int(_draw_seeds(path_rngs[p], 1)[0]) for p in todo])
             engine.batch_from_lbfgs(np.concatenate(seeds) if seeds else np.zeros(0, np.uint64))
             engine.run()
             res = engine.download(draws=want_draws, fit=True)
@@ -177,6 +181,7 @@ def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntr
                 traces.append(tr)  # a non-finite start leaves a 1-point trace (L = 0): the path fails
                 seeds.append(_draw_seeds(path_rngs[p], len(tr) - 1))  # src/elbo.jl:2
             offsets, X, G = Engine.pack([(t.points, t.gradients) for t in traces])
+            engine.set_fallback_seeds([int(_draw_seeds(path_rngs[p], 1)[0]) for p in todo])  # src/singlepath.jl:226-228
             res = engine.elbo_batch(offsets, X, G, np.concatenate(seeds) if seeds else np.zeros(0, np.uint64),
                                     draws=want_draws, fit=True)
         if ndraws_run is not None and ndraws_run > engine.K:
@@ -196,9 +201,6 @@ def _run_paths(engine, model, inits, path_rngs, *, history_length, maxiters, ntr
             else:
                 cur_init[p] = _uniform_init(path_rngs[p], model.n, init_scale, init_sampler)  # src/singlepath.jl:278
                 retry.append(p)
-        if retry and len(retry) < len(todo):
-            # keep the successful paths' device-resident results: assemble them now
-            pass
         todo = retry
     return final, last
 
@@ -221,6 +223,13 @@ def _assemble_path(model, rng, entry, ndraws, K):
         f = res.fit
         fit = FitDistribution(f["mu"][:, j].copy(), f["alpha"][:, j].copy(), f["vh"][:, :, j].copy(),
                               f["T"][j].copy(), f["Vc"][j].copy(), float(f["logdet"][j]), int(f["jeff"][j]))
+    elif res.fit is not None and len(trace) >= 1:
+        # no iteration at all: fit_distributions[1] = N(theta_0 + H_0 grad_0, H_0), H_0 = I
+        # (src/inverse_hessian.jl:38-40, src/mvnormal.jl:17) — the normal a failed path's draws come from
+        KP = res.fit["vh"].shape[1]
+        n = trace.points.shape[0]
+        fit = FitDistribution(trace.points[:, 0] + trace.gradients[:, 0], np.ones(n), np.zeros((n, KP)),
+                              np.zeros((KP, KP)), np.zeros((KP, KP)), 0.0, 0)
     if res.draws is None:  # still on the device (lazy): fetched on first access
         return PathfinderResult(model, rng, fit, None, int(res.best_iter[j]), ntry, trace, ests, rej, ok,
                                 lazy=(res, j, ndraws))
@@ -283,12 +292,16 @@ def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT
     inits = [(_uniform_init(path_rngs[p], model.n, init_scale, init_sampler) if x is None else x)
              for p, x in enumerate(inits)]
     seed = int(_draw_seeds(rng, 1)[0])
-    dist_on = D.is_distributed(group)
+    dist_on = group is not False and D.is_distributed(group)  # group=False: this process alone, whatever is initialised
     lo, hi = 0, nruns
     if dist_on:
         import torch.distributed as dist
 
         lo, hi = D.shard_range(nruns, dist.get_rank(group), dist.get_world_size(group))
+        import torch
+
+        if device == 0 and dist.get_backend(group) == "nccl":
+            device = torch.cuda.current_device()  # one process per GPU: the rank's device
     own = engine is None
     if own:
         engine = Engine.for_model(model, history_length, ndraws_elbo, device)
@@ -297,22 +310,29 @@ def multipathfinder(model, ndraws, *, nruns=None, init=None, ndraws_elbo=DEFAULT
     # closed on return, so its draws come back eagerly
     final, last = _run_paths(engine, model, inits[lo:hi], path_rngs[lo:hi], history_length=history_length,
                              maxiters=maxiters, ntries=ntries, init_scale=init_scale, ndraws_run=ndraws_per_run,
-                             optimizer=optimizer, lazy_draws=(not own and not dist_on), init_sampler=init_sampler)
+                             optimizer=optimizer, lazy_draws=not own, init_sampler=init_sampler)
     results = [_assemble_path(model, path_rngs[lo + j], final[j], ndraws_per_run, ndraws_elbo)
                for j in range(hi - lo)]
     # PSIS pool: draw-fastest, component-slowest (test/resample.jl:81-88)
     K_run = ndraws_per_run
     if dist_on:
-        import torch.distributed as dist
-
-        dev = f"cuda:{device}" if dist.get_backend(group) == "nccl" else "cpu"
-        pool = np.concatenate([pr.draws for pr in results], axis=1) if results else np.zeros((model.n, 0))
-        lp = np.concatenate([pr.draws_logp for pr in results]) if results else np.zeros(0)
-        lq = np.concatenate([pr.draws_logq for pr in results]) if results else np.zeros(0)
-        r = D.pooled_resample(
-            lp, lq, pool, K_run, nruns,
-            lambda logr, N: engine.psis_resample_host(logr, K_run, seed, ndraws, importance, N=N),
-            seed, ndraws, importance, group, dev)
+        # the exchange lives behind the C ABI (pfb_pool_exchange_resample): all-gather of the pools' log
+        # densities, PSIS + index draw replicated, owned columns regenerated on their rank, sum-reduce.
+        # Nothing of the pool crosses PCIe unless it had to be assembled on the host (retries, top-up).
+        counts = D.shard_counts(nruns, dist.get_world_size(group))
+        if getattr(engine, "_comm", None) != (dist.get_rank(group), dist.get_world_size(group)):
+            engine.comm_init(group)
+        P_loc = hi - lo
+        single_batch = (last is not None and len(last[0]) == P_loc and K_run == ndraws_elbo
+                        and not getattr(last[1], "topped_up", False))
+        if not single_batch:
+            if results:
+                engine.pool_set(P_loc, K_run, np.stack([pr.draws for pr in results], axis=2),
+                                np.stack([pr.draws_logp for pr in results], axis=1),
+                                np.stack([pr.draws_logq for pr in results], axis=1))
+            else:
+                engine.pool_set(0, K_run, None, np.zeros((K_run, 0)), np.zeros((K_run, 0)))
+        r = engine.pool_exchange_resample(counts, seed, ndraws, importance)
     else:
         single_batch = (last is not None and len(last[0]) == nruns and K_run == ndraws_elbo
                         and not getattr(last[1], "topped_up", False))

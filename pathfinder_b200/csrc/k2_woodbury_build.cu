@@ -472,9 +472,12 @@ static cudaError_t launch_k2(cudaStream_t st, int n, int u_base, int U, int J, c
     if (FR == nullptr) return cudaErrorInvalidValue;
     int threads = n >= PFB_K2_THREADS ? PFB_K2_THREADS : ((n + 31) / 32) * 32;
     if (threads < 64) threads = 64;
-    pfb_k2_woodbury_build<KP, false><<<U, threads, k2_scratch_bytes(KP), st>>>(n, J, X, G, unit_col, alpha, hist,
-                                                                              hist_cnt, FR, HDR, FR2, model, mp0,
-                                                                              mp1, u_base);
+    // static arrays + scratch exceed the 48 KB default at KP = 24: opt in like the shared-panel variant
+    auto kern = pfb_k2_woodbury_build<KP, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_scratch_bytes(KP));
+    if (e != cudaSuccess) return e;
+    kern<<<U, threads, k2_scratch_bytes(KP), st>>>(n, J, X, G, unit_col, alpha, hist, hist_cnt, FR, HDR, FR2, model, mp0,
+                                                   mp1, u_base);
     return cudaGetLastError();
 }
 

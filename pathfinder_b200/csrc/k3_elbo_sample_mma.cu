@@ -83,6 +83,18 @@ struct pfb_k3_sel {
     int cap;
 };
 
+// Paths whose optimisation recorded no iteration (L = 0): the reference still draws from
+// fit_distributions[1] = N(theta_0 + H_0 grad_0, H_0), H_0 = I (src/singlepath.jl:224-228 with
+// fit_iteration = 0; src/inverse_hessian.jl:38-40).  Slots with unit < 0 draw from that normal when
+// this block is given, and write NaN otherwise.
+struct pfb_k3_fb {
+    const double* X;           // trajectory points / gradients, n x T column-major
+    const double* G;
+    const int64_t* point_off;  // [P + 1] first column of every path
+    const uint64_t* seeds;     // [P] one seed per path
+    const int32_t* path_of_slot;  // nullptr: slot == path
+};
+
 struct pfb_model_params {
     const double* p0;  // DIAGNORMAL: mean[n]
     const double* p1;  // DIAGNORMAL: 1/sd[n]
@@ -192,7 +204,7 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
                    const double* __restrict__ FR2, const double* __restrict__ HDR,
                    const uint64_t* __restrict__ seeds, const double* __restrict__ u_host,
                    pfb_model_params mp, double* __restrict__ logp_out, double* __restrict__ logq_out,
-                   double* __restrict__ draws_out, pfb_k3_sel sel) {
+                   double* __restrict__ draws_out, pfb_k3_sel sel, pfb_k3_fb fb) {
     constexpr bool MATERIALIZE = (MODE == 1);
     constexpr bool QUAD = (MODE == 2);
     constexpr int RS2 = (KP == 12) ? 16 : 32;
@@ -229,6 +241,47 @@ pfb_k3_elbo_sample(int n, int K, int splits, int NS, const int32_t* __restrict__
     const int Kslot = SEL ? sel.cnt[slot] : K;   // draws this slot produces
     const int S = (Kslot + DPS - 1) / DPS;       // sweeps of this unit
     if (SEL && split >= S) return;               // (column selection: most CTAs of a slot have nothing to do)
+    if (unit < 0 && fb.X != nullptr) {
+        // identity fit of iteration 0: x = theta_0 + grad_0 + u, log q = -(n log 2 pi + |u|^2) / 2; one warp per draw
+        const int path = fb.path_of_slot ? fb.path_of_slot[slot] : slot;
+        const double* x0 = fb.X + fb.point_off[path] * (int64_t)n;
+        const double* g0 = fb.G + fb.point_off[path] * (int64_t)n;
+        const uint64_t fseed = fb.seeds[path];
+        const uint32_t f0 = (uint32_t)fseed, f1 = (uint32_t)(fseed >> 32);
+        for (int sw = split; sw < S; sw += splits) {
+            const int ka = sw * DPS, kb = min(Kslot, (sw + 1) * DPS);
+            for (int j = ka + warp; j < kb; j += NW) {
+                const uint32_t kdraw = SEL ? (uint32_t)sel_list[j].x : (uint32_t)j;
+                const int64_t oc = SEL ? (int64_t)sel_list[j].y : (int64_t)slot * K + j;
+                double usq = 0.0;
+                pfb_model_acc<MODEL> ma;
+                ma.init();
+                for (int rp = lane; 2 * rp < n; rp += 32) {
+                    double z0, z1;
+                    pf_normal_pair((uint32_t)rp, kdraw, f0, f1, PF_ZIG_XK_DEV, PF_ZIG_F_DEV, &z0, &z1);
+                    const int i = 2 * rp;
+                    const double xa = (x0[i] + g0[i]) + z0;
+                    usq = fma(z0, z0, usq);
+                    ma.add(i, xa, mp);
+                    if (MATERIALIZE && draws_out) draws_out[oc * n + i] = xa;
+                    if (i + 1 < n) {
+                        const double xb = (x0[i + 1] + g0[i + 1]) + z1;
+                        usq = fma(z1, z1, usq);
+                        ma.add(i + 1, xb, mp);
+                        if (MATERIALIZE && draws_out) draws_out[oc * n + i + 1] = xb;
+                    }
+                }
+                usq = pfb_warp_sum(usq);
+                ma.a = pfb_warp_sum(ma.a);
+                ma.b = pfb_warp_sum(ma.b);
+                if (lane == 0 && !SEL) {
+                    if (logp_out) logp_out[oc] = ma.finish(n, mp);
+                    if (logq_out) logq_out[oc] = (fma((double)n, PFB_LOG2PI, 0.0) + usq) / -2.0;
+                }
+            }
+        }
+        return;
+    }
     if (unit < 0) {  // path without a usable iteration (K5 only): no fitted normal, NaN draws
         for (int sw = split; sw < S; sw += splits) {
             const int ka = sw * DPS, kb = min(Kslot, (sw + 1) * DPS);
@@ -884,7 +937,7 @@ template <int KP, int MODEL>
 static cudaError_t launch_k3_m(cudaStream_t st, int n, int K, int nslots, const int32_t* unit_list,
                                const double* FR2, const double* HDR, const uint64_t* seeds,
                                const double* u_host, pfb_model_params mp, double* logp, double* logq,
-                               double* draws, int two_pass, pfb_k3_sel sel) {
+                               double* draws, int two_pass, pfb_k3_sel sel, pfb_k3_fb fb) {
     if (nslots <= 0) return cudaSuccess;
     if (sel.cnt != nullptr && draws == nullptr) return cudaErrorInvalidValue;
     if (n >= (1 << 20)) return cudaErrorInvalidValue;  // the slow-path queue packs the row into 20 bits
@@ -919,7 +972,7 @@ static cudaError_t launch_k3_m(cudaStream_t st, int n, int K, int nslots, const 
     const int64_t grid = (int64_t)nslots * splits;
     if (grid > 2147483647LL) return cudaErrorInvalidValue;
     void (*kern)(int, int, int, int, const int32_t*, const double*, const double*, const uint64_t*, const double*,
-                 pfb_model_params, double*, double*, double*, pfb_k3_sel);
+                 pfb_model_params, double*, double*, double*, pfb_k3_sel, pfb_k3_fb);
     if (sel.cnt != nullptr) {
         kern = pfb_k3_elbo_sample<KP, MODEL, 1, true>;
     } else if constexpr (MODEL == PFB_MODEL_EXTERNAL) {
@@ -931,7 +984,7 @@ static cudaError_t launch_k3_m(cudaStream_t st, int n, int K, int nslots, const 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<(unsigned)grid, NW * 32, smem, st>>>(n, K, splits, NS, unit_list, FR2, HDR, seeds, u_host, mp, logp,
-                                                logq, draws, sel);
+                                                logq, draws, sel, fb);
     return cudaGetLastError();
 }
 
@@ -939,23 +992,23 @@ template <int KP>
 static cudaError_t launch_k3_k(cudaStream_t st, int model, int n, int K, int nslots,
                                const int32_t* unit_list, const double* FR2, const double* HDR,
                                const uint64_t* seeds, const double* u_host, pfb_model_params mp,
-                               double* logp, double* logq, double* draws, int two_pass, pfb_k3_sel sel) {
+                               double* logp, double* logq, double* draws, int two_pass, pfb_k3_sel sel, pfb_k3_fb fb) {
     switch (model) {
         case PFB_MODEL_ISONORMAL:
             return launch_k3_m<KP, PFB_MODEL_ISONORMAL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host,
-                                                        mp, logp, logq, draws, two_pass, sel);
+                                                        mp, logp, logq, draws, two_pass, sel, fb);
         case PFB_MODEL_FUNNEL:
             return launch_k3_m<KP, PFB_MODEL_FUNNEL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host, mp,
-                                                     logp, logq, draws, two_pass, sel);
+                                                     logp, logq, draws, two_pass, sel, fb);
         case PFB_MODEL_DIAGNORMAL:
             return launch_k3_m<KP, PFB_MODEL_DIAGNORMAL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host,
-                                                         mp, logp, logq, draws, two_pass, sel);
+                                                         mp, logp, logq, draws, two_pass, sel, fb);
         case PFB_MODEL_DENSENORMAL:
         case PFB_MODEL_HLOGISTIC:
         case PFB_MODEL_HOSTCALLBACK:
             if (draws == nullptr) return cudaErrorInvalidValue;  // these families need x written out (K8)
             return launch_k3_m<KP, PFB_MODEL_EXTERNAL>(st, n, K, nslots, unit_list, FR2, HDR, seeds, u_host, mp,
-                                                       logp, logq, draws, 1, sel);
+                                                       logp, logq, draws, 1, sel, fb);
     }
     return cudaErrorInvalidValue;
 }
@@ -967,9 +1020,11 @@ extern "C" cudaError_t PFB_K3_ENTRY(cudaStream_t st, int model, int n, int K, in
                                     const uint64_t* seeds, const double* u_host, const double* mp0,
                                     const double* mp1, double mc0, double* logp, double* logq,
                                     double* draws, int two_pass, const int32_t* sel_cnt, const void* sel_list,
-                                    int sel_cap) {
+                                    int sel_cap, const double* fbX, const double* fbG, const int64_t* fb_off,
+                                    const uint64_t* fb_seeds, const int32_t* fb_path_of_slot) {
     pfb_model_params mp{mp0, mp1, mc0};
     pfb_k3_sel sel{sel_cnt, reinterpret_cast<const int2*>(sel_list), sel_cap};
+    pfb_k3_fb fb{fbX, fbG, fb_off, fb_seeds, fb_path_of_slot};
     return launch_k3_k<PFB_K3_KP>(st, model, n, K, nslots, unit_list, FR2, HDR, seeds, u_host, mp, logp, logq,
-                                  draws, two_pass, sel);
+                                  draws, two_pass, sel, fb);
 }

@@ -57,7 +57,10 @@ __global__ void pfb_k6a_keys(int N, const double* __restrict__ logp, const doubl
                              uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const double v = logr_in ? logr_in[i] : (logp[i] - logq[i]);
+    double v = logr_in ? logr_in[i] : (logp[i] - logq[i]);
+    // A NaN log ratio (a draw whose target or fitted density is undefined, e.g. from a failed path)
+    // gets zero weight instead of poisoning the normalising sum and with it every weight.
+    if (v != v) v = -INFINITY;
     logw[i] = v;
     keys[i] = pfb_ordered_key(v);
     idx[i] = (uint32_t)i;

@@ -23,7 +23,8 @@ cudaError_t pfb_launch_k2(cudaStream_t, int, int, int, int, const double*, const
 #define PFB_DECL_K3(name)                                                                                  \
     cudaError_t name(cudaStream_t, int, int, int, int, const int32_t*, const double*, const double*,        \
                      const uint64_t*, const double*, const double*, const double*, double, double*, double*, \
-                     double*, int, const int32_t*, const void*, int);
+                     double*, int, const int32_t*, const void*, int, const double*, const double*,           \
+                     const int64_t*, const uint64_t*, const int32_t*);
 PFB_DECL_K3(pfb_launch_k3_kp12)
 PFB_DECL_K3(pfb_launch_k3_kp20)
 PFB_DECL_K3(pfb_launch_k3_kp24)
@@ -107,8 +108,19 @@ struct pfb_engine {
     int64_t T = 0, U = 0;
     bool have_batch = false, ran = false, have_normals = false;
     int poolK = 0;  // draws per path in the device pool (K, or the count of the last pfb_draw_from_fits)
+    int poolP = 0;  // paths in the device pool (P, unless pfb_pool_set installed a pool assembled on the host)
     bool pool_ready = false;  // the pool's DRAWS are materialised (its logp / logq always are after a run)
     DevBuf dSelCnt, dSelList;
+    // failed paths (src/singlepath.jl:224-228): fresh draws from fit_distributions[fit_iteration + 1]
+    std::vector<uint64_t> fb_seeds_user;  // pfb_set_fallback_seeds (consumed by the next batch)
+    std::vector<uint64_t> fb_seeds;       // one per path of the current batch
+    DevBuf dFbSeeds, dPoolSeeds, dFbUnits, dFbPaths, dFbLogp, dFbLogq, dFbPairs, dTopFb;
+    const uint64_t* pool_seeds = nullptr;  // unit-indexed seeds of the pool's draws (dSeeds, or dPoolSeeds)
+    int n_failed = 0;
+    // multi-GPU (pfb_comm_init): NCCL communicator, the all-gathered log densities
+    void* comm = nullptr;
+    int comm_world = 1, comm_rank = 0;
+    DevBuf dGLogp, dGLogq;
     int launches = 0;
     std::vector<int64_t> h_off;
     DevBuf dX, dG, dOff, dSeeds, dUnitCol, dNormals;
@@ -142,6 +154,12 @@ struct pfb_engine {
     // psis
     DevBuf dLogw, dW, dCum, dScal, dInds, dIds, dOutDraws, dTmpLogr, dTmpPool, dSortWork, dSortTmp;
 };
+
+#define PFB_D2H(dst, src, bytes)                                                                   \
+    do {                                                                                           \
+        if ((dst) && (bytes) > 0)                                                                  \
+            PFB_CUDA(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, st));        \
+    } while (0)
 
 #define PFB_FAIL(h, code, msg)     \
     do {                           \
@@ -203,17 +221,20 @@ extern "C" int pfb_create(pfb_handle* out, const pfb_config* cfg) {
     return PFB_OK;
 }
 
+extern "C" int pfb_comm_destroy(pfb_handle h);
 extern "C" int pfb_destroy(pfb_handle h) {
     if (!h) return PFB_OK;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
+    if (h->comm) pfb_comm_destroy(h);
     DevBuf* bufs[] = {&h->dModel, &h->dX, &h->dG, &h->dOff, &h->dSeeds, &h->dUnitCol, &h->dNormals, &h->dAlpha,
                       &h->dHist, &h->dHistCnt, &h->dRej, &h->dFR, &h->dFR2, &h->dHDR, &h->dLogp, &h->dLogq, &h->dElbo,
                       &h->dSe, &h->dBestIter, &h->dBestUnit, &h->dSucc, &h->dPool, &h->dPoolLogp,
                       &h->dPoolLogq, &h->dAllDraws, &h->dFitMu, &h->dFitAlpha, &h->dFitVh, &h->dFitT,
                       &h->dFitVc, &h->dFitLogdet, &h->dFitJeff, &h->dLogw, &h->dW, &h->dCum, &h->dScal,
                       &h->dInds, &h->dIds, &h->dOutDraws, &h->dTmpLogr, &h->dTmpPool, &h->dGenX, &h->dGenY, &h->dIota, &h->dTopSeeds,
-                      &h->dLbX0, &h->dLbX, &h->dLbG, &h->dLbFX, &h->dLbWs, &h->dLbNp, &h->dLbSt, &h->dLbNev, &h->dLbSrc, &h->dSortWork, &h->dSortTmp, &h->dSelCnt, &h->dSelList};
+                      &h->dLbX0, &h->dLbX, &h->dLbG, &h->dLbFX, &h->dLbWs, &h->dLbNp, &h->dLbSt, &h->dLbNev, &h->dLbSrc, &h->dSortWork, &h->dSortTmp, &h->dSelCnt, &h->dSelList,
+                      &h->dFbSeeds, &h->dPoolSeeds, &h->dFbUnits, &h->dFbPaths, &h->dFbLogp, &h->dFbLogq, &h->dFbPairs, &h->dTopFb, &h->dGLogp, &h->dGLogq};
     for (auto* b : bufs) b->release();
     if (h->cublas) cublasDestroy(h->cublas);
     for (int i = 0; i < 2; ++i) {
@@ -528,20 +549,21 @@ static bool model_is_external(const pfb_engine* h) {
            h->model == PFB_MODEL_HOSTCALLBACK;
 }
 
+// fb_seeds != NULL: slots whose unit is < 0 draw from the identity fit of iteration 0 (one seed per path;
+// fb_paths maps slots to paths, NULL = identity) instead of writing NaN
 static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list, double* logp, double* logq,
                              double* draws, int K_over = 0, const uint64_t* seeds_over = nullptr,
-                             const int32_t* sel_cnt = nullptr, const void* sel_list = nullptr, int sel_cap = 0);
+                             const int32_t* sel_cnt = nullptr, const void* sel_list = nullptr, int sel_cap = 0,
+                             const uint64_t* fb_seeds = nullptr, const int32_t* fb_paths = nullptr);
 
 extern "C" int pfb_register_host_model(pfb_handle h, int n, pfb_logp_callback cb, void* user) {
     if (!h) return PFB_ERR_ARG;
     if (n < 1 || !cb) PFB_FAIL(h, PFB_ERR_ARG, "host model needs n >= 1 and a callback");
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
-    if (!h->copy_stream) {
-        PFB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            PFB_CUDA(h, cudaEventCreateWithFlags(&h->hc_k[i], cudaEventDisableTiming));
-            PFB_CUDA(h, cudaEventCreateWithFlags(&h->hc_c[i], cudaEventDisableTiming));
-        }
+    if (!h->copy_stream) PFB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {  // (the copy stream may already exist: pfb_elbo_batch creates it too)
+        if (!h->hc_k[i]) PFB_CUDA(h, cudaEventCreateWithFlags(&h->hc_k[i], cudaEventDisableTiming));
+        if (!h->hc_c[i]) PFB_CUDA(h, cudaEventCreateWithFlags(&h->hc_c[i], cudaEventDisableTiming));
     }
     h->host_cb = cb;
     h->host_user = user;
@@ -623,14 +645,16 @@ static int generic_logp(pfb_engine* h, const double* X, int64_t M, const int32_t
 // K_over > 0 / seeds_over != NULL: fresh draws from the fitted normals (top-up draws, resample()).
 static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list, double* logp, double* logq,
                              double* draws, int K_over, const uint64_t* seeds_over, const int32_t* sel_cnt,
-                             const void* sel_list, int sel_cap) {
+                             const void* sel_list, int sel_cap, const uint64_t* fb_seeds, const int32_t* fb_paths) {
     const double* mp0 = model_is_external(h) ? nullptr : h->dModel.as<double>();
     const double* mp1 = mp0 ? mp0 + h->model_n : nullptr;
-    const double* un = (h->have_normals && !seeds_over) ? h->dNormals.as<double>() : nullptr;
+    const double* un = (h->have_normals && (!seeds_over || seeds_over == h->dSeeds.as<uint64_t>()))
+                           ? h->dNormals.as<double>() : nullptr;
     auto fn = h->KP == 12 ? pfb_launch_k3_kp12 : (h->KP == 20 ? pfb_launch_k3_kp20 : pfb_launch_k3_kp24);
     return fn(h->stream, h->model, h->n, K_over > 0 ? K_over : h->K, nslots, unit_list, h->dFR2.as<double>(),
               h->dHDR.as<double>(), seeds_over ? seeds_over : h->dSeeds.as<uint64_t>(), un, mp0, mp1, h->model_c0,
-              logp, logq, draws, h->cfg.elbo_mode == 1, sel_cnt, sel_list, sel_cap);
+              logp, logq, draws, h->cfg.elbo_mode == 1, sel_cnt, sel_list, sel_cap,
+              fb_seeds ? h->dX.as<double>() : nullptr, h->dG.as<double>(), h->dOff.as<int64_t>(), fb_seeds, fb_paths);
 }
 
 // K5, on demand: materialise the best-iteration draws of every path into the pool (regenerated, hence
@@ -639,8 +663,10 @@ static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list
 // them (PathfinderResult.draws, pool exchange) — the resample stage regenerates just its columns.
 static int ensure_pool(pfb_engine* h) {
     if (h->pool_ready || h->P <= 0) return PFB_OK;
-    if (!h->ran || h->poolK != h->K) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
-    PFB_CUDA(h, launch_k3(h, h->P, h->dBestUnit.as<int32_t>(), nullptr, nullptr, h->dPool.as<double>()));
+    if (!h->ran || h->poolK != h->K || h->poolP != h->P)
+        PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
+    PFB_CUDA(h, launch_k3(h, h->P, h->dBestUnit.as<int32_t>(), nullptr, nullptr, h->dPool.as<double>(), 0,
+                          h->pool_seeds, nullptr, nullptr, 0, h->dFbSeeds.as<uint64_t>()));
     h->launches += 1;
     h->pool_ready = true;
     return PFB_OK;
@@ -654,8 +680,8 @@ static int regen_columns(pfb_engine* h, int m, const int64_t* d_inds, int64_t ba
     PFB_CUDA(h, h->dSelCnt.ensure((size_t)h->P * 4 + 8));
     PFB_CUDA(h, h->dSelList.ensure((size_t)h->P * (size_t)m * 8 + 8));
     PFB_CUDA(h, pfb_launch_k7r_bin(st, h->P, h->K, m, base, d_inds, h->dSelCnt.as<int32_t>(), h->dSelList.p));
-    PFB_CUDA(h, launch_k3(h, h->P, h->dBestUnit.as<int32_t>(), nullptr, nullptr, d_out, 0, nullptr,
-                          h->dSelCnt.as<int32_t>(), h->dSelList.p, m));
+    PFB_CUDA(h, launch_k3(h, h->P, h->dBestUnit.as<int32_t>(), nullptr, nullptr, d_out, 0, h->pool_seeds,
+                          h->dSelCnt.as<int32_t>(), h->dSelList.p, m, h->dFbSeeds.as<uint64_t>()));
     h->launches += 2;
     return PFB_OK;
 }
@@ -713,6 +739,103 @@ static int run_host_callback_stage(pfb_engine* h) {
             if (rc) return rc;
         }
     }
+    return PFB_OK;
+}
+
+__global__ void pfb_set_pool_seeds(int nf, const int64_t* __restrict__ pairs, uint64_t* __restrict__ pool_seeds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // pairs: (unit, seed)
+    if (i < nf && pairs[2 * i] >= 0) pool_seeds[pairs[2 * i]] = (uint64_t)pairs[2 * i + 1];
+}
+__global__ void pfb_scatter_rows(int K, const int32_t* __restrict__ slot_of_row, const double* __restrict__ src,
+                                 double* __restrict__ dst) {
+    const int s = slot_of_row[blockIdx.x];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) dst[(int64_t)s * K + k] = src[(int64_t)blockIdx.x * K + k];
+}
+
+static uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+// Failed paths (success = false: no iteration, or a NaN / -Inf best ELBO).  The reference draws
+//   rand(rng, fit_distributions[fit_iteration + 1], ndraws)       (src/singlepath.jl:224-228)
+// for them — fresh draws with the path's rng, which then enter the PSIS pool with their own log
+// densities (src/multipath.jl:217, src/resample.jl:81-95).  Here: K fresh draws per failed path from
+// the fit of its best iteration (the identity fit of iteration 0 when it has none) with the path's
+// fallback seed; the pool's log densities and the pool's seed table are updated, so that a later
+// materialisation / column regeneration reproduces exactly these draws.
+static int failed_path_draws(pfb_engine* h) {
+    const int P = h->P, K = h->K, n = h->n;
+    cudaStream_t st = h->stream;
+    h->pool_seeds = h->dSeeds.as<uint64_t>();
+    h->n_failed = 0;
+    if (P <= 0) return PFB_OK;
+    h->fb_seeds.resize((size_t)P);
+    for (int p = 0; p < P; ++p)
+        h->fb_seeds[(size_t)p] = ((int)h->fb_seeds_user.size() == P) ? h->fb_seeds_user[(size_t)p]
+                                                                      : splitmix64(0x5EEDFA11ULL + (uint64_t)p);
+    h->fb_seeds_user.clear();
+    PFB_CUDA(h, h->dFbSeeds.ensure((size_t)P * 8));
+    PFB_CUDA(h, cudaMemcpyAsync(h->dFbSeeds.p, h->fb_seeds.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
+    std::vector<int32_t> succ((size_t)P), bu((size_t)P);
+    PFB_CUDA(h, cudaMemcpyAsync(succ.data(), h->dSucc.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    PFB_CUDA(h, cudaMemcpyAsync(bu.data(), h->dBestUnit.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    std::vector<int32_t> paths, units;
+    std::vector<int64_t> pairs;
+    for (int p = 0; p < P; ++p)
+        if (!succ[(size_t)p]) {
+            paths.push_back(p);
+            units.push_back(bu[(size_t)p]);
+            pairs.push_back(bu[(size_t)p]);
+            pairs.push_back((int64_t)h->fb_seeds[(size_t)p]);
+        }
+    const int nf = (int)paths.size();
+    h->n_failed = nf;
+    if (nf == 0 || h->have_normals) return PFB_OK;  // (parity mode supplies the normals of the ELBO stage only)
+    const int64_t U = h->U;
+    PFB_CUDA(h, h->dPoolSeeds.ensure((size_t)std::max<int64_t>(U, 1) * 8));
+    PFB_CUDA(h, h->dFbUnits.ensure((size_t)nf * 4));
+    PFB_CUDA(h, h->dFbPaths.ensure((size_t)nf * 4));
+    PFB_CUDA(h, h->dFbPairs.ensure((size_t)nf * 16));
+    PFB_CUDA(h, h->dFbLogp.ensure((size_t)nf * K * 8));
+    PFB_CUDA(h, h->dFbLogq.ensure((size_t)nf * K * 8));
+    if (U > 0)
+        PFB_CUDA(h, cudaMemcpyAsync(h->dPoolSeeds.p, h->dSeeds.p, (size_t)U * 8, cudaMemcpyDeviceToDevice, st));
+    PFB_CUDA(h, cudaMemcpyAsync(h->dFbUnits.p, units.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    PFB_CUDA(h, cudaMemcpyAsync(h->dFbPaths.p, paths.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    PFB_CUDA(h, cudaMemcpyAsync(h->dFbPairs.p, pairs.data(), (size_t)nf * 16, cudaMemcpyHostToDevice, st));
+    pfb_set_pool_seeds<<<(nf + 127) / 128, 128, 0, st>>>(nf, h->dFbPairs.as<int64_t>(), h->dPoolSeeds.as<uint64_t>());
+    PFB_CUDA(h, cudaGetLastError());
+    h->pool_seeds = h->dPoolSeeds.as<uint64_t>();
+    const bool ext = h->model == PFB_MODEL_DENSENORMAL || h->model == PFB_MODEL_HLOGISTIC ||
+                     h->model == PFB_MODEL_HOSTCALLBACK;
+    double* xbuf = nullptr;
+    if (ext) {
+        PFB_CUDA(h, h->dGenX.ensure((size_t)nf * (size_t)n * (size_t)K * 8 + 8));
+        xbuf = h->dGenX.as<double>();
+    }
+    PFB_CUDA(h, launch_k3(h, nf, h->dFbUnits.as<int32_t>(), h->dFbLogp.as<double>(), h->dFbLogq.as<double>(), xbuf, 0,
+                          h->pool_seeds, nullptr, nullptr, 0, h->dFbSeeds.as<uint64_t>(), h->dFbPaths.as<int32_t>()));
+    if (h->model == PFB_MODEL_HOSTCALLBACK) {
+        int rc = host_logp_sync(h, xbuf, (int64_t)nf * K, h->dFbLogp.as<double>());
+        if (rc) return rc;
+    } else if (ext) {
+        int rc = generic_logp(h, xbuf, (int64_t)nf * K, nullptr, h->dFbLogp.as<double>(), 0);
+        if (rc) return rc;
+    }
+    pfb_scatter_rows<<<nf, 256, 0, st>>>(K, h->dFbPaths.as<int32_t>(), h->dFbLogp.as<double>(), h->dPoolLogp.as<double>());
+    pfb_scatter_rows<<<nf, 256, 0, st>>>(K, h->dFbPaths.as<int32_t>(), h->dFbLogq.as<double>(), h->dPoolLogq.as<double>());
+    PFB_CUDA(h, cudaGetLastError());
+    h->launches += 4;
+    return PFB_OK;
+}
+
+extern "C" int pfb_set_fallback_seeds(pfb_handle h, int P, const uint64_t* seeds) {
+    if (!h || P < 0 || (P > 0 && !seeds)) return PFB_ERR_ARG;
+    h->fb_seeds_user.assign(seeds, seeds + P);
     return PFB_OK;
 }
 
@@ -814,9 +937,14 @@ extern "C" int pfb_batch_run(pfb_handle h) {
         h->launches += 2;
     }
     h->pool_ready = false;
-    PFB_CUDA(h, cudaEventRecord(h->ev[5], st));
     h->ran = true;
     h->poolK = K;
+    h->poolP = P;
+    {
+        int rcf = failed_path_draws(h);
+        if (rcf) return rcf;
+    }
+    PFB_CUDA(h, cudaEventRecord(h->ev[5], st));
     return PFB_OK;
 }
 
@@ -853,7 +981,10 @@ extern "C" int pfb_batch_fit_only(pfb_handle h, const int64_t* best_iter) {
     for (int i = 0; i <= 5; ++i) PFB_CUDA(h, cudaEventRecord(h->ev[i], st));
     h->launches = 2;
     h->ran = true;
+    h->pool_seeds = h->dSeeds.as<uint64_t>();
+    h->n_failed = 0;
     h->poolK = 0;
+    h->poolP = 0;
     h->pool_ready = false;
     return PFB_OK;
 }
@@ -887,8 +1018,10 @@ extern "C" int pfb_draw_from_fits(pfb_handle h, int K_new, const uint64_t* seeds
     PFB_CUDA(h, X->ensure(n * (size_t)K_new * P * 8 + 8));
     PFB_CUDA(h, Lp->ensure((size_t)K_new * P * 8 + 8));
     PFB_CUDA(h, Lq->ensure((size_t)K_new * P * 8 + 8));
+    PFB_CUDA(h, h->dTopFb.ensure(P * 8));
+    PFB_CUDA(h, cudaMemcpyAsync(h->dTopFb.p, seeds, P * 8, cudaMemcpyHostToDevice, st));
     PFB_CUDA(h, launch_k3(h, (int)P, h->dBestUnit.as<int32_t>(), Lp->as<double>(), Lq->as<double>(), X->as<double>(),
-                          K_new, h->dTopSeeds.as<uint64_t>()));
+                          K_new, h->dTopSeeds.as<uint64_t>(), nullptr, nullptr, 0, h->dTopFb.as<uint64_t>()));
     if (h->model == PFB_MODEL_HOSTCALLBACK) {
         int rc = host_logp_sync(h, X->as<double>(), (int64_t)P * K_new, Lp->as<double>());
         if (rc) return rc;
@@ -903,6 +1036,7 @@ extern "C" int pfb_draw_from_fits(pfb_handle h, int K_new, const uint64_t* seeds
     PFB_CUDA(h, cudaStreamSynchronize(st));
     if (keep_as_pool) {
         h->poolK = K_new;
+        h->poolP = h->P;
         h->pool_ready = true;
     }
     return PFB_OK;
@@ -945,6 +1079,25 @@ extern "C" int pfb_unit_draws(pfb_handle h, int nunits, const int32_t* units, do
     if (logq) PFB_CUDA(h, cudaMemcpyAsync(logq, Lq, M * 8, cudaMemcpyDeviceToHost, st));
     PFB_CUDA(h, cudaStreamSynchronize(st));
     return PFB_OK;
+}
+
+static int gather_fits(pfb_engine* h, int cnt, const int32_t* d_units, double* mu, double* alpha, double* vh,
+                       double* T, double* Vc, double* logdet, int32_t* jeff);
+
+// fit_distributions[l + 1] of arbitrary (path, iteration) units of the current batch in the reference's
+// WoodburyPDMat form (src/singlepath.jl:64 keeps every iteration's; here they are exported on demand).
+extern "C" int pfb_unit_fits(pfb_handle h, int nunits, const int32_t* units, double* mu, double* alpha, double* vh,
+                             double* T, double* Vc, double* logdet, int32_t* jeff) {
+    if (!h || (nunits > 0 && !units)) return PFB_ERR_ARG;
+    if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "no fitted batch (pfb_batch_run / pfb_batch_fit_only)");
+    if (nunits <= 0) return PFB_OK;
+    for (int i = 0; i < nunits; ++i)
+        if (units[i] < 0 || units[i] >= h->U) PFB_FAIL(h, PFB_ERR_ARG, "unit index out of range");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    PFB_CUDA(h, h->dIota.ensure((size_t)std::max<int64_t>(h->U, nunits) * 4 + (size_t)nunits * 4));
+    int32_t* d_units = h->dIota.as<int32_t>() + std::max<int64_t>(h->U, nunits);
+    PFB_CUDA(h, cudaMemcpyAsync(d_units, units, (size_t)nunits * 4, cudaMemcpyHostToDevice, h->stream));
+    return gather_fits(h, nunits, d_units, mu, alpha, vh, T, Vc, logdet, jeff);
 }
 
 extern "C" int pfb_batch_sync(pfb_handle h) {
@@ -993,11 +1146,6 @@ extern "C" int pfb_batch_download(pfb_handle h, pfb_elbo_out* o) {
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = h->stream;
     const size_t n = h->n, P = h->P, K = h->K, U = (size_t)h->U, KP = h->KP;
-#define PFB_D2H(dst, src, bytes)                                                                   \
-    do {                                                                                           \
-        if ((dst) && (bytes) > 0)                                                                  \
-            PFB_CUDA(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, st));        \
-    } while (0)
     PFB_D2H(o->elbo, h->dElbo.p, U * 8);
     PFB_D2H(o->elbo_se, h->dSe.p, U * 8);
     PFB_D2H(o->logp, h->dLogp.p, U * K * 8);
@@ -1018,30 +1166,40 @@ extern "C" int pfb_batch_download(pfb_handle h, pfb_elbo_out* o) {
     }
     const bool want_fit = o->fit_mu || o->fit_alpha || o->fit_vh || o->fit_T || o->fit_Vc || o->fit_logdet ||
                           o->fit_jeff;
-    if (want_fit && P > 0) {
-        PFB_CUDA(h, h->dFitMu.ensure(n * P * 8));
-        PFB_CUDA(h, h->dFitAlpha.ensure(n * P * 8));
-        PFB_CUDA(h, h->dFitVh.ensure(n * KP * P * 8));
-        PFB_CUDA(h, h->dFitT.ensure(KP * KP * P * 8));
-        PFB_CUDA(h, h->dFitVc.ensure(KP * KP * P * 8));
-        PFB_CUDA(h, h->dFitLogdet.ensure(P * 8));
-        PFB_CUDA(h, h->dFitJeff.ensure(P * 4));
-        pfb_gather_fit<<<(unsigned)P, 256, 0, st>>>((int)n, (int)KP, h->dBestUnit.as<int32_t>(),
-                                                    h->dFR2.as<double>(), h->dHDR.as<double>(),
-                                                    h->dAlpha.as<double>(), h->dHistCnt.as<int32_t>(),
-                                                    h->dFitMu.as<double>(), h->dFitAlpha.as<double>(),
-                                                    h->dFitVh.as<double>(), h->dFitT.as<double>(),
-                                                    h->dFitVc.as<double>(), h->dFitLogdet.as<double>(),
-                                                    h->dFitJeff.as<int32_t>());
-        PFB_CUDA(h, cudaGetLastError());
-        PFB_D2H(o->fit_mu, h->dFitMu.p, n * P * 8);
-        PFB_D2H(o->fit_alpha, h->dFitAlpha.p, n * P * 8);
-        PFB_D2H(o->fit_vh, h->dFitVh.p, n * KP * P * 8);
-        PFB_D2H(o->fit_T, h->dFitT.p, KP * KP * P * 8);
-        PFB_D2H(o->fit_Vc, h->dFitVc.p, KP * KP * P * 8);
-        PFB_D2H(o->fit_logdet, h->dFitLogdet.p, P * 8);
-        PFB_D2H(o->fit_jeff, h->dFitJeff.p, P * 4);
-    }
+    if (want_fit && P > 0)
+        return gather_fits(h, (int)P, h->dBestUnit.as<int32_t>(), o->fit_mu, o->fit_alpha, o->fit_vh, o->fit_T,
+                           o->fit_Vc, o->fit_logdet, o->fit_jeff);
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    return PFB_OK;
+}
+
+// The fitted normals of `cnt` units (device list; < 0: NaN) in the reference's form, to host buffers
+// (any may be NULL); synchronises the engine stream.
+static int gather_fits(pfb_engine* h, int cnt, const int32_t* d_units, double* mu, double* alpha, double* vh,
+                       double* T, double* Vc, double* logdet, int32_t* jeff) {
+    cudaStream_t st = h->stream;
+    const size_t n = h->n, KP = h->KP, P = (size_t)cnt;
+    PFB_CUDA(h, h->dFitMu.ensure(n * P * 8));
+    PFB_CUDA(h, h->dFitAlpha.ensure(n * P * 8));
+    PFB_CUDA(h, h->dFitVh.ensure(n * KP * P * 8));
+    PFB_CUDA(h, h->dFitT.ensure(KP * KP * P * 8));
+    PFB_CUDA(h, h->dFitVc.ensure(KP * KP * P * 8));
+    PFB_CUDA(h, h->dFitLogdet.ensure(P * 8));
+    PFB_CUDA(h, h->dFitJeff.ensure(P * 4));
+    pfb_gather_fit<<<(unsigned)P, 256, 0, st>>>((int)n, (int)KP, d_units, h->dFR2.as<double>(), h->dHDR.as<double>(),
+                                                h->dAlpha.as<double>(), h->dHistCnt.as<int32_t>(),
+                                                h->dFitMu.as<double>(), h->dFitAlpha.as<double>(),
+                                                h->dFitVh.as<double>(), h->dFitT.as<double>(),
+                                                h->dFitVc.as<double>(), h->dFitLogdet.as<double>(),
+                                                h->dFitJeff.as<int32_t>());
+    PFB_CUDA(h, cudaGetLastError());
+    PFB_D2H(mu, h->dFitMu.p, n * P * 8);
+    PFB_D2H(alpha, h->dFitAlpha.p, n * P * 8);
+    PFB_D2H(vh, h->dFitVh.p, n * KP * P * 8);
+    PFB_D2H(T, h->dFitT.p, KP * KP * P * 8);
+    PFB_D2H(Vc, h->dFitVc.p, KP * KP * P * 8);
+    PFB_D2H(logdet, h->dFitLogdet.p, P * 8);
+    PFB_D2H(jeff, h->dFitJeff.p, P * 4);
     PFB_CUDA(h, cudaStreamSynchronize(st));
     return PFB_OK;
 }
@@ -1169,11 +1327,11 @@ extern "C" int pfb_batch_device_view(pfb_handle h, pfb_device_view* v) {
     return PFB_OK;
 }
 
-static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const double* d_logp,
-                              const double* d_logq, const double* d_logr, const double* d_pool, uint64_t seed,
-                              int ndraws, int importance, int replace, pfb_resample_out* o, bool regen = false) {
-    // regen: the engine's own pool, whose draws are not materialised: the selected columns are
-    // regenerated by K3 (bit-identical to the pool's) instead of gathered
+// K6 (PSIS) + the index draw K7 / K7b, enqueued on the engine stream.  d_pool != NULL: the selected
+// columns are gathered from it into dOutDraws by the same kernels.
+static int psis_enqueue(pfb_engine* h, int n, int64_t N, int K_run, const double* d_logp, const double* d_logq,
+                        const double* d_logr, const double* d_pool, uint64_t seed, int ndraws, int importance,
+                        int replace) {
     if (N < 1 || N > 2147483647LL) PFB_FAIL(h, PFB_ERR_SHAPE, "pool size out of range");
     if (K_run < 1 || ndraws < 0) PFB_FAIL(h, PFB_ERR_ARG, "bad K_run / ndraws");
     if (!replace && ndraws > N) PFB_FAIL(h, PFB_ERR_ARG, "Cannot draw more samples without replacement.");
@@ -1181,9 +1339,7 @@ static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const 
     PFB_CUDA(h, h->dScal.ensure(pfb_psis_scalars_size()));
     PFB_CUDA(h, h->dInds.ensure((size_t)ndraws * 8 + 8));
     PFB_CUDA(h, h->dIds.ensure((size_t)ndraws * 8 + 8));
-    const bool want_regen = regen && (o->draws != nullptr) && ndraws > 0;
-    const bool want_draws = (o->draws != nullptr) && (d_pool != nullptr) && !want_regen;
-    if (want_draws || want_regen) PFB_CUDA(h, h->dOutDraws.ensure((size_t)n * ndraws * 8 + 8));
+    PFB_CUDA(h, h->dOutDraws.ensure((size_t)n * ndraws * 8 + 8));
     if (importance) {
         // tail_length(r_eff = 1, S) = min(cld(S, 5), ceil(3 sqrt(S)));  grid m = 30 + floor(sqrt(M))
         const int M = (int)std::min<int64_t>((N + 4) / 5, (int64_t)ceil(3.0 * sqrt((double)N)));
@@ -1199,8 +1355,8 @@ static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const 
     }
     if (replace) {
         PFB_CUDA(h, pfb_launch_k7(st, n, (int)N, K_run, seed, ndraws, importance ? h->dCum.as<uint64_t>() : nullptr,
-                                  h->dScal.p, want_draws ? d_pool : nullptr, h->dInds.as<int64_t>(),
-                                  h->dIds.as<int64_t>(), want_draws ? h->dOutDraws.as<double>() : nullptr));
+                                  h->dScal.p, d_pool, h->dInds.as<int64_t>(), h->dIds.as<int64_t>(),
+                                  d_pool ? h->dOutDraws.as<double>() : nullptr));
     } else {
         // K7b: exponential-key order statistics (weighted sampling without replacement)
         size_t tmp_bytes = 0;
@@ -1212,14 +1368,16 @@ static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const 
         int32_t* i_in = reinterpret_cast<int32_t*>(k_out + N);
         int32_t* i_out = i_in + N;
         PFB_CUDA(h, pfb_launch_k7b(st, n, (int)N, K_run, seed, ndraws, importance ? h->dLogw.as<double>() : nullptr,
-                                   want_draws ? d_pool : nullptr, k_in, k_out, i_in, i_out, h->dSortTmp.p, tmp_bytes,
-                                   h->dInds.as<int64_t>(), h->dIds.as<int64_t>(),
-                                   want_draws ? h->dOutDraws.as<double>() : nullptr));
+                                   d_pool, k_in, k_out, i_in, i_out, h->dSortTmp.p, tmp_bytes, h->dInds.as<int64_t>(),
+                                   h->dIds.as<int64_t>(), d_pool ? h->dOutDraws.as<double>() : nullptr));
     }
-    if (want_regen) {
-        int rcr = regen_columns(h, ndraws, h->dInds.as<int64_t>(), 0, h->dOutDraws.as<double>());
-        if (rcr) return rcr;
-    }
+    return PFB_OK;
+}
+
+// Results of the last psis_enqueue to the caller's host buffers; one stream synchronisation.
+static int psis_finish(pfb_engine* h, int n, int64_t N, int ndraws, int importance, pfb_resample_out* o,
+                       bool have_draws) {
+    cudaStream_t st = h->stream;
     psis_scalars_host sc;
     memset(&sc, 0, sizeof(sc));
     if (importance) {
@@ -1229,11 +1387,31 @@ static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const 
     }
     PFB_D2H(o->inds, h->dInds.p, (size_t)ndraws * 8);
     PFB_D2H(o->ids, h->dIds.p, (size_t)ndraws * 8);
-    if (want_draws || want_regen) PFB_D2H(o->draws, h->dOutDraws.p, (size_t)n * ndraws * 8);
+    if (have_draws) PFB_D2H(o->draws, h->dOutDraws.p, (size_t)n * ndraws * 8);
     PFB_CUDA(h, cudaStreamSynchronize(st));
     if (o->pareto_k) *o->pareto_k = importance ? sc.pareto_k : NAN;
     if (o->tail_len) *o->tail_len = importance ? sc.tail_len : 0;
+    if (importance && sc.Z == 0ull)
+        PFB_FAIL(h, PFB_ERR_NUMERIC, "every importance weight is zero or undefined (all log ratios are NaN / -Inf): "
+                                     "nothing to resample from");
     return PFB_OK;
+}
+
+static int psis_resample_impl(pfb_engine* h, int n, int64_t N, int K_run, const double* d_logp,
+                              const double* d_logq, const double* d_logr, const double* d_pool, uint64_t seed,
+                              int ndraws, int importance, int replace, pfb_resample_out* o, bool regen = false) {
+    // regen: the engine's own pool, whose draws are not materialised: the selected columns are
+    // regenerated by K3 (bit-identical to the pool's) instead of gathered
+    const bool want_regen = regen && (o->draws != nullptr) && ndraws > 0;
+    const bool want_draws = (o->draws != nullptr) && (d_pool != nullptr) && !want_regen;
+    int rc = psis_enqueue(h, n, N, K_run, d_logp, d_logq, d_logr, want_draws ? d_pool : nullptr, seed, ndraws,
+                          importance, replace);
+    if (rc) return rc;
+    if (want_regen) {
+        int rcr = regen_columns(h, ndraws, h->dInds.as<int64_t>(), 0, h->dOutDraws.as<double>());
+        if (rcr) return rcr;
+    }
+    return psis_finish(h, n, N, ndraws, importance, o, want_draws || want_regen);
 }
 
 extern "C" int pfb_psis_resample(pfb_handle h, uint64_t seed, int ndraws, int importance, int replace,
@@ -1241,7 +1419,7 @@ extern "C" int pfb_psis_resample(pfb_handle h, uint64_t seed, int ndraws, int im
     if (!h || !o) return PFB_ERR_ARG;
     if (!h->ran || h->poolK <= 0) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
-    return psis_resample_impl(h, h->n, (int64_t)h->P * h->poolK, h->poolK, h->dPoolLogp.as<double>(),
+    return psis_resample_impl(h, h->n, (int64_t)h->poolP * h->poolK, h->poolK, h->dPoolLogp.as<double>(),
                               h->dPoolLogq.as<double>(), nullptr, h->dPool.as<double>(), seed, ndraws,
                               importance, replace, o, /*regen=*/!h->pool_ready);
 }
@@ -1277,6 +1455,313 @@ extern "C" int pfb_psis_resample_host(pfb_handle h, int n, int64_t N, int K_run,
         d_pool = h->dTmpPool.as<double>();
     }
     return psis_resample_impl(h, n, N, K_run, nullptr, nullptr, d_logr, d_pool, seed, ndraws, importance, replace, o);
+}
+
+// ---- multi-GPU: the PSIS pool exchange behind the ABI (src/multipath.jl:190-225) --------------
+// Paths shard over the GPUs with no communication until the pool.  The exchange is the lean form of
+// the "all-gather of the pool": every rank all-gathers the per-draw log densities (16 B per pool draw),
+// runs PSIS and the index draw replicated (deterministic kernels + counter RNG => identical on every
+// rank), regenerates the selected columns it owns, and the ranks sum-reduce the n x ndraws result.
+// NCCL is loaded lazily (dlopen), so the library has no link-time dependency on it: inside a PyTorch
+// process this resolves to the NCCL torch already loaded, elsewhere to the system libnccl.so.2.
+#include <dlfcn.h>
+
+namespace {
+struct pfb_nccl_uid { char internal[128]; };
+typedef void* pfb_nccl_comm_t;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(pfb_nccl_uid*) = nullptr;
+    int (*CommInitRank)(pfb_nccl_comm_t*, int, pfb_nccl_uid, int) = nullptr;
+    int (*CommDestroy)(pfb_nccl_comm_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, pfb_nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, pfb_nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, pfb_nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+};
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+
+NcclApi* nccl_api() {
+    static NcclApi api;
+    if (api.lib) return &api;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) {
+        api.err = std::string("cannot load NCCL: ") + dlerror();
+        return nullptr;
+    }
+#define PFB_NCCL_SYM(field, name)                                             \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name)); \
+    if (!api.field) {                                                         \
+        api.err = std::string("NCCL symbol missing: ") + name;               \
+        api.lib = nullptr;                                                    \
+        return nullptr;                                                       \
+    }
+    PFB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    PFB_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    PFB_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    PFB_NCCL_SYM(AllGather, "ncclAllGather")
+    PFB_NCCL_SYM(AllReduce, "ncclAllReduce")
+    PFB_NCCL_SYM(Broadcast, "ncclBroadcast")
+    PFB_NCCL_SYM(GroupStart, "ncclGroupStart")
+    PFB_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    PFB_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef PFB_NCCL_SYM
+    return &api;
+}
+}  // namespace
+
+#define PFB_NCCL(h, expr)                                                                          \
+    do {                                                                                           \
+        int r_ = (expr);                                                                           \
+        if (r_ != 0) {                                                                             \
+            (h)->err = std::string(#expr) + ": NCCL error " + nccl_api()->GetErrorString(r_);      \
+            return 1000 + r_;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+extern "C" int pfb_comm_unique_id(void* id128) {
+    if (!id128) return PFB_ERR_ARG;
+    NcclApi* a = nccl_api();
+    if (!a) {
+        g_create_err = "NCCL is not available (libnccl.so.2 could not be loaded)";
+        return PFB_ERR_UNSUPPORTED;
+    }
+    pfb_nccl_uid u;
+    int r = a->GetUniqueId(&u);
+    if (r != 0) return 1000 + r;
+    memcpy(id128, &u, sizeof(u));
+    return PFB_OK;
+}
+
+extern "C" int pfb_comm_destroy(pfb_handle h) {
+    if (!h) return PFB_ERR_ARG;
+    if (h->comm) {
+        cudaSetDevice(h->cfg.device);
+        cudaStreamSynchronize(h->stream);
+        nccl_api()->CommDestroy(h->comm);
+    }
+    h->comm = nullptr;
+    h->comm_world = 1;
+    h->comm_rank = 0;
+    return PFB_OK;
+}
+
+// One handle per GPU; every rank calls with the same id (from pfb_comm_unique_id on one of them).
+extern "C" int pfb_comm_init(pfb_handle h, const void* id128, int rank, int world) {
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return PFB_ERR_ARG;
+    NcclApi* a = nccl_api();
+    if (!a) PFB_FAIL(h, PFB_ERR_UNSUPPORTED, "NCCL is not available (libnccl.so.2 could not be loaded)");
+    pfb_comm_destroy(h);
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    pfb_nccl_uid u;
+    memcpy(&u, id128, sizeof(u));
+    pfb_nccl_comm_t c = nullptr;
+    PFB_NCCL(h, a->CommInitRank(&c, world, u, rank));
+    h->comm = c;
+    h->comm_world = world;
+    h->comm_rank = rank;
+    return PFB_OK;
+}
+
+// Single process, several GPUs (what a Julia caller without MPI does): handle i is rank i.
+extern "C" int pfb_comm_init_all(pfb_handle* hs, int nh) {
+    if (!hs || nh < 1) return PFB_ERR_ARG;
+    for (int i = 0; i < nh; ++i)
+        if (!hs[i]) return PFB_ERR_ARG;
+    NcclApi* a = nccl_api();
+    if (!a) PFB_FAIL(hs[0], PFB_ERR_UNSUPPORTED, "NCCL is not available (libnccl.so.2 could not be loaded)");
+    pfb_nccl_uid u;
+    PFB_NCCL(hs[0], a->GetUniqueId(&u));
+    for (int i = 0; i < nh; ++i) pfb_comm_destroy(hs[i]);
+    std::vector<pfb_nccl_comm_t> cs((size_t)nh, nullptr);
+    PFB_NCCL(hs[0], a->GroupStart());
+    for (int i = 0; i < nh; ++i) {
+        PFB_CUDA(hs[i], cudaSetDevice(hs[i]->cfg.device));
+        PFB_NCCL(hs[i], a->CommInitRank(&cs[(size_t)i], nh, u, i));
+    }
+    PFB_NCCL(hs[0], a->GroupEnd());
+    for (int i = 0; i < nh; ++i) {
+        hs[i]->comm = cs[(size_t)i];
+        hs[i]->comm_world = nh;
+        hs[i]->comm_rank = i;
+    }
+    return PFB_OK;
+}
+
+// out[t] = column inds[t] of this engine's materialised pool if it owns it (global 1-based index in
+// [base + 1, base + cnt]), else untouched
+__global__ void pfb_gather_owned_columns(int n, int m, const int64_t* __restrict__ inds, int64_t base, int64_t cnt,
+                                         const double* __restrict__ pool, double* __restrict__ out) {
+    const int t = blockIdx.x;
+    const int64_t j = inds[t] - 1 - base;
+    if (j < 0 || j >= cnt) return;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[(int64_t)t * n + i] = pool[j * n + i];
+}
+
+// The exchange for `nh` handles driven by this thread (nh = 1: one process per GPU; nh = world: one
+// process, all GPUs).  Every collective is issued for all local handles inside one NCCL group.
+static int pool_exchange_impl(pfb_engine** hs, int nh, const int32_t* paths_per_rank, uint64_t seed, int ndraws,
+                              int importance, int replace, pfb_resample_out** outs) {
+    NcclApi* a = nccl_api();
+    pfb_engine* h0 = hs[0];
+    if (!a) PFB_FAIL(h0, PFB_ERR_UNSUPPORTED, "NCCL is not available");
+    const int world = h0->comm_world;
+    int K_run = 0;
+    for (int i = 0; i < nh; ++i) {
+        pfb_engine* h = hs[i];
+        if (!h->comm || h->comm_world != world) PFB_FAIL(h, PFB_ERR_STATE, "pfb_comm_init has not been called");
+        if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
+        if (paths_per_rank[h->comm_rank] != h->poolP) PFB_FAIL(h, PFB_ERR_SHAPE, "paths_per_rank[rank] differs from this engine's pool");
+        if (h->poolP > 0) {
+            if (h->poolK <= 0) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
+            if (K_run && K_run != h->poolK) PFB_FAIL(h, PFB_ERR_SHAPE, "draws per run differ between engines");
+            K_run = h->poolK;
+        }
+    }
+    if (K_run == 0) K_run = h0->K;  // (a rank without runs: every rank uses ndraws_elbo draws per run)
+    std::vector<int64_t> off((size_t)world + 1, 0);
+    bool equal = true;
+    for (int r = 0; r < world; ++r) {
+        if (paths_per_rank[r] < 0) PFB_FAIL(h0, PFB_ERR_ARG, "negative paths_per_rank");
+        off[(size_t)r + 1] = off[(size_t)r] + (int64_t)paths_per_rank[r] * K_run;
+        equal = equal && paths_per_rank[r] == paths_per_rank[0];
+    }
+    const int64_t N = off[(size_t)world];
+    if (N < 1) PFB_FAIL(h0, PFB_ERR_SHAPE, "empty pool");
+    const int n = h0->n;
+    for (int i = 0; i < nh; ++i) {
+        pfb_engine* h = hs[i];
+        PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+        PFB_CUDA(h, h->dGLogp.ensure((size_t)N * 8));
+        PFB_CUDA(h, h->dGLogq.ensure((size_t)N * 8));
+        PFB_CUDA(h, h->dPoolLogp.ensure(8));  // (ranks without runs still need valid send pointers)
+        PFB_CUDA(h, h->dPoolLogq.ensure(8));
+    }
+    if (importance) {
+        // C1: all-gather of the per-draw log densities (ragged shards: one broadcast per owner)
+        PFB_NCCL(h0, a->GroupStart());
+        for (int i = 0; i < nh; ++i) {
+            pfb_engine* h = hs[i];
+            PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+            if (equal) {
+                const size_t cnt = (size_t)(off[1] - off[0]);
+                PFB_NCCL(h, a->AllGather(h->dPoolLogp.p, h->dGLogp.p, cnt, kNcclFloat64, h->comm, h->stream));
+                PFB_NCCL(h, a->AllGather(h->dPoolLogq.p, h->dGLogq.p, cnt, kNcclFloat64, h->comm, h->stream));
+            } else {
+                for (int r = 0; r < world; ++r) {
+                    const size_t cnt = (size_t)(off[(size_t)r + 1] - off[(size_t)r]);
+                    if (cnt == 0) continue;
+                    double* gp = h->dGLogp.as<double>() + off[(size_t)r];
+                    double* gq = h->dGLogq.as<double>() + off[(size_t)r];
+                    const bool mine = (r == h->comm_rank);
+                    PFB_NCCL(h, a->Broadcast(mine ? h->dPoolLogp.p : (const void*)gp, gp, cnt, kNcclFloat64, r, h->comm, h->stream));
+                    PFB_NCCL(h, a->Broadcast(mine ? h->dPoolLogq.p : (const void*)gq, gq, cnt, kNcclFloat64, r, h->comm, h->stream));
+                }
+            }
+        }
+        PFB_NCCL(h0, a->GroupEnd());
+    }
+    // K6 + K7 replicated; every rank writes the selected columns it owns into a zeroed n x ndraws buffer
+    for (int i = 0; i < nh; ++i) {
+        pfb_engine* h = hs[i];
+        PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+        int rc = psis_enqueue(h, n, N, K_run, importance ? h->dGLogp.as<double>() : nullptr,
+                              importance ? h->dGLogq.as<double>() : nullptr, nullptr, nullptr, seed, ndraws, importance,
+                              replace);
+        if (rc) return rc;
+        if (ndraws > 0) {
+            PFB_CUDA(h, cudaMemsetAsync(h->dOutDraws.p, 0, (size_t)n * ndraws * 8, h->stream));
+            const int64_t base = off[(size_t)h->comm_rank];
+            if (h->poolP > 0 && h->pool_ready) {
+                pfb_gather_owned_columns<<<ndraws, 128, 0, h->stream>>>(n, ndraws, h->dInds.as<int64_t>(), base,
+                                                                        (int64_t)h->poolP * K_run, h->dPool.as<double>(),
+                                                                        h->dOutDraws.as<double>());
+                PFB_CUDA(h, cudaGetLastError());
+            } else if (h->poolP > 0) {
+                if (h->poolK != h->K || h->poolP != h->P)
+                    PFB_FAIL(h, PFB_ERR_STATE, "column regeneration needs the pool of pfb_batch_run");
+                rc = regen_columns(h, ndraws, h->dInds.as<int64_t>(), base, h->dOutDraws.as<double>());
+                if (rc) return rc;
+            }
+        }
+    }
+    if (ndraws > 0) {
+        // C2: sum-reduce of the n x ndraws result (every column is non-zero on exactly one rank)
+        PFB_NCCL(h0, a->GroupStart());
+        for (int i = 0; i < nh; ++i) {
+            pfb_engine* h = hs[i];
+            PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+            PFB_NCCL(h, a->AllReduce(h->dOutDraws.p, h->dOutDraws.p, (size_t)n * ndraws, kNcclFloat64, kNcclSum, h->comm,
+                                     h->stream));
+        }
+        PFB_NCCL(h0, a->GroupEnd());
+    }
+    for (int i = 0; i < nh; ++i) {
+        pfb_engine* h = hs[i];
+        PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+        int rc = psis_finish(h, n, N, ndraws, importance, outs[i], outs[i]->draws != nullptr && ndraws > 0);
+        if (rc) return rc;
+    }
+    return PFB_OK;
+}
+
+// Replaces _compute_psis_result + _resample (src/multipath.jl:220-225) over the runs of ALL ranks:
+// paths_per_rank[world] = runs owned by each rank (rank order = run order, so the pool keeps the
+// reference's component order, src/multipath.jl:217); every rank passes the same seed / ndraws and
+// receives the same indices, ids, weights and draws.
+extern "C" int pfb_pool_exchange_resample(pfb_handle h, const int32_t* paths_per_rank, uint64_t seed, int ndraws,
+                                          int importance, int replace, pfb_resample_out* out) {
+    if (!h || !paths_per_rank || !out) return PFB_ERR_ARG;
+    pfb_engine* hs[1] = {h};
+    pfb_resample_out* os[1] = {out};
+    return pool_exchange_impl(hs, 1, paths_per_rank, seed, ndraws, importance, replace, os);
+}
+extern "C" int pfb_pool_exchange_resample_all(pfb_handle* hs, int nh, const int32_t* paths_per_rank, uint64_t seed,
+                                              int ndraws, int importance, int replace, pfb_resample_out* outs) {
+    if (!hs || nh < 1 || !paths_per_rank || !outs) return PFB_ERR_ARG;
+    std::vector<pfb_resample_out*> os((size_t)nh);
+    for (int i = 0; i < nh; ++i) {
+        if (!hs[i]) return PFB_ERR_ARG;
+        os[(size_t)i] = &outs[i];
+    }
+    return pool_exchange_impl(hs, nh, paths_per_rank, seed, ndraws, importance, replace, os.data());
+}
+
+// A device pool from HOST arrays (P runs, K_run draws each): draws[n x K_run x P], logp / logq
+// [K_run x P].  For pools assembled on the host (top-up draws beyond ndraws_elbo, retried paths, a rank
+// without runs: P = 0) that then take part in pfb_psis_resample / pfb_pool_exchange_resample.
+extern "C" int pfb_pool_set(pfb_handle h, int P, int K_run, const double* draws, const double* logp, const double* logq) {
+    if (!h || P < 0 || K_run < 1 || (P > 0 && (!logp || !logq))) return PFB_ERR_ARG;
+    if (h->model < 0) PFB_FAIL(h, PFB_ERR_STATE, "no model registered");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const size_t n = h->model_n, Ps = (size_t)P, K = (size_t)K_run;
+    if (!draws && P > 0 && (K_run != h->K || P != h->P || !h->ran))
+        PFB_FAIL(h, PFB_ERR_ARG, "a pool without draws must be the current batch's (its draws are regenerated)");
+    PFB_CUDA(h, h->dPoolLogp.ensure(K * Ps * 8 + 8));
+    PFB_CUDA(h, h->dPoolLogq.ensure(K * Ps * 8 + 8));
+    if (P > 0) {
+        PFB_CUDA(h, cudaMemcpyAsync(h->dPoolLogp.p, logp, K * Ps * 8, cudaMemcpyHostToDevice, st));
+        PFB_CUDA(h, cudaMemcpyAsync(h->dPoolLogq.p, logq, K * Ps * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (draws) {
+        PFB_CUDA(h, h->dPool.ensure(n * K * Ps * 8 + 8));
+        if (P > 0) PFB_CUDA(h, cudaMemcpyAsync(h->dPool.p, draws, n * K * Ps * 8, cudaMemcpyHostToDevice, st));
+    }
+    PFB_CUDA(h, cudaStreamSynchronize(st));
+    h->n = (int)n;
+    h->poolK = K_run;
+    h->poolP = P;
+    h->pool_ready = draws != nullptr;
+    h->ran = true;
+    return PFB_OK;
 }
 
 // Page-lock / unlock a caller-owned host buffer (cudaHostRegister): output buffers that a caller

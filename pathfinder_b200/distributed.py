@@ -1,6 +1,13 @@
 """Multi-GPU plumbing: one process per GPU over ``torch.distributed`` (NCCL on the GPUs, gloo in
 the CPU tests).
 
+On the GPUs the exchange itself lives behind the C ABI (``pfb_comm_init`` +
+``pfb_pool_exchange_resample``, NCCL inside libpfb200.so; ``Engine.comm_init`` /
+``Engine.pool_exchange_resample``) — this module keeps the sharding rules both sides use and
+``pooled_resample``, the same exchange written over ``torch.distributed`` tensors, which the CPU
+tests run under gloo (world size 2) to pin the host-side logic: ragged shards, ranks without runs,
+pool order.
+
 The reference is single-process (OhMyThreads tasks over runs, src/multipath.jl:190-208).  Here the
 paths shard across ranks; K1..K5 run with no communication, and the only exchange is the PSIS pool
 (lean variant): all-gather the per-draw log densities (16 B per pool draw), run PSIS

@@ -85,6 +85,8 @@ class Engine:
         self._U = 0
         self._offsets = None
         self._poolK = self.K
+        self._poolP = None  # paths in the device pool when it differs from the batch's (pool_set)
+        self._comm = None
         self._pending = []  # weakrefs of results whose draws are still on the device
 
     @classmethod
@@ -151,19 +153,26 @@ class Engine:
 
     # ---- ELBO stage ------------------------------------------------------------------------
     @staticmethod
-    def pack(trajectories):
-        """trajectories: list of (points [n, L+1], gradients [n, L+1]) -> offsets, X, G (F-order)."""
+    def pack(trajectories, n=None):
+        """trajectories: list of (points [n, L+1], gradients [n, L+1]) -> offsets, X, G (F-order).
+        n: the dimension, needed only for an empty list (a rank that owns no run)."""
         P = len(trajectories)
         offsets = np.zeros(P + 1, dtype=np.int64)
         for p, (x, _) in enumerate(trajectories):
             offsets[p + 1] = offsets[p] + x.shape[1]
-        n = trajectories[0][0].shape[0] if P else 0
+        n = trajectories[0][0].shape[0] if P else int(n or 0)
         X = np.empty((n, int(offsets[-1])), dtype=np.float64, order="F")
         G = np.empty_like(X)
         for p, (x, g) in enumerate(trajectories):
             X[:, offsets[p]:offsets[p + 1]] = x
             G[:, offsets[p]:offsets[p + 1]] = g
         return offsets, X, G
+
+    def set_fallback_seeds(self, seeds):
+        """One UInt64 seed per path of the NEXT batch: a failed path's draws are fresh draws from the fit
+        of its best iteration with this seed (src/singlepath.jl:224-228; pfb_set_fallback_seeds)."""
+        sd = np.ascontiguousarray(seeds, dtype=np.uint64)
+        _lib.check(self.h, self.lib.pfb_set_fallback_seeds(self.h, int(sd.size), _ptr(sd)))
 
     def upload(self, offsets, X, G, seeds, normals=None):
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -239,6 +248,7 @@ class Engine:
         _lib.check(self.h, self.lib.pfb_batch_run(self.h))
         self._raise_cb_error()
         self._poolK = self.K
+        self._poolP = None
 
     def sync(self):
         _lib.check(self.h, self.lib.pfb_batch_sync(self.h))
@@ -348,6 +358,7 @@ class Engine:
                                                    _ptr(normals), C.byref(out)))
         self._raise_cb_error()
         self._poolK = self.K
+        self._poolP = None
         res.success = succ.astype(bool)
         return res
 
@@ -356,6 +367,7 @@ class Engine:
         bi = np.ascontiguousarray(best_iter, dtype=np.int64)
         if bi.size != self._P:
             raise ValueError("need one best_iter per path")
+        self._flush_pending()  # the device pool is dropped: results that still point at it get their draws now
         _lib.check(self.h, self.lib.pfb_batch_fit_only(self.h, _ptr(bi)))
 
     def draw_from_fits(self, K_new, seeds, keep_as_pool=False, want_draws=True):
@@ -388,6 +400,61 @@ class Engine:
         _lib.check(self.h, self.lib.pfb_unit_draws(self.h, m, _ptr(u), _ptr(draws), _ptr(lp), _ptr(lq)))
         self._raise_cb_error()
         return draws, lp, lq
+
+    def unit_fits(self, units):
+        """fit_distributions[l + 1] (src/singlepath.jl:64) of the given 0-based units of the current batch
+        in the reference's WoodburyPDMat form: dict(mu [n, m], alpha [n, m], vh [n, KP, m], T [m, KP, KP],
+        Vc [m, KP, KP], logdet [m], jeff [m]).  Exported on demand instead of kept for every iteration."""
+        u = np.ascontiguousarray(units, dtype=np.int32)
+        m, n, KP = u.size, self.n, self.KP
+        f = dict(mu=np.empty((n, m), order="F"), alpha=np.empty((n, m), order="F"),
+                 vh=np.empty((n, KP, m), order="F"), T=np.empty((m, KP, KP)), Vc=np.empty((m, KP, KP)),
+                 logdet=np.empty(m), jeff=np.empty(m, dtype=np.int32))
+        _lib.check(self.h, self.lib.pfb_unit_fits(self.h, m, _ptr(u), _ptr(f["mu"]), _ptr(f["alpha"]), _ptr(f["vh"]),
+                                                  _ptr(f["T"]), _ptr(f["Vc"]), _ptr(f["logdet"]), _ptr(f["jeff"])))
+        return f
+
+    # ---- multi-GPU (one engine per GPU; NCCL behind the C ABI) ---------------------------------
+    def comm_init(self, group=None):
+        """Join the engines of a torch.distributed process group into one NCCL communicator owned by the
+        library (pfb_comm_init): rank 0 creates the id, the group broadcasts its 128 bytes."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            rc = self.lib.pfb_comm_unique_id(_ptr(buf))
+            if rc != 0:
+                raise _lib.PfbError(rc, (self.lib.pfb_last_error(None) or b"").decode())
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.from_numpy(buf).to(dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        buf = t.cpu().numpy()
+        _lib.check(self.h, self.lib.pfb_comm_init(self.h, _ptr(buf), rank, world))
+        self._comm = (rank, world)
+
+    def pool_set(self, P, K_run, draws, logp, logq):
+        """Install a device pool assembled on the host (pfb_pool_set): draws [n, K_run, P] or None."""
+        d = None if draws is None else np.asfortranarray(draws, dtype=np.float64)
+        lp = np.asfortranarray(logp, dtype=np.float64)
+        lq = np.asfortranarray(logq, dtype=np.float64)
+        self._flush_pending()
+        _lib.check(self.h, self.lib.pfb_pool_set(self.h, int(P), int(K_run), _ptr(d), _ptr(lp), _ptr(lq)))
+        self._poolK, self._poolP = int(K_run), int(P)
+
+    def pool_exchange_resample(self, paths_per_rank, seed, ndraws, importance=True, replace=True, want_weights=True,
+                               into=None):
+        """PSIS + resampling over the pools of ALL ranks (pfb_pool_exchange_resample): all-gather of the
+        per-draw log densities, replicated PSIS / index draw, owned columns regenerated, sum-reduce.
+        Every rank gets the same dict as psis_resample()."""
+        ppr = np.ascontiguousarray(paths_per_rank, dtype=np.int32)
+        N = int(ppr.sum()) * self._poolK
+        out, r = self._resample_out(N, ndraws, importance, True, want_weights, into=into)
+        _lib.check(self.h, self.lib.pfb_pool_exchange_resample(
+            self.h, _ptr(ppr), C.c_uint64(int(seed)), int(ndraws), int(bool(importance)), int(bool(replace)),
+            C.byref(out)))
+        return self._finish(r)
 
     def timings(self):
         ms = np.zeros(6)
@@ -446,7 +513,7 @@ class Engine:
     def psis_resample(self, seed, ndraws, importance=True, replace=True, into=None):
         """On the pool of the last batch / the last draw_from_fits(keep_as_pool=True) (device resident).
         into: the dict of an earlier call with the same shapes, whose arrays are reused."""
-        N = self._P * self._poolK
+        N = (self._poolP if self._poolP is not None else self._P) * self._poolK
         out, r = self._resample_out(N, ndraws, importance, True, into=into)
         _lib.check(self.h, self.lib.pfb_psis_resample(self.h, C.c_uint64(int(seed)), int(ndraws),
                                                       int(bool(importance)), int(bool(replace)), C.byref(out)))

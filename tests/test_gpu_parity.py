@@ -1041,3 +1041,144 @@ def test_gpu_index_streams_are_prefix_consistent():
         c = eng.psis_resample_host(lr, K_run, 6, 150, True, replace=replace)["inds"]
         assert np.array_equal(a[:150], b) and not np.array_equal(b, c)
     eng.close()
+
+
+def test_failed_path_draws_come_from_the_best_fit_with_the_path_seed():
+    """src/singlepath.jl:224-228: a failed path (here: every ELBO is -Inf because the target is -Inf on
+    half of the space) returns rand(rng, fit_distributions[fit_iteration + 1], ndraws) — fresh draws, not
+    the ELBO-stage draws — and they enter the pool with their own log densities."""
+    import pathfinder_b200 as pf
+    from oracle import pf_oracle as O
+    from tests.helpers import synthetic_trajectory
+
+    n, K, J = 14, 64, 6
+
+    def logp_host(X):  # -Inf on a half space that every fitted normal straddles
+        with np.errstate(all="ignore"):
+            return np.where(np.sum(X, axis=0) > 0.0, -0.5 * np.sum(X * X, axis=0), -np.inf)
+
+    model = pf.HostModel(n, logp_host, lambda x: -x)
+    good = pf.IsoNormal(n)
+    trajs = [synthetic_trajectory(n, L, 300 + L, scale=0.3) for L in (5, 3)]
+    seeds = _seeds(trajs, 12)
+    fb = np.array([0xABCDEF0123456789, 77], dtype=np.uint64)
+    offsets, X, G = pf.Engine.pack(trajs)
+    eng = pf.Engine.for_model(model, J, K, 0)
+    eng.set_fallback_seeds(fb)
+    res = eng.elbo_batch(offsets, X, G, np.concatenate(seeds), draws=True, per_draw=True, fit=True)
+    assert not res.success.any() and np.all(np.isneginf(res.elbo))
+    assert np.array_equal(res.best_iter, [1, 1])  # _findmax_skipnan keeps the first of equal values
+    for p, (Xp, Gp) in enumerate(trajs):
+        mus, Hs, _ = O.fit_mvnormals(Xp, Gp, history_length=J)
+        xd, lq = O.failed_path_draws(int(fb[p]), mus[:, 1], Hs[1], K)
+        assert _rel(res.draws[:, :, p], xd) < RTOL
+        np.testing.assert_allclose(res.draws_logq[:, p], lq, rtol=RTOL, atol=RTOL)
+        np.testing.assert_array_equal(res.draws_logp[:, p], logp_host(res.draws[:, :, p]))
+        # fresh draws: not the ELBO-stage draws of that iteration
+        ue = np.asarray(O.contract_normals(int(seeds[p][0]), n, K))
+        xe, _ = O.rand_and_logpdf(ue, mus[:, 1], Hs[1])
+        assert not np.allclose(res.draws[:, :, p], xe)
+    # the pool: finite weights only where the log ratio is finite; resampled columns are pool columns
+    r = eng.psis_resample(5, 40, True)
+    logr = (res.draws_logp - res.draws_logq).reshape(-1, order="F")
+    assert np.all(r["weights"][np.isneginf(logr)] == 0.0) and abs(r["weights"].sum() - 1.0) < 1e-12
+    pool = res.draws.reshape(n, -1, order="F")
+    assert np.array_equal(r["draws"], pool[:, r["inds"] - 1])
+    eng.close()
+
+    # a registered family on the same inputs succeeds, and its draws ARE the ELBO-stage draws
+    eng = pf.Engine.for_model(good, J, K, 0)
+    eng.set_fallback_seeds(fb)
+    res2 = eng.elbo_batch(offsets, X, G, np.concatenate(seeds), draws=True)
+    assert res2.success.all()
+    eng.close()
+
+
+def test_path_without_an_iteration_draws_from_the_identity_fit():
+    """L = 0 (the optimiser recorded only the start): fit_iteration = 0 and the reference draws from
+    fit_distributions[1] = N(theta_0 + grad_0, I) (src/inverse_hessian.jl:38-40, src/singlepath.jl:224-228)."""
+    import pathfinder_b200 as pf
+    from oracle import pf_oracle as O
+    from tests.helpers import synthetic_trajectory
+
+    n, K, J = 9, 48, 6
+    rng = np.random.default_rng(4)
+    x0, g0 = rng.normal(size=(n, 1)), rng.normal(size=(n, 1))
+    trajs = [synthetic_trajectory(n, 4, 41), (x0, g0)]
+    seeds = _seeds(trajs, 2)
+    fb = np.array([11, 2**63 + 12345], dtype=np.uint64)
+    offsets, X, G = pf.Engine.pack(trajs)
+    for model in (pf.Funnel(n), pf.DenseNormal(rng.normal(size=n), np.eye(n) * 2.0)):
+        eng = pf.Engine.for_model(model, J, K, 0)
+        eng.set_fallback_seeds(fb)
+        res = eng.elbo_batch(offsets, X, G, np.concatenate(seeds), draws=True, fit=True)
+        assert list(res.success) == [True, False] and res.best_iter[1] == 0
+        u = np.asarray(O.contract_normals(int(fb[1]), n, K))
+        xd = (x0 + g0) + u
+        assert _rel(res.draws[:, :, 1], xd) < 1e-14
+        np.testing.assert_allclose(res.draws_logq[:, 1], -(n * np.log(2 * np.pi) + np.sum(u * u, axis=0)) / 2,
+                                   rtol=1e-13)
+        from tests.helpers import oracle_logp_fn
+
+        np.testing.assert_allclose(res.draws_logp[:, 1], oracle_logp_fn(model)(xd), rtol=1e-10, atol=1e-10)
+        # the resample stage regenerates exactly these columns without materialising the pool
+        eng2 = pf.Engine.for_model(model, J, K, 0)
+        eng2.set_fallback_seeds(fb)
+        eng2.elbo_batch(offsets, X, G, np.concatenate(seeds), draws=False)
+        r = eng2.psis_resample(3, 30, False)
+        pool = res.draws.reshape(n, -1, order="F")
+        assert np.array_equal(r["draws"], pool[:, r["inds"] - 1])
+        eng.close(); eng2.close()
+
+
+def test_nan_log_ratios_get_zero_weight_and_an_all_nan_pool_is_an_error():
+    import pathfinder_b200 as pf
+    from oracle import psis as OP
+
+    rng = np.random.default_rng(0)
+    N = 3000
+    logr = rng.normal(size=N) * 2.0
+    logr[rng.choice(N, 400, replace=False)] = np.nan
+    eng = pf.Engine(4, 0, None, 6, 5, 0)
+    r = eng.psis_resample_host(logr, 100, 9, 64, True)
+    ref = OP.psis(logr)
+    assert np.array_equal(r["weights"], ref["weights"]) and np.array_equal(r["log_weights"], ref["log_weights"])
+    assert np.all(r["weights"][np.isnan(logr)] == 0.0) and abs(r["weights"].sum() - 1.0) < 1e-12
+    assert np.array_equal(r["inds"], OP.resample_indices(9, ref["weights"], N, 64))
+    assert not np.isnan(logr[r["inds"] - 1]).any()
+    with pytest.raises(pf.PfbError) as ei:
+        eng.psis_resample_host(np.full(200, np.nan), 10, 1, 8, True)
+    assert ei.value.code == -5
+    eng.close()
+
+
+def test_unit_fits_export_every_iteration():
+    """fit_distributions of ANY iteration on demand (src/singlepath.jl:64 keeps them all)."""
+    import pathfinder_b200 as pf
+    from oracle import pf_oracle as O
+    from tests.helpers import synthetic_trajectory
+
+    n, K, J = 20, 16, 6
+    trajs = [synthetic_trajectory(n, L, 70 + L) for L in (7, 3)]
+    seeds = _seeds(trajs, 3)
+    offsets, X, G = pf.Engine.pack(trajs)
+    eng = _engine(pf.IsoNormal(n), K, J)
+    res = eng.elbo_batch(offsets, X, G, np.concatenate(seeds), fit=True)
+    U = res.elbo.size
+    f = eng.unit_fits(np.arange(U))
+    for p, (Xp, Gp) in enumerate(trajs):
+        mus, Hs, _ = O.fit_mvnormals(Xp, Gp, history_length=J)
+        sl = res.unit_slice(p)
+        for l in range(1, Xp.shape[1]):
+            u = sl.start + l - 1
+            W = Hs[l]
+            np.testing.assert_allclose(f["mu"][:, u], mus[:, l], rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(f["alpha"][:, u], W.alpha, rtol=1e-10)
+            np.testing.assert_allclose(f["logdet"][u], W.logdet(), rtol=1e-9, atol=1e-9)
+            assert f["jeff"][u] * 2 == W.k or W.k == n
+            k = W.k
+            np.testing.assert_allclose(f["vh"][:, :k, u], W.Vh[:, :k], rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(f["Vc"][u][:k, :k], W.Vc[:k, :k], rtol=1e-6, atol=1e-9)
+        ub = sl.start + int(res.best_iter[p]) - 1
+        assert np.array_equal(f["mu"][:, ub], res.fit["mu"][:, p]) and np.array_equal(f["vh"][:, :, ub], res.fit["vh"][:, :, p])
+    eng.close()

@@ -9,13 +9,19 @@ Where the other parity tests run toy shapes, these run the shapes the bench runs
             global-memory panel, GEMM-shaped log density) — late units of a real path;
   KP 20/24  n = 2304, J = 10 and 12 on synthetic trajectories (ring + global panel + wide records).
 
-Tolerance policy (written out, and COUNTED): strict = 1e-6 relative on ELBO and draws
-(north_star).  A unit may fall back to the relaxed tolerance max(1e-6, 50 x the oracle's own
-response to a 1-ulp perturbation of its inputs) only when that measured response itself exceeds
-1e-6 / 50 — i.e. when the reference algorithm is ill-conditioned there (near-collinear L-BFGS
-history, cond(R_q) up to 1e17 on funnel paths).  Every test asserts a floor on the share of units
-that pass the strict tolerance and writes {units compared, max relative errors, units on the
-relaxed tolerance, worst cond(R_q)} to profiles/parity_report.json (and gpurun_out/ when present).
+Tolerance policy (written out, and COUNTED): strict = 1e-6 relative on ELBO, log q and draws
+(north_star).  The DRAWS of a unit may fall back to the relaxed tolerance max(1e-6, 50 x the oracle's
+own response to a 1-ulp perturbation of its inputs) only when that measured response itself exceeds
+1e-6 / 50 — i.e. when the reference algorithm is ill-conditioned there.  That is the rule on funnel
+paths, not the exception: the funnel's gradient is radial in x_2..x_n, so every L-BFGS pair (s, y) of a
+path lies (numerically) in ONE two-dimensional subspace, the QR of the n x 2J panel [aY | S/a] is rank
+deficient (cond(R_q) ~ 1e18 from iteration 2 on) and the reflectors beyond the second are determined by
+rounding noise — in LAPACK as much as here: the oracle's own draws move by O(1) relative under a 1-ulp
+input perturbation.  What IS well defined there, and compared strictly on every unit: log q (|u|^2 and
+logdet Sigma), the ELBO, and the draws against the GPU's OWN exported factor (x = mu + L u evaluated on
+the host from pfb_unit_fits — K3 applied exactly the factor K2 built).  Every test writes {units
+compared, max relative errors per quantity, units whose draws needed the relaxed tolerance, worst
+cond(R_q)} to profiles/parity_report.json (and gpurun_out/ when present) and asserts floors.
 
 Reference tests matched: test/mvnormal.jl:39-68 (rand_and_logpdf == rand + logpdf), test/elbo.jl:7-28.
 """
@@ -49,6 +55,15 @@ def _report(name, entry):
             pass
 
 
+def _check(entry):
+    """The assertions, after the report is on disk."""
+    assert not entry["failures"], entry["failures"]
+    floor = entry["tolerance"]["min_strict_share_asserted"]
+    assert entry["strict_share"] >= floor, (entry["strict_share"], floor)
+    floor = entry["tolerance"]["min_strict_share_elbo_asserted"]
+    assert entry["strict_share_elbo"] >= floor, (entry["strict_share_elbo"], floor)
+
+
 def _relerr(a, b):
     with np.errstate(all="ignore"):
         return float(np.nanmax(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
@@ -63,9 +78,26 @@ def _cond_rq(W):
     return float(s[0] / s[-1]) if s[-1] > 0 else float("inf")
 
 
-def _compare_units(model, X, G, seeds, K, J, units, eng_draws, eng_elbo, logp_fn, min_strict):
+def _draws_from_factor(f, j, u):
+    """x = mu + sqrt(alpha) .* Q diag(Vc', I) u with Q = I - Vh T Vh' (compact WY), from the exported
+    factor of unit j (src/woodbury.jl:136-143, src/mvnormal.jl:32-33), in plain NumPy."""
+    k = 2 * int(f["jeff"][j])
+    n = u.shape[0]
+    k = min(k, n)
+    z = np.array(u, copy=True)
+    if k:
+        Vc = f["Vc"][j][:k, :k]
+        T = f["T"][j][:k, :k]
+        Vh = f["vh"][:, :k, j]
+        z[:k] = Vc.T @ z[:k]
+        z = z - Vh @ (T @ (Vh.T @ z))
+    return f["mu"][:, j][:, None] + np.sqrt(f["alpha"][:, j])[:, None] * z
+
+
+def _compare_units(model, X, G, seeds, K, J, units, eng_draws, eng_elbo, logp_fn, min_strict, eng_fits=None,
+                   min_strict_elbo=0.9):
     """Oracle vs engine on the 1-based iterations `units` of ONE path.  eng_draws(l) -> (draws [n, K],
-    logp [K], logq [K]); eng_elbo(l) -> (elbo, se).  Returns the report entry."""
+    logp [K], logq [K]); eng_elbo(l) -> (elbo, se); eng_fits(l) -> (fit dict, index).  Returns the report entry."""
     from oracle import pf_oracle as O
 
     mus, Hs, _ = O.fit_mvnormals(X, G, history_length=J)
@@ -76,14 +108,17 @@ def _compare_units(model, X, G, seeds, K, J, units, eng_draws, eng_elbo, logp_fn
     n = X.shape[0]
     out = dict(units_compared=0, units_strict=0, units_relaxed=0, units_nan_both=0, max_rel_elbo_strict=0.0,
                max_rel_draws_strict=0.0, max_rel_elbo_all=0.0, max_rel_draws_all=0.0, worst_cond_Rq=1.0,
-               worst_cond_Rq_strict=1.0, max_oracle_1ulp_response=0.0, relaxed_units=[], k_eff_max=0)
+               worst_cond_Rq_strict=1.0, max_oracle_1ulp_response=0.0, relaxed_units=[], k_eff_max=0, per_unit=[])
+    failures = []
     for l in units:
         u = O.contract_normals(int(seeds[l - 1]), n, K)
         e = O.elbo_and_samples(u, logp_fn, mus[:, l], Hs[l])
         e2 = O.elbo_and_samples(u, logp_fn, mus2[:, l], Hs2[l])
         with np.errstate(all="ignore"):
-            sens = max(abs(e["value"] - e2["value"]) / max(1.0, abs(e["value"])), _relerr(e2["draws"], e["draws"]))
+            sens_elbo = abs(e["value"] - e2["value"]) / max(1.0, abs(e["value"]))
+            sens = _relerr(e2["draws"], e["draws"])
         sens = float(np.nan_to_num(sens, nan=0.0, posinf=1.0))
+        sens_elbo = float(np.nan_to_num(sens_elbo, nan=0.0, posinf=1.0))
         d, lp, lq = eng_draws(l)
         ev, se = eng_elbo(l)
         out["units_compared"] += 1
@@ -99,9 +134,26 @@ def _compare_units(model, X, G, seeds, K, J, units, eng_draws, eng_elbo, logp_fn
         r_elbo = abs(ev - e["value"]) / max(1.0, abs(e["value"]))
         r_draw = _relerr(d, e["draws"])
         r_logq = _relerr(lq, e["logq"])
+        r_own = None
+        if eng_fits is not None:  # K3 against the factor K2 exported, independent of the oracle's QR
+            f, j = eng_fits(l)
+            r_own = _relerr(d, _draws_from_factor(f, j, np.asarray(u)))
+            out["max_rel_draws_vs_own_factor"] = max(out.get("max_rel_draws_vs_own_factor", 0.0), r_own)
+            if not r_own < 1e-9:
+                failures.append(("draws differ from mu + L u of the exported factor", l, r_own))
+        if r_logq > RTOL:
+            failures.append(("log q misses the strict tolerance", l, r_logq))
+        tol_elbo = max(RTOL, 50.0 * sens_elbo)
+        if r_elbo > tol_elbo:
+            failures.append(("ELBO misses max(1e-6, 50 x oracle response)", l, r_elbo, tol_elbo))
+        out["units_elbo_strict"] = out.get("units_elbo_strict", 0) + int(r_elbo <= RTOL)
+        out["max_oracle_1ulp_response_elbo"] = max(out.get("max_oracle_1ulp_response_elbo", 0.0), sens_elbo)
         out["max_rel_elbo_all"] = max(out["max_rel_elbo_all"], r_elbo)
         out["max_rel_draws_all"] = max(out["max_rel_draws_all"], r_draw)
         strict_ok = r_elbo <= RTOL and r_draw < RTOL and r_logq <= RTOL
+        out["per_unit"].append(dict(iteration=int(l), k_eff=int(Hs[l].k), rel_elbo=r_elbo, rel_draws=r_draw,
+                                    rel_logq=r_logq, rel_draws_vs_own_factor=r_own, oracle_1ulp_response_draws=sens,
+                                    oracle_1ulp_response_elbo=sens_elbo, cond_Rq=cond, strict=bool(strict_ok)))
         if strict_ok:
             out["units_strict"] += 1
             out["max_rel_elbo_strict"] = max(out["max_rel_elbo_strict"], r_elbo)
@@ -114,16 +166,21 @@ def _compare_units(model, X, G, seeds, K, J, units, eng_draws, eng_elbo, logp_fn
             assert abs(se - e["std_err"]) <= 1e-5 * max(1e-4, abs(e["std_err"])) or np.isnan(e["std_err"]), (l, se)
         else:
             tol = max(RTOL, 50.0 * sens)
-            assert sens > RTOL / 50.0, ("strict tolerance missed on a WELL-conditioned unit", l, r_elbo, r_draw, sens)
-            assert r_elbo <= tol and r_draw < tol and r_logq <= tol, (l, r_elbo, r_draw, r_logq, tol)
+            if not sens > RTOL / 50.0:
+                failures.append(("strict tolerance missed on a WELL-conditioned unit", l, r_elbo, r_draw, sens))
+            if not (r_draw < tol):
+                failures.append(("relaxed tolerance missed", l, r_elbo, r_draw, r_logq, tol))
             out["units_relaxed"] += 1
             out["relaxed_units"].append(dict(iteration=int(l), rel_elbo=r_elbo, rel_draws=r_draw, tol=tol,
                                              cond_Rq=cond))
     live = out["units_compared"] - out["units_nan_both"]
     out["strict_share"] = out["units_strict"] / live if live else 1.0
-    out["tolerance"] = dict(strict=RTOL, relaxed="max(1e-6, 50 x oracle 1-ulp response), only where that response "
-                                                 "> 2e-8", min_strict_share_asserted=min_strict)
-    assert out["strict_share"] >= min_strict, out
+    out["strict_share_elbo"] = out.get("units_elbo_strict", 0) / live if live else 1.0
+    out["tolerance"] = dict(strict=RTOL, relaxed="draws only: max(1e-6, 50 x oracle 1-ulp response), only where "
+                            "that response > 2e-8; ELBO: max(1e-6, 50 x the oracle's ELBO response); log q and "
+                            "draws-vs-own-factor: strict on every unit", min_strict_share_asserted=min_strict,
+                            min_strict_share_elbo_asserted=min_strict_elbo)
+    out["failures"] = [str(f) for f in failures]
     return out
 
 
@@ -152,14 +209,19 @@ def test_config3_full_path_every_iteration():
     assert np.array_equal(fin, np.isfinite(a.elbo))
     np.testing.assert_allclose(a.logq, b.logq, rtol=1e-12, atol=1e-9)
 
+    fits = full.unit_fits(np.arange(L))
+    # draws: strict only where the reference itself is well conditioned — on a funnel path that is the
+    # first iteration (see the module docstring); ELBO: strict on >= 90 % of the iterations
     entry = _compare_units(model, X, G, seeds, K, J, range(1, L + 1),
                            lambda l: (b.all_draws[:, :, l - 1], a.logp[:, l - 1], a.logq[:, l - 1]),
-                           lambda l: (a.elbo[l - 1], a.elbo_se[l - 1]), O.logp_funnel, min_strict=0.5)
+                           lambda l: (a.elbo[l - 1], a.elbo_se[l - 1]), O.logp_funnel, min_strict=0.0,
+                           eng_fits=lambda l: (fits, l - 1), min_strict_elbo=0.9)
     entry.update(config="cfg3 funnel n=1024 K=1000 J=6, one full path", iterations=L,
                  kernel="K3 lean single pass (ELBO, logp, logq) + two-pass materialise (draws)")
     # argmax and success as the oracle's (on the engine's own ELBO table both rules agree exactly)
     assert a.best_iter[0] == O.findmax_skipnan(list(a.elbo))[1]
     _report("cfg3_funnel1024_k1000_j6", entry)
+    _check(entry)
     assert entry["k_eff_max"] == 12
     lean.close(); full.close()
 
@@ -195,10 +257,12 @@ def test_config5_shape_late_units():
 
     entry = _compare_units(model, X, G, seeds, K, J, units, draws_of,
                            lambda l: (a.elbo[l - 1], a.elbo_se[l - 1]),
-                           O.make_logp_dense_gaussian(model.mean, model.prec), min_strict=0.8)
+                           O.make_logp_dense_gaussian(model.mean, model.prec), min_strict=0.8,
+                           eng_fits=lambda l: (eng.unit_fits([l - 1]), 0))
     entry.update(config="cfg5 dense normal n=4096 K=500 J=10", iterations=L, units=[int(u) for u in units],
                  kernel="K2 global panel, K3 KP=20 ring mode materialise + K8")
     _report("cfg5_dense4096_k500_j10", entry)
+    _check(entry)
     assert entry["k_eff_max"] == 20
     eng.close()
 
@@ -232,10 +296,12 @@ def test_config4_full_size_units():
 
     entry = _compare_units(model, X, G, seeds, K, J, units, draws_of,
                            lambda l: (a.elbo[l - 1], a.elbo_se[l - 1]),
-                           O.make_logp_hier_logistic(model.X, model.y), min_strict=0.6)
+                           O.make_logp_hier_logistic(model.X, model.y), min_strict=0.6,
+                           eng_fits=lambda l: (eng.unit_fits([l - 1]), 0))
     entry.update(config="cfg4 hierarchical logistic p=254 nobs=2048 K=2000 J=6", iterations=L,
                  units=[int(u) for u in units], kernel="K3 KP=12 materialise + K8 logistic")
     _report("cfg4_hlogistic256_k2000_j6", entry)
+    _check(entry)
     eng.close()
 
 
@@ -258,10 +324,13 @@ def test_wide_history_large_n(J):
     full = pf.Engine(n, model.family, model.blob, J, K, 0, materialize_all=True, two_pass=True)
     b = full.elbo_batch(offsets, Xp, Gp, seeds, draws=False, per_draw=True, all_draws=True)
     np.testing.assert_allclose(a.logq, b.logq, rtol=1e-12, atol=1e-9)
+    fits = full.unit_fits(np.arange(L))
     entry = _compare_units(model, X, G, seeds, K, J, range(1, L + 1),
                            lambda l: (b.all_draws[:, :, l - 1], a.logp[:, l - 1], a.logq[:, l - 1]),
-                           lambda l: (a.elbo[l - 1], a.elbo_se[l - 1]), O.logp_isonormal, min_strict=0.9)
+                           lambda l: (a.elbo[l - 1], a.elbo_se[l - 1]), O.logp_isonormal, min_strict=0.9,
+                           eng_fits=lambda l: (fits, l - 1))
     entry.update(config=f"iso-normal n=2304 K=96 J={J} (KP={2 * J if J > 10 else 20})", iterations=L)
     _report(f"wide_history_n2304_j{J}", entry)
+    _check(entry)
     assert entry["k_eff_max"] == 2 * J
     lean.close(); full.close()

@@ -177,7 +177,7 @@ def _worker(rank, world, port, nruns, K_run, n, ndraws, importance, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nruns,importance", [(4, True), (5, True), (3, False)])
+@pytest.mark.parametrize("nruns,importance", [(4, True), (5, True), (3, False), (1, True)])
 def test_pool_exchange_world_size_2_gloo(nruns, importance):
     """Two ranks, ragged shards (5 runs -> 2 + 3): the gathered log ratios, the replicated index
     draw and the owner-contributed columns equal the single-process result bit for bit."""
