@@ -751,7 +751,9 @@ def test_edge_cases_single_draw_and_empty_batch():
     # every path has only its initial point: no units, nothing succeeds (src/singlepath.jl:309-314)
     res0 = eng.elbo_batch(np.array([0, 1, 2]), Xp[:, :2], Gp[:, :2], np.zeros(0, np.uint64))
     assert res0.elbo.size == 0 and list(res0.best_iter) == [0, 0] and not res0.success.any()
-    assert np.all(np.isnan(res0.draws))
+    # their draws come from the identity fit of iteration 0, N(theta_0 + grad_0, I) (src/singlepath.jl:224-228)
+    assert np.all(np.isfinite(res0.draws)) and res0.draws.shape == (6, 1, 2)
+    assert np.all(np.abs(res0.draws[:, 0, :] - (Xp[:, :2] + Gp[:, :2])) < 8.0)
     # no paths at all
     resE = eng.elbo_batch(np.array([0]), np.zeros((6, 0), order="F"), np.zeros((6, 0), order="F"),
                           np.zeros(0, np.uint64))

@@ -94,6 +94,21 @@ def _draws_from_factor(f, j, u):
     return f["mu"][:, j][:, None] + np.sqrt(f["alpha"][:, j])[:, None] * z
 
 
+def _lowrank_from_factor(f, j):
+    """Sigma - diag(alpha) implied by the exported factor: L L' = diag(alpha) + (a .* Q_k)(Vc'Vc - I)(a .* Q_k)',
+    Q_k = the first k columns of Q = I - Vh T Vh' (src/woodbury.jl:129-143, :201-207)."""
+    k = 2 * int(f["jeff"][j])
+    n = f["mu"].shape[0]
+    k = min(k, n)
+    if k == 0:
+        return np.zeros((n, n))
+    Vh, T, Vc = f["vh"][:, :k, j], f["T"][j][:k, :k], f["Vc"][j][:k, :k]
+    Qk = -Vh @ (T @ Vh[:k, :].T)
+    Qk[np.arange(k), np.arange(k)] += 1.0
+    A = np.sqrt(f["alpha"][:, j])[:, None] * Qk
+    return A @ (Vc.T @ Vc - np.eye(k)) @ A.T
+
+
 def _compare_units(model, X, G, seeds, K, J, units, eng_draws, eng_elbo, logp_fn, min_strict, eng_fits=None,
                    min_strict_elbo=0.9):
     """Oracle vs engine on the 1-based iterations `units` of ONE path.  eng_draws(l) -> (draws [n, K],
@@ -141,6 +156,20 @@ def _compare_units(model, X, G, seeds, K, J, units, eng_draws, eng_elbo, logp_fn
             out["max_rel_draws_vs_own_factor"] = max(out.get("max_rel_draws_vs_own_factor", 0.0), r_own)
             if not r_own < 1e-9:
                 failures.append(("draws differ from mu + L u of the exported factor", l, r_own))
+            # the fitted COVARIANCE, which is what the draws' distribution depends on: the GPU's L L'
+            # against the oracle's diag(alpha) + B D B' (informational where D itself is ill-conditioned:
+            # the oracle's own response to the 1-ulp perturbation is reported next to it)
+            if n <= 1100:
+                Pg = _lowrank_from_factor(f, j)
+                Po = Hs[l].B @ Hs[l].D @ Hs[l].B.T
+                Po2 = Hs2[l].B @ Hs2[l].D @ Hs2[l].B.T
+                scale = max(float(np.max(np.abs(Po))), float(np.max(Hs[l].alpha)))
+                r_sigma = float(np.max(np.abs(Pg - Po))) / scale
+                s_sigma = float(np.max(np.abs(Po2 - Po))) / scale
+                out["max_rel_sigma"] = max(out.get("max_rel_sigma", 0.0), r_sigma)
+                out["max_oracle_1ulp_response_sigma"] = max(out.get("max_oracle_1ulp_response_sigma", 0.0), s_sigma)
+                if r_sigma > max(1e-6, 50.0 * s_sigma):
+                    failures.append(("covariance L L' differs from diag(alpha) + B D B'", l, r_sigma, s_sigma))
         if r_logq > RTOL:
             failures.append(("log q misses the strict tolerance", l, r_logq))
         tol_elbo = max(RTOL, 50.0 * sens_elbo)
@@ -152,7 +181,10 @@ def _compare_units(model, X, G, seeds, K, J, units, eng_draws, eng_elbo, logp_fn
         out["max_rel_draws_all"] = max(out["max_rel_draws_all"], r_draw)
         strict_ok = r_elbo <= RTOL and r_draw < RTOL and r_logq <= RTOL
         out["per_unit"].append(dict(iteration=int(l), k_eff=int(Hs[l].k), rel_elbo=r_elbo, rel_draws=r_draw,
-                                    rel_logq=r_logq, rel_draws_vs_own_factor=r_own, oracle_1ulp_response_draws=sens,
+                                    rel_logq=r_logq, rel_draws_vs_own_factor=r_own,
+                                    rel_sigma=(r_sigma if eng_fits is not None and n <= 1100 else None),
+                                    oracle_1ulp_response_sigma=(s_sigma if eng_fits is not None and n <= 1100 else None),
+                                    oracle_1ulp_response_draws=sens,
                                     oracle_1ulp_response_elbo=sens_elbo, cond_Rq=cond, strict=bool(strict_ok)))
         if strict_ok:
             out["units_strict"] += 1
@@ -251,7 +283,9 @@ def test_config5_shape_late_units():
     def draws_of(l):
         if l not in cache:
             d, lp, lq = eng.unit_draws([l - 1])
-            assert np.array_equal(lp[:, 0], a.logp[:, l - 1]) and np.array_equal(lq[:, 0], a.logq[:, l - 1])
+            # (log p comes out of a cuBLAS GEMM whose blocking depends on the batch shape: not bit-identical)
+            np.testing.assert_allclose(lp[:, 0], a.logp[:, l - 1], rtol=1e-11)
+            assert np.array_equal(lq[:, 0], a.logq[:, l - 1])
             cache[l] = (d[:, :, 0], lp[:, 0], lq[:, 0])
         return cache[l]
 
