@@ -1619,8 +1619,8 @@ static int pool_exchange_impl(pfb_engine** hs, int nh, const int32_t* paths_per_
         if (!h->comm || h->comm_world != world) PFB_FAIL(h, PFB_ERR_STATE, "pfb_comm_init has not been called");
         if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
         if (paths_per_rank[h->comm_rank] != h->poolP) PFB_FAIL(h, PFB_ERR_SHAPE, "paths_per_rank[rank] differs from this engine's pool");
-        if (h->poolP > 0) {
-            if (h->poolK <= 0) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
+        if (h->poolP > 0 && h->poolK <= 0) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
+        if (h->poolK > 0) {  // (a rank without runs states its draws per run through pfb_pool_set(P = 0, K_run))
             if (K_run && K_run != h->poolK) PFB_FAIL(h, PFB_ERR_SHAPE, "draws per run differ between engines");
             K_run = h->poolK;
         }

@@ -32,7 +32,7 @@ for case in cases:
                       float(r.sample_inds.sum())], dtype=torch.float64, device=f"cuda:{local}")
     g = [torch.empty_like(h) for _ in range(world)]
     dist.all_gather(g, h)
-    assert all(torch.equal(g[0], x) for x in g), ("ranks disagree", case)
+    assert all(torch.equal(g[0], x) for x in g), ("ranks disagree", case, [x.tolist() for x in g])
     # the rank's own runs: columns attributed to them exist in their pools
     lo, hi = nruns * rank // world, nruns * (rank + 1) // world
     assert len(r.pathfinder_results) == hi - lo
