@@ -16,13 +16,21 @@
 
 #define PFB_K2_THREADS 256
 #define PFB_K2_THREADS_SMEM 512
+#define PFB_K2_THREADS_REG 256  // REGCOLS variant: two CTAs per SM
+#define PFB_K2_RPT 4            // rows per thread whose sqrt(alpha) / mu entries live in registers (n <= 1024)
 #define PFB_K2_SCRATCH(KP) ((KP) * 16 * 8 + (KP) + 1)  // doubles; keeps the panel 16-byte aligned for even KP
+#define PFB_K2_SCRATCH_REG(KP) ((KP) * 8 * 8 + (KP) + 1)  // the same for the 8 warps of the REGCOLS variant
 
 // The unit's n x (KP+2) panel { A~ -> Vh, sqrt(alpha), t -> mu } lives in shared memory, column-major
 // (conflict-free for thread-per-row access), when it fits (SMEM_PANEL: n (KP+2) 8 bytes <= ~200 KB,
 // i.e. n <= 1800 at history 6); otherwise in the FR rows in global memory (L2 resident).
-template <int KP, bool SMEM_PANEL>
-__global__ void __launch_bounds__(SMEM_PANEL ? PFB_K2_THREADS_SMEM : PFB_K2_THREADS)
+// REGCOLS (n <= 1024, 256 threads): the two extra columns { sqrt(alpha), t -> mu } stay in the registers
+// of the thread that owns the row (4 rows per thread), which shrinks the panel to n x KP — 98 KB at
+// n = 1024, KP = 12 — so that TWO CTAs share an SM and one unit's block-wide reductions (a dozen
+// Householder steps, each a barrier) overlap the other's arithmetic.
+template <int KP, bool SMEM_PANEL, bool REGCOLS = false>
+__global__ void __launch_bounds__(REGCOLS ? PFB_K2_THREADS_REG : (SMEM_PANEL ? PFB_K2_THREADS_SMEM : PFB_K2_THREADS),
+                                  REGCOLS ? 2 : 1)
 pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* __restrict__ G,
                       const int32_t* __restrict__ unit_col, const double* __restrict__ alpha_all,
                       const int32_t* __restrict__ hist, const int32_t* __restrict__ hist_cnt,
@@ -44,12 +52,28 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
     const int kq = min(n, kc);
     extern __shared__ __align__(16) double s_dyn[];  // scratch of pfb_block_sum_fast, then the panel
     double* scratch = s_dyn;                          // KP * 16 * 8 + KP (<= 16 warps)
-    double* s_panel = s_dyn + PFB_K2_SCRATCH(KP);     // SMEM_PANEL: [KP+2][ldp]
+    double* s_panel = s_dyn + (REGCOLS ? PFB_K2_SCRATCH_REG(KP) : PFB_K2_SCRATCH(KP));  // SMEM_PANEL: [KP+2][ldp] ([KP][ldp] under REGCOLS)
     const int ldp = (n + 1) | 1;  // odd leading dimension
     double* fr = SMEM_PANEL ? nullptr : FR + (int64_t)u * n * RS;
     // element (row i, column c) of the panel
 #define PNL(i, c) (*(SMEM_PANEL ? (s_panel + (c) * ldp + (i)) : (fr + (int64_t)(i) * RS + (c))))
     double* hdr = HDR + (int64_t)u * pfb_hs_of(KP);
+    // the two extra columns: registers (REGCOLS) or panel columns KP, KP + 1
+    double rsa[REGCOLS ? PFB_K2_RPT : 1], rtm[REGCOLS ? PFB_K2_RPT : 1];
+#define XSA(r, i) (*(REGCOLS ? &rsa[r] : &PNL(i, KP)))
+#define XTM(r, i) (*(REGCOLS ? &rtm[r] : &PNL(i, KP + 1)))
+    // f(r, i) for every row i this thread owns (r = its register slot under REGCOLS)
+    auto each_row = [&](auto&& f) {
+        if constexpr (REGCOLS) {
+#pragma unroll
+            for (int r = 0; r < PFB_K2_RPT; ++r) {
+                const int i = tid + r * PFB_K2_THREADS_REG;
+                if (i < n) f(r, i);
+            }
+        } else {
+            for (int i = tid; i < n; i += nt) f(0, i);
+        }
+    };
 
     // Weighted Gram matrix of the panel's first KP columns on the FP64 tensor cores:
     //   Gm[a][b] = sum_i wgt(i) P(i, a) P(i, b),  a, b < KP  (row-major, KP x KP, shared memory).
@@ -118,7 +142,7 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
     const int32_t* hu = hist + (int64_t)u * J;
 
     // ---- Phase A: A~ = U' \ B = [ (alpha .* Y) ./ sqrt(alpha) | S ./ sqrt(alpha) ] -------------
-    for (int i = tid; i < n; i += nt) {
+    each_row([&](int r, int i) {
         double a = alpha[i];
         double sa = sqrt(a);
         for (int j = 0; j < jeff; ++j) {
@@ -129,9 +153,9 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
             PNL(i, jeff + j) = s / sa;
         }
         for (int j = kc; j < KP; ++j) PNL(i, j) = 0.0;
-        PNL(i, KP) = sa;
-        PNL(i, KP + 1) = sa * g[i];  // scratch for phase H: t = U g
-    }
+        XSA(r, i) = sa;
+        XTM(r, i) = sa * g[i];  // scratch for phase H: t = U g
+    });
     if (tid == 0) sFlag = 1;
     // zero-init small matrices
     for (int e = tid; e < KP * KP; e += nt) {
@@ -310,7 +334,7 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
 
     // ---- Phase G: logdet = 2 (logdet U + logdet V) ---------------------------------------------
     double ld[1] = {0.0};
-    for (int i = tid; i < n; i += nt) ld[0] += log(PNL(i, KP));
+    each_row([&](int r, int i) { ld[0] += log(XSA(r, i)); });
     pfb_block_sum_fast<1>(ld, scratch, 1u);
     double ldv = 0.0;
     for (int j = 0; j < kq; ++j) ldv += log(sVc[j][j]);
@@ -323,12 +347,12 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
             double acc[KP];
 #pragma unroll
             for (int c = 0; c < KP; ++c) acc[c] = 0.0;
-            for (int i = tid; i < n; i += nt) {
-                double t = PNL(i, KP + 1);
+            each_row([&](int r, int i) {
+                double t = XTM(r, i);
 #pragma unroll
                 for (int c = 0; c < KP; ++c)
                     if (c < kq) acc[c] = fma(PNL(i, c), t, acc[c]);
-            }
+            });
             pfb_block_sum_fast<KP>(acc, scratch, (1u << kq) - 1u);
             if (tid == 0) {
 #pragma unroll
@@ -346,14 +370,14 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
                 sW[tid] = s;
             }
             __syncthreads();
-            for (int i = tid; i < n; i += nt) {
-                double t = PNL(i, KP + 1);
+            each_row([&](int r, int i) {
+                double t = XTM(r, i);
 #pragma unroll
                 for (int c = 0; c < KP; ++c)
                     if (c < kq) t = fma(-PNL(i, c), sW[c], t);
-                PNL(i, KP + 1) = t;
+                XTM(r, i) = t;
                 if (pass == 0 && i < kq) sHead[i] = t;
-            }
+            });
             __syncthreads();
             if (pass == 0) {
                 // head <- Vc' (Vc head)      (lmul!(R.V, .) then lmul!(R.V', .))
@@ -366,7 +390,7 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
                 if (tid < kq) {
                     double s = 0.0;
                     for (int c = 0; c <= tid; ++c) s = fma(sVc[c][tid], sW2[c], s);
-                    PNL(tid, KP + 1) = s;
+                    XTM(0, tid) = s;  // row tid < kq <= KP belongs to thread tid, register slot 0
                 }
                 __syncthreads();
             }
@@ -381,11 +405,11 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
     };
     auto model_m = [&](int i) -> double { return model == PFB_MODEL_DIAGNORMAL ? mp0[i] : 0.0; };
     double e0acc[1] = {0.0};
-    for (int i = tid; i < n; i += nt) {
+    each_row([&](int r, int i) {
         // kq == 0: Sigma = diag(alpha): t = sqrt(alpha) g, mu = theta + sqrt(alpha) t
-        const double sa = PNL(i, KP);
-        const double mu = fma(sa, PNL(i, KP + 1), theta[i]);
-        PNL(i, KP + 1) = mu;
+        const double sa = XSA(r, i);
+        const double mu = fma(sa, XTM(r, i), theta[i]);
+        XTM(r, i) = mu;
         const double d = model_d(i), e = mu - model_m(i);
         e0acc[0] = fma(d * e, e, e0acc[0]);
         if (FR2 != nullptr) {
@@ -402,7 +426,7 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
                 r2[c ^ sw] = v;
             }
         }
-    }
+    });
     if (FR2 != nullptr) {
         constexpr int RS2 = (KP == 12) ? 16 : 32;
         const int npad = pfb_npad8(n);
@@ -416,12 +440,12 @@ pfb_k2_woodbury_build(int n, int J, const double* __restrict__ X, const double* 
         double acc[KP];
 #pragma unroll
         for (int b = 0; b < KP; ++b) acc[b] = 0.0;
-        for (int i = tid; i < n; i += nt) {
-            const double wgt = model_d(i) * PNL(i, KP) * (PNL(i, KP + 1) - model_m(i));
+        each_row([&](int r, int i) {
+            const double wgt = model_d(i) * XSA(r, i) * (XTM(r, i) - model_m(i));
 #pragma unroll
             for (int b = 0; b < KP; ++b)
                 if (b < kq) acc[b] = fma(wgt, PNL(i, b), acc[b]);
-        }
+        });
         if (kq > 0) pfb_block_sum_fast<KP>(acc, scratch, (1u << kq) - 1u);
         if (tid == 0) {
 #pragma unroll
@@ -453,11 +477,31 @@ extern "C" int pfb_k2_uses_smem_panel(int KP, int n) {
     return k2_panel_bytes(KP, n) + k2_scratch_bytes(KP) + stat <= (size_t)smem_max;
 }
 
+// REGCOLS: two CTAs (dynamic + static shared memory + 1 KB reserved each) must fit one SM
+static bool pfb_k2_regcols_fits(int KP, int n) {
+    int dev = 0, smem_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    const size_t stat = (size_t)(7 * KP * KP + KP * KP + 4 * KP + 8) * 8 + 256;
+    const size_t per_cta = (size_t)KP * (size_t)((n + 1) | 1) * 8 + (size_t)PFB_K2_SCRATCH_REG(KP) * 8 + stat + 1024;
+    return 2 * per_cta <= (size_t)smem_sm;
+}
+
 template <int KP>
 static cudaError_t launch_k2(cudaStream_t st, int n, int u_base, int U, int J, const double* X, const double* G,
                              const int32_t* unit_col, const double* alpha, const int32_t* hist,
                              const int32_t* hist_cnt, double* FR, double* HDR, double* FR2, int model,
                              const double* mp0, const double* mp1) {
+    if (KP == 12 && n > 512 && n <= PFB_K2_RPT * PFB_K2_THREADS_REG && FR2 != nullptr && pfb_k2_regcols_fits(KP, n)) {
+        // two CTAs per SM: panel without the two extra columns (registers), 256 threads
+        auto kern = pfb_k2_woodbury_build<KP, true, true>;
+        const size_t smem = (size_t)KP * (size_t)((n + 1) | 1) * 8 + (size_t)PFB_K2_SCRATCH_REG(KP) * 8;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<U, PFB_K2_THREADS_REG, smem, st>>>(n, J, X, G, unit_col, alpha, hist, hist_cnt, nullptr, HDR, FR2, model, mp0,
+                                                  mp1, u_base);
+        return cudaGetLastError();
+    }
     if (pfb_k2_uses_smem_panel(KP, n)) {
         int threads = n >= PFB_K2_THREADS_SMEM ? PFB_K2_THREADS_SMEM : ((n + 31) / 32) * 32;
         if (threads < 64) threads = 64;  // >= KP threads are needed by the small-matrix phases
