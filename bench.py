@@ -64,7 +64,7 @@ def make_model(kind, n):
     raise ValueError(kind)
 
 
-def build_workload(name, rank, world, strong=False):
+def build_workload(name, rank, world, strong=False, assign="lpt"):
     """Trajectories of this rank's paths.  N > 1: every rank optimises all paths (seeded, identical
     everywhere, untimed set-up) and takes its share of an LPT assignment on the iteration counts
     (SURVEY §8e: work is proportional to L_p).  Weak scaling: P paths per rank (world x P in total);
@@ -84,8 +84,10 @@ def build_workload(name, rank, world, strong=False):
         tr = pf.optimize_with_trace(model, x0, J, 1000)
         return (tr.points, tr.gradients), rng.integers(0, 2**64, size=len(tr) - 1, dtype=np.uint64)
 
-    if world == 1:
-        mine = list(range(P))
+    if world == 1 or assign == "static":
+        # static: rank r owns the contiguous block of paths [r P, (r + 1) P) and optimises only those (targets
+        # whose paths all take about the same number of iterations; the host L-BFGS of config 5 costs ~2 s a path)
+        mine = list(range(rank * P, (rank + 1) * P))
         paths = {gp: one(gp) for gp in mine}
     else:
         paths = {gp: one(gp) for gp in range(world * P)}
@@ -280,6 +282,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the config's paths PER GPU; strong: the config's paths in total, split over the GPUs")
     ap.add_argument("--no-wall", action="store_true", help="skip the multipathfinder() wall-clock legs")
+    ap.add_argument("--assign", default=None, choices=["lpt", "static"],
+                    help="N > 1: LPT-balanced on iteration counts (default for the funnels; every rank optimises every "
+                         "path during set-up) or contiguous blocks (default for the GEMM-shaped targets)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -307,8 +312,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     name = args.config
+    assign = args.assign or ("lpt" if CONFIGS[name][0] == "funnel" else "static")
     model, trajs, seeds, (n, P, K, J, ndraws, model_flops) = build_workload(name, rank, world,
-                                                                            strong=args.scaling == "strong")
+                                                                            strong=args.scaling == "strong", assign=assign)
     P = len(trajs)
     U = sum(X.shape[1] - 1 for X, _ in trajs)
     offsets, X, G = pf.Engine.pack(trajs)
