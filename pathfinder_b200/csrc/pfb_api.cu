@@ -742,6 +742,10 @@ static int run_host_callback_stage(pfb_engine* h) {
     return PFB_OK;
 }
 
+__global__ void pfb_iota(int n, int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
 __global__ void pfb_set_pool_seeds(int nf, const int64_t* __restrict__ pairs, uint64_t* __restrict__ pool_seeds) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // pairs: (unit, seed)
     if (i < nf && pairs[2 * i] >= 0) pool_seeds[pairs[2 * i]] = (uint64_t)pairs[2 * i + 1];
@@ -851,6 +855,13 @@ extern "C" int pfb_batch_run(pfb_handle h) {
     const int k2_model = model_is_external(h) ? PFB_MODEL_ISONORMAL : h->model;
     const double* k2_mp0 = model_is_external(h) ? nullptr : h->dModel.as<double>();
     const double* k2_mp1 = (h->dModel.p && !model_is_external(h)) ? h->dModel.as<double>() + h->model_n : nullptr;
+    const bool k3_by_group = h->up_ngroups >= 2 && !model_is_external(h) && U > 0;
+    int k3_done = 0;
+    if (k3_by_group) {
+        PFB_CUDA(h, h->dIota.ensure((size_t)U * 4));
+        pfb_iota<<<(U + 255) / 256, 256, 0, st>>>(U, h->dIota.as<int32_t>());
+        PFB_CUDA(h, cudaGetLastError());
+    }
     if (h->up_ngroups > 0) {
         // pfb_elbo_batch: the trajectories are still arriving group by group on the copy stream; K1 and
         // K2 of a group start as soon as its points are resident (timers: k1 = first group, k2 = the rest)
@@ -871,6 +882,21 @@ extern "C" int pfb_batch_run(pfb_handle h) {
                                             h->dHistCnt.as<int32_t>(), h->dFR.as<double>(), h->dHDR.as<double>(),
                                             h->dFR2.as<double>(), k2_model, k2_mp0, k2_mp1));
             h->launches += (p1 > p0) + (u1 > u0);
+            if (k3_by_group && (g == h->up_ngroups / 2 - 1 || g == h->up_ngroups - 1)) {
+                // K3 in two launches, after the first and the second half of the groups: the copy stream
+                // keeps uploading the second half while the tensor cores already work on the first.  Measured
+                // (config 3, one B200, end-to-end step): one launch 14.76 ms, two halves 14.70 ms, a quarter
+                // then the rest 15.05 ms, one launch per group 15.18 ms (every launch adds a partial last wave)
+                const int ua = (g == h->up_ngroups - 1) ? k3_done : 0;
+                if (ua == 0) PFB_CUDA(h, cudaEventRecord(h->ev[2], st));
+                if (u1 > ua) {
+                    PFB_CUDA(h, launch_k3(h, u1 - ua, h->dIota.as<int32_t>() + ua, h->dLogp.as<double>() + (size_t)ua * K,
+                                          h->dLogq.as<double>() + (size_t)ua * K,
+                                          h->cfg.materialize_all ? h->dAllDraws.as<double>() + (size_t)ua * n * K : nullptr));
+                    h->launches += 1;
+                }
+                k3_done = u1;
+            }
         }
         h->up_ngroups = 0;
     } else {
@@ -885,8 +911,10 @@ extern "C" int pfb_batch_run(pfb_handle h) {
                                   k2_mp1));
         h->launches += (U > 0);
     }
-    PFB_CUDA(h, cudaEventRecord(h->ev[2], st));
-    if (!model_is_external(h)) {
+    if (!k3_by_group) PFB_CUDA(h, cudaEventRecord(h->ev[2], st));
+    if (k3_by_group) {
+        // (already launched group by group)
+    } else if (!model_is_external(h)) {
         PFB_CUDA(h, launch_k3(h, U, nullptr, h->dLogp.as<double>(), h->dLogq.as<double>(),
                               h->cfg.materialize_all ? h->dAllDraws.as<double>() : nullptr));
         h->launches += (U > 0);
