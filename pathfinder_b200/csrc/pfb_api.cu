@@ -1,6 +1,5 @@
 // pfb_api.cu — the C ABI of libpfb200.so (declared in include/pfb200.h): engine handle,
 // device workspace (grow-only, engine-owned), and the orchestration of K1..K7 on one stream.
-#include <cublas_v2.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -36,10 +35,10 @@ cudaError_t pfb_launch_k2_range(cudaStream_t, int, int, int, int, int, const dou
                                 const double*, const int32_t*, const int32_t*, double*, double*, double*, int,
                                 const double*, const double*);
 int pfb_k2_uses_smem_panel(int KP, int n);
-cudaError_t pfb_launch_k8_dense(cudaStream_t, int, int64_t, int, const int32_t*, const double*, const double*,
-                                const double*, double, double*);
-cudaError_t pfb_launch_k8_logistic(cudaStream_t, int, int, int64_t, int, const int32_t*, const double*,
-                                   const double*, const double*, double*);
+cudaError_t pfb_launch_k8g_dense(cudaStream_t, int, int64_t, int, const int32_t*, const double*, const double*,
+                                 const double*, double, double*);
+cudaError_t pfb_launch_k8g_logistic(cudaStream_t, int, int, int64_t, int, const int32_t*, const double*,
+                                    const double*, const double*, double*);
 cudaError_t pfb_launch_k0(cudaStream_t, int, int, int, int, const double*, const double*, const double*, double, int, int,
                           int, double,
                           double, const double*, double*, double*, double*, double*, int64_t*, int32_t*, int32_t*);
@@ -101,8 +100,7 @@ struct pfb_engine {
     DevBuf dModel;
     double model_c0 = 0.0;
     int model_nobs = 0;                 // HLOGISTIC
-    cublasHandle_t cublas = nullptr;    // families whose log p needs a GEMM over the draws (K8)
-    DevBuf dGenX, dGenY, dIota, dTopSeeds;
+    DevBuf dGenX, dIota, dTopSeeds;
     // batch state
     int n = 0, P = 0, K = 0;
     int64_t T = 0, U = 0;
@@ -232,11 +230,10 @@ extern "C" int pfb_destroy(pfb_handle h) {
                       &h->dSe, &h->dBestIter, &h->dBestUnit, &h->dSucc, &h->dPool, &h->dPoolLogp,
                       &h->dPoolLogq, &h->dAllDraws, &h->dFitMu, &h->dFitAlpha, &h->dFitVh, &h->dFitT,
                       &h->dFitVc, &h->dFitLogdet, &h->dFitJeff, &h->dLogw, &h->dW, &h->dCum, &h->dScal,
-                      &h->dInds, &h->dIds, &h->dOutDraws, &h->dTmpLogr, &h->dTmpPool, &h->dGenX, &h->dGenY, &h->dIota, &h->dTopSeeds,
+                      &h->dInds, &h->dIds, &h->dOutDraws, &h->dTmpLogr, &h->dTmpPool, &h->dGenX, &h->dIota, &h->dTopSeeds,
                       &h->dLbX0, &h->dLbX, &h->dLbG, &h->dLbFX, &h->dLbWs, &h->dLbNp, &h->dLbSt, &h->dLbNev, &h->dLbSrc, &h->dSortWork, &h->dSortTmp, &h->dSelCnt, &h->dSelList,
                       &h->dFbSeeds, &h->dPoolSeeds, &h->dFbUnits, &h->dFbPaths, &h->dFbLogp, &h->dFbLogq, &h->dFbPairs, &h->dTopFb, &h->dGLogp, &h->dGLogq};
     for (auto* b : bufs) b->release();
-    if (h->cublas) cublasDestroy(h->cublas);
     for (int i = 0; i < 2; ++i) {
         if (h->hX[i]) cudaFreeHost(h->hX[i]);
         if (h->hc_k[i]) cudaEventDestroy(h->hc_k[i]);
@@ -328,10 +325,6 @@ extern "C" int pfb_register_model(pfb_handle h, int family, int n, const double*
         }
         default:
             PFB_FAIL(h, PFB_ERR_UNSUPPORTED, "unknown model family");
-    }
-    if ((family == PFB_MODEL_DENSENORMAL || family == PFB_MODEL_HLOGISTIC) && !h->cublas) {
-        if (cublasCreate(&h->cublas) != CUBLAS_STATUS_SUCCESS) PFB_FAIL(h, 1, "cublasCreate failed");
-        cublasSetStream(h->cublas, h->stream);
     }
     h->model = family;
     h->model_n = n;
@@ -615,29 +608,20 @@ static int host_logp_sync(pfb_engine* h, const double* dX, int64_t M, double* d_
     return PFB_OK;
 }
 
-// K8: log p of M = nslots * K materialised draws X [n x M] for the GEMM-shaped families.
+// K8g: log p of M = nslots * K materialised draws X [n x M] for the GEMM-shaped families — one fused
+// FP64 tensor-core GEMM + reduction kernel (k8_gemm_logp.cu); no library GEMM, no product matrix in HBM.
 static int generic_logp(pfb_engine* h, const double* X, int64_t M, const int32_t* slot_unit, double* logp,
                         int K_over = 0) {
     if (M <= 0) return PFB_OK;
     const int n = h->n, K = K_over > 0 ? K_over : h->K;
-    const double one = 1.0, zero = 0.0;
     if (h->model == PFB_MODEL_DENSENORMAL) {
-        const double* d = h->dModel.as<double>();
-        PFB_CUDA(h, h->dGenY.ensure((size_t)n * (size_t)M * 8));
-        if (cublasDgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_N, n, (int)M, n, &one, d + 2 * (size_t)n, n, X, n, &zero,
-                        h->dGenY.as<double>(), n) != CUBLAS_STATUS_SUCCESS)
-            PFB_FAIL(h, 1, "cublasDgemm failed");
-        PFB_CUDA(h, pfb_launch_k8_dense(h->stream, n, M, K, slot_unit, X, h->dGenY.as<double>(), d + n, h->model_c0,
-                                        logp));
+        const double* d = h->dModel.as<double>();  // { m[n], P m[n], P[n x n] }
+        PFB_CUDA(h, pfb_launch_k8g_dense(h->stream, n, M, K, slot_unit, X, d + 2 * (size_t)n, d + n, h->model_c0, logp));
     } else {
         const int nobs = h->model_nobs, nb = n - 2;
-        const double* Xm = h->dModel.as<double>();
+        const double* Xm = h->dModel.as<double>();  // { X[nobs x (n-2)], y[nobs], X' }
         const double* yobs = Xm + (size_t)nobs * nb;
-        PFB_CUDA(h, h->dGenY.ensure((size_t)nobs * (size_t)M * 8));
-        if (cublasDgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_N, nobs, (int)M, nb, &one, Xm, nobs, X + 2, n, &zero,
-                        h->dGenY.as<double>(), nobs) != CUBLAS_STATUS_SUCCESS)
-            PFB_FAIL(h, 1, "cublasDgemm failed");
-        PFB_CUDA(h, pfb_launch_k8_logistic(h->stream, n, nobs, M, K, slot_unit, X, h->dGenY.as<double>(), yobs, logp));
+        PFB_CUDA(h, pfb_launch_k8g_logistic(h->stream, n, nobs, M, K, slot_unit, X, Xm, yobs, logp));
     }
     return PFB_OK;
 }
@@ -924,7 +908,7 @@ extern "C" int pfb_batch_run(pfb_handle h) {
             if (rc) return rc;
         }
     } else if (U > 0) {
-        // GEMM-shaped log p: materialise the draws of a chunk of units (K3), then K8 (cuBLAS + epilogue)
+        // GEMM-shaped log p: materialise the draws of a chunk of units (K3), then K8g (fused FP64 tensor-core GEMM + log p reduction)
         const size_t per_unit = (size_t)n * (size_t)K * 8;
         int chunk = (int)std::max<size_t>(1, ((size_t)1 << 30) / per_unit);
         if (h->cfg.materialize_all || chunk > U) chunk = U;
@@ -945,7 +929,7 @@ extern "C" int pfb_batch_run(pfb_handle h) {
                                   xbuf));
             int rc = generic_logp(h, xbuf, (int64_t)cnt * K, nullptr, lp);
             if (rc) return rc;
-            h->launches += 3;
+            h->launches += 2;
         }
     }
     PFB_CUDA(h, cudaEventRecord(h->ev[3], st));

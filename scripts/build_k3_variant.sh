@@ -9,5 +9,5 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=fals
   -DPFB_K3_KP=12 -DPFB_K3_ENTRY=pfb_launch_k3_kp12 $FLAGS -c k3_elbo_sample_mma.cu -o _build/var_$NAME/k3_kp12.o \
   2> _build/var_$NAME/k3_kp12.ptxas.log || (cat _build/var_$NAME/k3_kp12.ptxas.log; exit 1)
 OBJS=$(ls _build/*.o | grep -v k3_kp12.o)
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libpfb200_$NAME.so $OBJS _build/var_$NAME/k3_kp12.o -lcublas -ldl -Xlinker -rpath=/usr/local/cuda/lib64
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libpfb200_$NAME.so $OBJS _build/var_$NAME/k3_kp12.o -ldl -Xlinker -rpath=/usr/local/cuda/lib64
 grep -A2 "pfb_k3_elbo_sampleILi12ELi1ELi2ELb0" _build/var_$NAME/k3_kp12.ptxas.log | tail -2
