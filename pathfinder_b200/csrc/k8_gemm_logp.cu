@@ -8,8 +8,8 @@
 //                   e_i = eta_i + b0                                                         SURVEY §8d config 4
 //
 // C[Mr x 128 draws] = A[Mr x Kd] * B[Kd x 128 draws] per CTA, row block by row block (128 rows), on
-// mma.sync.m8n8k4.f64 (SASS DMMA — FP64 has no tcgen05 kind): 8 warps, warp tile 64 x 32 (32 DMMA per
-// 12 fragment loads), 16-deep k-tiles staged through a 3-stage cp.async ring in shared memory with
+// mma.sync.m8n8k4.f64 (SASS DMMA — FP64 has no tcgen05 kind): 16 warps, warp tile 32 x 32 (16 DMMA per
+// 8 fragment loads; four warps per scheduler keep the FP64 pipe fed), 16-deep k-tiles staged through a 3-stage cp.async ring in shared memory with
 // padded leading dimensions (132 / 20 doubles) that make both fragment patterns bank-conflict free.
 // After the last k-tile of a row block the accumulators are folded into per-draw sums
 // (x .* (y - 2 P m), or the Bernoulli terms) and cleared; a CTA owns its 128 draws for ALL rows, so
@@ -22,13 +22,21 @@
 #define K8G_LDA (K8G_BM + 4)
 #define K8G_LDB (K8G_BK + 4)
 #define K8G_STAGES 3
-#define K8G_THREADS 256
+#ifndef K8G_WARPS_M
+#define K8G_WARPS_M 4  // warps along the rows of the 128 x 128 tile (x 4 along the draws): 16 warps, warp tile 32 x 32
+#endif
+#define K8G_MI (K8G_BM / K8G_WARPS_M / 8)  // 8 x 8 row tiles per warp
+#define K8G_THREADS (K8G_WARPS_M * 4 * 32)
+#define K8G_CPT (1024 / K8G_THREADS)  // 16-byte chunks per thread, operand and tile
 #define K8G_STAGE_DOUBLES (K8G_BK * K8G_LDA + K8G_BN * K8G_LDB)
 
 __device__ __forceinline__ void k8g_cp_async8(double* smem_dst, const double* gmem_src, bool valid) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     const int sz = valid ? 8 : 0;  // src-size 0: zero fill
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void k8g_cp_async16(uint32_t smem_dst, const double* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void k8g_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -57,18 +65,42 @@ struct k8g_params {
 template <int MODEL>
 __global__ void __launch_bounds__(K8G_THREADS, 1) pfb_k8_gemm_logp(k8g_params p) {
     extern __shared__ __align__(16) double k8g_smem[];
-    __shared__ double sPart[2][K8G_BN];
+    __shared__ double sPart[K8G_WARPS_M][K8G_BN];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp & 1, wn = warp >> 1;
+    const int wm = warp % K8G_WARPS_M, wn = warp / K8G_WARPS_M;
     const int64_t d0 = (int64_t)blockIdx.x * K8G_BN;
     const int nkt = (p.Kd + K8G_BK - 1) / K8G_BK;
     const int nrb = (p.Mr + K8G_BM - 1) / K8G_BM;
     const int ntiles = nkt * nrb;
 
+    // Interior tiles of 16-byte-aligned operands take the cheap path: four 16-byte cp.async per operand and
+    // thread from per-thread base pointers (the generic path below spends ~19 integer instructions per
+    // 8-byte copy on addresses and predicates, which cost 28 % of the tensor pipe's time).
+    const bool aligned = ((p.lda & 1) == 0) && ((p.n & 1) == 0) && ((p.brow0 & 1) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0);
+    const bool cols_full = d0 + K8G_BN <= p.Ncols;
+    // A chunk (k = tid / 64 + (T / 64) i, m = 2 (tid % 64)), B chunk (d = tid / 8 + (T / 8) i, k = 2 (tid % 8)), i < 1024 / T
+    const double* a_thr = p.A + (int64_t)(tid >> 6) * p.lda + 2 * (tid & 63);
+    const double* b_thr = p.X + (d0 + (tid >> 3)) * (int64_t)p.n + p.brow0 + 2 * (tid & 7);
+    const uint32_t sa_thr = (uint32_t)__cvta_generic_to_shared(k8g_smem) + 8u * ((tid >> 6) * K8G_LDA + 2 * (tid & 63));
+    const uint32_t sb_thr = (uint32_t)__cvta_generic_to_shared(k8g_smem) + 8u * (K8G_BK * K8G_LDA + (tid >> 3) * K8G_LDB + 2 * (tid & 7));
+    const int64_t a_step = (K8G_THREADS / 64) * (int64_t)p.lda, b_step = (K8G_THREADS / 8) * (int64_t)p.n;
+
     auto load_tile = [&](int tile, int stage) {
         const int rb = tile / nkt, kt = tile - rb * nkt;
         const int m0 = rb * K8G_BM, k0 = kt * K8G_BK;
+        if (aligned && cols_full && k0 + K8G_BK <= p.Kd && m0 + K8G_BM <= p.Mr) {
+            const double* pa = a_thr + (int64_t)k0 * p.lda + m0;
+            const double* pb = b_thr + k0;
+            const uint32_t so = (uint32_t)stage * (K8G_STAGE_DOUBLES * 8u);
+#pragma unroll
+            for (int i = 0; i < K8G_CPT; ++i) {
+                k8g_cp_async16(sa_thr + so + 8u * ((K8G_THREADS / 64) * i * K8G_LDA), pa + i * a_step);
+                k8g_cp_async16(sb_thr + so + 8u * ((K8G_THREADS / 8) * i * K8G_LDB), pb + i * b_step);
+            }
+            return;
+        }
         double* sA = k8g_smem + (size_t)stage * K8G_STAGE_DOUBLES;
         double* sB = sA + K8G_BK * K8G_LDA;
 #pragma unroll
@@ -89,9 +121,9 @@ __global__ void __launch_bounds__(K8G_THREADS, 1) pfb_k8_gemm_logp(k8g_params p)
         }
     };
 
-    double acc[8][4][2];
+    double acc[K8G_MI][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < K8G_MI; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     double part[4][2];
@@ -125,13 +157,13 @@ __global__ void __launch_bounds__(K8G_THREADS, 1) pfb_k8_gemm_logp(k8g_params p)
         const double* sB = sA + K8G_BK * K8G_LDA;
 #pragma unroll
         for (int kk = 0; kk < K8G_BK; kk += 4) {
-            double a[8], b[4];
+            double a[K8G_MI], b[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = sA[(kk + t) * K8G_LDA + wm * 64 + i * 8 + g];
+            for (int i = 0; i < K8G_MI; ++i) a[i] = sA[(kk + t) * K8G_LDA + wm * (K8G_MI * 8) + i * 8 + g];
 #pragma unroll
             for (int j = 0; j < 4; ++j) b[j] = sB[(wn * 32 + j * 8 + g) * K8G_LDB + kk + t];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < K8G_MI; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -143,8 +175,8 @@ __global__ void __launch_bounds__(K8G_THREADS, 1) pfb_k8_gemm_logp(k8g_params p)
             // ---- the row block is complete: fold it into the per-draw sums ----------------------------
             const int m0 = rb * K8G_BM;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int m = m0 + wm * 64 + i * 8 + g;
+            for (int i = 0; i < K8G_MI; ++i) {
+                const int m = m0 + wm * (K8G_MI * 8) + i * 8 + g;
                 const bool mok = m < p.Mr;
                 const double vm = mok ? p.v0[m] : 0.0;
 #pragma unroll
@@ -167,7 +199,7 @@ __global__ void __launch_bounds__(K8G_THREADS, 1) pfb_k8_gemm_logp(k8g_params p)
         }
     }
     k8g_wait<0>();
-    // ---- reduce over the 8 row lanes (g) of the warp, then over the two row warps ------------------------
+    // ---- reduce over the 8 row lanes (g) of the warp, then over the row warps ----------------------------
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -182,7 +214,9 @@ __global__ void __launch_bounds__(K8G_THREADS, 1) pfb_k8_gemm_logp(k8g_params p)
     if (tid < K8G_BN) {
         const int64_t d = d0 + tid;
         if (d < p.Ncols) {
-            const double s = sPart[0][tid] + sPart[1][tid];
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < K8G_WARPS_M; ++w) s += sPart[w][tid];
             double out;
             if (p.slot_unit && p.slot_unit[d / p.K] < 0) {
                 out = NAN;

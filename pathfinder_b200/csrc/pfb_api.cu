@@ -910,8 +910,21 @@ extern "C" int pfb_batch_run(pfb_handle h) {
     } else if (U > 0) {
         // GEMM-shaped log p: materialise the draws of a chunk of units (K3), then K8g (fused FP64 tensor-core GEMM + log p reduction)
         const size_t per_unit = (size_t)n * (size_t)K * 8;
-        int chunk = (int)std::max<size_t>(1, ((size_t)1 << 30) / per_unit);
+        int chunk = (int)std::max<size_t>(1, ((size_t)4 << 30) / per_unit);
         if (h->cfg.materialize_all || chunk > U) chunk = U;
+        if (chunk < U) {
+            // K8g runs one CTA per 128 draws: prefer a chunk whose CTA count fills its last wave of SMs
+            int nsm = 148;
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->cfg.device);
+            int best = chunk;
+            double best_fill = 0.0;
+            for (int c = chunk; c >= std::max(1, chunk / 2); --c) {
+                const int64_t ctas = ((int64_t)c * K + 127) / 128;
+                const double fill = (double)ctas / (double)(((ctas + nsm - 1) / nsm) * nsm);
+                if (fill > best_fill + 1e-9) { best_fill = fill; best = c; }
+            }
+            chunk = best;
+        }
         if (!h->cfg.materialize_all) PFB_CUDA(h, h->dGenX.ensure(per_unit * (size_t)chunk));
         PFB_CUDA(h, h->dIota.ensure((size_t)U * 4));
         {
