@@ -9,8 +9,9 @@
 //
 // C[Mr x 128 draws] = A[Mr x Kd] * B[Kd x 128 draws] per CTA, row block by row block (128 rows), on
 // mma.sync.m8n8k4.f64 (SASS DMMA — FP64 has no tcgen05 kind): 16 warps, warp tile 32 x 32 (16 DMMA per
-// 8 fragment loads; four warps per scheduler keep the FP64 pipe fed), 16-deep k-tiles staged through a 3-stage cp.async ring in shared memory with
-// padded leading dimensions (132 / 20 doubles) that make both fragment patterns bank-conflict free.
+// 8 fragment loads; four warps per scheduler keep the FP64 pipe fed), 32-deep k-tiles double-buffered through
+// cp.async in shared memory with padded leading dimensions (132 / 36 doubles) that make both fragment
+// patterns bank-conflict free (16-deep tiles in a 3-stage ring spend twice as long at barriers).
 // After the last k-tile of a row block the accumulators are folded into per-draw sums
 // (x .* (y - 2 P m), or the Bernoulli terms) and cleared; a CTA owns its 128 draws for ALL rows, so
 // every log p is written once, in a fixed summation order (deterministic).
@@ -18,16 +19,23 @@
 
 #define K8G_BM 128
 #define K8G_BN 128
-#define K8G_BK 16
+#ifndef K8G_BK
+#define K8G_BK 32
+#endif
 #define K8G_LDA (K8G_BM + 4)
 #define K8G_LDB (K8G_BK + 4)
-#define K8G_STAGES 3
+#ifndef K8G_STAGES
+#define K8G_STAGES 2
+#endif
 #ifndef K8G_WARPS_M
 #define K8G_WARPS_M 4  // warps along the rows of the 128 x 128 tile (x 4 along the draws): 16 warps, warp tile 32 x 32
 #endif
 #define K8G_MI (K8G_BM / K8G_WARPS_M / 8)  // 8 x 8 row tiles per warp
 #define K8G_THREADS (K8G_WARPS_M * 4 * 32)
-#define K8G_CPT (1024 / K8G_THREADS)  // 16-byte chunks per thread, operand and tile
+#define K8G_CPT (K8G_BK * 64 / K8G_THREADS)  // 16-byte chunks per thread, operand and tile
+#define K8G_BCH (K8G_BK / 2)                 // 16-byte chunks per draw of a B tile
+static_assert((K8G_LDA % 16) == 4 && (K8G_LDB % 16) == 4, "padded leading dimensions: conflict-free fragment loads");
+static_assert(K8G_STAGES >= 2, "at least double buffering");
 #define K8G_STAGE_DOUBLES (K8G_BK * K8G_LDA + K8G_BN * K8G_LDB)
 
 __device__ __forceinline__ void k8g_cp_async8(double* smem_dst, const double* gmem_src, bool valid) {
@@ -80,12 +88,13 @@ __global__ void __launch_bounds__(K8G_THREADS, 1) pfb_k8_gemm_logp(k8g_params p)
     const bool aligned = ((p.lda & 1) == 0) && ((p.n & 1) == 0) && ((p.brow0 & 1) == 0) &&
                          ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0);
     const bool cols_full = d0 + K8G_BN <= p.Ncols;
-    // A chunk (k = tid / 64 + (T / 64) i, m = 2 (tid % 64)), B chunk (d = tid / 8 + (T / 8) i, k = 2 (tid % 8)), i < 1024 / T
+    // A chunk (k = tid / 64 + (T / 64) i, m = 2 (tid % 64)), B chunk (d = tid / BCH + (T / BCH) i, k = 2 (tid % BCH))
     const double* a_thr = p.A + (int64_t)(tid >> 6) * p.lda + 2 * (tid & 63);
-    const double* b_thr = p.X + (d0 + (tid >> 3)) * (int64_t)p.n + p.brow0 + 2 * (tid & 7);
+    const double* b_thr = p.X + (d0 + (tid / K8G_BCH)) * (int64_t)p.n + p.brow0 + 2 * (tid % K8G_BCH);
     const uint32_t sa_thr = (uint32_t)__cvta_generic_to_shared(k8g_smem) + 8u * ((tid >> 6) * K8G_LDA + 2 * (tid & 63));
-    const uint32_t sb_thr = (uint32_t)__cvta_generic_to_shared(k8g_smem) + 8u * (K8G_BK * K8G_LDA + (tid >> 3) * K8G_LDB + 2 * (tid & 7));
-    const int64_t a_step = (K8G_THREADS / 64) * (int64_t)p.lda, b_step = (K8G_THREADS / 8) * (int64_t)p.n;
+    const uint32_t sb_thr = (uint32_t)__cvta_generic_to_shared(k8g_smem) +
+                            8u * (K8G_BK * K8G_LDA + (tid / K8G_BCH) * K8G_LDB + 2 * (tid % K8G_BCH));
+    const int64_t a_step = (K8G_THREADS / 64) * (int64_t)p.lda, b_step = (K8G_THREADS / K8G_BCH) * (int64_t)p.n;
 
     auto load_tile = [&](int tile, int stage) {
         const int rb = tile / nkt, kt = tile - rb * nkt;
@@ -97,7 +106,7 @@ __global__ void __launch_bounds__(K8G_THREADS, 1) pfb_k8_gemm_logp(k8g_params p)
 #pragma unroll
             for (int i = 0; i < K8G_CPT; ++i) {
                 k8g_cp_async16(sa_thr + so + 8u * ((K8G_THREADS / 64) * i * K8G_LDA), pa + i * a_step);
-                k8g_cp_async16(sb_thr + so + 8u * ((K8G_THREADS / 8) * i * K8G_LDB), pb + i * b_step);
+                k8g_cp_async16(sb_thr + so + 8u * ((K8G_THREADS / K8G_BCH) * i * K8G_LDB), pb + i * b_step);
             }
             return;
         }
