@@ -68,6 +68,17 @@ mutable struct PfbResampleOut
     draws::Ptr{Float64}
 end
 PfbResampleOut() = PfbResampleOut(ntuple(_ -> C_NULL, 7)...)
+# isbits twin (same layout): a Vector of these is the contiguous pfb_resample_out[ndev] of the *_all calls
+struct PfbResampleOutC
+    log_weights::Ptr{Float64}
+    weights::Ptr{Float64}
+    pareto_k::Ptr{Float64}
+    tail_len::Ptr{Int64}
+    inds::Ptr{Int64}
+    ids::Ptr{Int64}
+    draws::Ptr{Float64}
+end
+PfbResampleOutC(o::PfbResampleOut) = PfbResampleOutC(o.log_weights, o.weights, o.pareto_k, o.tail_len, o.inds, o.ids, o.draws)
 
 mutable struct Engine
     handle::Ptr{Cvoid}
@@ -119,9 +130,16 @@ end
 `num_bfgs_updates_rejected`, `draws[n, K, P]`, `logp`, `logq`, and the best-iteration
 `WoodburyPDMat` ingredients (`mu, alpha, vh, T, Vc, logdet, jeff`).
 """
-function elbo_batch(e::Engine, traces, seeds::Vector{Vector{UInt64}}; normals=nothing)
+function elbo_batch(e::Engine, traces, seeds::Vector{Vector{UInt64}}; normals=nothing, fallback_seeds=nothing)
     P = length(traces)
     n, K = e.n, e.K
+    if fallback_seeds !== nothing
+        # one UInt64 per path, drawn from the PATH's rng: a failed path returns
+        # rand(rng, fit_distributions[fit_iteration + 1], ndraws) (src/singlepath.jl:224-228)
+        fs = Vector{UInt64}(fallback_seeds)
+        GC.@preserve fs check(e, ccall((:pfb_set_fallback_seeds, LIB[]), Cint, (Ptr{Cvoid}, Cint, Ptr{UInt64}),
+                                       e.handle, length(fs), fs))
+    end
     offsets = zeros(Int64, P + 1)
     for (p, (pts, _)) in enumerate(traces)
         offsets[p + 1] = offsets[p] + length(pts)
@@ -190,6 +208,133 @@ function psis_resample(e::Engine, P::Integer, seed::UInt64, ndraws::Integer; imp
     end
     return (; log_weights=lw, weights=w, pareto_shape=k[], tail_length=tl[], sample_inds=inds,
             draw_component_ids=ids, draws)
+end
+
+"""
+    unit_fits(engine, units) -> NamedTuple
+
+`fit_distributions[l + 1]` of arbitrary (path, iteration) units of the current batch
+(src/singlepath.jl:64 keeps every iteration's; the engine exports them on demand) in the
+WoodburyPDMat ingredients of `elbo_batch`.  `units` are 0-based, path-major / iteration-minor.
+"""
+function unit_fits(e::Engine, units::Vector{Int32})
+    m = length(units); n = e.n
+    kp = ccall((:pfb_kp, LIB[]), Cint, (Ptr{Cvoid},), e.handle)
+    mu = Matrix{Float64}(undef, n, m); alpha = similar(mu); vh = Array{Float64}(undef, n, kp, m)
+    Tm = Array{Float64}(undef, kp, kp, m); Vc = similar(Tm)
+    logdet = Vector{Float64}(undef, m); jeff = Vector{Int32}(undef, m)
+    GC.@preserve units mu alpha vh Tm Vc logdet jeff check(e, ccall((:pfb_unit_fits, LIB[]), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Int32}), e.handle, m, units, mu, alpha, vh, Tm, Vc, logdet, jeff))
+    return (; mu, alpha, vh, T=permutedims(Tm, (2, 1, 3)), Vc=permutedims(Vc, (2, 1, 3)), logdet, jeff)
+end
+
+# ---- multi-GPU: the pool exchange behind the ABI (NCCL is dlopen'ed by the library) -----------------------
+
+"128-byte communicator id: create it on one rank, ship it to the others (MPI.Bcast!, a file, ...)."
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    rc = ccall((:pfb_comm_unique_id, LIB[]), Cint, (Ptr{UInt8},), id)
+    rc == 0 || error("pfb_comm_unique_id failed with code $rc (is libnccl.so.2 loadable?)")
+    return id
+end
+
+"One process per GPU: every rank calls this with the same id."
+comm_init!(e::Engine, id::Vector{UInt8}, rank::Integer, world::Integer) =
+    check(e, ccall((:pfb_comm_init, LIB[]), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), e.handle, id, rank, world))
+
+"One process, all GPUs: engine i (created with device = i - 1) becomes rank i - 1."
+function comm_init_all!(engines::Vector{Engine})
+    hs = [e.handle for e in engines]
+    rc = GC.@preserve hs ccall((:pfb_comm_init_all, LIB[]), Cint, (Ptr{Ptr{Cvoid}}, Cint), hs, length(hs))
+    check(engines[1], rc)
+end
+
+function _resample_out(n, N, ndraws, importance)
+    lw = Vector{Float64}(undef, N); w = similar(lw)
+    k = Ref(NaN); tl = Ref(Int64(0))
+    inds = Vector{Int64}(undef, ndraws); ids = similar(inds)
+    draws = Matrix{Float64}(undef, n, ndraws)
+    out = PfbResampleOut()
+    if importance
+        out.log_weights = pointer(lw); out.weights = pointer(w)
+    end
+    out.pareto_k = Base.unsafe_convert(Ptr{Float64}, k)
+    out.tail_len = Base.unsafe_convert(Ptr{Int64}, tl)
+    out.inds = pointer(inds); out.ids = pointer(ids); out.draws = pointer(draws)
+    return out, (lw, w, k, tl, inds, ids, draws)
+end
+
+"""
+    pool_exchange_resample(engine, paths_per_rank, seed, ndraws; importance=true, replace=true)
+
+`_compute_psis_result` + `_resample` (src/multipath.jl:220-225) over the runs of ALL ranks: all-gather of
+the pools' per-draw log densities, PSIS and the index draw replicated, owned columns regenerated on their
+rank, sum-reduce.  Every rank calls it with the same arguments and receives the same result.
+"""
+function pool_exchange_resample(e::Engine, paths_per_rank::Vector{Int32}, seed::UInt64, ndraws::Integer;
+                                importance::Bool=true, replace::Bool=true)
+    N = Int(sum(paths_per_rank)) * e.K
+    out, keep = _resample_out(e.n, N, ndraws, importance)
+    GC.@preserve keep paths_per_rank check(e, ccall((:pfb_pool_exchange_resample, LIB[]), Cint,
+        (Ptr{Cvoid}, Ptr{Int32}, UInt64, Cint, Cint, Cint, Ref{PfbResampleOut}), e.handle, paths_per_rank, seed,
+        ndraws, importance, replace, out))
+    lw, w, k, tl, inds, ids, draws = keep
+    return (; log_weights=lw, weights=w, pareto_shape=k[], tail_length=tl[], sample_inds=inds,
+            draw_component_ids=ids, draws)
+end
+
+"""
+    multipathfinder_b200_multi(optimize_one, family, dim, ndraws; nruns, devices, ...)
+
+`multipathfinder` on several GPUs of ONE process, no MPI: the runs shard over `devices` in contiguous
+blocks (the pool keeps the run order of src/multipath.jl:217), every shard's ELBO stage runs on its own
+task, and one `pfb_pool_exchange_resample_all` call does the PSIS pool exchange for all of them.
+"""
+function multipathfinder_b200_multi(optimize_one, family::Integer, dim::Integer, ndraws::Integer;
+                                    nruns::Integer, devices::Vector{Int}, ndraws_elbo::Integer=5,
+                                    history_length::Integer=6, init_scale::Real=2,
+                                    rng::AbstractRNG=Random.default_rng(), importance::Bool=true,
+                                    blob::Vector{Float64}=Float64[])
+    world = length(devices)
+    run_seeds = rand(rng, UInt64, nruns)                       # src/multipath.jl:162
+    engines = [Engine(dim, family, blob; history_length, ndraws_elbo, device=d) for d in devices]
+    try
+        comm_init_all!(engines)
+        bounds = [div(nruns * r, world) for r in 0:world]      # contiguous, balanced blocks of runs
+        fits = Vector{Any}(undef, world)
+        @sync for r in 1:world
+            Threads.@spawn begin
+                runs = (bounds[r] + 1):bounds[r + 1]
+                traces = Vector{Any}(undef, length(runs)); seeds = Vector{Vector{UInt64}}(undef, length(runs))
+                fb = Vector{UInt64}(undef, length(runs))
+                for (j, p) in enumerate(runs)
+                    prng = copy(rng); Random.seed!(prng, run_seeds[p])
+                    x0 = (rand(prng, dim) .* 2 .- 1) .* init_scale
+                    traces[j] = optimize_one(x0)
+                    seeds[j] = rand(prng, UInt64, length(traces[j][1]) - 1)
+                    fb[j] = rand(prng, UInt64)
+                end
+                fits[r] = elbo_batch(engines[r], traces, seeds; fallback_seeds=fb)
+            end
+        end
+        ppr = Int32[bounds[r + 1] - bounds[r] for r in 1:world]
+        N = nruns * ndraws_elbo
+        outs = Vector{PfbResampleOutC}(undef, world); keeps = Vector{Any}(undef, world)
+        for r in 1:world
+            o, keeps[r] = _resample_out(dim, N, ndraws, importance)
+            outs[r] = PfbResampleOutC(o)
+        end
+        hs = [e.handle for e in engines]
+        GC.@preserve hs keeps ppr outs check(engines[1], ccall((:pfb_pool_exchange_resample_all, LIB[]), Cint,
+            (Ptr{Ptr{Cvoid}}, Cint, Ptr{Int32}, UInt64, Cint, Cint, Cint, Ptr{PfbResampleOutC}), hs, world, ppr,
+            rand(rng, UInt64), ndraws, importance, true, outs))
+        lw, w, k, tl, inds, ids, draws = keeps[1]              # identical on every rank
+        return (; fits, log_weights=lw, weights=w, pareto_shape=k[], tail_length=tl[], sample_inds=inds,
+                draw_component_ids=ids, draws)
+    finally
+        foreach(close, engines)
+    end
 end
 
 # mirrors `pfb_lbfgs_opts`
@@ -302,13 +447,15 @@ function multipathfinder_b200(optimize_one, family::Integer, dim::Integer, ndraw
     try
         traces = Vector{Any}(undef, nruns)
         seeds = Vector{Vector{UInt64}}(undef, nruns)
+        fb = Vector{UInt64}(undef, nruns)
         for p in 1:nruns                                       # host phase A; use @threads / ntasks freely
             prng = copy(rng); Random.seed!(prng, run_seeds[p]) # src/multipath.jl:191-193
             x0 = (rand(prng, dim) .* 2 .- 1) .* init_scale     # UniformSampler, src/singlepath.jl:340-344
             traces[p] = optimize_one(x0)
             seeds[p] = rand(prng, UInt64, length(traces[p][1]) - 1)   # src/elbo.jl:2
+            fb[p] = rand(prng, UInt64)                         # the path's rng, used only if the path fails
         end
-        fit = elbo_batch(eng, traces, seeds)
+        fit = elbo_batch(eng, traces, seeds; fallback_seeds=fb)
         res = psis_resample(eng, nruns, rand(rng, UInt64), ndraws; importance)
         return (; fit, res...)
     finally
