@@ -457,14 +457,15 @@ def main():
     roofline = {"bound": "tensor", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": ach_tf / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
                 "kernel": "pfb_k3_elbo_sample (lean: FP64 DMMA Q-apply, Philox/ziggurat normals; single pass for the "
-                          "diagonal-quadratic families, K3 + cuBLAS DGEMM epilogue K8 for the GEMM-shaped ones)",
+                          "diagonal-quadratic families, K3 + the fused FP64 tensor-core GEMM K8g for the GEMM-shaped ones)",
                 "kernel_ms": k3_avg_ms, "algorithmic_flops_per_launch": flops,
                 "peak_source": "measured live: pfb_measure_fp64_dmma_tflops (mma.sync m8n8k4 f64 chains); "
                                "MEASURED_PEAKS.json has bf16 and HBM figures only",
                 "dfma_peak_tflops": peak2.value,
-                "note": "co-bound by the FP64 pipe (12 DMMA + 20 scalar FP64 per 8-row x 16-draw block) and the "
-                        "Philox4x32-10 integer multiplies, which serialise on this part instead of overlapping "
-                        "(profiles/r1_microbench_fp64.md); HBM is idle: see DESIGN.md section 4",
+                "note": "FP64-pipe bound: per 8-row x 16-draw block 12 DMMA (192 clk of pipe) + 20 scalar FP64 (~66 clk) + one "
+                        "Philox4x32-7 call (12 IMAD.WIDE) for the lane's four 32-bit ziggurat variates; the pipe is 86 % busy "
+                        "inside the hot loop, 26 % of the instructions are outside it (profiles/r2_k3_queue_ncu.md, "
+                        "profiles/r2_k3_experiments.md); HBM is idle: see DESIGN.md section 4",
                 "k3_share_of_step": k3_avg_ms * args.steps / max_ms}
 
     line = {
