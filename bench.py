@@ -482,7 +482,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         # K1..K5 as counted by the engine + the PSIS stage's own kernels (K6a..K6g, K7; CUB's sort
         # launches inside K6 are library kernels and not counted)
-        "gpu_launches": int((stage_ms[-1]["launches"] + 8) * args.steps),
+        "gpu_launches": int((stage_ms[-1]["launches"] + 10) * args.steps),
         "clocks": clocks,
         "roofline": roofline,
         "stage_ms": {k: float(np.mean([s[k] for s in stage_ms])) for k in ("k1", "k2", "k3", "k4", "k5", "total")},
