@@ -35,6 +35,19 @@ cudaError_t pfb_launch_k2_range(cudaStream_t, int, int, int, int, int, const dou
                                 const double*, const int32_t*, const int32_t*, double*, double*, double*, int,
                                 const double*, const double*);
 int pfb_k2_uses_smem_panel(int KP, int n);
+// generic (runtime-width) kernels for history_length > 12 (kg_generic_history.cu)
+size_t pfb_kg_k2_workspace_doubles(int KP, int grid);
+int pfb_kg_k2_grid(int U);
+cudaError_t pfb_launch_k2g(cudaStream_t, int, int, int, int, int, const double*, const double*, const int32_t*,
+                           const double*, const int32_t*, const int32_t*, double*, double*, double*);
+size_t pfb_kg_k3_scratch_doubles(int KP, int n, int nslots);
+cudaError_t pfb_launch_k3g(cudaStream_t, int, int, int, int, int, const int32_t*, const double*, const double*,
+                           const uint64_t*, const double*, const double*, const double*, double, double*, double*,
+                           double*, const int32_t*, const void*, int, const double*, const double*, const int64_t*,
+                           const uint64_t*, const int32_t*, double*);
+cudaError_t pfb_launch_kg_gather_fit(cudaStream_t, int, int, int, const int32_t*, const double*, const double*,
+                                     const double*, const int32_t*, double*, double*, double*, double*, double*,
+                                     double*, int32_t*);
 cudaError_t pfb_launch_k8g_dense(cudaStream_t, int, int64_t, int, const int32_t*, const double*, const double*,
                                  const double*, double, double*);
 cudaError_t pfb_launch_k8g_logistic(cudaStream_t, int, int, int64_t, int, const int32_t*, const double*,
@@ -92,6 +105,8 @@ struct psis_scalars_host {
 struct pfb_engine {
     pfb_config cfg;
     int KP = 12;
+    bool generic = false;  // history_length > 12: the runtime-width kernels K2g / K3g (KP = 2 J)
+    DevBuf dKgWs, dKgScratch;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[7] = {};
     std::string err;
@@ -184,9 +199,15 @@ extern "C" int pfb_create(pfb_handle* out, const pfb_config* cfg) {
         return PFB_ERR_ARG;
     }
     int kp = pfb_kp_of(cfg->history_length);
-    if (kp == 0) {
-        g_create_err = "history_length > 12 is not supported";
-        return PFB_ERR_UNSUPPORTED;
+    const bool generic = (kp == 0);
+    if (generic) {
+        // any history length like the reference (src/inverse_hessian.jl:25): beyond 12 the generic kernels
+        // take over (K1's ring buffer holds 64 pairs)
+        if (cfg->history_length > 64) {
+            g_create_err = "history_length > 64 is not supported";
+            return PFB_ERR_UNSUPPORTED;
+        }
+        kp = 2 * cfg->history_length;
     }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -207,6 +228,7 @@ extern "C" int pfb_create(pfb_handle* out, const pfb_config* cfg) {
     h->cfg = *cfg;
     if (h->cfg.eps == 0.0) h->cfg.eps = 1e-12;
     h->KP = kp;
+    h->generic = generic;
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         g_create_err = cudaGetErrorString(e);
@@ -232,7 +254,8 @@ extern "C" int pfb_destroy(pfb_handle h) {
                       &h->dFitVc, &h->dFitLogdet, &h->dFitJeff, &h->dLogw, &h->dW, &h->dCum, &h->dScal,
                       &h->dInds, &h->dIds, &h->dOutDraws, &h->dTmpLogr, &h->dTmpPool, &h->dGenX, &h->dIota, &h->dTopSeeds,
                       &h->dLbX0, &h->dLbX, &h->dLbG, &h->dLbFX, &h->dLbWs, &h->dLbNp, &h->dLbSt, &h->dLbNev, &h->dLbSrc, &h->dSortWork, &h->dSortTmp, &h->dSelCnt, &h->dSelList,
-                      &h->dFbSeeds, &h->dPoolSeeds, &h->dFbUnits, &h->dFbPaths, &h->dFbLogp, &h->dFbLogq, &h->dFbPairs, &h->dTopFb, &h->dGLogp, &h->dGLogq};
+                      &h->dFbSeeds, &h->dPoolSeeds, &h->dFbUnits, &h->dFbPaths, &h->dFbLogp, &h->dFbLogq, &h->dFbPairs, &h->dTopFb, &h->dGLogp, &h->dGLogq,
+                      &h->dKgWs, &h->dKgScratch};
     for (auto* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         if (h->hX[i]) cudaFreeHost(h->hX[i]);
@@ -362,9 +385,14 @@ static int batch_prepare(pfb_engine* h, int n, int P, const int64_t* offsets) {
     PFB_CUDA(h, h->dHist.ensure((size_t)U * J * 4 + 8));
     PFB_CUDA(h, h->dHistCnt.ensure((size_t)U * 4 + 8));
     PFB_CUDA(h, h->dRej.ensure((size_t)P * 8 + 8));
-    if (!pfb_k2_uses_smem_panel(KP, n))  // K2's global-memory workspace (large n only)
-        PFB_CUDA(h, h->dFR.ensure(nU * (size_t)pfb_rs_of(KP) * 8 + 16));
-    PFB_CUDA(h, h->dFR2.ensure((size_t)pfb_npad8(n) * (size_t)U * (size_t)pfb_rs2_of(KP) * 8 + 16));
+    if (h->generic) {
+        PFB_CUDA(h, h->dFR.ensure(nU * (size_t)pfb_rs_of(KP) * 8 + 16));  // the generic record layout
+        PFB_CUDA(h, h->dKgWs.ensure(pfb_kg_k2_workspace_doubles(KP, pfb_kg_k2_grid((int)U)) * 8 + 16));
+    } else {
+        if (!pfb_k2_uses_smem_panel(KP, n))  // K2's global-memory workspace (large n only)
+            PFB_CUDA(h, h->dFR.ensure(nU * (size_t)pfb_rs_of(KP) * 8 + 16));
+        PFB_CUDA(h, h->dFR2.ensure((size_t)pfb_npad8(n) * (size_t)U * (size_t)pfb_rs2_of(KP) * 8 + 16));
+    }
     PFB_CUDA(h, h->dHDR.ensure((size_t)U * pfb_hs_of(KP) * 8 + 8));
     PFB_CUDA(h, h->dLogp.ensure((size_t)U * K * 8 + 8));
     PFB_CUDA(h, h->dLogq.ensure((size_t)U * K * 8 + 8));
@@ -537,6 +565,19 @@ extern "C" int pfb_lbfgs_ms(pfb_handle h, double* ms) {
     return PFB_OK;
 }
 
+// K2 over units [u0, u0 + cnt): the tensor-core kernel, or the generic one for wide histories
+static cudaError_t launch_k2_any(pfb_engine* h, int u0, int cnt, int k2_model, const double* mp0, const double* mp1) {
+    if (h->generic)
+        return pfb_launch_k2g(h->stream, h->KP, h->n, u0, cnt, h->cfg.history_length, h->dX.as<double>(),
+                              h->dG.as<double>(), h->dUnitCol.as<int32_t>(), h->dAlpha.as<double>(),
+                              h->dHist.as<int32_t>(), h->dHistCnt.as<int32_t>(), h->dFR.as<double>(),
+                              h->dHDR.as<double>(), h->dKgWs.as<double>());
+    return pfb_launch_k2_range(h->stream, h->KP, h->n, u0, cnt, h->cfg.history_length, h->dX.as<double>(),
+                               h->dG.as<double>(), h->dUnitCol.as<int32_t>(), h->dAlpha.as<double>(),
+                               h->dHist.as<int32_t>(), h->dHistCnt.as<int32_t>(), h->dFR.as<double>(),
+                               h->dHDR.as<double>(), h->dFR2.as<double>(), k2_model, mp0, mp1);
+}
+
 static bool model_is_external(const pfb_engine* h) {
     return h->model == PFB_MODEL_DENSENORMAL || h->model == PFB_MODEL_HLOGISTIC ||
            h->model == PFB_MODEL_HOSTCALLBACK;
@@ -634,6 +675,15 @@ static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list
     const double* mp1 = mp0 ? mp0 + h->model_n : nullptr;
     const double* un = (h->have_normals && (!seeds_over || seeds_over == h->dSeeds.as<uint64_t>()))
                            ? h->dNormals.as<double>() : nullptr;
+    if (h->generic) {
+        cudaError_t e = h->dKgScratch.ensure(pfb_kg_k3_scratch_doubles(h->KP, h->n, nslots) * 8 + 16);
+        if (e != cudaSuccess) return e;
+        return pfb_launch_k3g(h->stream, h->KP, h->model, h->n, K_over > 0 ? K_over : h->K, nslots, unit_list,
+                              h->dFR.as<double>(), h->dHDR.as<double>(), seeds_over ? seeds_over : h->dSeeds.as<uint64_t>(),
+                              un, mp0, mp1, h->model_c0, logp, logq, draws, sel_cnt, sel_list, sel_cap,
+                              fb_seeds ? h->dX.as<double>() : nullptr, h->dG.as<double>(), h->dOff.as<int64_t>(), fb_seeds,
+                              fb_paths, h->dKgScratch.as<double>());
+    }
     auto fn = h->KP == 12 ? pfb_launch_k3_kp12 : (h->KP == 20 ? pfb_launch_k3_kp20 : pfb_launch_k3_kp24);
     return fn(h->stream, h->model, h->n, K_over > 0 ? K_over : h->K, nslots, unit_list, h->dFR2.as<double>(),
               h->dHDR.as<double>(), seeds_over ? seeds_over : h->dSeeds.as<uint64_t>(), un, mp0, mp1, h->model_c0,
@@ -861,10 +911,7 @@ extern "C" int pfb_batch_run(pfb_handle h) {
             PFB_CUDA(h, cudaEventRecord(h->k1_ev[g], h->k1_stream));
             PFB_CUDA(h, cudaStreamWaitEvent(st, h->k1_ev[g], 0));
             if (g == 0) PFB_CUDA(h, cudaEventRecord(h->ev[1], st));
-            PFB_CUDA(h, pfb_launch_k2_range(st, KP, n, u0, u1 - u0, J, h->dX.as<double>(), h->dG.as<double>(),
-                                            h->dUnitCol.as<int32_t>(), h->dAlpha.as<double>(), h->dHist.as<int32_t>(),
-                                            h->dHistCnt.as<int32_t>(), h->dFR.as<double>(), h->dHDR.as<double>(),
-                                            h->dFR2.as<double>(), k2_model, k2_mp0, k2_mp1));
+            PFB_CUDA(h, launch_k2_any(h, u0, u1 - u0, k2_model, k2_mp0, k2_mp1));
             h->launches += (p1 > p0) + (u1 > u0);
             if (k3_by_group && (g == h->up_ngroups / 2 - 1 || g == h->up_ngroups - 1)) {
                 // K3 in two launches, after the first and the second half of the groups: the copy stream
@@ -889,10 +936,7 @@ extern "C" int pfb_batch_run(pfb_handle h) {
                                   h->dHistCnt.as<int32_t>(), h->dRej.as<int64_t>()));
         h->launches += (P > 0);
         PFB_CUDA(h, cudaEventRecord(h->ev[1], st));
-        PFB_CUDA(h, pfb_launch_k2(st, KP, n, U, J, h->dX.as<double>(), h->dG.as<double>(), h->dUnitCol.as<int32_t>(),
-                                  h->dAlpha.as<double>(), h->dHist.as<int32_t>(), h->dHistCnt.as<int32_t>(),
-                                  h->dFR.as<double>(), h->dHDR.as<double>(), h->dFR2.as<double>(), k2_model, k2_mp0,
-                                  k2_mp1));
+        PFB_CUDA(h, launch_k2_any(h, 0, U, k2_model, k2_mp0, k2_mp1));
         h->launches += (U > 0);
     }
     if (!k3_by_group) PFB_CUDA(h, cudaEventRecord(h->ev[2], st));
@@ -993,10 +1037,7 @@ extern "C" int pfb_batch_fit_only(pfb_handle h, const int64_t* best_iter) {
     PFB_CUDA(h, pfb_launch_k1(st, n, P, J, h->cfg.eps, h->dX.as<double>(), h->dG.as<double>(),
                               h->dOff.as<int64_t>(), h->dAlpha.as<double>(), h->dHist.as<int32_t>(),
                               h->dHistCnt.as<int32_t>(), h->dRej.as<int64_t>()));
-    PFB_CUDA(h, pfb_launch_k2(st, KP, n, U, J, h->dX.as<double>(), h->dG.as<double>(), h->dUnitCol.as<int32_t>(),
-                              h->dAlpha.as<double>(), h->dHist.as<int32_t>(), h->dHistCnt.as<int32_t>(),
-                              h->dFR.as<double>(), h->dHDR.as<double>(), h->dFR2.as<double>(),
-                              model_is_external(h) ? PFB_MODEL_ISONORMAL : h->model,
+    PFB_CUDA(h, launch_k2_any(h, 0, U, model_is_external(h) ? PFB_MODEL_ISONORMAL : h->model,
                               model_is_external(h) ? nullptr : h->dModel.as<double>(),
                               (h->dModel.p && !model_is_external(h)) ? h->dModel.as<double>() + h->model_n : nullptr));
     PFB_CUDA(h, cudaMemcpyAsync(h->dBestUnit.p, bu.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
@@ -1211,13 +1252,21 @@ static int gather_fits(pfb_engine* h, int cnt, const int32_t* d_units, double* m
     PFB_CUDA(h, h->dFitVc.ensure(KP * KP * P * 8));
     PFB_CUDA(h, h->dFitLogdet.ensure(P * 8));
     PFB_CUDA(h, h->dFitJeff.ensure(P * 4));
-    pfb_gather_fit<<<(unsigned)P, 256, 0, st>>>((int)n, (int)KP, d_units, h->dFR2.as<double>(), h->dHDR.as<double>(),
-                                                h->dAlpha.as<double>(), h->dHistCnt.as<int32_t>(),
-                                                h->dFitMu.as<double>(), h->dFitAlpha.as<double>(),
-                                                h->dFitVh.as<double>(), h->dFitT.as<double>(),
-                                                h->dFitVc.as<double>(), h->dFitLogdet.as<double>(),
-                                                h->dFitJeff.as<int32_t>());
-    PFB_CUDA(h, cudaGetLastError());
+    if (h->generic) {
+        PFB_CUDA(h, pfb_launch_kg_gather_fit(st, (int)P, (int)n, (int)KP, d_units, h->dFR.as<double>(), h->dHDR.as<double>(),
+                                             h->dAlpha.as<double>(), h->dHistCnt.as<int32_t>(), h->dFitMu.as<double>(),
+                                             h->dFitAlpha.as<double>(), h->dFitVh.as<double>(), h->dFitT.as<double>(),
+                                             h->dFitVc.as<double>(), h->dFitLogdet.as<double>(),
+                                             h->dFitJeff.as<int32_t>()));
+    } else {
+        pfb_gather_fit<<<(unsigned)P, 256, 0, st>>>((int)n, (int)KP, d_units, h->dFR2.as<double>(), h->dHDR.as<double>(),
+                                                    h->dAlpha.as<double>(), h->dHistCnt.as<int32_t>(),
+                                                    h->dFitMu.as<double>(), h->dFitAlpha.as<double>(),
+                                                    h->dFitVh.as<double>(), h->dFitT.as<double>(),
+                                                    h->dFitVc.as<double>(), h->dFitLogdet.as<double>(),
+                                                    h->dFitJeff.as<int32_t>());
+        PFB_CUDA(h, cudaGetLastError());
+    }
     PFB_D2H(mu, h->dFitMu.p, n * P * 8);
     PFB_D2H(alpha, h->dFitAlpha.p, n * P * 8);
     PFB_D2H(vh, h->dFitVh.p, n * KP * P * 8);

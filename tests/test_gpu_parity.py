@@ -1184,3 +1184,44 @@ def test_unit_fits_export_every_iteration():
         ub = sl.start + int(res.best_iter[p]) - 1
         assert np.array_equal(f["mu"][:, ub], res.fit["mu"][:, p]) and np.array_equal(f["vh"][:, :, ub], res.fit["vh"][:, :, p])
     eng.close()
+
+
+@pytest.mark.parametrize("J,n", [(13, 80), (16, 20), (24, 130)])
+def test_history_longer_than_12_uses_the_generic_kernels(J, n):
+    """The reference accepts any history_length (src/inverse_hessian.jl:25).  Beyond 12 the runtime-width
+    kernels K2g / K3g take over: same algorithm and conventions, every iteration against the oracle
+    (n = 20 < 2J exercises min(n, 2J) reflectors), lean and materialising calls, fit export, resampling."""
+    import pathfinder_b200 as pf
+    from oracle import psis as OP
+    from tests.helpers import synthetic_trajectory
+
+    model = pf.IsoNormal(n)
+    trajs = [synthetic_trajectory(n, L, 500 + J + L) for L in (2 * J + 5, 3)]
+    res, orc = _compare_batch(model, trajs, K=32, J=J)
+    assert max(o["Hs"][-1].k for o in orc) == min(n, 2 * J)
+    # funnel target, lean call (no draws): ELBO table vs oracle, then PSIS + regenerated resampled columns
+    model = pf.Funnel(n)
+    trajs = [synthetic_trajectory(n, 2 * J + 3, 900 + J, scale=0.3), synthetic_trajectory(n, 5, 901 + J, scale=0.3)]
+    seeds = _seeds(trajs, 3)
+    offsets, X, G = pf.Engine.pack(trajs)
+    from tests.helpers import oracle_batch
+
+    orc = oracle_batch(model, trajs, seeds, 40, J)
+    lean = _engine(model, 40, J)
+    a = lean.elbo_batch(offsets, X, G, np.concatenate(seeds), draws=False, per_draw=True)
+    for p, o in enumerate(orc):
+        ev = np.array([e["value"] for e in o["ests"]])
+        np.testing.assert_allclose(a.elbo[a.unit_slice(p)], ev, rtol=RTOL, atol=RTOL)
+    r = lean.psis_resample(4, 30, True)
+    full = _engine(model, 40, J)
+    b = full.elbo_batch(offsets, X, G, np.concatenate(seeds), draws=True)
+    pool = b.draws.reshape(n, -1, order="F")
+    assert np.array_equal(r["draws"], pool[:, r["inds"] - 1])
+    logr = (b.draws_logp - b.draws_logq).reshape(-1, order="F")
+    assert np.array_equal(r["weights"], OP.psis(logr)["weights"])
+    lean.close(); full.close()
+    # a GEMM-shaped target through K3g + K8g
+    rng = np.random.default_rng(J)
+    Pm = np.linalg.inv(_rand_pd(rng, n))
+    dm = pf.DenseNormal(rng.normal(size=n), 0.5 * (Pm + Pm.T))
+    _compare_batch(dm, [synthetic_trajectory(n, 2 * J + 2, 77 + J, scale=0.3)], K=24, J=J)

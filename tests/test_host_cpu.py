@@ -68,7 +68,7 @@ def test_argument_errors_do_not_need_a_device():
     h = C.c_void_p()
     bad = _lib.pfb_config(0, 0, 5, 0, 0, 0, 1e-12)  # history_length = 0
     assert lib.pfb_create(C.byref(h), C.byref(bad)) == -1
-    bad = _lib.pfb_config(0, 13, 5, 0, 0, 0, 1e-12)  # history_length > 12 unsupported
+    bad = _lib.pfb_config(0, 65, 5, 0, 0, 0, 1e-12)  # history_length > 64 unsupported (13..64: generic kernels)
     assert lib.pfb_create(C.byref(h), C.byref(bad)) == -3
     assert lib.pfb_create(None, None) == -1
     assert lib.pfb_batch_run(None) == -1 and lib.pfb_destroy(None) == 0
