@@ -78,7 +78,8 @@ typedef struct {
     double* fit_mu;      /* [n x P]    MvNormal.mu                              src/mvnormal.jl:17 */
     double* fit_alpha;   /* [n x P]    diag(A)                                                 */
     double* fit_vh;      /* [n x KP x P] Householder reflectors of F.Q (unit diagonal explicit) */
-    double* fit_T;       /* [KP x KP x P] compact-WY T of F.Q, row-major                       */
+    double* fit_T;       /* [KP x KP x P] compact-WY T of F.Q, row-major: the FULL k x k factor (LAPACK's
+                            geqrt, which Julia's qr calls with nb = min(k, 36), stores its diagonal blocks) */
     double* fit_Vc;      /* [KP x KP x P] F.V (upper Cholesky factor), row-major               */
     double* fit_logdet;  /* [P]        logdet(Sigma)                     src/woodbury.jl:77-80 */
     int32_t* fit_jeff;   /* [P]        history_length_effective                                */
@@ -100,7 +101,8 @@ typedef struct {
 int pfb_create(pfb_handle* out, const pfb_config* cfg);
 int pfb_destroy(pfb_handle h);
 const char* pfb_last_error(pfb_handle h);
-int pfb_kp(pfb_handle h); /* padded reflector count KP (12, 20 or 24) for history_length     */
+int pfb_kp(pfb_handle h); /* padded reflector count KP: 12, 20, 24 for history_length <= 6, 10, 12 (tensor-core
+                             kernels); 2 * history_length for 13..64 (generic runtime-width kernels K2g / K3g) */
 
 /* Target density: replaces the Julia closure logp(x) (src/singlepath.jl:186, src/multipath.jl:159)
  * by a registered device-side family + parameter blob (doubles). */
