@@ -546,16 +546,16 @@ def main():
         from threadpoolctl import threadpool_limits
 
         full_cpu = mpf is not None and not args.no_cpu_baseline and args.cpu_budget <= 0
-        if args.no_cpu_baseline:
+        if args.no_cpu_baseline or world > 1:  # (the CPU baseline is timed at N = 1 only)
             done, secs = 0, 1.0
         else:
             with threadpool_limits(limits=1):
                 done, secs = oracle_elbo_stage(n, trajs, seeds, K, J, 1e9 if full_cpu else max(args.cpu_budget, 15.0),
                                                logp_fn=oracle_logp(CONFIGS[name][0], model))
-        line["cpu_baseline"] = {"value": done / secs, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": f"oracle ELBO stage on {'all' if done == U * K else 'the first'} "
-                                          f"{done // K} (path, iteration) units of this workload, {secs:.1f} s, "
-                                          f"single thread"}
+        line["cpu_baseline"] = {"value": (done / secs) if done else None, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": (f"oracle ELBO stage on {'all' if done == U * K else 'the first'} "
+                                           f"{done // K} (path, iteration) units of this workload, {secs:.1f} s, "
+                                           f"single thread") if done else "not timed in this run (N > 1 or --no-cpu-baseline)"}
         if mpf is not None and done > 0:
             from oracle import psis as OP
 
@@ -578,6 +578,10 @@ def main():
                                        "elbo_stage_measured": bool(done == U * K)}
             for opt in ("host", "device"):
                 mpf[opt]["speedup_vs_cpu_port"] = float(cpu_s / mpf[opt]["ours_s"])
+                # (the device optimiser does not stop where SciPy does: it may run many more iterations, i.e.
+                # units; the per-sample rates make the two comparable)
+                mpf[opt]["elbo_samples_per_s_wall"] = float(mpf[opt]["units"] * K / mpf[opt]["ours_s"])
+            mpf["cpu_port_elbo_samples_per_s_wall"] = float(U * K / cpu_s)
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
