@@ -68,6 +68,7 @@ def _compare_batch(model, trajs, K, J, seed=1, normals=False, rtol=RTOL, cond_aw
     orc = oracle_batch(model, trajs, seeds, K, J, normals=nrm)
     sens = _sensitivity(model, trajs, seeds, K, J, orc) if cond_aware else None
     worst_well_conditioned = 0.0
+    n_units = n_relaxed = 0
     for p, o in enumerate(orc):
         sl = res.unit_slice(p)
         L = trajs[p][0].shape[1] - 1
@@ -83,6 +84,8 @@ def _compare_batch(model, trajs, K, J, seed=1, normals=False, rtol=RTOL, cond_aw
             assert abs(res.elbo_se[u] - se[l]) <= max(10 * t, 1e-5) * max(1e-4, abs(se[l])) or np.isnan(se[l]), (p, l)
             d = _rel(res.all_draws[:, :, u], e["draws"])
             assert d < t, (p, l, d, t)
+            n_units += 1
+            n_relaxed += int(t > rtol)
             if t == rtol:
                 worst_well_conditioned = max(worst_well_conditioned, d)
             np.testing.assert_allclose(res.logq[:, u], e["logq"], rtol=t, atol=t)
@@ -125,7 +128,14 @@ def _compare_batch(model, trajs, K, J, seed=1, normals=False, rtol=RTOL, cond_aw
                                                atol=1e-9)
                 np.testing.assert_allclose(res.fit["Vc"][p][:k, :k], W.Vc[:k, :k], rtol=1e-6, atol=1e-9)
     eng.close()
+    # how many units needed the relaxed (conditioning-aware) tolerance: counted, never silent
+    RELAXED_LOG.append(dict(n=model.n, K=K, J=J, units=n_units, relaxed=n_relaxed))
+    if not cond_aware:
+        assert n_relaxed == 0
     return res, orc
+
+
+RELAXED_LOG = []
 
 
 def test_synthetic_small_device_rng():
@@ -166,6 +176,27 @@ def test_funnel_config2_trajectories():
     model = pf.Funnel(100)
     trajs = make_trajectories(model, 3, seed=5, init_scale=10, maxiters=60, min_len=5)
     _compare_batch(model, trajs, K=200, J=6, cond_aware=True)
+    # the funnel's histories are rank deficient (tests/test_gpu_parity_fullsize.py): report, and bound, the share of
+    # units whose draws needed the relaxed tolerance
+    rec = RELAXED_LOG[-1]
+    assert rec["units"] > 50 and rec["relaxed"] < rec["units"], rec
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for d in ("profiles", "gpurun_out"):
+        path = os.path.join(root, d, "parity_report.json")
+        if os.path.isdir(os.path.dirname(path)):
+            try:
+                rep = json.load(open(path))
+            except Exception:
+                rep = {}
+            rep["cfg2_funnel100_k200_j6_three_paths"] = dict(units_compared=rec["units"], units_relaxed=rec["relaxed"],
+                                                             strict_share=1.0 - rec["relaxed"] / rec["units"])
+            try:
+                json.dump(rep, open(path, "w"), indent=1, sort_keys=True)
+            except OSError:
+                pass
 
 
 def test_history_10():
@@ -531,6 +562,45 @@ def test_device_lbfgs_trajectories_bit_exact(kind, n, J, scale, maxiters):
         assert np.array_equal(G[:, sl], Go, equal_nan=True)
         assert np.array_equal(FX[sl], FXo, equal_nan=True)
     eng.close()
+
+
+def test_device_lbfgs_independent_anchors_on_the_gpu():
+    """K0 against anchors that do NOT share its source (the bit-exact oracle compiles the same pf_lbfgs.h):
+    analytic optima of the Gaussian families, SciPy's L-BFGS-B optimum of the hierarchical logistic model,
+    monotone log densities and recorded gradients equal to the model's own gradient (src/optimize.jl:94-101)."""
+    import pathfinder_b200 as pf
+    from scipy.optimize import minimize
+
+    rng = np.random.default_rng(12)
+    n = 60
+    Sg = _rand_pd(rng, n)
+    Pm = np.linalg.inv(Sg)
+    mean = rng.normal(size=n)
+    nobs = 300
+    Xo = rng.normal(size=(nobs, 10))
+    yo = (rng.random(nobs) < 1.0 / (1.0 + np.exp(-(Xo @ (rng.normal(size=10) * 0.7))))).astype(np.float64)
+    cases = [(pf.IsoNormal(n), np.zeros(n)), (pf.DiagNormal(mean, rng.uniform(0.2, 5.0, size=n)), mean),
+             (pf.DenseNormal(mean, 0.5 * (Pm + Pm.T)), mean), (pf.HierLogistic(Xo, yo), None)]
+    for model, opt in cases:
+        m = model.n
+        x0s = np.asfortranarray(rng.uniform(-2, 2, size=(m, 4)))
+        eng = _engine(model, 8, 6)
+        npts, st, _ = eng.lbfgs_batch(x0s, 1000)
+        off, X, FX, G = eng.lbfgs_download()
+        if opt is None:
+            r = minimize(lambda x: -model.logp(x), x0s[:, 0], jac=lambda x: -model.grad(x), method="L-BFGS-B",
+                         options=dict(maxiter=2000, ftol=1e-15, gtol=1e-10))
+            opt = r.x
+        for p in range(4):
+            sl = slice(off[p], off[p + 1])
+            assert st[p] in (0, 1), st[p]                                   # a tolerance, not maxiters / failure
+            assert np.all(np.diff(FX[sl]) >= -1e-9 * np.maximum(1.0, np.abs(FX[sl][:-1])))   # monotone ascent
+            xL = X[:, sl][:, -1]
+            assert np.max(np.abs(xL - opt)) < 2e-4 * max(1.0, np.max(np.abs(opt))), np.max(np.abs(xL - opt))
+            for l in (0, (off[p + 1] - off[p]) // 2, off[p + 1] - off[p] - 1):
+                np.testing.assert_allclose(G[:, sl][:, l], model.grad(X[:, sl][:, l]), rtol=1e-9, atol=1e-9)
+                np.testing.assert_allclose(FX[sl][l], model.logp(X[:, sl][:, l]), rtol=1e-10, atol=1e-9)
+        eng.close()
 
 
 def test_device_lbfgs_capacity_nonfinite_and_unsupported_family():
