@@ -281,6 +281,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing (profiling runs)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the config's paths PER GPU; strong: the config's paths in total, split over the GPUs")
+    ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-wall", action="store_true", help="skip the multipathfinder() wall-clock legs")
     ap.add_argument("--assign", default=None, choices=["lpt", "static"],
                     help="N > 1: LPT-balanced on iteration counts (default for the funnels; every rank optimises every "
@@ -304,6 +305,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists for the product path)")
     torch.cuda.set_device(local_rank)
+    # several ranks on one host: keep each rank (and the page-locked staging it first-touches) on its GPU's NUMA node
+    numa = None
+    if world > 1 and not args.no_numa:
+        from pathfinder_b200._numa import bind_to_device_numa
+        numa = bind_to_device_numa(local_rank)
     # NCCL prints its version banner on stdout (NCCL_DEBUG=VERSION): keep stdout = the one JSON line
     sys.stdout.flush()
     real_stdout = os.dup(1)
@@ -488,6 +494,8 @@ def main():
         "stage_ms": {k: float(np.mean([s[k] for s in stage_ms])) for k in ("k1", "k2", "k3", "k4", "k5", "total")},
         "wall_s_timed_region": wall,
     }
+    if world > 1:
+        line["numa_bind_rank0"] = numa  # {"node", "cpus"} when the rank was bound to its GPU's NUMA node, else null
 
     # ---- whole multipathfinder() call, trajectories included (north_star's wall-clock target) ----------
     # The DEFAULT call (maxiters = 1000, ntries = 1) with the host optimiser (the reference's split:
