@@ -234,3 +234,17 @@ def test_product_code_never_touches_the_oracle():
     if os.path.exists(so):
         deps = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
         assert "pforacle" not in deps
+
+
+def test_numa_cpulist_parse_and_bind_is_harmless():
+    # pathfinder_b200/_numa.py: host plumbing of the multi-rank bench (bind a rank to its GPU's NUMA node);
+    # without a GPU nothing may change and nothing may raise
+    import os
+
+    from pathfinder_b200 import _numa
+
+    assert _numa._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _numa._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert _numa.bind_to_device_numa(0) is None
+    assert os.sched_getaffinity(0) == before
