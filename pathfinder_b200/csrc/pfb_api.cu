@@ -130,6 +130,12 @@ struct pfb_engine {
     DevBuf dFbSeeds, dPoolSeeds, dFbUnits, dFbPaths, dFbLogp, dFbLogq, dFbPairs, dTopFb;
     const uint64_t* pool_seeds = nullptr;  // unit-indexed seeds of the pool's draws (dSeeds, or dPoolSeeds)
     int n_failed = 0;
+    // lazy failure resolution: pfb_batch_run leaves the success flags / best units on their way to this
+    // page-locked pair and returns without synchronising; the first consumer of the pool resolves them
+    bool fail_pending = false;
+    cudaEvent_t ev_fail = nullptr;
+    int32_t* hSuccBu = nullptr;  // [2 x cap]: success flags, best units
+    int hSuccBuCap = 0;
     // multi-GPU (pfb_comm_init): NCCL communicator, the all-gathered log densities
     void* comm = nullptr;
     int comm_world = 1, comm_rank = 0;
@@ -263,6 +269,8 @@ extern "C" int pfb_destroy(pfb_handle h) {
         if (h->hc_c[i]) cudaEventDestroy(h->hc_c[i]);
     }
     if (h->hLp) cudaFreeHost(h->hLp);
+    if (h->hSuccBu) cudaFreeHost(h->hSuccBu);
+    if (h->ev_fail) cudaEventDestroy(h->ev_fail);
     for (auto& ev : h->up_ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->k1_ev)
@@ -369,7 +377,7 @@ static int batch_prepare(pfb_engine* h, int n, int P, const int64_t* offsets) {
     const int K = h->cfg.ndraws_elbo, J = h->cfg.history_length, KP = h->KP;
     h->n = n; h->P = P; h->K = K; h->T = T; h->U = U;
     h->h_off.assign(offsets, offsets + P + 1);
-    h->have_batch = false; h->ran = false;
+    h->have_batch = false; h->ran = false; h->fail_pending = false;
     std::vector<int32_t> unit_col((size_t)U);
     for (int p = 0; p < P; ++p) {
         const int64_t L = offsets[p + 1] - offsets[p] - 1;
@@ -695,6 +703,7 @@ static cudaError_t launch_k3(pfb_engine* h, int nslots, const int32_t* unit_list
 // identical to the ELBO-stage draws because the RNG is counter based).  The pool's logp / logq are
 // gathered from the ELBO stage by pfb_batch_run; the draws are only produced when somebody looks at
 // them (PathfinderResult.draws, pool exchange) — the resample stage regenerates just its columns.
+static int resolve_failed(pfb_engine* h);
 static int ensure_pool(pfb_engine* h) {
     if (h->pool_ready || h->P <= 0) return PFB_OK;
     if (!h->ran || h->poolK != h->K || h->poolP != h->P)
@@ -804,11 +813,12 @@ static uint64_t splitmix64(uint64_t x) {
 // the fit of its best iteration (the identity fit of iteration 0 when it has none) with the path's
 // fallback seed; the pool's log densities and the pool's seed table are updated, so that a later
 // materialisation / column regeneration reproduces exactly these draws.
-static int failed_path_draws(pfb_engine* h) {
-    const int P = h->P, K = h->K, n = h->n;
+static int failed_path_enqueue(pfb_engine* h) {
+    const int P = h->P;
     cudaStream_t st = h->stream;
     h->pool_seeds = h->dSeeds.as<uint64_t>();
     h->n_failed = 0;
+    h->fail_pending = false;
     if (P <= 0) return PFB_OK;
     h->fb_seeds.resize((size_t)P);
     for (int p = 0; p < P; ++p)
@@ -817,10 +827,33 @@ static int failed_path_draws(pfb_engine* h) {
     h->fb_seeds_user.clear();
     PFB_CUDA(h, h->dFbSeeds.ensure((size_t)P * 8));
     PFB_CUDA(h, cudaMemcpyAsync(h->dFbSeeds.p, h->fb_seeds.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
-    std::vector<int32_t> succ((size_t)P), bu((size_t)P);
-    PFB_CUDA(h, cudaMemcpyAsync(succ.data(), h->dSucc.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
-    PFB_CUDA(h, cudaMemcpyAsync(bu.data(), h->dBestUnit.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
-    PFB_CUDA(h, cudaStreamSynchronize(st));
+    if (P > h->hSuccBuCap) {
+        if (h->hSuccBu) cudaFreeHost(h->hSuccBu);
+        h->hSuccBu = nullptr;
+        h->hSuccBuCap = 0;
+        PFB_CUDA(h, cudaMallocHost((void**)&h->hSuccBu, (size_t)P * 8));
+        h->hSuccBuCap = P;
+    }
+    if (!h->ev_fail) PFB_CUDA(h, cudaEventCreateWithFlags(&h->ev_fail, cudaEventDisableTiming));
+    PFB_CUDA(h, cudaMemcpyAsync(h->hSuccBu, h->dSucc.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    PFB_CUDA(h, cudaMemcpyAsync(h->hSuccBu + h->hSuccBuCap, h->dBestUnit.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    PFB_CUDA(h, cudaEventRecord(h->ev_fail, st));
+    h->fail_pending = true;
+    return PFB_OK;
+}
+
+// Second half, run by the first consumer of the pool (or by the optimistic consumers after their own
+// synchronisation, see pfb_psis_resample / pfb_batch_download): waits for the flags, and for failed
+// paths replaces their pool entries as described above.  No failed path (the common case): nothing to do.
+static int resolve_failed(pfb_engine* h) {
+    if (!h->fail_pending) return PFB_OK;
+    h->fail_pending = false;
+    const int P = h->P, K = h->K, n = h->n;
+    cudaStream_t st = h->stream;
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    PFB_CUDA(h, cudaEventSynchronize(h->ev_fail));
+    const int32_t* succ = h->hSuccBu;
+    const int32_t* bu = h->hSuccBu + h->hSuccBuCap;
     std::vector<int32_t> paths, units;
     std::vector<int64_t> pairs;
     for (int p = 0; p < P; ++p)
@@ -833,6 +866,7 @@ static int failed_path_draws(pfb_engine* h) {
     const int nf = (int)paths.size();
     h->n_failed = nf;
     if (nf == 0 || h->have_normals) return PFB_OK;  // (parity mode supplies the normals of the ELBO stage only)
+    h->pool_ready = false;  // an optimistically materialised pool holds the wrong draws for the failed paths
     const int64_t U = h->U;
     PFB_CUDA(h, h->dPoolSeeds.ensure((size_t)std::max<int64_t>(U, 1) * 8));
     PFB_CUDA(h, h->dFbUnits.ensure((size_t)nf * 4));
@@ -1010,7 +1044,7 @@ extern "C" int pfb_batch_run(pfb_handle h) {
     h->poolK = K;
     h->poolP = P;
     {
-        int rcf = failed_path_draws(h);
+        int rcf = failed_path_enqueue(h);
         if (rcf) return rcf;
     }
     PFB_CUDA(h, cudaEventRecord(h->ev[5], st));
@@ -1049,6 +1083,7 @@ extern "C" int pfb_batch_fit_only(pfb_handle h, const int64_t* best_iter) {
     h->ran = true;
     h->pool_seeds = h->dSeeds.as<uint64_t>();
     h->n_failed = 0;
+    h->fail_pending = false;
     h->poolK = 0;
     h->poolP = 0;
     h->pool_ready = false;
@@ -1066,6 +1101,7 @@ extern "C" int pfb_draw_from_fits(pfb_handle h, int K_new, const uint64_t* seeds
     if (K_new < 1) PFB_FAIL(h, PFB_ERR_ARG, "K_new must be positive");
     if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "no fitted batch (pfb_batch_run / pfb_batch_fit_only)");
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    { int rf = resolve_failed(h); if (rf) return rf; }
     cudaStream_t st = h->stream;
     const size_t n = h->n, P = h->P, U = (size_t)h->U;
     if (P == 0) return PFB_OK;
@@ -1206,10 +1242,9 @@ __global__ void pfb_gather_fit(int n, int KP, const int32_t* __restrict__ best_u
     }
 }
 
-extern "C" int pfb_batch_download(pfb_handle h, pfb_elbo_out* o) {
-    if (!h || !o) return PFB_ERR_ARG;
-    if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "pfb_batch_run has not been called");
-    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+static int gather_fits(pfb_engine* h, int cnt, const int32_t* d_units, double* mu, double* alpha, double* vh,
+                       double* T, double* Vc, double* logdet, int32_t* jeff);
+static int batch_download_impl(pfb_engine* h, pfb_elbo_out* o) {
     cudaStream_t st = h->stream;
     const size_t n = h->n, P = h->P, K = h->K, U = (size_t)h->U, KP = h->KP;
     PFB_D2H(o->elbo, h->dElbo.p, U * 8);
@@ -1237,6 +1272,24 @@ extern "C" int pfb_batch_download(pfb_handle h, pfb_elbo_out* o) {
                            o->fit_Vc, o->fit_logdet, o->fit_jeff);
     PFB_CUDA(h, cudaStreamSynchronize(st));
     return PFB_OK;
+}
+
+extern "C" int pfb_batch_download(pfb_handle h, pfb_elbo_out* o) {
+    if (!h || !o) return PFB_ERR_ARG;
+    if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "pfb_batch_run has not been called");
+    PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    // optimistic: the copies are enqueued behind the kernels without waiting for the success flags;
+    // only when a path did fail (known after the download's own synchronisation) is the pool part
+    // fetched again after the fallback draws replaced it
+    const bool was_pending = h->fail_pending;
+    int rc = batch_download_impl(h, o);
+    if (was_pending) {
+        int r2 = resolve_failed(h);
+        if (r2) return r2;
+        if (h->n_failed > 0 && !h->have_normals && (o->draws || o->draws_logp || o->draws_logq))
+            rc = batch_download_impl(h, o);
+    }
+    return rc;
 }
 
 // The fitted normals of `cnt` units (device list; < 0: NaN) in the reference's form, to host buffers
@@ -1286,6 +1339,7 @@ extern "C" int pfb_pool_download(pfb_handle h, int p0, int p1, double* draws, do
     if (!h->ran || h->poolK <= 0) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
     if (p0 < 0 || p1 < p0 || p1 > h->P) PFB_FAIL(h, PFB_ERR_ARG, "path range out of bounds");
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    { int rf = resolve_failed(h); if (rf) return rf; }
     cudaStream_t st = h->stream;
     const size_t n = h->n, K = (size_t)h->poolK, cnt = (size_t)(p1 - p0);
     if (draws && cnt) {
@@ -1374,6 +1428,7 @@ extern "C" int pfb_elbo_batch(pfb_handle h, int n, int P, const int64_t* offsets
 extern "C" int pfb_pool_materialize(pfb_handle h) {
     if (!h) return PFB_ERR_ARG;
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    { int rf = resolve_failed(h); if (rf) return rf; }
     return ensure_pool(h);
 }
 
@@ -1385,12 +1440,14 @@ extern "C" int pfb_pool_columns_device(pfb_handle h, int m, const void* d_inds, 
     if (!h->ran || h->poolK <= 0) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
     if (h->poolK != h->K) PFB_FAIL(h, PFB_ERR_STATE, "column regeneration needs the pool of pfb_batch_run");
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    { int rf = resolve_failed(h); if (rf) return rf; }
     return regen_columns(h, m, (const int64_t*)d_inds, base, (double*)d_out);
 }
 
 extern "C" int pfb_batch_device_view(pfb_handle h, pfb_device_view* v) {
     if (!h || !v) return PFB_ERR_ARG;
     if (!h->have_batch) PFB_FAIL(h, PFB_ERR_STATE, "no batch");
+    { int rf = resolve_failed(h); if (rf) return rf; }  // the caller is about to read the pool's log densities
     // pool_draws is valid after pfb_pool_materialize (or a draws download); the log densities always are
     v->pool_draws = h->dPool.p;
     v->pool_logp = h->dPoolLogp.p;
@@ -1493,9 +1550,22 @@ extern "C" int pfb_psis_resample(pfb_handle h, uint64_t seed, int ndraws, int im
     if (!h || !o) return PFB_ERR_ARG;
     if (!h->ran || h->poolK <= 0) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
-    return psis_resample_impl(h, h->n, (int64_t)h->poolP * h->poolK, h->poolK, h->dPoolLogp.as<double>(),
-                              h->dPoolLogq.as<double>(), nullptr, h->dPool.as<double>(), seed, ndraws,
-                              importance, replace, o, /*regen=*/!h->pool_ready);
+    // optimistic like pfb_batch_download: the whole PSIS chain is enqueued behind the ELBO stage (no host
+    // round trip between pfb_batch_run and here); a failed path, known after the chain's own
+    // synchronisation, repeats it on the corrected pool
+    const bool was_pending = h->fail_pending;
+    int rc = psis_resample_impl(h, h->n, (int64_t)h->poolP * h->poolK, h->poolK, h->dPoolLogp.as<double>(),
+                                h->dPoolLogq.as<double>(), nullptr, h->dPool.as<double>(), seed, ndraws,
+                                importance, replace, o, /*regen=*/!h->pool_ready);
+    if (was_pending) {
+        int r2 = resolve_failed(h);
+        if (r2) return r2;
+        if (h->n_failed > 0 && !h->have_normals)
+            rc = psis_resample_impl(h, h->n, (int64_t)h->poolP * h->poolK, h->poolK, h->dPoolLogp.as<double>(),
+                                    h->dPoolLogq.as<double>(), nullptr, h->dPool.as<double>(), seed, ndraws,
+                                    importance, replace, o, /*regen=*/!h->pool_ready);
+    }
+    return rc;
 }
 
 extern "C" int pfb_psis_resample_device(pfb_handle h, int n, int64_t N, int K_run, const void* d_logp,
@@ -1692,6 +1762,7 @@ static int pool_exchange_impl(pfb_engine** hs, int nh, const int32_t* paths_per_
         pfb_engine* h = hs[i];
         if (!h->comm || h->comm_world != world) PFB_FAIL(h, PFB_ERR_STATE, "pfb_comm_init has not been called");
         if (!h->ran) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
+        { int rf = resolve_failed(h); if (rf) return rf; }
         if (paths_per_rank[h->comm_rank] != h->poolP) PFB_FAIL(h, PFB_ERR_SHAPE, "paths_per_rank[rank] differs from this engine's pool");
         if (h->poolP > 0 && h->poolK <= 0) PFB_FAIL(h, PFB_ERR_STATE, "no device pool (pfb_batch_run / pfb_draw_from_fits)");
         if (h->poolK > 0) {  // (a rank without runs states its draws per run through pfb_pool_set(P = 0, K_run))
@@ -1815,6 +1886,7 @@ extern "C" int pfb_pool_set(pfb_handle h, int P, int K_run, const double* draws,
     if (!h || P < 0 || K_run < 1 || (P > 0 && (!logp || !logq))) return PFB_ERR_ARG;
     if (h->model < 0) PFB_FAIL(h, PFB_ERR_STATE, "no model registered");
     PFB_CUDA(h, cudaSetDevice(h->cfg.device));
+    { int rf = resolve_failed(h); if (rf) return rf; }
     cudaStream_t st = h->stream;
     const size_t n = h->model_n, Ps = (size_t)P, K = (size_t)K_run;
     if (!draws && P > 0 && (K_run != h->K || P != h->P || !h->ran))
