@@ -1366,7 +1366,9 @@ extern "C" int pfb_elbo_batch(pfb_handle h, int n, int P, const int64_t* offsets
     // up in path groups on a copy stream and K1 / K2 of a group start when its points are resident
     // (the host buffers are not touched after the final synchronisation in pfb_batch_download).
     if (!h) return PFB_ERR_ARG;
-    if (normals || P < 8 || !offsets || n < 1) {  // parity mode / tiny batches: the plain sequence
+    // parity mode / small batches (under 4 MB of trajectories the group-wise launches and events cost more
+    // than the overlap returns: config 2 is 0.65 MB): the plain sequence
+    if (normals || P < 8 || !offsets || n < 1 || (int64_t)offsets[P] * n * 16 < ((int64_t)4 << 20)) {
         int rc0 = pfb_batch_upload(h, n, P, offsets, positions, gradients, seeds, normals);
         if (rc0) return rc0;
         rc0 = pfb_batch_run(h);
