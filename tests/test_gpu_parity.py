@@ -1206,7 +1206,20 @@ def test_path_without_an_iteration_draws_from_the_identity_fit():
         r = eng2.psis_resample(3, 30, False)
         pool = res.draws.reshape(n, -1, order="F")
         assert np.array_equal(r["draws"], pool[:, r["inds"] - 1])
-        eng.close(); eng2.close()
+        # failures are resolved lazily: run() returns without looking at the success flags, and a resample
+        # issued straight behind it (no download in between) runs optimistically, notices the failed path
+        # after its own synchronisation and repeats on the corrected pool — same result as above
+        eng3 = pf.Engine.for_model(model, J, K, 0)
+        eng3.set_fallback_seeds(fb)
+        eng3.upload(offsets, X, G, np.concatenate(seeds))
+        eng3.run()
+        r3 = eng3.psis_resample(3, 30, False)
+        assert np.array_equal(r3["inds"], r["inds"]) and np.array_equal(r3["draws"], r["draws"])
+        eng3.set_fallback_seeds(fb)
+        eng3.run()
+        r3w, r2w = eng3.psis_resample(8, 30, True), eng2.psis_resample(8, 30, True)
+        assert np.array_equal(r3w["weights"], r2w["weights"]) and np.array_equal(r3w["draws"], r2w["draws"])
+        eng.close(); eng2.close(); eng3.close()
 
 
 def test_nan_log_ratios_get_zero_weight_and_an_all_nan_pool_is_an_error():
