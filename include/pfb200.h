@@ -144,7 +144,12 @@ int pfb_set_fallback_seeds(pfb_handle h, int P, const uint64_t* seeds);
 /* The same, split so that callers can keep inputs resident / overlap / time the stages. */
 int pfb_batch_upload(pfb_handle h, int n, int P, const int64_t* offsets, const double* positions,
                      const double* gradients, const uint64_t* seeds, const double* normals_or_null);
-int pfb_batch_run(pfb_handle h);  /* K1..K5, asynchronous on the engine stream */
+/* K1..K5, asynchronous on the engine stream: returns without a host round trip (with a host-callback
+ * target it returns once the last chunk has been evaluated).  Whether a path failed is resolved by the first
+ * consumer of the pool: pfb_psis_resample and pfb_batch_download queue up behind the ELBO stage and repeat
+ * their pool part only when a path did fail; pfb_batch_device_view, pfb_pool_*, pfb_draw_from_fits and the
+ * pool exchange wait for the flags first. */
+int pfb_batch_run(pfb_handle h);
 int pfb_batch_sync(pfb_handle h);
 int pfb_batch_download(pfb_handle h, pfb_elbo_out* out);
 
