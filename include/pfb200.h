@@ -114,8 +114,9 @@ int pfb_register_model(pfb_handle h, int family, int n, const double* blob, size
  * them to pinned host memory, and calls `cb(user, x, n, m, logp_out)` with x = n x m column-major
  * draws (what `logp.(eachcol(x))` consumes, src/elbo.jl:15; src/resample.jl:90-92) while the next
  * chunk is being sampled and copied; logp_out[m] goes back to the device for the ELBO reduction.
- * The callback runs on the thread that called pfb_batch_run / pfb_draw_from_fits, never
- * concurrently with itself.  Non-finite values propagate as in src/elbo.jl:16-17. */
+ * The callback runs on the thread that called pfb_batch_run / pfb_draw_from_fits (for the fallback draws
+ * of a FAILED path: the first call that consumes the pool afterwards — pfb_batch_download,
+ * pfb_psis_resample, ...), never concurrently with itself.  Non-finite values propagate as in src/elbo.jl:16-17. */
 typedef void (*pfb_logp_callback)(void* user, const double* x, int64_t n, int64_t m, double* logp_out);
 int pfb_register_host_model(pfb_handle h, int n, pfb_logp_callback cb, void* user);
 
