@@ -248,3 +248,39 @@ def test_numa_cpulist_parse_and_bind_is_harmless():
     before = os.sched_getaffinity(0)
     assert _numa.bind_to_device_numa(0) is None
     assert os.sched_getaffinity(0) == before
+
+
+def _run_bench(args, env=None, timeout=300):
+    import json
+    import os
+    import pathlib
+    import subprocess
+    import sys
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, str(root / "bench.py")] + args, capture_output=True, text=True,
+                       timeout=timeout, env={**os.environ, **(env or {})}, cwd=str(root))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    return [json.loads(ln) for ln in lines]
+
+
+def test_reference_arm_prints_the_contract_line_and_only_rank_0_works():
+    """bench.py --impl reference: the CPU algorithm (oracle port) on the host cores with the SAME metric,
+    unit and config keys as the product arm, a measured ms_per_step, e2e = value with zero copies; under
+    torchrun only rank 0 runs it, the other ranks exit 0 silently."""
+    cfg = "cfg2_funnel100_p8_k1000_j6"
+    (line,) = _run_bench(["--impl", "reference", "--config", cfg, "--steps", "2", "--warmup", "1"])
+    assert line["impl"] == "reference" and line["metric"] == "elbo_mc_samples_per_sec" and line["unit"] == "samples/s"
+    assert line["higher_is_better"] is True and line["steps"] == 2 and line["warmup"] == 1
+    assert line["config"] == {"workload": cfg, "n": 100, "paths_per_gpu": 8, "K": 1000, "history": 6, "ndraws": 1000}
+    assert line["value"] > 0 and line["ms_per_step"] > 0
+    # value = samples of a step / its measured duration
+    units = line["details"]["units_per_step"]
+    assert abs(line["value"] - units * 1000 / (line["ms_per_step"] / 1e3)) / line["value"] < 0.2
+    assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "paths" in cb["sample"]
+    # a non-zero rank of a multi-rank launch does nothing and prints nothing
+    assert _run_bench(["--impl", "reference", "--config", cfg, "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                      env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
