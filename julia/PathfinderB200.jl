@@ -17,7 +17,8 @@ module PathfinderB200
 
 using Random
 
-const LIB = Ref{String}(get(ENV, "PFB200_LIB", "libpfb200.so"))
+# a constant path: ccall resolves (symbol, library) once per call site
+const LIB = get(ENV, "PFB200_LIB", "libpfb200.so")
 
 const PFB_MODEL_ISONORMAL = Cint(0)
 const PFB_MODEL_FUNNEL = Cint(1)
@@ -90,11 +91,11 @@ mutable struct Engine
                     materialize_all::Bool=false, eps::Float64=1e-12)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         cfg = Ref(PfbConfig(device, history_length, ndraws_elbo, materialize_all, 0, 0, eps))
-        rc = ccall((:pfb_create, LIB[]), Cint, (Ref{Ptr{Cvoid}}, Ref{PfbConfig}), h, cfg)
+        rc = ccall((:pfb_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{PfbConfig}), h, cfg)
         rc == 0 || throw(ErrorException("pfb_create failed ($rc): " * last_error(C_NULL)))
         e = new(h[], n, ndraws_elbo, history_length)
         finalizer(close, e)
-        rc = ccall((:pfb_register_model, LIB[]), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Csize_t),
+        rc = ccall((:pfb_register_model, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Csize_t),
                    e.handle, family, n, isempty(blob) ? C_NULL : pointer(blob), length(blob))
         check(e, rc)
         return e
@@ -103,13 +104,13 @@ end
 
 function Base.close(e::Engine)
     if e.handle != C_NULL
-        ccall((:pfb_destroy, LIB[]), Cint, (Ptr{Cvoid},), e.handle)
+        ccall((:pfb_destroy, LIB), Cint, (Ptr{Cvoid},), e.handle)
         e.handle = C_NULL
     end
     return nothing
 end
 
-last_error(h) = unsafe_string(ccall((:pfb_last_error, LIB[]), Cstring, (Ptr{Cvoid},), h))
+last_error(h) = unsafe_string(ccall((:pfb_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
 
 # error convention of include/pfb200.h: < 0 argument / shape error, > 0 CUDA runtime error
 function check(e::Engine, rc::Integer)
@@ -137,7 +138,7 @@ function elbo_batch(e::Engine, traces, seeds::Vector{Vector{UInt64}}; normals=no
         # one UInt64 per path, drawn from the PATH's rng: a failed path returns
         # rand(rng, fit_distributions[fit_iteration + 1], ndraws) (src/singlepath.jl:224-228)
         fs = Vector{UInt64}(fallback_seeds)
-        GC.@preserve fs check(e, ccall((:pfb_set_fallback_seeds, LIB[]), Cint, (Ptr{Cvoid}, Cint, Ptr{UInt64}),
+        GC.@preserve fs check(e, ccall((:pfb_set_fallback_seeds, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{UInt64}),
                                        e.handle, length(fs), fs))
     end
     offsets = zeros(Int64, P + 1)
@@ -154,7 +155,7 @@ function elbo_batch(e::Engine, traces, seeds::Vector{Vector{UInt64}}; normals=no
     end
     sd = reduce(vcat, seeds; init=UInt64[])
     length(sd) == U || throw(DimensionMismatch("need one seed per (path, iteration)"))
-    kp = ccall((:pfb_kp, LIB[]), Cint, (Ptr{Cvoid},), e.handle)
+    kp = ccall((:pfb_kp, LIB), Cint, (Ptr{Cvoid},), e.handle)
     elbo = Vector{Float64}(undef, U); se = similar(elbo)
     best = Vector{Int64}(undef, P); succ = Vector{Int32}(undef, P); rej = Vector{Int64}(undef, P)
     draws = Array{Float64}(undef, n, K, P); lp = Matrix{Float64}(undef, K, P); lq = similar(lp)
@@ -169,7 +170,7 @@ function elbo_batch(e::Engine, traces, seeds::Vector{Vector{UInt64}}; normals=no
         out.fit_mu = pointer(mu); out.fit_alpha = pointer(alpha); out.fit_vh = pointer(vh)
         out.fit_T = pointer(Tm); out.fit_Vc = pointer(Vc)
         out.fit_logdet = pointer(logdet); out.fit_jeff = pointer(jeff)
-        rc = ccall((:pfb_elbo_batch, LIB[]), Cint,
+        rc = ccall((:pfb_elbo_batch, LIB), Cint,
                    (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt64},
                     Ptr{Float64}, Ref{PfbElboOut}),
                    e.handle, n, P, offsets, X, G, sd, normals === nothing ? C_NULL : pointer(normals), out)
@@ -194,14 +195,14 @@ function psis_resample(e::Engine, P::Integer, seed::UInt64, ndraws::Integer; imp
     inds = Vector{Int64}(undef, ndraws); ids = similar(inds)
     draws = Matrix{Float64}(undef, e.n, ndraws)
     out = PfbResampleOut()
-    GC.@preserve lw w inds ids draws begin
+    GC.@preserve lw w k tl inds ids draws begin
         if importance
             out.log_weights = pointer(lw); out.weights = pointer(w)
         end
         out.pareto_k = Base.unsafe_convert(Ptr{Float64}, k)
         out.tail_len = Base.unsafe_convert(Ptr{Int64}, tl)
         out.inds = pointer(inds); out.ids = pointer(ids); out.draws = pointer(draws)
-        rc = ccall((:pfb_psis_resample, LIB[]), Cint,
+        rc = ccall((:pfb_psis_resample, LIB), Cint,
                    (Ptr{Cvoid}, UInt64, Cint, Cint, Cint, Ref{PfbResampleOut}), e.handle, seed, ndraws, importance,
                    replace, out)
         check(e, rc)
@@ -219,11 +220,11 @@ WoodburyPDMat ingredients of `elbo_batch`.  `units` are 0-based, path-major / it
 """
 function unit_fits(e::Engine, units::Vector{Int32})
     m = length(units); n = e.n
-    kp = ccall((:pfb_kp, LIB[]), Cint, (Ptr{Cvoid},), e.handle)
+    kp = ccall((:pfb_kp, LIB), Cint, (Ptr{Cvoid},), e.handle)
     mu = Matrix{Float64}(undef, n, m); alpha = similar(mu); vh = Array{Float64}(undef, n, kp, m)
     Tm = Array{Float64}(undef, kp, kp, m); Vc = similar(Tm)
     logdet = Vector{Float64}(undef, m); jeff = Vector{Int32}(undef, m)
-    GC.@preserve units mu alpha vh Tm Vc logdet jeff check(e, ccall((:pfb_unit_fits, LIB[]), Cint,
+    GC.@preserve units mu alpha vh Tm Vc logdet jeff check(e, ccall((:pfb_unit_fits, LIB), Cint,
         (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
          Ptr{Float64}, Ptr{Int32}), e.handle, m, units, mu, alpha, vh, Tm, Vc, logdet, jeff))
     return (; mu, alpha, vh, T=permutedims(Tm, (2, 1, 3)), Vc=permutedims(Vc, (2, 1, 3)), logdet, jeff)
@@ -234,19 +235,19 @@ end
 "128-byte communicator id: create it on one rank, ship it to the others (MPI.Bcast!, a file, ...)."
 function comm_unique_id()
     id = Vector{UInt8}(undef, 128)
-    rc = ccall((:pfb_comm_unique_id, LIB[]), Cint, (Ptr{UInt8},), id)
+    rc = ccall((:pfb_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id)
     rc == 0 || error("pfb_comm_unique_id failed with code $rc (is libnccl.so.2 loadable?)")
     return id
 end
 
 "One process per GPU: every rank calls this with the same id."
 comm_init!(e::Engine, id::Vector{UInt8}, rank::Integer, world::Integer) =
-    check(e, ccall((:pfb_comm_init, LIB[]), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), e.handle, id, rank, world))
+    check(e, ccall((:pfb_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), e.handle, id, rank, world))
 
 "One process, all GPUs: engine i (created with device = i - 1) becomes rank i - 1."
 function comm_init_all!(engines::Vector{Engine})
     hs = [e.handle for e in engines]
-    rc = GC.@preserve hs ccall((:pfb_comm_init_all, LIB[]), Cint, (Ptr{Ptr{Cvoid}}, Cint), hs, length(hs))
+    rc = GC.@preserve hs ccall((:pfb_comm_init_all, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint), hs, length(hs))
     check(engines[1], rc)
 end
 
@@ -276,7 +277,7 @@ function pool_exchange_resample(e::Engine, paths_per_rank::Vector{Int32}, seed::
                                 importance::Bool=true, replace::Bool=true)
     N = Int(sum(paths_per_rank)) * e.K
     out, keep = _resample_out(e.n, N, ndraws, importance)
-    GC.@preserve keep paths_per_rank check(e, ccall((:pfb_pool_exchange_resample, LIB[]), Cint,
+    GC.@preserve keep paths_per_rank check(e, ccall((:pfb_pool_exchange_resample, LIB), Cint,
         (Ptr{Cvoid}, Ptr{Int32}, UInt64, Cint, Cint, Cint, Ref{PfbResampleOut}), e.handle, paths_per_rank, seed,
         ndraws, importance, replace, out))
     lw, w, k, tl, inds, ids, draws = keep
@@ -326,7 +327,7 @@ function multipathfinder_b200_multi(optimize_one, family::Integer, dim::Integer,
             outs[r] = PfbResampleOutC(o)
         end
         hs = [e.handle for e in engines]
-        GC.@preserve hs keeps ppr outs check(engines[1], ccall((:pfb_pool_exchange_resample_all, LIB[]), Cint,
+        GC.@preserve hs keeps ppr outs check(engines[1], ccall((:pfb_pool_exchange_resample_all, LIB), Cint,
             (Ptr{Ptr{Cvoid}}, Cint, Ptr{Int32}, UInt64, Cint, Cint, Cint, Ptr{PfbResampleOutC}), hs, world, ppr,
             rand(rng, UInt64), ndraws, importance, true, outs))
         lw, w, k, tl, inds, ids, draws = keeps[1]              # identical on every rank
@@ -345,13 +346,7 @@ struct PfbLbfgsOpts
     ftol::Float64
 end
 
-"""
-    register_host_model!(engine, logp)
-
-Row f2: make an arbitrary Julia closure `logp(x::AbstractVector)` the target density
-(src/singlepath.jl:186; `logp.(eachcol(ϕ))`, src/elbo.jl:15).  The engine calls it on pinned tiles
-of draws while the next tile is being sampled.  Keep `logp` alive as long as the engine.
-"""
+# the C callback of row f2 (pfb_logp_callback): one tile of draws -> one log density per column
 function _logp_tile(user::Ptr{Cvoid}, x::Ptr{Float64}, n::Int64, m::Int64, out::Ptr{Float64})::Cvoid
     logp = unsafe_pointer_to_objref(user).x
     X = unsafe_wrap(Array, x, (n, m)); o = unsafe_wrap(Array, out, m)
@@ -360,10 +355,17 @@ function _logp_tile(user::Ptr{Cvoid}, x::Ptr{Float64}, n::Int64, m::Int64, out::
     end
     return nothing
 end
+"""
+    register_host_model!(engine, logp)
+
+Row f2: make an arbitrary Julia closure `logp(x::AbstractVector)` the target density
+(src/singlepath.jl:186; `logp.(eachcol(ϕ))`, src/elbo.jl:15).  The engine calls it on pinned tiles
+of draws while the next tile is being sampled.  Keep `logp` alive as long as the engine.
+"""
 function register_host_model!(e::Engine, logp)
     box = Ref{Any}(logp)
     cb = @cfunction(_logp_tile, Cvoid, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}))
-    rc = ccall((:pfb_register_host_model, LIB[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+    rc = ccall((:pfb_register_host_model, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
                e.handle, e.n, cb, pointer_from_objref(box))
     check(e, rc)
     return box  # the caller GC.@preserve's this around every engine call
@@ -380,19 +382,19 @@ function lbfgs_batch(e::Engine, inits::Matrix{Float64}; maxiters::Integer=1000, 
     P = size(inits, 2)
     npts = Vector{Int64}(undef, P); status = Vector{Int32}(undef, P)
     opts = Ref(PfbLbfgsOpts(maxiters, maxiters + 1, gtol, ftol))
-    rc = ccall((:pfb_lbfgs_batch, LIB[]), Cint,
+    rc = ccall((:pfb_lbfgs_batch, LIB), Cint,
                (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ref{PfbLbfgsOpts}, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}),
                e.handle, e.n, P, inits, opts, npts, status, C_NULL)
     check(e, rc)
     return npts, status
 end
 function batch_from_lbfgs(e::Engine, seeds::Vector{UInt64})
-    check(e, ccall((:pfb_batch_from_lbfgs, LIB[]), Cint, (Ptr{Cvoid}, Ptr{UInt64}), e.handle, seeds))
+    check(e, ccall((:pfb_batch_from_lbfgs, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt64}), e.handle, seeds))
 end
 function lbfgs_download(e::Engine, npts::Vector{Int64})
     T = sum(npts)
     X = Matrix{Float64}(undef, e.n, T); G = similar(X); fx = Vector{Float64}(undef, T)
-    check(e, ccall((:pfb_lbfgs_download, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+    check(e, ccall((:pfb_lbfgs_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                    e.handle, X, G, fx))
     return X, G, fx
 end
@@ -407,7 +409,7 @@ iterations of the current batch, regenerated on the device from their seeds (0-b
 function unit_draws(e::Engine, units::Vector{Int32})
     m = length(units)
     draws = Array{Float64}(undef, e.n, e.K, m); lp = Matrix{Float64}(undef, e.K, m); lq = similar(lp)
-    check(e, ccall((:pfb_unit_draws, LIB[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+    check(e, ccall((:pfb_unit_draws, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                    e.handle, m, units, draws, lp, lq))
     return draws, lp, lq
 end
@@ -420,7 +422,7 @@ materialises the pool's draws only on request — `psis_resample` regenerates ju
 """
 function pool_draws(e::Engine, P::Integer)
     draws = Array{Float64}(undef, e.n, e.K, P); lp = Matrix{Float64}(undef, e.K, P); lq = similar(lp)
-    check(e, ccall((:pfb_pool_download, LIB[]), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+    check(e, ccall((:pfb_pool_download, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                    e.handle, 0, P, draws, lp, lq))
     return draws, lp, lq
 end
