@@ -284,3 +284,48 @@ def test_reference_arm_prints_the_contract_line_and_only_rank_0_works():
     # a non-zero rank of a multi-rank launch does nothing and prints nothing
     assert _run_bench(["--impl", "reference", "--config", cfg, "--gpus", "2", "--steps", "1", "--warmup", "0"],
                       env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_julia_shim_ccalls_match_the_header():
+    """julia/PathfinderB200.jl cannot be executed here (no Julia): at least every ccall in it must name a
+    function that include/pfb200.h declares, with the same number of arguments and a pointer / scalar
+    pattern that agrees with the C prototype."""
+    import pathlib
+    import re
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+    hdr = re.sub(r"/\*.*?\*/", " ", (root / "include" / "pfb200.h").read_text(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char\s*\*|size_t)\s+(pfb_\w+)\s*\(([^;{}]*?)\)\s*;", hdr, flags=re.S):
+        args = [a.strip() for a in m.group(2).split(",")] if m.group(2).strip() not in ("", "void") else []
+        protos[m.group(1)] = args
+    assert len(protos) >= 35
+
+    jl = (root / "julia" / "PathfinderB200.jl").read_text()
+    calls = re.findall(r"ccall\(\(:(pfb_\w+), LIB\),\s*(\w+),\s*\((.*?)\)\s*,", jl, flags=re.S)
+    assert len(calls) >= 15 and "LIB[]" not in jl
+    # the binding shown in INTEGRATION.md is held to the same standard
+    doc_calls = re.findall(r"ccall\(\(:(pfb_\w+), LIB\),\s*(\w+),\s*\((.*?)\)\s*,", (root / "INTEGRATION.md").read_text(),
+                           flags=re.S)
+    assert len(doc_calls) >= 4
+    calls = calls + doc_calls
+    seen = set()
+    for name, ret, types in calls:
+        assert name in protos, f"{name} is not declared in pfb200.h"
+        seen.add(name)
+        jt = [t.strip() for t in types.replace("\n", " ").split(",") if t.strip()]
+        ct = protos[name]
+        assert len(jt) == len(ct), (name, jt, ct)
+        assert ret in ("Cint", "Cstring"), (name, ret)
+        for j, c in zip(jt, ct):
+            c_is_ptr = "*" in c or "pfb_handle" in c or "pfb_logp_callback" in c
+            j_is_ptr = j.startswith(("Ptr{", "Ref{")) or j == "Cstring"
+            assert c_is_ptr == j_is_ptr, (name, j, c)
+            if not c_is_ptr:
+                width = {"Cint": "int", "Int32": "int32_t", "Int64": "int64_t", "UInt64": "uint64_t", "Csize_t": "size_t",
+                         "Cdouble": "double", "Float64": "double"}[j]
+                assert re.search(rf"\b{width}\b", c), (name, j, c)
+    # the calls a drop-in needs are all there
+    assert {"pfb_create", "pfb_destroy", "pfb_register_model", "pfb_elbo_batch", "pfb_psis_resample",
+            "pfb_set_fallback_seeds", "pfb_unit_fits", "pfb_comm_init", "pfb_pool_exchange_resample",
+            "pfb_pool_exchange_resample_all", "pfb_register_host_model", "pfb_lbfgs_batch"} <= seen
