@@ -329,3 +329,24 @@ def test_julia_shim_ccalls_match_the_header():
     assert {"pfb_create", "pfb_destroy", "pfb_register_model", "pfb_elbo_batch", "pfb_psis_resample",
             "pfb_set_fallback_seeds", "pfb_unit_fits", "pfb_comm_init", "pfb_pool_exchange_resample",
             "pfb_pool_exchange_resample_all", "pfb_register_host_model", "pfb_lbfgs_batch"} <= seen
+
+
+def test_julia_shim_structs_mirror_the_header_field_for_field():
+    import pathlib
+    import re
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+    hdr = re.sub(r"/\*.*?\*/", " ", (root / "include" / "pfb200.h").read_text(), flags=re.S)
+    jl = (root / "julia" / "PathfinderB200.jl").read_text()
+    ctype = {"Int32": "int32_t", "Int64": "int64_t", "Float64": "double", "Ptr{Float64}": "double*",
+             "Ptr{Int64}": "int64_t*", "Ptr{Int32}": "int32_t*"}
+    pairs = {"PfbConfig": "pfb_config", "PfbElboOut": "pfb_elbo_out", "PfbResampleOut": "pfb_resample_out",
+             "PfbResampleOutC": "pfb_resample_out", "PfbLbfgsOpts": "pfb_lbfgs_opts"}
+    for jname, cname in pairs.items():
+        body = re.search(rf"typedef struct\s*\{{([^}}]*)\}}\s*{cname}\s*;", hdr).group(1)
+        cfields = [(re.sub(r"\s+", "", t), n) for t, n in re.findall(r"([\w ]+?\*?)\s*(\w+)\s*;", body)]
+        jbody = re.search(rf"struct {jname}\n(.*?)\nend", jl, flags=re.S).group(1)
+        jfields = [(n, t) for n, t in re.findall(r"^\s*(\w+)::([\w{{}}]+)\s*$", jbody, flags=re.M)]
+        assert len(cfields) == len(jfields) > 0, (jname, cfields, jfields)
+        for (ct, cn), (jn, jt) in zip(cfields, jfields):
+            assert cn == jn and ctype[jt] == ct, (jname, (ct, cn), (jn, jt))
