@@ -350,3 +350,29 @@ def test_julia_shim_structs_mirror_the_header_field_for_field():
         assert len(cfields) == len(jfields) > 0, (jname, cfields, jfields)
         for (ct, cn), (jn, jt) in zip(cfields, jfields):
             assert cn == jn and ctype[jt] == ct, (jname, (ct, cn), (jn, jt))
+
+
+def test_reference_citations_point_at_existing_lines():
+    """Every `src/...jl:LINE` style citation in the header, the docs and the oracle names a file of the
+    reference that exists and is at least that long (checked where /root/reference is present)."""
+    import pathlib
+    import re
+
+    ref = pathlib.Path("/root/reference")
+    if not ref.is_dir():
+        pytest.skip("/root/reference is not present on this machine")
+    root = pathlib.Path(__file__).resolve().parents[1]
+    files = [root / "include" / "pfb200.h", root / "DESIGN.md", root / "INTEGRATION.md", root / "julia" / "PathfinderB200.jl"]
+    files += sorted((root / "oracle").glob("*.py")) + sorted((root / "pathfinder_b200").glob("*.py"))
+    pat = re.compile(r"\b((?:src|test|ext|docs/src)/[\w/.\-]+\.(?:jl|md)):(\d+)(?:-(\d+))?")
+    nlines, checked = {}, 0
+    for f in files:
+        for m in pat.finditer(f.read_text()):
+            path = ref / m.group(1)
+            assert path.is_file(), f"{f.name}: cites {m.group(1)}, which the reference does not have"
+            if path not in nlines:
+                nlines[path] = len(path.read_text().splitlines())
+            last = int(m.group(3) or m.group(2))
+            assert 1 <= int(m.group(2)) <= last <= nlines[path], f"{f.name}: {m.group(0)} (file has {nlines[path]} lines)"
+            checked += 1
+    assert checked > 100
