@@ -364,6 +364,9 @@ def test_reference_citations_point_at_existing_lines():
     root = pathlib.Path(__file__).resolve().parents[1]
     files = [root / "include" / "pfb200.h", root / "DESIGN.md", root / "INTEGRATION.md", root / "julia" / "PathfinderB200.jl"]
     files += sorted((root / "oracle").glob("*.py")) + sorted((root / "pathfinder_b200").glob("*.py"))
+    files += sorted((root / "oracle").glob("*.c*")) + [root / "bench.py", root / "README.md"]
+    files += [f for ext in ("*.cu", "*.cuh", "*.h") for f in sorted((root / "pathfinder_b200" / "csrc").glob(ext))
+              if f.name != "pf_zig_tables.h"]
     pat = re.compile(r"\b((?:src|test|ext|docs/src)/[\w/.\-]+\.(?:jl|md)):(\d+)(?:-(\d+))?")
     nlines, checked = {}, 0
     for f in files:
