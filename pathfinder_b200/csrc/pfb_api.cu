@@ -828,6 +828,7 @@ static int failed_path_enqueue(pfb_engine* h) {
     PFB_CUDA(h, h->dFbSeeds.ensure((size_t)P * 8));
     PFB_CUDA(h, cudaMemcpyAsync(h->dFbSeeds.p, h->fb_seeds.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
     if (P > h->hSuccBuCap) {
+        PFB_CUDA(h, cudaStreamSynchronize(st));  // an earlier batch's flags may still be on their way into the old pair
         if (h->hSuccBu) cudaFreeHost(h->hSuccBu);
         h->hSuccBu = nullptr;
         h->hSuccBuCap = 0;
