@@ -655,3 +655,56 @@ def test_psis_and_resample_contract_properties():
     rank_of[nr_all - 1] = np.arange(lr.size)
     top = np.argsort(-w)[:50]
     assert rank_of[top].mean() < 0.25 * lr.size
+
+
+def test_lbfgs_contract_agrees_with_an_independent_restatement():
+    """pf_lbfgs.h is compiled into both K0 and the oracle, so their bit-exact agreement is one source under
+    two compilers.  tests/indep_lbfgs.py states the same algorithm separately in plain NumPy (other
+    summation order, libm exp): iterates, log densities, gradients, statuses and evaluation counts must
+    agree — up to rounding, which grows along a funnel trajectory, hence short runs with a line search
+    that brackets and zooms (more evaluations than iterations)."""
+    from oracle import lbfgs as OL
+    from tests import indep_lbfgs as IL
+
+    def close(a, b, tol):
+        assert a.shape == b.shape, (a.shape, b.shape)
+        assert np.max(np.abs(a - b)) <= tol * max(1.0, np.max(np.abs(a))), np.max(np.abs(a - b))
+
+    zoomed = 0
+    for seed in range(8):
+        rng = np.random.default_rng(100 + seed)
+        n, scale, iters = ((16, 2.0, 12), (32, 3.0, 14))[seed % 2]
+        x0 = rng.uniform(-scale, scale, size=n)
+        X, FX, G, st, nev = OL.lbfgs_path(OL.FAMILY_FUNNEL, x0, maxiters=iters)
+        Xi, FXi, Gi, sti, nevi = IL.lbfgs_path(IL.density("funnel"), x0, maxiters=iters)
+        assert OL.STATUS[st] == sti and nev == nevi, (seed, OL.STATUS[st], sti, nev, nevi)
+        close(X, Xi, 1e-7); close(FX, FXi, 1e-7); close(G, Gi, 1e-6)
+        zoomed += nev > X.shape[1] + 3
+    assert zoomed >= 4  # the bracketing / zoom phase was exercised, not just first-trial acceptance
+
+    rng = np.random.default_rng(7)
+    x0 = rng.uniform(-2, 2, size=10)
+    a, b = OL.lbfgs_path(OL.FAMILY_ISONORMAL, x0), IL.lbfgs_path(IL.density("isonormal"), x0)
+    assert OL.STATUS[a[3]] == b[3] and a[4] == b[4]
+    close(a[0], b[0], 1e-12); close(a[2], b[2], 1e-12)
+
+    n = 24
+    A = rng.normal(size=(n, n)) / np.sqrt(n)
+    prec, mean = A @ A.T + np.diag(rng.uniform(0.5, 2.0, size=n)), rng.normal(size=n)
+    x0 = rng.uniform(-2, 2, size=n)
+    a = OL.lbfgs_path(OL.FAMILY_DENSENORMAL, x0, mean=mean, prec=prec)
+    b = IL.lbfgs_path(IL.density("densenormal", mean=mean, prec=prec), x0)
+    assert OL.STATUS[a[3]] == b[3] and a[4] == b[4]
+    close(a[0], b[0], 1e-9); close(a[1], b[1], 1e-9); close(a[2], b[2], 1e-8)
+
+    n = 37
+    mean, sd = rng.normal(size=n) * 3, rng.uniform(0.05, 20.0, size=n)
+    x0 = rng.uniform(-2, 2, size=n)
+    a = OL.lbfgs_path(OL.FAMILY_DIAGNORMAL, x0, mean=mean, sd=sd, maxiters=30)
+    b = IL.lbfgs_path(IL.density("diagnormal", mean=mean, sd=sd), x0, maxiters=30)
+    assert a[4] == b[4]
+    close(a[0], b[0], 1e-7); close(a[1], b[1], 1e-9)
+    # both reach the same optimum when left to converge
+    a = OL.lbfgs_path(OL.FAMILY_DIAGNORMAL, x0, mean=mean, sd=sd)
+    b = IL.lbfgs_path(IL.density("diagnormal", mean=mean, sd=sd), x0)
+    assert OL.STATUS[a[3]] == b[3] and abs(a[1][-1] - b[1][-1]) < 1e-8
