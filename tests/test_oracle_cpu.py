@@ -708,3 +708,42 @@ def test_lbfgs_contract_agrees_with_an_independent_restatement():
     a = OL.lbfgs_path(OL.FAMILY_DIAGNORMAL, x0, mean=mean, sd=sd)
     b = IL.lbfgs_path(IL.density("diagnormal", mean=mean, sd=sd), x0)
     assert OL.STATUS[a[3]] == b[3] and abs(a[1][-1] - b[1][-1]) < 1e-8
+
+
+def test_normal_contract_agrees_with_an_independent_restatement():
+    """pf_rng.h is compiled into both the kernels and the oracle.  tests/indep_rng.py states the contract a
+    second time in pure Python (integer Philox4x32-7, tables recomputed by the generator script, exact
+    rational arithmetic for the fast path's single rounding, libm on the slow path): every variate of the
+    C stream must be reproduced — bit for bit on the table-only path, to 1e-13 where exp / log enter."""
+    from tests import indep_rng as IR
+
+    lib = O.clib()
+    lib.pfo_normal_elem.restype = ctypes.c_double
+    total = slow = 0
+    for seed, n, K in ((77, 120, 100), (2**63 + 5, 64, 80), (123456789012345, 33, 50)):
+        U = np.asarray(O.contract_normals(seed, n, K))
+        for i in range(n):
+            for k in range(K):
+                z, was_slow = IR.normal_elem(seed, i, k)
+                total += 1
+                slow += was_slow
+                if was_slow:
+                    assert abs(z - U[i, k]) <= 1e-13 * abs(U[i, k]), (seed, i, k, z, U[i, k])
+                else:
+                    assert z == U[i, k], (seed, i, k, z, U[i, k])
+    assert 0.002 < slow / total < 0.008  # 0.43 % leave the fast path
+    # the tail beyond r = 4.04 (5e-5 of the variates): find elements whose first word lands in the base
+    # strip outside its core, and compare those too
+    seed, tails = 1, 0
+    for i in range(0, 400, 2):
+        for dp in range(128):
+            o = IR._call(i >> 1, 0, dp, seed, 0)
+            for word in range(4):
+                w = o[word]
+                if (w >> 21) & 1023 == 0 and (w & 0xFFFFF) >= (IR._tables_cached()[0][0] & 0xFFFFF):
+                    row, k = i + (word & 1), (dp >> 3) * 16 + (dp & 7) + 8 * (word >> 1)
+                    z, was_slow = IR.normal_elem(seed, row, k)
+                    ref = lib.pfo_normal_elem(ctypes.c_uint64(seed), ctypes.c_uint32(row), ctypes.c_uint32(k))
+                    assert was_slow and abs(z) > 4.0 and abs(z - ref) <= 1e-13 * abs(ref), (row, k, z, ref)
+                    tails += 1
+    assert tails >= 2
