@@ -747,3 +747,32 @@ def test_normal_contract_agrees_with_an_independent_restatement():
                     assert was_slow and abs(z) > 4.0 and abs(z - ref) <= 1e-13 * abs(ref), (row, k, z, ref)
                     tails += 1
     assert tails >= 2
+
+
+def test_resample_index_stream_agrees_with_an_independent_restatement():
+    """_resample with replacement (src/resample.jl:58-72) under the engine's contract, restated on Python
+    integers: draw t takes 64 bits of Philox4x32-10 call t >> 1 on stream 3 (low pair for even t, high pair
+    for odd t), target = floor(bits * Z / 2^64) on the fixed-point (2^52) cumulative weights, index = the
+    first entry whose cumulative weight exceeds the target."""
+    from tests import indep_rng as IR
+
+    rng = np.random.default_rng(5)
+    for seed, N, ndraws in ((9, 4, 300), (2**64 - 3, 257, 500), (123456789, 5000, 400)):
+        w = rng.dirichlet(np.full(N, 0.3))
+        fixed = [int(v * 4503599627370496.0) if v > 0.0 else 0 for v in w]
+        cum, acc = [], 0
+        for v in fixed:
+            acc += v
+            cum.append(acc)
+        want = []
+        for t in range(ndraws):
+            q = t >> 1
+            o = IR.philox4x32(10, ((q & 0x0FFFFFFF) | 3 << 28, q >> 28, seed & 0xFFFFFFFF, seed >> 32))
+            bits = (o[2] | o[3] << 32) if t & 1 else (o[0] | o[1] << 32)
+            target = (bits * acc) >> 64
+            want.append(next(i for i, c in enumerate(cum) if c > target) + 1)
+        assert np.array_equal(OP.resample_indices(seed, w, N, ndraws), want)
+        uniform = [((lambda o, t: (o[2] | o[3] << 32) if t & 1 else (o[0] | o[1] << 32))(
+            IR.philox4x32(10, (((t >> 1) & 0x0FFFFFFF) | 3 << 28, (t >> 1) >> 28, seed & 0xFFFFFFFF, seed >> 32)), t) * N >> 64) + 1
+            for t in range(ndraws)]
+        assert np.array_equal(OP.resample_indices(seed, None, N, ndraws), uniform)
