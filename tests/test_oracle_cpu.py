@@ -776,3 +776,27 @@ def test_resample_index_stream_agrees_with_an_independent_restatement():
             IR.philox4x32(10, (((t >> 1) & 0x0FFFFFFF) | 3 << 28, (t >> 1) >> 28, seed & 0xFFFFFFFF, seed >> 32)), t) * N >> 64) + 1
             for t in range(ndraws)]
         assert np.array_equal(OP.resample_indices(seed, None, N, ndraws), uniform)
+
+
+def test_resample_without_replacement_agrees_with_an_independent_restatement():
+    """replace = false (src/resample.jl:61-66) under the engine's contract, restated with Python integers
+    and libm: key_i = log(E_i) - log w_i, E_i = -log(u_i), u_i = (top 53 bits of draw i's 64 + 0.5) 2^-53;
+    the ndraws smallest keys in ascending order."""
+    import math
+
+    from tests import indep_rng as IR
+
+    rng = np.random.default_rng(8)
+    for seed, N, ndraws in ((4, 60, 60), (2**62 + 1, 700, 90)):
+        lw = np.log(rng.dirichlet(np.full(N, 0.5)))
+        keys = []
+        for t in range(N):
+            q = t >> 1
+            o = IR.philox4x32(10, ((q & 0x0FFFFFFF) | 3 << 28, q >> 28, seed & 0xFFFFFFFF, seed >> 32))
+            bits = (o[2] | o[3] << 32) if t & 1 else (o[0] | o[1] << 32)
+            u = ((bits >> 11) + 0.5) * 2.0 ** -53
+            keys.append(math.log(-math.log(u)) - lw[t])
+        want = np.argsort(np.array(keys), kind="stable")[:ndraws] + 1
+        got = OP.resample_indices_norep(seed, lw, N, ndraws)
+        assert np.array_equal(got, want)
+        assert len(set(got.tolist())) == ndraws
